@@ -1,0 +1,1297 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the shipped product path.
+//
+// CPU restatement (C++17, g++ -O2 -ffp-contract=off) of the line-search-solver hot path of
+// fedemagnani/optimization-solvers (pure Rust; no Rust toolchain exists in this image, so the
+// reference itself cannot be compiled here).  Every function cites the reference file:line it
+// follows.  All dense arithmetic of the reference lives in the un-vendored dependency
+// nalgebra 0.33.2 (Cargo.lock:398-401) + matrixmultiply 0.3.9 (Cargo.lock:360-362); their
+// published algorithms (operation order of dot / gemv / gemm / Cholesky / LU-inverse) are restated
+// in the "nalgebra semantics" section below.
+//
+// PARITY PIN: this oracle is pinned against (a) the reference's only exact known-answer check,
+// examples/quadratic.rs:43 (f == 0.0), (b) every |f| < 1e-6 / |x0| < 1e-6 assert of the
+// reference's inline unit tests (bfgs.rs:187,238; dfp.rs:182,233; broyden.rs:180,231;
+// dfp_b.rs:216; broyden_b.rs:215; sr1_b.rs:211; gradient_descent.rs:129; newton/mod.rs:117,162;
+// backtracking.rs:111; morethuente.rs:350; morethuente_b.rs:377) — see tests/test_oracle_golden.py.
+// Nothing in the reference pins n > 3, Rosenbrock, logistic regression or any active set, so for
+// the large configs parity is "GPU == this restatement on identical synthetic inputs".
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+// load this library.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <limits>
+#include <memory>
+#include <string>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace orc {
+
+using Vec = std::vector<double>;
+static const double INF = std::numeric_limits<double>::infinity();
+
+// ------------------------------------------------------------------------------------------
+// nalgebra semantics (column-major DMatrix, DVector)
+// ------------------------------------------------------------------------------------------
+struct Mat {
+  size_t r = 0, c = 0;
+  std::vector<double> a;  // column-major, like nalgebra's VecStorage
+  Mat() {}
+  Mat(size_t r_, size_t c_, double v = 0.0) : r(r_), c(c_), a(r_ * c_, v) {}
+  double& operator()(size_t i, size_t j) { return a[i + j * r]; }
+  double operator()(size_t i, size_t j) const { return a[i + j * r]; }
+  double* col(size_t j) { return a.data() + j * r; }
+  const double* col(size_t j) const { return a.data() + j * r; }
+  static Mat identity(size_t n) {
+    Mat m(n, n);
+    for (size_t i = 0; i < n; ++i) m(i, i) = 1.0;
+    return m;
+  }
+};
+
+// Rust f64::max / f64::min: if one operand is NaN the other is returned (number.rs:19 sup/inf,
+// morethuente.rs:290 clamp).  std::fmax / std::fmin have the same contract.
+static inline double rmax(double a, double b) { return std::fmax(a, b); }
+static inline double rmin(double a, double b) { return std::fmin(a, b); }
+
+// nalgebra base/blas.rs `dotx`: 8 interleaved accumulators over strides of 8, combined pairwise,
+// then the <8 tail sequentially.  Call sites: line_search/mod.rs:35,47,55; morethuente.rs:137;
+// bfgs.rs:115; dfp.rs:117-118; spg.rs:135,141; backtracking_b.rs:33; newton/mod.rs:40.
+static double dot(const double* a, const double* b, size_t n) {
+  double res = 0.0;
+  double acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0, acc4 = 0, acc5 = 0, acc6 = 0, acc7 = 0;
+  size_t i = 0;
+  while (n - i >= 8) {
+    acc0 += a[i + 0] * b[i + 0];
+    acc1 += a[i + 1] * b[i + 1];
+    acc2 += a[i + 2] * b[i + 2];
+    acc3 += a[i + 3] * b[i + 3];
+    acc4 += a[i + 4] * b[i + 4];
+    acc5 += a[i + 5] * b[i + 5];
+    acc6 += a[i + 6] * b[i + 6];
+    acc7 += a[i + 7] * b[i + 7];
+    i += 8;
+  }
+  res += acc0 + acc4;
+  res += acc1 + acc5;
+  res += acc2 + acc6;
+  res += acc3 + acc7;
+  for (; i < n; ++i) res += a[i] * b[i];
+  return res;
+}
+static double dot(const Vec& a, const Vec& b) { return dot(a.data(), b.data(), a.size()); }
+// nalgebra norm() = sqrt(norm_squared()) = sqrt(dot(v,v))  (bfgs.rs:74,97,99)
+static double norm(const Vec& a) { return std::sqrt(dot(a, a)); }
+
+// number.rs:27-31 InfinityNorm: fold from 0.0 with f64::max (NaN-dropping)
+static double infinity_norm(const Vec& v) {
+  double acc = 0.0;
+  for (double x : v) acc = rmax(acc, std::fabs(x));
+  return acc;
+}
+// number.rs:13-21 BoxProjection: x.sup(lb).inf(ub)
+static Vec box_projection(const Vec& x, const Vec& lb, const Vec& ub) {
+  Vec r(x.size());
+  for (size_t i = 0; i < x.size(); ++i) r[i] = rmin(rmax(x[i], lb[i]), ub[i]);
+  return r;
+}
+static Vec add(const Vec& a, const Vec& b) {
+  Vec r(a.size());
+  for (size_t i = 0; i < a.size(); ++i) r[i] = a[i] + b[i];
+  return r;
+}
+static Vec sub(const Vec& a, const Vec& b) {
+  Vec r(a.size());
+  for (size_t i = 0; i < a.size(); ++i) r[i] = a[i] - b[i];
+  return r;
+}
+static Vec scale(double t, const Vec& a) {
+  Vec r(a.size());
+  for (size_t i = 0; i < a.size(); ++i) r[i] = t * a[i];
+  return r;
+}
+static Vec neg(const Vec& a) {
+  Vec r(a.size());
+  for (size_t i = 0; i < a.size(); ++i) r[i] = -a[i];
+  return r;
+}
+// x + t*d : two roundings fl(x + fl(t*d))  (ls_solver.rs:60, backtracking.rs:32)
+static Vec axpy_new(const Vec& x, double t, const Vec& d) {
+  Vec r(x.size());
+  for (size_t i = 0; i < x.size(); ++i) {
+    double td = t * d[i];
+    r[i] = x[i] + td;
+  }
+  return r;
+}
+
+// nalgebra gemv (blas.rs gemv / axcpy): y = A[:,0]*x0 ; y += A[:,j]*xj for j = 1.. — per element
+// a strict left-to-right sum of separately rounded products.  `threads` only splits the rows,
+// which does not change any element's operation order.
+static void gemv_into(const Mat& A, const double* x, double* y) {
+  const size_t n = A.r, m = A.c;
+  if (m == 0) {
+    for (size_t i = 0; i < n; ++i) y[i] = 0.0;
+    return;
+  }
+#pragma omp parallel
+  {
+    size_t lo = 0, hi = n;
+#ifdef _OPENMP
+    int nt = omp_get_num_threads(), id = omp_get_thread_num();
+    size_t chunk = (n + nt - 1) / nt;
+    lo = std::min(n, chunk * id);
+    hi = std::min(n, lo + chunk);
+#endif
+    const double* c0 = A.col(0);
+    double x0 = x[0];
+    for (size_t i = lo; i < hi; ++i) y[i] = c0[i] * x0;
+    for (size_t j = 1; j < m; ++j) {
+      const double* cj = A.col(j);
+      double xj = x[j];
+      for (size_t i = lo; i < hi; ++i) y[i] = cj[i] * xj + y[i];
+    }
+  }
+}
+static Vec gemv(const Mat& A, const Vec& x) {
+  Vec y(A.r);
+  gemv_into(A, x.data(), y.data());
+  return y;
+}
+
+// nalgebra gemm (blas.rs): when result rows/cols and lhs rows/cols are all > 5 (and every dim is
+// Dyn) the product goes to matrixmultiply::dgemm — a packed, blocked kernel that accumulates each
+// k-panel (kc = 256) in registers with hardware FMA when the CPU has it and then adds the panel to
+// C.  That path is not bit-reproducible across hosts by construction; it is restated here as
+// "per element: for each kc-panel, ab = fma-chain over k ascending; C = first ? ab : C + ab".
+// Otherwise: column-by-column gemv (blas.rs gemm fallback).
+static const size_t SMALL_DIM = 5, KC = 256;
+static Mat matmul(const Mat& A, const Mat& B) {
+  Mat C(A.r, B.c);
+  const size_t n = A.r, kk = A.c, m = B.c;
+  if (n > SMALL_DIM && m > SMALL_DIM && A.r > SMALL_DIM && A.c > SMALL_DIM) {
+#pragma omp parallel
+    {
+      std::vector<double> tmp(n);
+#pragma omp for schedule(static)
+      for (long jj = 0; jj < (long)m; ++jj) {
+        size_t j = (size_t)jj;
+        double* cj = C.col(j);
+        for (size_t k0 = 0; k0 < kk; k0 += KC) {
+          size_t k1 = std::min(kk, k0 + KC);
+          std::fill(tmp.begin(), tmp.end(), 0.0);
+          for (size_t k = k0; k < k1; ++k) {
+            const double* ak = A.col(k);
+            double b = B(k, j);
+            for (size_t i = 0; i < n; ++i) tmp[i] = __builtin_fma(ak[i], b, tmp[i]);
+          }
+          if (k0 == 0)
+            for (size_t i = 0; i < n; ++i) cj[i] = tmp[i];
+          else
+            for (size_t i = 0; i < n; ++i) cj[i] = cj[i] + tmp[i];
+        }
+      }
+    }
+  } else {
+    for (size_t j = 0; j < m; ++j) gemv_into(A, B.col(j), C.col(j));
+  }
+  return C;
+}
+// s * y^T : DVector * RowDVector is not all-Dyn -> gemv path -> one rounded product per element
+static Mat outer(const Vec& s, const Vec& y) {
+  Mat M(s.size(), y.size());
+  for (size_t j = 0; j < y.size(); ++j) {
+    double yj = y[j];
+    double* c = M.col(j);
+    for (size_t i = 0; i < s.size(); ++i) c[i] = s[i] * yj;
+  }
+  return M;
+}
+static Mat transpose(const Mat& A) {
+  Mat T(A.c, A.r);
+  for (size_t j = 0; j < A.c; ++j)
+    for (size_t i = 0; i < A.r; ++i) T(j, i) = A(i, j);
+  return T;
+}
+static Mat mscale(const Mat& A, double s) {
+  Mat R = A;
+  for (auto& v : R.a) v = v * s;
+  return R;
+}
+static Mat mdiv(const Mat& A, double s) {  // true division, not multiply-by-reciprocal
+  Mat R = A;
+  for (auto& v : R.a) v = v / s;
+  return R;
+}
+static Mat msub(const Mat& A, const Mat& B) {
+  Mat R = A;
+  for (size_t i = 0; i < R.a.size(); ++i) R.a[i] = A.a[i] - B.a[i];
+  return R;
+}
+static Mat madd(const Mat& A, const Mat& B) {
+  Mat R = A;
+  for (size_t i = 0; i < R.a.size(); ++i) R.a[i] = A.a[i] + B.a[i];
+  return R;
+}
+
+// nalgebra linalg/cholesky.rs Cholesky::new (left-looking) + solve  (projected_newton.rs:75, spn.rs:86)
+static bool cholesky_inplace(Mat& M) {
+  const size_t n = M.r;
+  for (size_t j = 0; j < n; ++j) {
+    for (size_t k = 0; k < j; ++k) {
+      double factor = -M(j, k);
+      double* cj = M.col(j);
+      const double* ck = M.col(k);
+      for (size_t i = j; i < n; ++i) cj[i] = factor * ck[i] + cj[i];
+    }
+    double diag = M(j, j);
+    if (diag != 0.0 && diag >= 0.0) {  // try_sqrt: Some only for diag >= 0 (NaN fails)
+      double denom = std::sqrt(diag);
+      M(j, j) = denom;
+      for (size_t i = j + 1; i < n; ++i) M(i, j) = M(i, j) / denom;
+      continue;
+    }
+    return false;
+  }
+  return true;
+}
+static Vec cholesky_solve(const Mat& L, const Vec& rhs) {
+  const size_t n = L.r;
+  Vec b = rhs;
+  // solve_lower_triangular_unchecked_mut: column-oriented forward substitution
+  for (size_t i = 0; i < n; ++i) {
+    double coeff = b[i] / L(i, i);
+    b[i] = coeff;
+    double nc = -coeff;
+    const double* ci = L.col(i);
+    for (size_t r = i + 1; r < n; ++r) b[r] = nc * ci[r] + b[r];
+  }
+  // ad_solve_lower_triangular_unchecked_mut: dot-oriented backward substitution with L^T
+  for (size_t ii = n; ii-- > 0;) {
+    double d = dot(L.col(ii) + ii + 1, b.data() + ii + 1, n - ii - 1);
+    b[ii] = (b[ii] - d) / L(ii, ii);
+  }
+  return b;
+}
+
+// nalgebra linalg/inverse.rs try_inverse: closed forms n<=4, LU with partial pivoting above
+// (newton/mod.rs:36).  n = 4 follows the cofactor expansion nalgebra takes from MESA's
+// gluInvertMatrix.
+static bool try_inverse(const Mat& Min, Mat& out) {
+  const size_t n = Min.r;
+  out = Min;
+  if (n == 0) return true;
+  if (n == 1) {
+    double det = Min(0, 0);
+    if (det == 0.0) return false;
+    out(0, 0) = 1.0 / det;
+    return true;
+  }
+  if (n == 2) {
+    double m11 = Min(0, 0), m12 = Min(0, 1), m21 = Min(1, 0), m22 = Min(1, 1);
+    double det = m11 * m22 - m21 * m12;
+    if (det == 0.0) return false;
+    out(0, 0) = m22 / det;
+    out(0, 1) = -m12 / det;
+    out(1, 0) = -m21 / det;
+    out(1, 1) = m11 / det;
+    return true;
+  }
+  if (n == 3) {
+    double m11 = Min(0, 0), m12 = Min(0, 1), m13 = Min(0, 2);
+    double m21 = Min(1, 0), m22 = Min(1, 1), m23 = Min(1, 2);
+    double m31 = Min(2, 0), m32 = Min(2, 1), m33 = Min(2, 2);
+    double minor_m12_m23 = m22 * m33 - m32 * m23;
+    double minor_m11_m23 = m21 * m33 - m31 * m23;
+    double minor_m11_m22 = m21 * m32 - m31 * m22;
+    double det = m11 * minor_m12_m23 - m12 * minor_m11_m23 + m13 * minor_m11_m22;
+    if (det == 0.0) return false;
+    out(0, 0) = minor_m12_m23 / det;
+    out(0, 1) = (m13 * m32 - m33 * m12) / det;
+    out(0, 2) = (m12 * m23 - m22 * m13) / det;
+    out(1, 0) = -minor_m11_m23 / det;
+    out(1, 1) = (m11 * m33 - m31 * m13) / det;
+    out(1, 2) = (m13 * m21 - m23 * m11) / det;
+    out(2, 0) = minor_m11_m22 / det;
+    out(2, 1) = (m12 * m31 - m32 * m11) / det;
+    out(2, 2) = (m11 * m22 - m21 * m12) / det;
+    return true;
+  }
+  if (n == 4) {
+    const double* m = Min.a.data();
+    double o[16];
+    o[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+    o[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+    o[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+    o[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+    o[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+    o[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+    o[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+    o[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+    o[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+    o[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+    o[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+    o[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+    o[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+    o[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+    o[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+    o[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+    double det = m[0] * o[0] + m[1] * o[4] + m[2] * o[8] + m[3] * o[12];
+    if (det == 0.0) return false;
+    double inv_det = 1.0 / det;
+    for (int i = 0; i < 16; ++i) out.a[i] = o[i] * inv_det;
+    return true;
+  }
+  // n >= 5: linalg/lu.rs try_invert_to — Gauss elimination with partial pivoting on a copy, the
+  // same row swaps applied to an identity, then unit-lower and upper triangular solves.
+  Mat A = Min;
+  out = Mat::identity(n);
+  for (size_t i = 0; i < n; ++i) {
+    size_t piv = i;
+    double best = std::fabs(A(i, i));
+    for (size_t r = i + 1; r < n; ++r) {
+      double v = std::fabs(A(r, i));
+      if (v > best) { best = v; piv = r; }
+    }
+    double diag = A(piv, i);
+    if (diag == 0.0) return false;
+    if (piv != i) {
+      for (size_t c = 0; c < n; ++c) std::swap(out(i, c), out(piv, c));
+      for (size_t c = 0; c < i; ++c) std::swap(A(i, c), A(piv, c));
+      std::swap(A(i, i), A(piv, i));  // gauss_step_swap: coeffs.swap((0,0),(piv,0))
+    }
+    double inv_diag = 1.0 / diag;
+    for (size_t r = i + 1; r < n; ++r) A(r, i) = A(r, i) * inv_diag;
+    for (size_t c = i + 1; c < n; ++c) {
+      if (piv != i) std::swap(A(i, c), A(piv, c));
+      double np = -A(i, c);
+      double* cc = A.col(c);
+      const double* ci = A.col(i);
+      for (size_t r = i + 1; r < n; ++r) cc[r] = np * ci[r] + cc[r];
+    }
+  }
+  for (size_t c = 0; c < n; ++c) {
+    double* b = out.col(c);
+    // solve_lower_triangular_with_diag_mut(out, 1)
+    for (size_t i = 0; i + 1 < n; ++i) {
+      double coeff = b[i] / 1.0;
+      double nc = -coeff;
+      const double* ci = A.col(i);
+      for (size_t r = i + 1; r < n; ++r) b[r] = nc * ci[r] + b[r];
+    }
+    // solve_upper_triangular_mut
+    for (size_t ii = n; ii-- > 0;) {
+      double diag = A(ii, ii);
+      if (diag == 0.0) return false;
+      double coeff = b[ii] / diag;
+      b[ii] = coeff;
+      double nc = -coeff;
+      const double* ci = A.col(ii);
+      for (size_t r = 0; r < ii; ++r) b[r] = nc * ci[r] + b[r];
+    }
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// Synthetic-input hash shared (as a specification) with the device generators: SURVEY §8(d)
+// ------------------------------------------------------------------------------------------
+static inline uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ULL;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+  return x ^ (x >> 31);
+}
+static inline uint64_t hash3(uint64_t seed, uint64_t i, uint64_t j) {
+  return splitmix64(seed ^ (i * 0x9E3779B97F4A7C15ULL + j));
+}
+static inline int h16(uint64_t seed, uint64_t i, uint64_t j) { return (int)(int16_t)(hash3(seed, i, j) & 0xFFFF); }
+
+// ------------------------------------------------------------------------------------------
+// func_eval.rs:5-41  FuncEval{f, g, hessian: Option<H>}
+// ------------------------------------------------------------------------------------------
+struct Eval {
+  double f = 0.0;
+  Vec g;
+  bool has_h = false;
+  Mat h;
+};
+
+struct Objective {
+  size_t calls = 0;
+  virtual ~Objective() {}
+  virtual Eval eval_impl(const Vec& x) = 0;
+  Eval eval(const Vec& x) {
+    ++calls;
+    return eval_impl(x);
+  }
+};
+
+typedef int (*host_eval_fn)(void* user, const double* x, int64_t n, double* f, double* g, double* h);
+// user closure `FnMut(&DVector) -> FuncEvalMultivariate` (ls_solver.rs:34).  h is column-major n*n.
+struct HostObjective : Objective {
+  host_eval_fn fn;
+  void* user;
+  bool with_h;
+  HostObjective(host_eval_fn f, void* u, bool wh) : fn(f), user(u), with_h(wh) {}
+  Eval eval_impl(const Vec& x) override {
+    Eval e;
+    size_t n = x.size();
+    e.g.assign(n, 0.0);
+    if (with_h) e.h = Mat(n, n);
+    int got_h = fn(user, x.data(), (int64_t)n, &e.f, e.g.data(), with_h ? e.h.a.data() : nullptr);
+    e.has_h = with_h && got_h;
+    return e;
+  }
+};
+
+// examples/quadratic.rs:10-14 oracle pattern: f = x.dot(&(&A * x)); g = 2. * &A * x  [- shift terms]
+// (2.*A)*x == 2*(A*x) bit-for-bit (power-of-two scaling), so one gemv serves both.
+struct DenseQuadratic : Objective {
+  Mat A;
+  Vec b;  // empty => unshifted
+  Eval eval_impl(const Vec& x) override {
+    Eval e;
+    Vec Ax = gemv(A, x);
+    e.f = dot(x, Ax);
+    e.g.resize(x.size());
+    if (b.empty()) {
+      for (size_t i = 0; i < x.size(); ++i) e.g[i] = 2.0 * Ax[i];
+    } else {
+      e.f = e.f - 2.0 * dot(b, x);
+      for (size_t i = 0; i < x.size(); ++i) e.g[i] = 2.0 * (Ax[i] - b[i]);
+    }
+    return e;
+  }
+  // SURVEY §8(d) C2 generator
+  static void generate(size_t n, Mat& A, Vec& b, Vec& x0) {
+    int lg = 0;
+    while (((size_t)1 << lg) < n) ++lg;
+    double sc = std::ldexp(1.0, -(15 + lg));
+    A = Mat(n, n);
+    for (size_t j = 0; j < n; ++j)
+      for (size_t i = 0; i < n; ++i) {
+        if (i == j) A(i, j) = 2.0 + (double)(i % 7);
+        else {
+          size_t lo = std::min(i, j), hi = std::max(i, j);
+          A(i, j) = (double)h16(1, lo, hi) * sc;
+        }
+      }
+    b.resize(n);
+    x0.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+      b[i] = (double)h16(9, i, 0) * std::ldexp(1.0, -13);
+      x0[i] = (double)h16(2, i, 0) * std::ldexp(1.0, -13);
+    }
+  }
+};
+
+// Extended Rosenbrock (not in the reference beyond the 2-D form in wasm/demo/index.html:441-453):
+// f = sum_{i<n/2} 100 (x_{2i+1} - x_{2i}^2)^2 + (1 - x_{2i})^2, sequential sum.
+struct Rosenbrock : Objective {
+  Eval eval_impl(const Vec& x) override {
+    Eval e;
+    size_t n = x.size();
+    e.g.assign(n, 0.0);
+    double f = 0.0;
+    for (size_t i = 0; i + 1 < n; i += 2) {
+      double a = x[i], b = x[i + 1];
+      double t1 = b - a * a;
+      double t2 = 1.0 - a;
+      f += 100.0 * (t1 * t1) + t2 * t2;
+      e.g[i] = -400.0 * (a * t1) - 2.0 * t2;
+      e.g[i + 1] = 200.0 * t1;
+    }
+    e.f = f;
+    return e;
+  }
+};
+
+// SURVEY §8(d) C5b separable box quadratic: f = sum 0.5 c_i (x_i - a_i)^2
+struct SeparableQuadratic : Objective {
+  Vec c, a;
+  Eval eval_impl(const Vec& x) override {
+    Eval e;
+    size_t n = x.size();
+    e.g.resize(n);
+    double f = 0.0;
+    for (size_t i = 0; i < n; ++i) {
+      double d = x[i] - a[i];
+      double cd = c[i] * d;
+      f += 0.5 * (cd * d);
+      e.g[i] = cd;
+    }
+    e.f = f;
+    return e;
+  }
+  void generate(size_t n) {
+    c.resize(n);
+    a.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+      c[i] = 1.0 + (double)(hash3(7, i, 0) & 0xFF) / 16.0;
+      a[i] = (double)h16(8, i, 0) * std::ldexp(1.0, -14);
+    }
+  }
+};
+
+// SURVEY §8(d) C5a synthetic logistic regression.  Labels are decided in exact integer arithmetic
+// so that every implementation sees the same problem.
+struct Logistic : Objective {
+  size_t m = 0, n = 0;
+  double lambda = 1.0;
+  bool want_h = true;
+  std::vector<double> X;  // row-major m x n (sample-major)
+  std::vector<double> ysign;
+  void generate(size_t m_, size_t n_, double lam) {
+    m = m_; n = n_; lambda = lam;
+    X.resize(m * n);
+    ysign.resize(m);
+    std::vector<int> w(n);
+    for (size_t j = 0; j < n; ++j) w[j] = h16(5, j, 0);
+#pragma omp parallel for schedule(static)
+    for (long ii = 0; ii < (long)m; ++ii) {
+      size_t i = (size_t)ii;
+      int64_t acc = 0;
+      for (size_t j = 0; j < n; ++j) {
+        int xi = h16(4, i, j);
+        X[i * n + j] = (double)xi * std::ldexp(1.0, -15);
+        acc += (int64_t)xi * (int64_t)w[j];
+      }
+      acc += (int64_t)h16(6, i, 0) * (int64_t)8192;  // noise * 2^-17 in units of 2^-30
+      ysign[i] = acc > 0 ? 1.0 : -1.0;
+    }
+  }
+  Eval eval_impl(const Vec& wv) override {
+    Eval e;
+    e.g.assign(n, 0.0);
+    std::vector<double> dcoef(m);
+    double f = 0.0;
+    for (size_t i = 0; i < m; ++i) {
+      const double* xi = &X[i * n];
+      double z = dot(xi, wv.data(), n);
+      double u = -ysign[i] * z;  // loss = log(1 + exp(u))
+      double loss = u > 0 ? u + std::log1p(std::exp(-u)) : std::log1p(std::exp(u));
+      f += loss;
+      double sig = 1.0 / (1.0 + std::exp(-u));  // sigma(u)
+      double gc = -ysign[i] * sig;
+      for (size_t j = 0; j < n; ++j) e.g[j] += gc * xi[j];
+      dcoef[i] = sig * (1.0 - sig);
+    }
+    f += 0.5 * lambda * dot(wv, wv);
+    for (size_t j = 0; j < n; ++j) e.g[j] += lambda * wv[j];
+    e.f = f;
+    if (want_h) {
+      e.has_h = true;
+      e.h = Mat(n, n);
+#pragma omp parallel for schedule(dynamic, 4)
+      for (long aa = 0; aa < (long)n; ++aa) {
+        size_t a = (size_t)aa;
+        for (size_t b2 = 0; b2 <= a; ++b2) {
+          double s = 0.0;
+          for (size_t i = 0; i < m; ++i) s += dcoef[i] * X[i * n + a] * X[i * n + b2];
+          if (a == b2) s += lambda;
+          e.h(a, b2) = s;
+          e.h(b2, a) = s;
+        }
+      }
+    }
+    return e;
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// line_search/mod.rs:25-86 condition predicates
+// ------------------------------------------------------------------------------------------
+static bool sufficient_decrease(double c1, double f_k, double f_kp1, const Vec& grad_k, double t, const Vec& d) {
+  return f_kp1 - f_k <= c1 * t * dot(grad_k, d);  // mod.rs:35
+}
+static bool strong_curvature(double c2, const Vec& grad_k, const Vec& grad_kp1, const Vec& d) {
+  return std::fabs(dot(grad_kp1, d)) <= c2 * std::fabs(dot(grad_k, d));  // mod.rs:55
+}
+
+struct LineSearch {
+  virtual ~LineSearch() {}
+  virtual double compute_step_len(const Vec& x, const Eval& e, const Vec& d, Objective& o, size_t max_iter) = 0;
+};
+struct NoSearch : LineSearch {  // nosearch.rs:3-15
+  double compute_step_len(const Vec&, const Eval&, const Vec&, Objective&, size_t) override { return 1.0; }
+};
+struct BackTracking : LineSearch {  // backtracking.rs:19-59
+  double c1, beta;
+  BackTracking(double c, double b) : c1(c), beta(b) {}
+  double compute_step_len(const Vec& x, const Eval& e, const Vec& d, Objective& o, size_t max_iter) override {
+    double t = 1.0;
+    size_t i = 0;
+    while (max_iter > i) {
+      Vec xn = axpy_new(x, t, d);
+      Eval en = o.eval(xn);
+      if (std::isnan(en.f) || std::isinf(en.f)) {  // :37-41 — i is NOT incremented
+        t *= beta;
+        continue;
+      }
+      if (sufficient_decrease(c1, e.f, en.f, e.g, t, d)) return t;
+      t *= beta;
+      i += 1;
+    }
+    return t;
+  }
+};
+struct BackTrackingB : LineSearch {  // backtracking_b.rs:24-34,52-90
+  double c1, beta;
+  Vec lb, ub;
+  BackTrackingB(double c, double b, Vec l, Vec u) : c1(c), beta(b), lb(std::move(l)), ub(std::move(u)) {}
+  double compute_step_len(const Vec& x, const Eval& e, const Vec& d, Objective& o, size_t max_iter) override {
+    double t = 1.0;
+    size_t i = 0;
+    while (max_iter > i) {
+      Vec xn = box_projection(axpy_new(x, t, d), lb, ub);
+      Eval en = o.eval(xn);
+      if (std::isnan(en.f) || std::isinf(en.f)) {
+        t *= beta;
+        continue;
+      }
+      Vec diff = sub(xn, x);
+      if (en.f - e.f <= (-c1 / t) * dot(diff, diff)) return t;  // :33
+      t *= beta;
+      i += 1;
+    }
+    return t;
+  }
+};
+struct GLLQuadratic : LineSearch {  // gll_quadratic.rs:3-99
+  double c1;
+  size_t m;
+  std::vector<double> f_previous;
+  double sigma1 = 0.1, sigma2 = 0.9;
+  GLLQuadratic(double c, size_t mm) : c1(c), m(mm) {}
+  double compute_step_len(const Vec& x, const Eval& e, const Vec& d, Objective& o, size_t max_iter) override {
+    if (f_previous.size() == m) f_previous.erase(f_previous.begin());  // :30-35
+    f_previous.push_back(e.f);
+    double t = 1.0;
+    double f_max = -INF;
+    for (double v : f_previous) f_max = rmax(v, f_max);  // :37-43
+    size_t i = 0;
+    while (max_iter > i) {
+      Vec xn = axpy_new(x, t, d);
+      Eval en = o.eval(xn);
+      if (sufficient_decrease(c1, f_max, en.f, e.g, t, d)) return t;  // :72
+      if (t <= 0.1) {
+        t *= 0.5;
+      } else {
+        double gd = dot(e.g, d);
+        double t_tmp = -0.5 * t * t * gd / (en.f - e.f - t * dot(e.g, d));  // :83-84
+        if (t_tmp > sigma1 && t_tmp < sigma2 * t) t = t_tmp;
+        else t = t_tmp * 0.5;
+      }
+      i += 1;
+    }
+    return t;
+  }
+};
+
+// morethuente.rs:5-298 (and morethuente_b.rs, identical but for the t_max scan :185-201)
+struct MoreThuente : LineSearch {
+  double c1 = 1e-4, c2 = 0.9, t_min = 0.0, t_max = INF, delta_min = 0.58333333, delta = 0.66, delta_max = 1.1;
+  bool bounded = false;
+  Vec lb, ub;
+  struct Uni { double f, g; };
+  static bool update_interval(double f_tl, double f_t, double g_t, double& tl, double t, double& tu) {  // :64-91
+    if (f_t > f_tl) { tu = t; return false; }
+    else if (g_t * (tl - t) > 0.) { tl = t; return false; }
+    else if (g_t * (tl - t) < 0.) { tu = tl; tl = t; return false; }
+    else return true;
+  }
+  static double cubic_minimizer(double ta, double tb, double f_ta, double f_tb, double g_ta, double g_tb) {  // :93-108
+    double s = 3. * (f_tb - f_ta) / (tb - ta);
+    double z = s - g_ta - g_tb;
+    double w = std::sqrt(z * z - g_ta * g_tb);
+    return ta + ((tb - ta) * ((w - g_ta - z) / (g_tb - g_ta + 2. * w)));
+  }
+  static double quadratic_minimizer_1(double ta, double tb, double f_ta, double f_tb, double g_ta) {  // :110-121
+    double lin_int = (f_ta - f_tb) / (ta - tb);
+    return ta - 0.5 * ((ta - tb) * g_ta / (g_ta - lin_int));
+  }
+  static double quadratic_minimizer_2(double ta, double tb, double g_ta, double g_tb) {  // :123-132
+    return ta - g_ta * ((ta - tb) / (g_ta - g_tb));
+  }
+  static Uni phi(const Eval& e, const Vec& d) { return Uni{e.f, dot(e.g, d)}; }  // :134-139
+  Uni psi(const Uni& phi_0, const Uni& phi_t, double t) const {                // :140-149
+    return Uni{phi_t.f - phi_0.f - c1 * t * phi_0.g, phi_t.g - c1 * phi_0.g};
+  }
+  double compute_step_len(const Vec& x, const Eval& e0, const Vec& d, Objective& o, size_t max_iter) override {
+    if (bounded) {  // morethuente_b.rs:185-201 — permanently shrinks t_max
+      double cand = INF;
+      for (size_t i = 0; i < d.size(); ++i) {
+        double v;
+        if (d[i] > 0.0) v = (ub[i] - x[i]) / d[i];
+        else if (d[i] < 0.0) v = (lb[i] - x[i]) / d[i];
+        else v = INF;
+        cand = rmin(v, cand);
+      }
+      t_max = rmin(t_max, cand);
+    }
+    bool use_modified_updating = false, interval_converged = false;
+    double t = rmin(rmax(1.0, t_min), t_max);
+    double tl = t_min, tu = t_max;
+    for (size_t i = 0; i < max_iter; ++i) {
+      Eval et = o.eval(axpy_new(x, t, d));  // :182
+      if (sufficient_decrease(c1, e0.f, et.f, e0.g, t, d) && strong_curvature(c2, e0.g, et.g, d)) return t;
+      else if (interval_converged) return t;
+      else if (t == tl) return t;
+      else if (t == tu) return t;
+      Uni phi_t = phi(et, d), phi_0 = phi(e0, d);
+      Uni psi_t = psi(phi_0, phi_t, t);
+      if (!use_modified_updating && psi_t.f <= 0. && phi_t.g > 0.) use_modified_updating = true;
+      Eval etl = o.eval(axpy_new(x, tl, d));  // :217 re-evaluated every iteration
+      Uni phi_tl = phi(etl, d);
+      double f_tl, g_tl, f_t, g_t;
+      if (use_modified_updating) {
+        f_tl = phi_tl.f; g_tl = phi_tl.g; f_t = phi_t.f; g_t = phi_t.g;
+      } else {
+        Uni psi_tl = psi(phi_0, phi_tl, tl);
+        f_tl = psi_tl.f; g_tl = psi_tl.g; f_t = psi_t.f; g_t = psi_t.g;
+      }
+      if (f_t > f_tl) {  // case 1 :230-241
+        double tc = cubic_minimizer(tl, t, f_tl, f_t, g_tl, g_t);
+        double tq = quadratic_minimizer_1(tl, t, f_tl, f_t, g_tl);
+        if (std::fabs(tc - tl) < std::fabs(tq - tl)) t = tc;
+        else t = 0.5 * (tq + tc);
+      } else if (g_t * g_tl < 0.) {  // case 2 :243-254
+        double tc = cubic_minimizer(tl, t, f_tl, f_t, g_tl, g_t);
+        double ts = quadratic_minimizer_2(tl, t, g_tl, g_t);
+        if (std::fabs(tc - t) >= std::fabs(ts - t)) t = tc;
+        else t = ts;
+      } else if (std::fabs(g_t) <= std::fabs(g_tl)) {  // case 3 :256-272
+        double tc = cubic_minimizer(tl, t, f_tl, f_t, g_tl, g_t);
+        double ts = quadratic_minimizer_2(tl, t, g_tl, g_t);
+        double t_plus = (std::fabs(tc - t) < std::fabs(ts - t)) ? tc : ts;
+        if (t > tl) t = rmin(t_plus, t + delta * (tu - t));
+        else t = rmax(t_plus, t + delta * (tu - t));
+      } else {  // case 4 :274-287 — oracle at tu (possibly +inf)
+        Eval etu = o.eval(axpy_new(x, tu, d));
+        Uni phi_tu = phi(etu, d);
+        double f_tu, g_tu;
+        if (use_modified_updating) { f_tu = phi_tu.f; g_tu = phi_tu.g; }
+        else { Uni p = psi(phi_0, phi_tu, tu); f_tu = p.f; g_tu = p.g; }
+        t = cubic_minimizer(tu, t, f_t, f_tu, g_t, g_tu);
+      }
+      t = rmin(rmax(t, t_min), t_max);  // :290 NaN -> t_min
+      interval_converged = update_interval(f_tl, f_t, g_t, tl, t, tu);  // :293 receives the NEW t
+    }
+    return t;
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// ls_solver.rs: SolverError, LineSearchSolver::minimize
+// ------------------------------------------------------------------------------------------
+enum Status { OK = 0, MAX_ITER = 1, OUT_OF_DOMAIN = 2, ERR_INPUT = 3, ABNORMAL = 4, PANIC_NO_HESSIAN = 101, PANIC_NOT_SPD = 102 };
+enum Reason { R_NONE = 0, R_GRAD = 1, R_SNORM = 2, R_YNORM = 3, R_PROJ_GRAD = 4, R_DECREMENT = 5 };
+
+struct IterRecord { double f, t, s_norm, y_norm; };
+
+struct Solver {
+  Vec x;
+  size_t k = 0;
+  double tol = 0;
+  int reason = R_NONE;
+  std::vector<IterRecord> trace;
+  bool record_x = false;
+  std::vector<Vec> xs;
+  virtual ~Solver() {}
+  virtual bool has_converged(const Eval& e) = 0;
+  virtual int compute_direction(const Eval& e, Vec& d) = 0;
+  // default ls_solver.rs:44-64
+  virtual int update_next_iterate(LineSearch& ls, const Eval& e, Objective& o, const Vec& d, size_t max_ls, double& t_out) {
+    double t = ls.compute_step_len(x, e, d, o, max_ls);
+    t_out = t;
+    x = axpy_new(x, t, d);
+    return OK;
+  }
+  virtual double rec_s() { return NAN; }
+  virtual double rec_y() { return NAN; }
+  int minimize(LineSearch& ls, Objective& o, size_t max_iter, size_t max_ls) {  // ls_solver.rs:66-111
+    k = 0;
+    reason = R_NONE;
+    trace.clear();
+    xs.clear();
+    while (max_iter > k) {
+      Eval e = o.eval(x);  // evaluate_x_k :32-42
+      if (std::isnan(e.f) || std::isinf(e.f)) return OUT_OF_DOMAIN;
+      if (has_converged(e)) return OK;
+      Vec d;
+      int st = compute_direction(e, d);
+      if (st != OK) return st;
+      double t = NAN;
+      st = update_next_iterate(ls, e, o, d, max_ls, t);
+      if (st != OK) return st;
+      trace.push_back(IterRecord{e.f, t, rec_s(), rec_y()});
+      if (record_x) xs.push_back(x);
+      k += 1;
+    }
+    return MAX_ITER;
+  }
+};
+
+struct Bounded {
+  Vec lb, ub;
+  // ls_solver.rs:121-133 projected_gradient: exact == tests define the active set
+  Vec projected_gradient(const Vec& x, const Eval& e) const {
+    Vec pg = e.g;
+    for (size_t i = 0; i < x.size(); ++i)
+      if ((x[i] == lb[i] && pg[i] > 0.0) || (x[i] == ub[i] && pg[i] < 0.0)) pg[i] = 0.0;
+    return pg;
+  }
+};
+
+struct GradientDescent : Solver {  // gradient_descent.rs:24-79
+  bool has_converged(const Eval& e) override {
+    double acc = -INF;
+    for (double v : e.g) acc = rmax(std::fabs(v), acc);
+    if (acc < tol) { reason = R_GRAD; return true; }
+    return false;
+  }
+  int compute_direction(const Eval& e, Vec& d) override { d = neg(e.g); return OK; }
+};
+
+struct ProjectedGradientDescent : Solver, Bounded {  // projected_gradient_descent.rs:50-109
+  bool has_converged(const Eval& e) override {
+    if (infinity_norm(projected_gradient(x, e)) < tol) { reason = R_PROJ_GRAD; return true; }
+    return false;
+  }
+  int compute_direction(const Eval& e, Vec& d) override {
+    d = sub(box_projection(sub(x, e.g), lb, ub), x);
+    return OK;
+  }
+};
+
+struct SpectralBase : Solver, Bounded {
+  double lambda = 1.0, lambda_min = 1e-3, lambda_max = 1e3;
+  // spg.rs:28-58 constructor: one oracle call for lambda0
+  void init_lambda(Objective& o) {
+    Eval e0 = o.eval(x);
+    Vec d0 = sub(box_projection(sub(x, e0.g), lb, ub), x);
+    lambda = rmax(rmin(1. / infinity_norm(d0), lambda_max), lambda_min);
+  }
+  bool has_converged(const Eval& e) override {
+    if (infinity_norm(projected_gradient(x, e)) < tol) { reason = R_PROJ_GRAD; return true; }
+    return false;
+  }
+  // spg.rs:108-145 / spn.rs:113-150
+  int update_next_iterate(LineSearch& ls, const Eval& e, Objective& o, const Vec& d, size_t max_ls, double& t_out) override {
+    double t = ls.compute_step_len(x, e, d, o, max_ls);
+    t_out = t;
+    Vec next = axpy_new(x, t, d);
+    Vec s = sub(next, x);
+    Vec y = sub(o.eval(next).g, e.g);
+    x = next;
+    double sy = dot(s, y);
+    if (sy <= 0.) { lambda = lambda_max; return OK; }
+    double ss = dot(s, s);
+    lambda = rmax(rmin(ss / sy, lambda_max), lambda_min);
+    return OK;
+  }
+};
+struct SpectralProjectedGradient : SpectralBase {  // spg.rs:76-86
+  int compute_direction(const Eval& e, Vec& d) override {
+    d = sub(box_projection(sub(x, scale(lambda, e.g)), lb, ub), x);
+    return OK;
+  }
+};
+struct SpectralProjectedNewton : SpectralBase {  // spn.rs:76-91
+  int compute_direction(const Eval& e, Vec& d) override {
+    if (!e.has_h) return PANIC_NO_HESSIAN;
+    Mat L = e.h;
+    if (!cholesky_inplace(L)) return PANIC_NOT_SPD;
+    d = sub(box_projection(sub(x, scale(lambda, cholesky_solve(L, e.g))), lb, ub), x);
+    return OK;
+  }
+};
+
+struct Newton : Solver {  // newton/mod.rs:26-69
+  bool has_dec = false;
+  double decrement_squared = NAN;
+  bool has_converged(const Eval&) override {
+    if (has_dec && decrement_squared * 0.5 < tol) { reason = R_DECREMENT; return true; }
+    return false;
+  }
+  int compute_direction(const Eval& e, Vec& d) override {
+    if (!e.has_h) return PANIC_NO_HESSIAN;
+    Mat inv;
+    if (try_inverse(e.h, inv)) {
+      d = neg(gemv(inv, e.g));  // (-Hinv) * g == -(Hinv * g)
+      decrement_squared = dot(gemv(inv, d), d);
+      has_dec = true;
+    } else {
+      d = neg(e.g);
+    }
+    return OK;
+  }
+};
+
+struct SYNorms : Solver {
+  bool has_s = false, has_y = false;
+  double s_norm = NAN, y_norm = NAN;
+  double rec_s() override { return s_norm; }
+  double rec_y() override { return y_norm; }
+  bool too_close_s() const { return has_s && s_norm < tol; }
+  bool too_close_y() const { return has_y && y_norm < tol; }
+};
+
+struct ProjectedNewton : SYNorms, Bounded {  // projected_newton.rs:64-141
+  bool has_converged(const Eval& e) override {
+    if (too_close_s()) { reason = R_SNORM; return true; }
+    if (too_close_y()) { reason = R_YNORM; return true; }
+    if (infinity_norm(projected_gradient(x, e)) < tol) { reason = R_PROJ_GRAD; return true; }
+    return false;
+  }
+  int compute_direction(const Eval& e, Vec& d) override {
+    if (!e.has_h) return PANIC_NO_HESSIAN;
+    Mat L = e.h;
+    if (!cholesky_inplace(L)) return PANIC_NOT_SPD;
+    d = sub(box_projection(sub(x, cholesky_solve(L, e.g)), lb, ub), x);
+    return OK;
+  }
+  int update_next_iterate(LineSearch& ls, const Eval& e, Objective& o, const Vec& d, size_t max_ls, double& t_out) override {
+    double t = ls.compute_step_len(x, e, d, o, max_ls);
+    t_out = t;
+    Vec next = axpy_new(x, t, d);
+    Vec s = sub(next, x);
+    s_norm = norm(s); has_s = true;
+    Vec y = sub(o.eval(next).g, e.g);
+    y_norm = norm(y); has_y = true;
+    x = next;
+    return OK;
+  }
+};
+
+enum QNKind { QN_BFGS, QN_DFP, QN_BROYDEN, QN_SR1 };
+enum QNForm { FORM_FAITHFUL = 0, FORM_RANK2 = 1 };
+
+// quasi_newton/{bfgs,dfp,broyden,bfgs_b,dfp_b,broyden_b,sr1_b}.rs
+struct QuasiNewton : SYNorms, Bounded {
+  QNKind kind = QN_BFGS;
+  bool bounded = false;
+  int form = FORM_FAITHFUL;
+  Mat H, I;  // approx_inv_hessian (column-major), stored identity (bfgs.rs:5,11)
+  void init(size_t n) { I = Mat::identity(n); H = I; }
+  bool has_converged(const Eval& e) override {  // bfgs.rs:64-76 (unprojected ||g||_2 also for *B: bfgs_b.rs:92-104)
+    if (too_close_s()) { reason = R_SNORM; return true; }
+    if (too_close_y()) { reason = R_YNORM; return true; }
+    if (norm(e.g) < tol) { reason = R_GRAD; return true; }
+    return false;
+  }
+  int compute_direction(const Eval& e, Vec& d) override {
+    if (!bounded) d = neg(gemv(H, e.g));  // bfgs.rs:47  (-H)*g
+    else d = sub(box_projection(sub(x, gemv(H, e.g)), lb, ub), x);  // bfgs_b.rs:72-75
+    return OK;
+  }
+  int update_next_iterate(LineSearch& ls, const Eval& e, Objective& o, const Vec& d, size_t max_ls, double& t_out) override {
+    double t = ls.compute_step_len(x, e, d, o, max_ls);  // bfgs.rs:86-92
+    t_out = t;
+    Vec next = axpy_new(x, t, d);
+    Vec s = sub(next, x);
+    s_norm = norm(s); has_s = true;
+    Vec y = sub(o.eval(next).g, e.g);  // bfgs.rs:98 extra oracle call
+    y_norm = norm(y); has_y = true;
+    x = next;
+    if (too_close_s()) return OK;
+    if (too_close_y()) return OK;
+    if (form == FORM_RANK2) { rank2_update(s, y); return OK; }
+    switch (kind) {
+      case QN_BFGS: {  // bfgs.rs:115-124 ; bfgs_b.rs:142-151 (w_b = y s^T built explicitly: same values)
+        double ys = dot(y, s);
+        double rho = 1.0 / ys;
+        Mat w_a = outer(s, y);
+        Mat w_b = bounded ? outer(y, s) : transpose(w_a);
+        Mat innovation = outer(s, s);
+        Mat left = msub(I, mscale(w_a, rho));
+        Mat right = msub(I, mscale(w_b, rho));
+        H = madd(matmul(matmul(left, H), right), mscale(innovation, rho));
+        break;
+      }
+      case QN_DFP: {  // dfp.rs:115-120
+        Mat ss = outer(s, s);
+        Mat yy = outer(y, y);
+        double sy = dot(s, y);
+        double yhy = dot(y, gemv(H, y));
+        Mat corr = msub(mdiv(ss, sy), mdiv(matmul(matmul(H, yy), H), yhy));
+        H = madd(H, corr);
+        break;
+      }
+      case QN_BROYDEN: {  // broyden.rs:115-118
+        Vec hy = gemv(H, y);
+        Mat numerator = matmul(outer(sub(s, hy), s), H);
+        double denominator = dot(s, y);
+        H = madd(H, mdiv(numerator, denominator));
+        break;
+      }
+      case QN_SR1: {  // sr1_b.rs:143-146
+        Vec hy = gemv(H, y);
+        Vec shy = sub(s, hy);
+        H = madd(H, mdiv(outer(shy, shy), dot(shy, y)));
+        break;
+      }
+    }
+    return OK;
+  }
+  // The algebraically equal O(n^2) forms the device kernels implement (DESIGN.md "update forms"),
+  // with this oracle's (nalgebra-ordered) reductions.  Used to separate "algebra" from
+  // "summation order" effects in the parity protocol.
+  void rank2_update(const Vec& s, const Vec& y) {
+    const size_t n = s.size();
+    Vec h = gemv(H, y);
+    if (kind == QN_BFGS) {
+      double ys = dot(y, s), rho = 1.0 / ys, yh = dot(y, h);
+      double c = rho * rho * yh + rho;
+      for (size_t j = 0; j < n; ++j)
+        for (size_t i = 0; i < n; ++i) {
+          double cross = s[i] * h[j] + h[i] * s[j];
+          double ssq = s[i] * s[j];
+          H(i, j) = (H(i, j) - rho * cross) + c * ssq;
+        }
+    } else if (kind == QN_DFP) {
+      double sy = dot(s, y), yhy = dot(y, h);
+      for (size_t j = 0; j < n; ++j)
+        for (size_t i = 0; i < n; ++i) H(i, j) = (H(i, j) + (s[i] * s[j]) / sy) - (h[i] * h[j]) / yhy;
+    } else if (kind == QN_BROYDEN) {
+      // H += (s - Hy) (s^T H) / (s.y) ; v = H^T s
+      Vec v(n);
+      for (size_t j = 0; j < n; ++j) v[j] = dot(H.col(j), s.data(), n);
+      double den = dot(s, y);
+      for (size_t j = 0; j < n; ++j)
+        for (size_t i = 0; i < n; ++i) H(i, j) = H(i, j) + ((s[i] - h[i]) * v[j]) / den;
+    } else {
+      Vec u = sub(s, h);
+      double den = dot(u, y);
+      for (size_t j = 0; j < n; ++j)
+        for (size_t i = 0; i < n; ++i) H(i, j) = H(i, j) + (u[i] * u[j]) / den;
+    }
+  }
+};
+
+}  // namespace orc
+
+// ------------------------------------------------------------------------------------------
+// C API for ctypes (tests / bench cpu_baseline only)
+// ------------------------------------------------------------------------------------------
+using namespace orc;
+extern "C" {
+
+enum { ORC_GD = 0, ORC_PGD = 1, ORC_SPG = 2, ORC_BFGS = 3, ORC_DFP = 4, ORC_BROYDEN = 5, ORC_BFGSB = 6, ORC_DFPB = 7,
+       ORC_BROYDENB = 8, ORC_SR1B = 9, ORC_NEWTON = 10, ORC_PROJ_NEWTON = 11, ORC_SPN = 12 };
+
+void orc_set_threads(int t) {
+#ifdef _OPENMP
+  omp_set_num_threads(t > 0 ? t : 1);
+#else
+  (void)t;
+#endif
+}
+int orc_max_threads() {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+// ---- objectives
+void* orc_obj_host(host_eval_fn fn, void* user, int with_hessian) { return new HostObjective(fn, user, with_hessian != 0); }
+void* orc_obj_dense_quadratic(int64_t n, const double* A_colmajor, const double* b) {
+  auto* o = new DenseQuadratic();
+  o->A = Mat(n, n);
+  std::memcpy(o->A.a.data(), A_colmajor, sizeof(double) * n * n);
+  if (b) o->b.assign(b, b + n);
+  return o;
+}
+void* orc_obj_dense_quadratic_generated(int64_t n, int shifted, double* x0_out) {
+  auto* o = new DenseQuadratic();
+  Vec b, x0;
+  DenseQuadratic::generate(n, o->A, b, x0);
+  if (shifted) o->b = b;
+  if (x0_out) std::memcpy(x0_out, x0.data(), sizeof(double) * n);
+  return o;
+}
+void* orc_obj_rosenbrock() { return new Rosenbrock(); }
+void* orc_obj_separable_quadratic_generated(int64_t n) {
+  auto* o = new SeparableQuadratic();
+  o->generate(n);
+  return o;
+}
+void* orc_obj_logistic_generated(int64_t m, int64_t n, double lambda, int want_h) {
+  auto* o = new Logistic();
+  o->generate(m, n, lambda);
+  o->want_h = want_h != 0;
+  return o;
+}
+void orc_obj_destroy(void* o) { delete (Objective*)o; }
+int64_t orc_obj_calls(void* o) { return (int64_t)((Objective*)o)->calls; }
+int orc_obj_eval(void* o, int64_t n, const double* x, double* f, double* g, double* h_colmajor) {
+  Eval e = ((Objective*)o)->eval(Vec(x, x + n));
+  *f = e.f;
+  if (g) std::memcpy(g, e.g.data(), sizeof(double) * n);
+  if (h_colmajor && e.has_h) std::memcpy(h_colmajor, e.h.a.data(), sizeof(double) * n * n);
+  return e.has_h ? 1 : 0;
+}
+
+// ---- line searches
+void* orc_ls_backtracking(double c1, double beta) { return new BackTracking(c1, beta); }
+void* orc_ls_backtracking_b(double c1, double beta, int64_t n, const double* lb, const double* ub) {
+  return new BackTrackingB(c1, beta, Vec(lb, lb + n), Vec(ub, ub + n));
+}
+void* orc_ls_morethuente(double c1, double c2, double t_min, double t_max, double delta) {
+  auto* m = new MoreThuente();
+  m->c1 = c1; m->c2 = c2; m->t_min = t_min; m->t_max = t_max; m->delta = delta;
+  return m;
+}
+void* orc_ls_morethuente_b(double c1, double c2, double t_min, double t_max, double delta, int64_t n, const double* lb, const double* ub) {
+  auto* m = (MoreThuente*)orc_ls_morethuente(c1, c2, t_min, t_max, delta);
+  m->bounded = true;
+  m->lb.assign(lb, lb + n);
+  m->ub.assign(ub, ub + n);
+  return m;
+}
+void* orc_ls_gll(double c1, int64_t m, double sigma1, double sigma2) {
+  auto* g = new GLLQuadratic(c1, (size_t)m);
+  g->sigma1 = sigma1; g->sigma2 = sigma2;
+  return g;
+}
+void* orc_ls_nosearch() { return new NoSearch(); }
+void orc_ls_destroy(void* l) { delete (LineSearch*)l; }
+double orc_ls_t_max(void* l) {
+  auto* m = dynamic_cast<MoreThuente*>((LineSearch*)l);
+  return m ? m->t_max : NAN;
+}
+double orc_ls_compute_step_len(void* l, void* obj, int64_t n, const double* x, const double* d, int64_t max_iter) {
+  Objective* o = (Objective*)obj;
+  Vec xv(x, x + n), dv(d, d + n);
+  Eval e = o->eval(xv);
+  return ((LineSearch*)l)->compute_step_len(xv, e, dv, *o, (size_t)max_iter);
+}
+
+// ---- solvers.  lb/ub may be NULL for unbounded kinds; obj_for_lambda0 only for SPG/SPN (spg.rs:28-46)
+void* orc_solver_create(int kind, int64_t n, double tol, const double* x0, const double* lb, const double* ub, void* obj_for_lambda0) {
+  Vec x(x0, x0 + n);
+  Vec l, u;
+  if (lb) l.assign(lb, lb + n);
+  if (ub) u.assign(ub, ub + n);
+  auto proj = [&]() { return box_projection(x, l, u); };
+  Solver* s = nullptr;
+  switch (kind) {
+    case ORC_GD: { auto* p = new GradientDescent(); p->x = x; s = p; break; }
+    case ORC_PGD: { auto* p = new ProjectedGradientDescent(); p->lb = l; p->ub = u; p->x = proj(); s = p; break; }
+    case ORC_SPG: case ORC_SPN: {
+      SpectralBase* p = kind == ORC_SPG ? (SpectralBase*)new SpectralProjectedGradient() : (SpectralBase*)new SpectralProjectedNewton();
+      p->lb = l; p->ub = u; p->x = proj();
+      p->init_lambda(*(Objective*)obj_for_lambda0);
+      s = p; break;
+    }
+    case ORC_BFGS: case ORC_DFP: case ORC_BROYDEN: {
+      auto* p = new QuasiNewton();
+      p->kind = kind == ORC_BFGS ? QN_BFGS : kind == ORC_DFP ? QN_DFP : QN_BROYDEN;
+      p->x = x; p->init(n); s = p; break;
+    }
+    case ORC_BFGSB: case ORC_DFPB: case ORC_BROYDENB: case ORC_SR1B: {
+      auto* p = new QuasiNewton();
+      p->kind = kind == ORC_BFGSB ? QN_BFGS : kind == ORC_DFPB ? QN_DFP : kind == ORC_BROYDENB ? QN_BROYDEN : QN_SR1;
+      p->bounded = true; p->lb = l; p->ub = u; p->x = proj(); p->init(n); s = p; break;
+    }
+    case ORC_NEWTON: { auto* p = new Newton(); p->x = x; s = p; break; }
+    case ORC_PROJ_NEWTON: { auto* p = new ProjectedNewton(); p->lb = l; p->ub = u; p->x = proj(); s = p; break; }
+    default: return nullptr;
+  }
+  s->tol = tol;
+  return s;
+}
+void orc_solver_destroy(void* s) { delete (Solver*)s; }
+void orc_solver_set_form(void* s, int form) {
+  if (auto* q = dynamic_cast<QuasiNewton*>((Solver*)s)) q->form = form;
+}
+void orc_solver_set_lambdas(void* s, double lmin, double lmax) {
+  if (auto* q = dynamic_cast<SpectralBase*>((Solver*)s)) { q->lambda_min = lmin; q->lambda_max = lmax; }
+}
+void orc_solver_record_iterates(void* s, int on) { ((Solver*)s)->record_x = on != 0; }
+int orc_minimize(void* s, void* ls, void* obj, int64_t max_iter, int64_t max_ls) {
+  return ((Solver*)s)->minimize(*(LineSearch*)ls, *(Objective*)obj, (size_t)max_iter, (size_t)max_ls);
+}
+int64_t orc_solver_k(void* s) { return (int64_t)((Solver*)s)->k; }
+int orc_solver_reason(void* s) { return ((Solver*)s)->reason; }
+void orc_solver_x(void* s, double* out) { auto& x = ((Solver*)s)->x; std::memcpy(out, x.data(), sizeof(double) * x.size()); }
+void orc_solver_set_x(void* s, const double* in) { auto& x = ((Solver*)s)->x; std::memcpy(x.data(), in, sizeof(double) * x.size()); }
+double orc_solver_s_norm(void* s) { auto* q = dynamic_cast<SYNorms*>((Solver*)s); return q && q->has_s ? q->s_norm : NAN; }
+double orc_solver_y_norm(void* s) { auto* q = dynamic_cast<SYNorms*>((Solver*)s); return q && q->has_y ? q->y_norm : NAN; }
+void orc_solver_clear_norms(void* s) { if (auto* q = dynamic_cast<SYNorms*>((Solver*)s)) { q->has_s = q->has_y = false; } }
+double orc_solver_lambda(void* s) { auto* q = dynamic_cast<SpectralBase*>((Solver*)s); return q ? q->lambda : NAN; }
+double orc_solver_decrement_squared(void* s) { auto* q = dynamic_cast<Newton*>((Solver*)s); return q && q->has_dec ? q->decrement_squared : NAN; }
+// row-major copy-out / copy-in of the inverse-Hessian approximation (H is stored column-major here)
+int orc_solver_inv_hessian(void* s, double* out_rowmajor) {
+  auto* q = dynamic_cast<QuasiNewton*>((Solver*)s);
+  if (!q) return -1;
+  size_t n = q->H.r;
+  for (size_t i = 0; i < n; ++i)
+    for (size_t j = 0; j < n; ++j) out_rowmajor[i * n + j] = q->H(i, j);
+  return 0;
+}
+int orc_solver_set_inv_hessian(void* s, const double* in_rowmajor) {
+  auto* q = dynamic_cast<QuasiNewton*>((Solver*)s);
+  if (!q) return -1;
+  size_t n = q->H.r;
+  for (size_t i = 0; i < n; ++i)
+    for (size_t j = 0; j < n; ++j) q->H(i, j) = in_rowmajor[i * n + j];
+  return 0;
+}
+// active set bitmap: bit i set iff x_i == lb_i or x_i == ub_i (exact compare, ls_solver.rs:125-126)
+int orc_solver_active_set(void* s, uint8_t* out) {
+  auto* b = dynamic_cast<Bounded*>((Solver*)s);
+  if (!b) return -1;
+  auto& x = ((Solver*)s)->x;
+  for (size_t i = 0; i < x.size(); ++i) out[i] = (x[i] == b->lb[i] ? 1 : 0) | (x[i] == b->ub[i] ? 2 : 0);
+  return 0;
+}
+int64_t orc_solver_trace_len(void* s) { return (int64_t)((Solver*)s)->trace.size(); }
+void orc_solver_trace(void* s, double* f, double* t, double* sn, double* yn) {
+  auto& tr = ((Solver*)s)->trace;
+  for (size_t i = 0; i < tr.size(); ++i) { f[i] = tr[i].f; t[i] = tr[i].t; sn[i] = tr[i].s_norm; yn[i] = tr[i].y_norm; }
+}
+void orc_solver_iterate(void* s, int64_t idx, double* out) {
+  auto& v = ((Solver*)s)->xs[(size_t)idx];
+  std::memcpy(out, v.data(), sizeof(double) * v.size());
+}
+
+// ---- timing helpers for bench.py's cpu_baseline leg: one faithful BFGS update (bfgs.rs:115-124)
+// restricted to `rows` sampled rows of the two dense products, so that n = 16384 is measurable.
+// Returns seconds for the sample; flops of the sample = 4*rows*n*n.
+double orc_time_bfgs_update_rowsample(int64_t n, int64_t rows, int threads) {
+  orc_set_threads(threads);
+  Mat H((size_t)n, (size_t)n);
+  for (size_t j = 0; j < (size_t)n; ++j)
+    for (size_t i = 0; i < (size_t)n; ++i) H(i, j) = (i == j ? 1.0 : 0.0) + 1e-3 * (double)h16(11, std::min(i, j), std::max(i, j)) / 32768.0;
+  Vec s(n), y(n);
+  for (size_t i = 0; i < (size_t)n; ++i) { s[i] = (double)h16(12, i, 0) / 32768.0; y[i] = s[i] + 0.1 * (double)h16(13, i, 0) / 32768.0; }
+  double rho = 1.0 / dot(y, s);
+  // left rows sample (rows x n), right (n x n) built on the fly column by column
+  Mat Lrows((size_t)rows, (size_t)n);
+  for (size_t j = 0; j < (size_t)n; ++j)
+    for (size_t i = 0; i < (size_t)rows; ++i) Lrows(i, j) = (i == j ? 1.0 : 0.0) - (s[i] * y[j]) * rho;
+  Mat R((size_t)n, (size_t)n);
+  for (size_t j = 0; j < (size_t)n; ++j)
+    for (size_t i = 0; i < (size_t)n; ++i) R(i, j) = (i == j ? 1.0 : 0.0) - (y[i] * s[j]) * rho;
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  Mat M1 = matmul(Lrows, H);
+  Mat M2 = matmul(M1, R);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  volatile double sink = M2(0, 0);
+  (void)sink;
+  return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+}  // extern "C"
