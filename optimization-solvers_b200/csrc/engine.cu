@@ -1,0 +1,538 @@
+// engine.cu — context, buffers and the solver state machines.
+//
+// Solver::minimize is LineSearchSolver::minimize (src/ls_solver.rs:66-111) for every solver struct
+// on the hot path.  Two control engines drive the same kernels:
+//   * host-driven   — every solver x line search x objective; the scalar automaton
+//                     (ls_automaton.cuh) runs on the host, one small D2H fetch per decision;
+//   * device-resident — dense quasi-Newton + block-functor objective: convergence test, direction,
+//                     the whole line search and the s/y bookkeeping run in one single-CTA kernel,
+//                     the H passes are predicated on device flags, and the host only polls a
+//                     `done` flag a few iterations behind (no host round trip on the critical path).
+#include "engine.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+namespace osb {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& s) { g_last_error = s; }
+const std::string& get_last_error() { return g_last_error; }
+
+// ---- Ctx / DBuf ---------------------------------------------------------------------------
+Ctx::Ctx(int dev) : device(dev) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    throw Error(OSB_ERR_CUDA, "no CUDA device available: this library has no CPU fallback");
+  OSB_REQUIRE(dev >= 0 && dev < count, OSB_ERROR_INPUT_PARAMS, "bad device index");
+  OSB_CUDA(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  OSB_CUDA(cudaGetDeviceProperties(&prop, dev));
+  num_sms = prop.multiProcessorCount;
+  OSB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  red_max_grid = num_sms * 4;
+  OSB_CUDA(cudaMalloc(&red_partials, sizeof(double) * 8 * red_max_grid));
+  OSB_CUDA(cudaMalloc(&red_ticket, sizeof(unsigned int)));
+  OSB_CUDA(cudaMemsetAsync(red_ticket, 0, sizeof(unsigned int), stream));
+  OSB_CUDA(cudaMalloc(&d_dummy, sizeof(double) * 8));
+  OSB_CUDA(cudaHostAlloc(&h_pinned, sizeof(double) * 4096, cudaHostAllocDefault));
+  OSB_CUDA(cudaStreamSynchronize(stream));
+}
+Ctx::~Ctx() {
+  cudaSetDevice(device);
+  if (stream) cudaStreamSynchronize(stream);
+  cudaFree(red_partials);
+  cudaFree(red_ticket);
+  cudaFree(d_dummy);
+  cudaFreeHost(h_pinned);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+void DBuf::alloc(int64_t n_) {
+  release();
+  n = n_;
+  if (n > 0) {
+    cudaError_t e = cudaMalloc(&p, sizeof(double) * (size_t)n);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      throw Error(OSB_ERR_ALLOC, std::string("cudaMalloc of ") + std::to_string(n * 8) + " bytes failed: " + cudaGetErrorString(e));
+    }
+  }
+}
+void DBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  n = 0;
+}
+void DBuf::zero(cudaStream_t s) {
+  if (p) OSB_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * (size_t)n, s));
+}
+void DBuf::upload(const double* h, int64_t cnt, cudaStream_t s) {
+  OSB_CUDA(cudaMemcpyAsync(p, h, sizeof(double) * (size_t)cnt, cudaMemcpyHostToDevice, s));
+}
+void DBuf::download(double* h, int64_t cnt, cudaStream_t s) const {
+  OSB_CUDA(cudaMemcpyAsync(h, p, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, s));
+}
+
+// ---- small state kernels ------------------------------------------------------------------
+__global__ void set_identity_kernel(double* H, int64_t ld, int64_t nrows, int64_t row0) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nrows; i += (int64_t)gridDim.x * blockDim.x)
+    H[i * ld + row0 + i] = 1.0;
+}
+__global__ void accept_trial_kernel(DevState* st) { st->f = st->ft; }
+
+// ---- Solver -------------------------------------------------------------------------------
+static bool kind_is_qn(int k) { return k >= OSB_BFGS && k <= OSB_SR1B; }
+static bool kind_is_bounded(int k) {
+  return k == OSB_PGD || k == OSB_SPG || k == OSB_BFGSB || k == OSB_DFPB || k == OSB_BROYDENB || k == OSB_SR1B ||
+         k == OSB_PROJ_NEWTON || k == OSB_SPN;
+}
+static bool kind_needs_hessian(int k) { return k == OSB_NEWTON || k == OSB_PROJ_NEWTON || k == OSB_SPN; }
+static bool kind_needs_y(int k) { return kind_is_qn(k) || k == OSB_SPG || k == OSB_SPN || k == OSB_PROJ_NEWTON; }
+
+Solver::Solver(Ctx* c, int kind_, int64_t n_, double tol_, const double* x0, const double* lb_h, const double* ub_h,
+               Objective* obj0)
+    : ctx(c), kind(kind_), n(n_), tol(tol_) {
+  ctx->use();
+  OSB_REQUIRE(kind >= OSB_GD && kind <= OSB_SPN, OSB_ERROR_INPUT_PARAMS, "unknown solver kind");
+  OSB_REQUIRE(n >= 1 && x0 != nullptr, OSB_ERROR_INPUT_PARAMS, "n >= 1 and x0 required");
+  bounded = kind_is_bounded(kind);
+  is_qn = kind_is_qn(kind);
+  OSB_REQUIRE(!bounded || (lb_h && ub_h), OSB_ERROR_INPUT_PARAMS, "bounded solver needs lower and upper bounds");
+  ld = qn_ld(n);
+  cudaStream_t st = ctx->stream;
+  for (DBuf* b : {&x, &g, &d, &xt, &gt, &s, &y, &w}) {
+    b->alloc(ld);
+    b->zero(st);
+  }
+  x.upload(x0, n, st);
+  if (bounded) {
+    lb.alloc(ld);
+    ub.alloc(ld);
+    lb.zero(st);
+    ub.zero(st);
+    lb.upload(lb_h, n, st);
+    ub.upload(ub_h, n, st);
+    vec_project_inplace(ctx, n, x.p, lb.p, ub.p);  // constructors project x0: bfgs_b.rs:50, spg.rs:35
+  }
+  OSB_CUDA(cudaMalloc(&d_state, sizeof(DevState)));
+  OSB_CUDA(cudaMemsetAsync(d_state, 0, sizeof(DevState), st));
+  OSB_CUDA(cudaHostAlloc(&h_state, sizeof(DevState), cudaHostAllocDefault));
+  std::memset(h_state, 0, sizeof(DevState));
+  OSB_CUDA(cudaEventCreate(&ev0));
+  OSB_CUDA(cudaEventCreate(&ev1));
+  if (is_qn) {
+    qn_kind = (kind == OSB_BFGS || kind == OSB_BFGSB) ? QN_BFGS
+              : (kind == OSB_DFP || kind == OSB_DFPB) ? QN_DFP
+              : (kind == OSB_SR1B)                    ? QN_SR1
+                                                      : QN_BROYDEN;
+    if (ctx->world > 1) {
+      OSB_REQUIRE(n % (ctx->world * 8) == 0, OSB_ERROR_INPUT_PARAMS, "row-sharded H needs n divisible by 8 * world");
+      OSB_REQUIRE(qn_kind != QN_BROYDEN, OSB_ERR_UNSUPPORTED, "Broyden (non-symmetric H) is single-GPU only");
+      nrows = n / ctx->world;
+      row0 = nrows * ctx->rank;
+    } else {
+      nrows = n;
+      row0 = 0;
+    }
+    H.alloc(qn_rows_padded(nrows) * ld);
+    H.zero(st);
+    set_identity_kernel<<<ctx->red_grid(nrows), RED_THREADS, 0, st>>>(H.p, ld, nrows, row0);  // bfgs.rs:30-33
+    ctx->counters[0]++;
+    for (DBuf* b : {&u, &h, &pvec, &vvec}) {
+      b->alloc(ld);
+      b->zero(st);
+    }
+    if (qn_kind == QN_BROYDEN) scratch.alloc(((nrows + 63) / 64) * ld);
+  }
+  if (kind_needs_hessian(kind)) {
+    hess.alloc(qn_rows_padded(n) * ld);
+    hess.zero(st);
+    chol.alloc(qn_rows_padded(n) * ld);
+    chol.zero(st);
+  }
+  if (kind == OSB_SPG || kind == OSB_SPN) {
+    // spg.rs:40-46: lambda0 = clamp(1 / ||P(x0 - g0) - x0||_inf, lambda_min, lambda_max) — one oracle call
+    OSB_REQUIRE(obj0 != nullptr, OSB_ERROR_INPUT_PARAMS, "SPG/SPN constructors need the oracle");
+    obj0->eval(x.p, &d_state->f, g.p, nullptr);
+    vec_projected_direction(ctx, n, x.p, g.p, 1.0, false, lb.p, ub.p, g.p, d.p, &d_state->gd0);
+    fetch_state();
+    double dinf = rmax(0.0, h_state->dinf);
+    lambda = rmax(rmin(1. / dinf, lambda_max), lambda_min);
+    have_eval = true;
+  }
+  ctx->sync();
+}
+
+Solver::~Solver() {
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (d_state) cudaFree(d_state);
+  if (h_state) cudaFreeHost(h_state);
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
+}
+
+void Solver::fetch_state() {
+  OSB_CUDA(cudaMemcpyAsync(h_state, d_state, sizeof(DevState), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->sync();
+}
+void Solver::push_state() {
+  OSB_CUDA(cudaMemcpyAsync(d_state, h_state, sizeof(DevState), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->sync();
+}
+
+void Solver::compute_conv_scalar(Objective*) {
+  double* out = &d_state->conv;
+  if (is_qn) vec_conv_gnorm2(ctx, n, g.p, out);                        // bfgs.rs:74
+  else if (kind == OSB_GD) vec_conv_gmax(ctx, n, g.p, out);            // gradient_descent.rs:46-53
+  else if (kind == OSB_NEWTON) return;                                 // newton/mod.rs:64-69 ignores the eval
+  else vec_conv_pginf(ctx, n, x.p, g.p, lb.p, ub.p, out);              // projected_gradient_descent.rs:76-83
+}
+
+// dense SPD solve for the Newton family (newton.cu)
+int newton_solve(Ctx* ctx, int64_t n, int64_t ld, const double* hess, double* chol, const double* g, double* w_out);
+
+int Solver::compute_direction(Objective*, LineSearch* ls) {
+  double* out3 = &d_state->gd0;  // {gd0, tmaxc, dinf}
+  switch (kind) {
+    case OSB_GD:
+      vec_neg(ctx, n, g.p, d.p, g.p, out3);  // gradient_descent.rs:29
+      break;
+    case OSB_PGD:
+      vec_projected_direction(ctx, n, x.p, g.p, 1.0, false, lb.p, ub.p, g.p, d.p, out3);  // projected_gradient_descent.rs:56-59
+      break;
+    case OSB_SPG:
+      vec_projected_direction(ctx, n, x.p, g.p, lambda, true, lb.p, ub.p, g.p, d.p, out3);  // spg.rs:81-84
+      break;
+    case OSB_BFGS:
+    case OSB_DFP:
+    case OSB_BROYDEN:
+      vec_neg(ctx, n, u.p, d.p, g.p, out3);  // bfgs.rs:47: (-H) g == -(H g)
+      break;
+    case OSB_BFGSB:
+    case OSB_DFPB:
+    case OSB_BROYDENB:
+    case OSB_SR1B:
+      vec_projected_direction(ctx, n, x.p, u.p, 1.0, false, lb.p, ub.p, g.p, d.p, out3);  // bfgs_b.rs:72-75
+      break;
+    case OSB_NEWTON: {
+      // newton/mod.rs:31-47.  The reference inverts with LU; for the SPD Hessians of the configs a
+      // Cholesky solve gives the same direction to O(cond * eps); a non-SPD Hessian is reported.
+      int rc = newton_solve(ctx, n, ld, hess.p, chol.p, g.p, w.p);
+      if (rc != OSB_OK) return rc;
+      vec_neg(ctx, n, w.p, d.p, g.p, out3);  // d = -(H^-1 g)
+      // decrement^2 = (H^-1 d) . d
+      rc = newton_solve(ctx, n, ld, nullptr, chol.p, d.p, w.p);
+      if (rc != OSB_OK) return rc;
+      vec_dot(ctx, n, w.p, d.p, &d_state->dinf);
+      break;
+    }
+    case OSB_PROJ_NEWTON:
+    case OSB_SPN: {
+      int rc = newton_solve(ctx, n, ld, hess.p, chol.p, g.p, w.p);  // projected_newton.rs:75, spn.rs:86
+      if (rc != OSB_OK) return rc;
+      vec_projected_direction(ctx, n, x.p, w.p, lambda, kind == OSB_SPN, lb.p, ub.p, g.p, d.p, out3);
+      break;
+    }
+  }
+  if (ls->p.kind == LS_MORETHUENTE_B)  // morethuente_b.rs:185-197 with the line search's own bounds
+    vec_tmax_candidate(ctx, n, x.p, d.p, ls->lb.p, ls->ub.p, &d_state->tmaxc);
+  return OSB_OK;
+}
+
+// after the step: s, y are formed, x/g hold the NEW iterate; all launches are predicated on the
+// device flags (done / skip), so no host decision is needed here.
+void Solver::prof_mark() {
+  if (!profile_kernels || prof_events.size() >= 4 * 4096) return;
+  cudaEvent_t e;
+  OSB_CUDA(cudaEventCreate(&e));
+  OSB_CUDA(cudaEventRecord(e, ctx->stream));
+  prof_events.push_back(e);
+}
+void Solver::prof_collect() {
+  prof_ms[0] = prof_ms[1] = prof_ms[2] = 0.0;
+  const size_t iters = prof_events.size() / 4;
+  for (size_t i = 0; i < iters; ++i) {
+    float a = 0.f, b = 0.f;
+    OSB_CUDA(cudaEventElapsedTime(&a, prof_events[4 * i], prof_events[4 * i + 1]));
+    OSB_CUDA(cudaEventElapsedTime(&b, prof_events[4 * i + 2], prof_events[4 * i + 3]));
+    prof_ms[0] += a;
+    prof_ms[1] += b;
+  }
+  if (iters) {
+    prof_ms[0] /= iters;
+    prof_ms[1] /= iters;
+  }
+  prof_ms[2] = (double)iters;
+  for (cudaEvent_t e : prof_events) cudaEventDestroy(e);
+  prof_events.clear();
+}
+
+void Solver::qn_after_step() {
+  const DevState* st = d_state;
+  // pass 1: h = H y   (skip: u = H g_new, H unchanged — bfgs.rs:106-112)
+  prof_mark();
+  qn_launch_gemv(ctx, H.p, ld, nrows, row0, st, y.p, h.p, g.p, u.p, qn_variant);
+  prof_mark();
+  if (ctx->world > 1) {
+    ctx->all_gather_inplace(h.p, nrows);
+    ctx->all_gather_inplace(u.p, nrows);
+  }
+  if (qn_kind == QN_BROYDEN) qn_launch_gemvT(ctx, H.p, ld, nrows, row0, st, s.p, vvec.p, scratch.p);
+  qn_launch_coef(ctx, qn_kind, n, d_state, s.p, y.p, h.p, pvec.p);
+  const double* p = (qn_kind == QN_BFGS || qn_kind == QN_DFP) ? s.p : pvec.p;
+  // pass 2: fused rank-2 read-modify-write + u = H' g_new
+  prof_mark();
+  qn_launch_update(ctx, qn_kind, H.p, ld, nrows, row0, st, p, h.p, vvec.p, g.p, u.p, qn_variant);
+  prof_mark();
+  if (ctx->world > 1) ctx->all_gather_inplace(u.p, nrows);
+  u_valid = true;
+}
+
+bool Solver::device_engine_supported(const LineSearch* ls, const Objective* obj) const {
+  if (!is_qn) return false;
+  if (obj->functor_kind() == FN_NONE) return false;
+  (void)ls;
+  return true;
+}
+
+int Solver::minimize(LineSearch* ls, Objective* obj, int64_t max_iter, int64_t max_ls, osb_callback_fn cb, void* user) {
+  ctx->use();
+  OSB_REQUIRE(obj->n == n, OSB_ERROR_INPUT_PARAMS, "objective dimension does not match the solver");
+  OSB_REQUIRE(!kind_needs_hessian(kind) || obj->provides_hessian(), OSB_PANIC_NO_HESSIAN, "Hessian not available in the oracle");
+  if ((ls->p.kind == LS_BACKTRACKING_B || ls->p.kind == LS_MORETHUENTE_B))
+    OSB_REQUIRE(ls->n == n, OSB_ERROR_INPUT_PARAMS, "line-search bounds dimension does not match the solver");
+  bool dev_ok = device_engine_supported(ls, obj) && cb == nullptr && !record_trace;
+  OSB_REQUIRE(engine != 2 || dev_ok, OSB_ERR_UNSUPPORTED,
+              "device-resident engine needs a quasi-Newton solver, a block-functor objective, no callback and no trace");
+  OSB_CUDA(cudaEventRecord(ev0, ctx->stream));
+  int rc;
+  if (dev_ok && engine != 1) rc = minimize_device(ls, obj, max_iter, max_ls);
+  else rc = minimize_host(ls, obj, max_iter, max_ls, cb, user);
+  OSB_CUDA(cudaEventRecord(ev1, ctx->stream));
+  OSB_CUDA(cudaEventSynchronize(ev1));
+  float ms = 0.f;
+  OSB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+  last_ms = ms;
+  last_iters = k;
+  if (profile_kernels) prof_collect();
+  return rc;
+}
+
+int Solver::minimize_host(LineSearch* ls, Objective* obj, int64_t max_iter, int64_t max_ls, osb_callback_fn cb, void* user) {
+  k = 0;  // ls_solver.rs:74
+  reason = OSB_REASON_NONE;
+  trace.clear();
+  const bool needs_h = kind_needs_hessian(kind);
+  const bool needs_y = kind_needs_y(kind);
+  bool have_hess = false;
+  LSParams& lp = ls->p;
+  cudaStream_t stm = ctx->stream;
+  while (max_iter > k) {
+    // ---- evaluate_x_k (ls_solver.rs:32-42); cached when the point was already evaluated
+    if (!have_eval || (needs_h && !have_hess)) {
+      obj->eval(x.p, &d_state->f, g.p, needs_h ? hess.p : nullptr);
+      have_eval = true;
+      have_hess = needs_h;
+      u_valid = false;
+    }
+    if (is_qn && !u_valid) {
+      qn_launch_gemv(ctx, H.p, ld, nrows, row0, nullptr, g.p, u.p, nullptr, nullptr, qn_variant);
+      if (ctx->world > 1) ctx->all_gather_inplace(u.p, nrows);
+      u_valid = true;
+    }
+    compute_conv_scalar(obj);
+    bool dir_done = false;
+    if (!needs_h) {  // cheap directions are issued speculatively so that one fetch serves both decisions
+      compute_direction(obj, ls);
+      dir_done = true;
+    }
+    fetch_state();
+    const double f = h_state->f;
+    if (is_qn || kind == OSB_PROJ_NEWTON) {
+      has_s = h_state->has_s != 0;
+      has_y = h_state->has_y != 0;
+      s_norm = h_state->s_norm;
+      y_norm = h_state->y_norm;
+    }
+    if (is_bad(f)) return OSB_OUT_OF_DOMAIN;  // ls_solver.rs:37-40
+    // ---- has_converged
+    bool conv = false;
+    if (is_qn || kind == OSB_PROJ_NEWTON) {
+      if (has_s && s_norm < tol) { reason = OSB_REASON_S_NORM; conv = true; }        // bfgs.rs:67-69
+      else if (has_y && y_norm < tol) { reason = OSB_REASON_Y_NORM; conv = true; }   // bfgs.rs:70-72
+      else if (is_qn) {
+        if (sqrt(h_state->conv) < tol) { reason = OSB_REASON_GRAD_TOL; conv = true; }  // bfgs.rs:74
+      } else if (rmax(0.0, h_state->conv) < tol) { reason = OSB_REASON_PROJ_GRAD_TOL; conv = true; }
+    } else if (kind == OSB_GD) {
+      if (h_state->conv < tol) { reason = OSB_REASON_GRAD_TOL; conv = true; }
+    } else if (kind == OSB_NEWTON) {
+      if (has_dec && decrement_squared * 0.5 < tol) { reason = OSB_REASON_NEWTON_DECREMENT; conv = true; }
+    } else {
+      if (rmax(0.0, h_state->conv) < tol) { reason = OSB_REASON_PROJ_GRAD_TOL; conv = true; }
+    }
+    if (conv) return OSB_OK;
+    if (!dir_done) {
+      int rc = compute_direction(obj, ls);
+      if (rc != OSB_OK) return rc;
+      fetch_state();
+      if (kind == OSB_NEWTON) {
+        decrement_squared = h_state->dinf;
+        has_dec = true;
+      }
+    }
+    // ---- line search: scalar automaton on the host, one fused trial kernel per requested step
+    LSMachine m;
+    m.begin(lp, f, h_state->gd0, max_ls, h_state->tmaxc);
+    while (!m.done) {
+      const double t = m.request(lp);
+      obj->trial(x.p, d.p, t, m.wants_projection(lp), ls->lb.p, ls->ub.p, xt.p, gt.p, &d_state->ft);
+      ctx->counters[2]++;
+      fetch_state();
+      m.feed(lp, h_state->ft, h_state->gdt, h_state->dn);
+    }
+    const double t = m.result;
+    const bool current = m.last_eval_is_result;
+    // ---- update_next_iterate: next = x + t*d (ls_solver.rs:60)
+    if (!current) vec_axpy_project(ctx, n, x.p, d.p, t, false, nullptr, nullptr, xt.p, nullptr);
+    if (needs_y) {
+      if (!current) obj->eval(xt.p, &d_state->ft, gt.p, nullptr);  // bfgs.rs:98 (re-used when already evaluated)
+      vec_sy(ctx, n, xt.p, x.p, gt.p, g.p, s.p, y.p, &d_state->ss);
+      if (is_qn || kind == OSB_PROJ_NEWTON) state_finish_sy(ctx, d_state, tol);
+      accept_trial_kernel<<<1, 1, 0, stm>>>(d_state);
+      ctx->counters[0]++;
+      std::swap(x.p, xt.p);
+      std::swap(g.p, gt.p);
+      have_eval = true;
+      have_hess = false;
+      if (is_qn) qn_after_step();
+      if (kind == OSB_SPG || kind == OSB_SPN) {  // spg.rs:134-143
+        fetch_state();
+        const double sy = h_state->ys;
+        if (sy <= 0.) lambda = lambda_max;
+        else lambda = rmax(rmin(h_state->ss / sy, lambda_max), lambda_min);
+      }
+    } else {
+      std::swap(x.p, xt.p);
+      if (current) {
+        std::swap(g.p, gt.p);
+        accept_trial_kernel<<<1, 1, 0, stm>>>(d_state);
+        ctx->counters[0]++;
+        have_eval = true;
+      } else {
+        have_eval = false;
+      }
+      have_hess = false;
+    }
+    if (record_trace) {
+      if (is_qn || kind == OSB_PROJ_NEWTON) fetch_state();
+      trace.push_back(TraceRec{f, t, (is_qn || kind == OSB_PROJ_NEWTON) ? h_state->s_norm : NAN,
+                               (is_qn || kind == OSB_PROJ_NEWTON) ? h_state->y_norm : NAN});
+    }
+    k += 1;  // ls_solver.rs:104
+    if (cb) {
+      fetch_state();
+      if (is_qn || kind == OSB_PROJ_NEWTON) {
+        has_s = has_y = true;
+        s_norm = h_state->s_norm;
+        y_norm = h_state->y_norm;
+      }
+      cb(user, reinterpret_cast<osb_solver*>(this));
+    }
+  }
+  fetch_state();
+  if (is_qn || kind == OSB_PROJ_NEWTON) {
+    has_s = h_state->has_s != 0;
+    has_y = h_state->has_y != 0;
+    s_norm = h_state->s_norm;
+    y_norm = h_state->y_norm;
+  }
+  return OSB_MAX_ITER_REACHED;  // ls_solver.rs:109-110
+}
+
+int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, int64_t max_ls) {
+  k = 0;
+  reason = OSB_REASON_NONE;
+  trace.clear();
+  cudaStream_t stm = ctx->stream;
+  if (!have_eval) {
+    obj->eval(x.p, &d_state->f, g.p, nullptr);
+    have_eval = true;
+    u_valid = false;
+  }
+  if (!u_valid) {
+    qn_launch_gemv(ctx, H.p, ld, nrows, row0, nullptr, g.p, u.p, nullptr, nullptr, qn_variant);
+    if (ctx->world > 1) ctx->all_gather_inplace(u.p, nrows);
+    u_valid = true;
+  }
+  // control block: keep f / norms, reset the run flags
+  fetch_state();
+  h_state->k = 0;
+  h_state->done = 0;
+  h_state->status = OSB_MAX_ITER_REACHED;
+  h_state->reason = OSB_REASON_NONE;
+  h_state->skip = 0;
+  h_state->ls_evals = 0;
+  push_state();
+  LSParams* d_ls = nullptr;
+  OSB_CUDA(cudaMalloc(&d_ls, sizeof(LSParams)));
+  OSB_CUDA(cudaMemcpyAsync(d_ls, &ls->p, sizeof(LSParams), cudaMemcpyHostToDevice, stm));
+  // polling: a snapshot of the control block every POLL iterations, at most two in flight
+  const int POLL = 4;
+  DevState* snap = nullptr;
+  OSB_CUDA(cudaHostAlloc(&snap, 2 * sizeof(DevState), cudaHostAllocDefault));
+  cudaEvent_t sev[2];
+  OSB_CUDA(cudaEventCreateWithFlags(&sev[0], cudaEventDisableTiming));
+  OSB_CUDA(cudaEventCreateWithFlags(&sev[1], cudaEventDisableTiming));
+  bool pending[2] = {false, false};
+  int slot = 0;
+  bool stop = false;
+  const bool ls_bounded = ls->p.kind == LS_BACKTRACKING_B || ls->p.kind == LS_MORETHUENTE_B;
+  for (int64_t it = 0; it < max_iter && !stop; ++it) {
+    qn_device_launch_head(ctx, obj->functor_kind(), obj->functor_ptr(0), obj->functor_ptr(1), bounded, d_ls, n, tol, max_ls,
+                          d_state, x.p, g.p, d.p, xt.p, gt.p, s.p, y.p, u.p, bounded ? lb.p : nullptr, bounded ? ub.p : nullptr,
+                          ls_bounded ? ls->lb.p : nullptr, ls_bounded ? ls->ub.p : nullptr);
+    qn_after_step();
+    if ((it + 1) % POLL == 0) {
+      if (pending[slot]) {  // bound the run-ahead: wait for the older snapshot of this slot
+        OSB_CUDA(cudaEventSynchronize(sev[slot]));
+        ctx->counters[3]++;
+        if (snap[slot].done) stop = true;
+        pending[slot] = false;
+      }
+      if (!stop) {
+        OSB_CUDA(cudaMemcpyAsync(&snap[slot], d_state, sizeof(DevState), cudaMemcpyDeviceToHost, stm));
+        OSB_CUDA(cudaEventRecord(sev[slot], stm));
+        pending[slot] = true;
+        slot ^= 1;
+        // opportunistic early look (single GPU only: ranks must take identical stop decisions)
+        if (ctx->world == 1 && pending[slot] && cudaEventQuery(sev[slot]) == cudaSuccess) {
+          if (snap[slot].done) stop = true;
+          pending[slot] = false;
+        }
+      }
+    }
+  }
+  fetch_state();
+  OSB_CUDA(cudaMemcpyAsync(&ls->p, d_ls, sizeof(LSParams), cudaMemcpyDeviceToHost, stm));
+  ctx->sync();
+  cudaFree(d_ls);
+  cudaFreeHost(snap);
+  cudaEventDestroy(sev[0]);
+  cudaEventDestroy(sev[1]);
+  k = h_state->k;
+  has_s = h_state->has_s != 0;
+  has_y = h_state->has_y != 0;
+  s_norm = h_state->s_norm;
+  y_norm = h_state->y_norm;
+  ctx->counters[2] += h_state->ls_evals;
+  if (h_state->done) {
+    reason = h_state->reason;
+    return h_state->status;
+  }
+  return OSB_MAX_ITER_REACHED;
+}
+
+}  // namespace osb

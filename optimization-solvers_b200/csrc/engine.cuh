@@ -1,0 +1,253 @@
+// engine.cuh — host-side objects behind the C ABI: context, objectives, line searches, solvers.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "ls_automaton.cuh"
+#include "reduce.cuh"
+
+namespace osb {
+
+// ---- device-resident control block of one solver ------------------------------------------
+// Written by kernels, mirrored to pinned host memory when the host needs a decision.  Groups of
+// fields that one reduction kernel produces are contiguous (the kernel writes K consecutive doubles).
+struct DevState {
+  double f;       // f(x_k) of the cached evaluate_x_k (ls_solver.rs:32-42)
+  double conv;    // kind-specific convergence scalar: ||g||^2 | max|g_i| | ||proj grad||_inf
+  double gd0;     // g(x_k) . d_k
+  double tmaxc;   // MoreThuenteB feasible-step candidate (morethuente_b.rs:185-197)
+  double dinf;    // spare (SPG lambda0: ||P(x-g)-x||_inf)
+  // trial outputs (3 contiguous)
+  double ft, gdt, dn;
+  // post-step dots (4 contiguous): s.s, y.y, y.s, spare
+  double ss, yy, ys, sp;
+  // update dots (2 contiguous): y.h, spare
+  double yh, sp2;
+  double s_norm, y_norm;
+  double c0, c1, c2;  // rank-2 update coefficients (kind-specific, see qn_kernels.cu)
+  double t_last;
+  long long k;
+  int has_s, has_y;
+  int skip;    // bfgs.rs:106-112: s_norm < tol || y_norm < tol -> H not updated
+  int done;    // device-resident engine: minimize() has terminated
+  int status;  // OSB_* status when done
+  int reason;  // OSB_REASON_*
+  int ls_evals;
+  int pad;
+};
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int num_sms = 148;
+  int rank = 0, world = 1;
+  void* nccl_comm = nullptr;
+  // reduction scratch
+  double* red_partials = nullptr;
+  unsigned int* red_ticket = nullptr;
+  int red_max_grid = 0;
+  // counters: launches, objective evals, ls trials, host syncs, collectives
+  int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // pinned staging for small transfers
+  double* h_pinned = nullptr;  // 4096 doubles
+  double* d_dummy = nullptr;   // 8 doubles: sink for reductions whose result is unused
+
+  explicit Ctx(int dev);
+  ~Ctx();
+  void sync() {
+    OSB_CUDA(cudaStreamSynchronize(stream));
+    counters[3]++;
+  }
+  void all_gather_inplace(double* buf, int64_t count_per_rank);  // dist.cu
+  void use() { OSB_CUDA(cudaSetDevice(device)); }
+  int red_grid(int64_t count) const {
+    int64_t g = (count + RED_THREADS * 8 - 1) / (RED_THREADS * 8);
+    if (g < 1) g = 1;
+    if (g > red_max_grid) g = red_max_grid;
+    return (int)g;
+  }
+};
+
+// RAII device buffer
+struct DBuf {
+  double* p = nullptr;
+  int64_t n = 0;
+  DBuf() {}
+  explicit DBuf(int64_t n_) { alloc(n_); }
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  ~DBuf() { release(); }
+  void alloc(int64_t n_);
+  void release();
+  void zero(cudaStream_t s);
+  void upload(const double* h, int64_t cnt, cudaStream_t s);
+  void download(double* h, int64_t cnt, cudaStream_t s) const;
+};
+
+template <int K, class F, class Fin>
+inline void launch_mapreduce_fin(Ctx* ctx, F f, Fin fin, int64_t count, RedOps<K> ops, double* out) {
+  static_assert(K <= RED_THREADS / 32, "final fold uses one warp per output");
+  int grid = ctx->red_grid(count);
+  mapreduce_kernel<K, F, Fin><<<grid, RED_THREADS, 0, ctx->stream>>>(f, fin, count, ops, ctx->red_partials, ctx->red_ticket, out);
+  ctx->counters[0]++;
+}
+template <int K, class F>
+inline void launch_mapreduce(Ctx* ctx, F f, int64_t count, RedOps<K> ops, double* out) {
+  launch_mapreduce_fin<K>(ctx, f, FinStore{}, count, ops, out);
+}
+
+// ---- objectives ---------------------------------------------------------------------------
+enum FunctorKind : int { FN_NONE = 0, FN_ROSENBROCK = 1, FN_SEPQUAD = 2 };
+
+struct Objective {
+  Ctx* ctx;
+  int64_t n;
+  int64_t calls = 0;
+  Objective(Ctx* c, int64_t n_) : ctx(c), n(n_) {}
+  virtual ~Objective() {}
+  virtual bool provides_hessian() const { return false; }
+  virtual int functor_kind() const { return FN_NONE; }
+  virtual const double* functor_ptr(int) const { return nullptr; }
+  // f -> *d_f (device), g -> d_g[n], Hessian -> d_hess[n*n] (row-major; symmetric) when non-null
+  virtual void eval(const double* d_x, double* d_f, double* d_g, double* d_hess) = 0;
+  // one line-search trial: xt = [P](x + t d); (ft, gt) = eval(xt); out3 = {ft, gt.d, ||xt - x||^2}
+  virtual void trial(const double* x, const double* d, double t, bool project, const double* lb, const double* ub,
+                     double* xt, double* gt, double* d_out3);
+};
+
+Objective* make_dense_quadratic(Ctx*, int64_t n, const double* A_host, const double* b_host);
+Objective* make_dense_quadratic_generated(Ctx*, int64_t n, bool shifted, double* x0_host);
+Objective* make_rosenbrock(Ctx*, int64_t n);
+Objective* make_sepquad_generated(Ctx*, int64_t n);
+Objective* make_logistic_generated(Ctx*, int64_t m, int64_t n, double lambda);
+Objective* make_host_objective(Ctx*, int64_t n, osb_host_eval_fn fn, void* user, bool with_h);
+Objective* make_user_objective(Ctx*, int64_t n, osb_device_eval_fn fn, void* user, bool with_h);
+
+// ---- line search handle -------------------------------------------------------------------
+struct LineSearch {
+  LSParams p;
+  Ctx* ctx = nullptr;
+  DBuf lb, ub;  // bounded kinds
+  int64_t n = 0;
+};
+
+// ---- dense quasi-Newton kernels (qn_kernels.cu) -------------------------------------------
+enum QNKind : int { QN_BFGS = 0, QN_DFP = 1, QN_BROYDEN = 2, QN_SR1 = 3 };
+// out = H v over the local row block.  `sel` chooses the operand at run time ON DEVICE from
+// DevState.skip: skip ? (v_skip -> out_skip) : (v -> out); a null `st` means unconditional (v -> out).
+void qn_launch_gemv(Ctx* ctx, const double* H, int64_t ld, int64_t nrows, int64_t row0, const DevState* st, const double* v,
+                    double* out, const double* v_skip, double* out_skip, int variant);
+// out[j] = sum_i H_ij s_i over the local row block (Broyden's H^T s), two-stage deterministic
+void qn_launch_gemvT(Ctx* ctx, const double* H, int64_t ld, int64_t nrows, int64_t row0, const DevState* st,
+                     const double* s, double* out, double* scratch);
+// coefficients c0..c2 (and p = s - h for SR1/Broyden) from y.h etc.; single CTA
+void qn_launch_coef(Ctx* ctx, int kind, int64_t n, DevState* st, const double* s, const double* y, const double* h,
+                    double* p_out);
+// fused: H <- H + rank-2(kind; p, q, r; c0..c2) and u = H' g over the local row block
+void qn_launch_update(Ctx* ctx, int kind, double* H, int64_t ld, int64_t nrows, int64_t row0, const DevState* st,
+                      const double* p, const double* q, const double* r, const double* g, double* u_out, int variant);
+int64_t qn_ld(int64_t n);
+int64_t qn_rows_padded(int64_t nrows);
+
+// ---- solver -------------------------------------------------------------------------------
+struct TraceRec {
+  double f, t, s_norm, y_norm;
+};
+
+struct Solver {
+  Ctx* ctx;
+  int kind;
+  int64_t n;
+  double tol;
+  int64_t k = 0;
+  int reason = OSB_REASON_NONE;
+  // options
+  int engine = 0;
+  int record_trace = 0;
+  int qn_variant = 0;
+  // state vectors (device)
+  DBuf x, g, d, xt, gt, s, y, lb, ub, w;
+  bool bounded = false;
+  // quasi-Newton
+  bool is_qn = false;
+  int qn_kind = QN_BFGS;
+  int64_t ld = 0, row0 = 0, nrows = 0;  // local row block of H
+  DBuf H, u, h, pvec, vvec, scratch;
+  // Newton family
+  DBuf hess, chol;
+  bool has_dec = false;
+  double decrement_squared = NAN;
+  // spectral
+  double lambda = 1.0, lambda_min = 1e-3, lambda_max = 1e3;
+  // norms (host mirror)
+  bool has_s = false, has_y = false;
+  double s_norm = NAN, y_norm = NAN;
+  // control block
+  DevState* d_state = nullptr;
+  DevState* h_state = nullptr;  // pinned
+  bool have_eval = false;       // (f, g) valid for the current x
+  bool u_valid = false;         // u == H g for the current (H, g)
+  std::vector<TraceRec> trace;
+  double last_ms = 0.0;
+  int64_t last_iters = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // optional per-kernel timing (option "profile_kernels"): CUDA-event pairs around the two H passes
+  int profile_kernels = 0;
+  std::vector<cudaEvent_t> prof_events;  // 4 per iteration: gemv begin/end, update begin/end
+  double prof_ms[3] = {0.0, 0.0, 0.0};   // mean ms: pass 1 (gemv), pass 2 (update), count
+  void prof_mark();
+  void prof_collect();
+
+  Solver(Ctx* c, int kind_, int64_t n_, double tol_, const double* x0, const double* lb_h, const double* ub_h,
+         Objective* obj_for_lambda0);
+  ~Solver();
+  int minimize(LineSearch* ls, Objective* obj, int64_t max_iter, int64_t max_ls, osb_callback_fn cb, void* user);
+  void fetch_state();
+  void push_state();
+
+ private:
+  int minimize_host(LineSearch* ls, Objective* obj, int64_t max_iter, int64_t max_ls, osb_callback_fn cb, void* user);
+  int minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, int64_t max_ls);
+  bool device_engine_supported(const LineSearch* ls, const Objective* obj) const;
+  void compute_conv_scalar(Objective* obj);
+  int compute_direction(Objective* obj, LineSearch* ls);
+  void qn_after_step();
+};
+
+// vector kernels (vec_kernels.cu)
+void vec_axpy_project(Ctx*, int64_t n, const double* x, const double* d, double t, bool project, const double* lb,
+                      const double* ub, double* out, double* d_dn /*nullable*/);
+void vec_dot(Ctx*, int64_t n, const double* a, const double* b, double* d_out);
+void vec_project_inplace(Ctx*, int64_t n, double* x, const double* lb, const double* ub);
+void vec_neg(Ctx*, int64_t n, const double* a, double* out, const double* g, double* d_gd0);
+// d = P(x - lam*w) - x ; gd0 = g.d ; tmaxc = min feasible step (only if lb given) ; dinf = ||d||_inf
+void vec_projected_direction(Ctx*, int64_t n, const double* x, const double* w, double lam, bool scale, const double* lb,
+                             const double* ub, const double* g, double* d, double* d_gd0_tmaxc_dinf);
+void vec_tmax_candidate(Ctx*, int64_t n, const double* x, const double* d, const double* lb, const double* ub,
+                        double* d_out);
+void vec_conv_gnorm2(Ctx*, int64_t n, const double* g, double* d_out);
+void vec_conv_gmax(Ctx*, int64_t n, const double* g, double* d_out);
+void vec_conv_pginf(Ctx*, int64_t n, const double* x, const double* g, const double* lb, const double* ub, double* d_out);
+// s = xn - x ; y = gn - g ; out4 = {s.s, y.y, y.s, 0}
+void vec_sy(Ctx*, int64_t n, const double* xn, const double* x, const double* gn, const double* g, double* s, double* y,
+            double* d_out4);
+void vec_active_set(Ctx*, int64_t n, const double* x, const double* lb, const double* ub, uint8_t* out);
+// device-side: s_norm = sqrt(ss), y_norm = sqrt(yy), skip flag, has_s/has_y
+void state_finish_sy(Ctx*, DevState* st, double tol);
+
+// device-resident engine (qn_device.cu)
+void qn_device_launch_head(Ctx* ctx, int functor_kind, const double* fn_a, const double* fn_b, bool bounded,
+                           LSParams* d_ls, int64_t n, double tol, int64_t max_ls, DevState* st, double* x, double* g,
+                           double* d, double* xt, double* gt, double* s, double* y, const double* u, const double* lb,
+                           const double* ub, const double* ls_lb, const double* ls_ub);
+
+// batched (batched.cu)
+int batched_bfgs_rosenbrock(Ctx* ctx, int64_t n, int64_t np, const double* x0_host, bool generated, int64_t problem0,
+                            double tol, int64_t max_iter, int64_t max_ls, double c1, double beta, double* x_out,
+                            double* f_out, int32_t* k_out, int32_t* st_out, int32_t* reason_out, double* ms_out);
+
+void set_last_error(const std::string& s);
+
+}  // namespace osb

@@ -1,0 +1,251 @@
+// objectives.cu — device objectives: the counterpart of the user closure
+// `FnMut(&DVector<f64>) -> FuncEvalMultivariate` (src/ls_solver.rs:34, src/func_eval.rs:5-41).
+// Built-ins: dense quadratic (examples/quadratic.rs:10-14 pattern), extended Rosenbrock,
+// separable box quadratic; plus host-closure and user-device-functor adapters.
+#include "engine.cuh"
+#include "functors.cuh"
+
+namespace osb {
+
+// default trial: x + t d [projected] -> eval -> g.d      (three launches; built-ins fuse them)
+void Objective::trial(const double* x, const double* d, double t, bool project, const double* lb, const double* ub, double* xt,
+                      double* gt, double* d_out3) {
+  vec_axpy_project(ctx, n, x, d, t, project, lb, ub, xt, d_out3 + 2);
+  eval(xt, d_out3, gt, nullptr);
+  vec_dot(ctx, n, gt, d, d_out3 + 1);
+}
+
+// ---- block-functor objectives: one fused kernel per evaluation / per line-search trial -----
+template <class Fn>
+struct FunctorObjective : Objective {
+  Fn fn;
+  int fkind;
+  DBuf pa, pb;
+  FunctorObjective(Ctx* c, int64_t n_, int kind) : Objective(c, n_), fkind(kind) {}
+  int functor_kind() const override { return fkind; }
+  const double* functor_ptr(int i) const override { return i == 0 ? pa.p : pb.p; }
+
+  void eval(const double* x, double* d_f, double* g, double* hess) override {
+    OSB_REQUIRE(hess == nullptr, OSB_PANIC_NO_HESSIAN, "Hessian not available in the oracle");
+    calls++;
+    ctx->counters[1]++;
+    const Fn f_ = fn;
+    auto f = [=] __device__(int64_t b, double(&acc)[1]) {
+      double xb[Fn::BS], gb[Fn::BS];
+      const int64_t i0 = b * Fn::BS;
+#pragma unroll
+      for (int j = 0; j < Fn::BS; ++j) xb[j] = x[i0 + j];
+      const double fb = f_.block(i0, xb, gb);
+#pragma unroll
+      for (int j = 0; j < Fn::BS; ++j) g[i0 + j] = gb[j];
+      acc[0] = acc[0] + fb;
+    };
+    launch_mapreduce<1>(ctx, f, n / Fn::BS, RedOps<1>{{RED_SUM}}, d_f);
+  }
+
+  // "one trial step is one kernel": axpy, projection, objective, gradient, g.d and ||xt-x||^2 fused
+  void trial(const double* x, const double* d, double t, bool project, const double* lb, const double* ub, double* xt,
+             double* gt, double* d_out3) override {
+    calls++;
+    ctx->counters[1]++;
+    const Fn f_ = fn;
+    auto f = [=] __device__(int64_t b, double(&acc)[3]) {
+      double xb[Fn::BS], gb[Fn::BS], db[Fn::BS];
+      const int64_t i0 = b * Fn::BS;
+#pragma unroll
+      for (int j = 0; j < Fn::BS; ++j) {
+        const double xi = x[i0 + j];
+        db[j] = d[i0 + j];
+        const double td = t * db[j];
+        double v = xi + td;
+        if (project) v = fmin(fmax(v, lb[i0 + j]), ub[i0 + j]);
+        xb[j] = v;
+        xt[i0 + j] = v;
+        const double df = v - xi;
+        acc[2] = acc[2] + df * df;
+      }
+      const double fb = f_.block(i0, xb, gb);
+#pragma unroll
+      for (int j = 0; j < Fn::BS; ++j) {
+        gt[i0 + j] = gb[j];
+        acc[1] = fma(gb[j], db[j], acc[1]);
+      }
+      acc[0] = acc[0] + fb;
+    };
+    launch_mapreduce<3>(ctx, f, n / Fn::BS, RedOps<3>{{RED_SUM, RED_SUM, RED_SUM}}, d_out3);
+  }
+};
+
+Objective* make_rosenbrock(Ctx* ctx, int64_t n) {
+  OSB_REQUIRE(n >= 2 && n % 2 == 0, OSB_ERROR_INPUT_PARAMS, "extended Rosenbrock needs an even n >= 2");
+  return new FunctorObjective<RosenbrockFn>(ctx, n, FN_ROSENBROCK);
+}
+
+__global__ void gen_sepquad_kernel(int64_t n, double* c, double* a) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    c[i] = 1.0 + (double)(hash3(7, (uint64_t)i, 0) & 0xFF) / 16.0;
+    a[i] = (double)h16(8, (uint64_t)i, 0) * 6.103515625e-05;  // 2^-14
+  }
+}
+Objective* make_sepquad_generated(Ctx* ctx, int64_t n) {
+  auto* o = new FunctorObjective<SepQuadFn>(ctx, n, FN_SEPQUAD);
+  o->pa.alloc(qn_ld(n));
+  o->pb.alloc(qn_ld(n));
+  gen_sepquad_kernel<<<ctx->red_grid(n), RED_THREADS, 0, ctx->stream>>>(n, o->pa.p, o->pb.p);
+  ctx->counters[0]++;
+  o->fn.c = o->pa.p;
+  o->fn.a = o->pb.p;
+  return o;
+}
+
+// ---- dense quadratic ----------------------------------------------------------------------
+__global__ void gen_quad_kernel(int64_t n, int64_t ld, double sc, double* A) {
+  const int64_t total = n * ld;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / ld, j = e % ld;
+    double v = 0.0;
+    if (j < n) {
+      if (i == j) v = 2.0 + (double)(i % 7);
+      else {
+        const int64_t lo = i < j ? i : j, hi = i < j ? j : i;
+        v = (double)h16(1, (uint64_t)lo, (uint64_t)hi) * sc;
+      }
+    }
+    A[e] = v;
+  }
+}
+__global__ void scale_copy_kernel(int64_t total, const double* in, double* out, double sc) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) out[e] = sc * in[e];
+}
+
+struct DenseQuadratic : Objective {
+  DBuf A, b, Ax;
+  int64_t ld;
+  bool shifted = false;
+  DenseQuadratic(Ctx* c, int64_t n_) : Objective(c, n_), ld(qn_ld(n_)) {
+    A.alloc(qn_rows_padded(n_) * ld);
+    A.zero(c->stream);
+    Ax.alloc(ld);
+    Ax.zero(c->stream);
+  }
+  bool provides_hessian() const override { return true; }
+  void eval(const double* x, double* d_f, double* g, double* hess) override {
+    calls++;
+    ctx->counters[1]++;
+    // one read of A yields A x, hence f and g  (n^2 * 8 B per evaluation)
+    qn_launch_gemv(ctx, A.p, ld, n, 0, nullptr, x, Ax.p, nullptr, nullptr, 0);
+    const double* ax = Ax.p;
+    const double* bb = shifted ? b.p : nullptr;
+    auto f = [=] __device__(int64_t i, double(&acc)[2]) {
+      const double xi = x[i], axi = ax[i];
+      acc[0] = fma(xi, axi, acc[0]);
+      if (bb) {
+        acc[1] = fma(bb[i], xi, acc[1]);
+        g[i] = 2.0 * (axi - bb[i]);
+      } else {
+        g[i] = 2.0 * axi;
+      }
+    };
+    auto fin = [=] __device__(const double(&v)[2], double* out) { out[0] = bb ? v[0] - 2.0 * v[1] : v[0]; };
+    launch_mapreduce_fin<2>(ctx, f, fin, n, RedOps<2>{{RED_SUM, RED_SUM}}, d_f);
+    if (hess) {  // constant Hessian 2A (same padded layout as A)
+      scale_copy_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(n * ld, A.p, hess, 2.0);
+      ctx->counters[0]++;
+    }
+  }
+};
+
+Objective* make_dense_quadratic(Ctx* ctx, int64_t n, const double* A_host, const double* b_host) {
+  auto* o = new DenseQuadratic(ctx, n);
+  OSB_CUDA(cudaMemcpy2DAsync(o->A.p, o->ld * sizeof(double), A_host, n * sizeof(double), n * sizeof(double), n,
+                             cudaMemcpyHostToDevice, ctx->stream));
+  if (b_host) {
+    o->shifted = true;
+    o->b.alloc(o->ld);
+    o->b.zero(ctx->stream);
+    o->b.upload(b_host, n, ctx->stream);
+  }
+  ctx->sync();
+  return o;
+}
+
+Objective* make_dense_quadratic_generated(Ctx* ctx, int64_t n, bool shifted, double* x0_host) {
+  auto* o = new DenseQuadratic(ctx, n);
+  int lg = 0;
+  while (((int64_t)1 << lg) < n) ++lg;
+  const double sc = std::ldexp(1.0, -(15 + lg));
+  gen_quad_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(n, o->ld, sc, o->A.p);
+  ctx->counters[0]++;
+  if (shifted) {
+    std::vector<double> b(n);
+    for (int64_t i = 0; i < n; ++i) b[i] = (double)h16(9, (uint64_t)i, 0) * std::ldexp(1.0, -13);
+    o->shifted = true;
+    o->b.alloc(o->ld);
+    o->b.zero(ctx->stream);
+    o->b.upload(b.data(), n, ctx->stream);
+  }
+  if (x0_host)
+    for (int64_t i = 0; i < n; ++i) x0_host[i] = (double)h16(2, (uint64_t)i, 0) * std::ldexp(1.0, -13);
+  ctx->sync();
+  return o;
+}
+
+// ---- host closure (compatibility path) ----------------------------------------------------
+struct HostObjective : Objective {
+  osb_host_eval_fn fn;
+  void* user;
+  bool with_h;
+  std::vector<double> hx, hg, hh;
+  HostObjective(Ctx* c, int64_t n_, osb_host_eval_fn f, void* u, bool wh) : Objective(c, n_), fn(f), user(u), with_h(wh) {
+    hx.resize(n_);
+    hg.resize(n_);
+    if (wh) hh.resize(n_ * n_);
+  }
+  bool provides_hessian() const override { return with_h; }
+  void eval(const double* x, double* d_f, double* g, double* hess) override {
+    calls++;
+    ctx->counters[1]++;
+    OSB_CUDA(cudaMemcpyAsync(hx.data(), x, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
+    double f = NAN;
+    int got = fn(user, hx.data(), n, &f, hg.data(), (hess && with_h) ? hh.data() : nullptr);
+    OSB_REQUIRE(!(hess && !got), OSB_PANIC_NO_HESSIAN, "Hessian not available in the oracle");
+    ctx->h_pinned[0] = f;
+    OSB_CUDA(cudaMemcpyAsync(d_f, ctx->h_pinned, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    OSB_CUDA(cudaMemcpyAsync(g, hg.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (hess) {
+      const int64_t ld = qn_ld(n);
+      OSB_CUDA(cudaMemcpy2DAsync(hess, ld * sizeof(double), hh.data(), n * sizeof(double), n * sizeof(double), n,
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ctx->sync();  // staging buffers are reused by the next call
+  }
+};
+Objective* make_host_objective(Ctx* ctx, int64_t n, osb_host_eval_fn fn, void* user, bool with_h) {
+  return new HostObjective(ctx, n, fn, user, with_h);
+}
+
+// ---- user-supplied device functor ---------------------------------------------------------
+struct UserObjective : Objective {
+  osb_device_eval_fn fn;
+  void* user;
+  bool with_h;
+  UserObjective(Ctx* c, int64_t n_, osb_device_eval_fn f, void* u, bool wh) : Objective(c, n_), fn(f), user(u), with_h(wh) {}
+  bool provides_hessian() const override { return with_h; }
+  void eval(const double* x, double* d_f, double* g, double* hess) override {
+    calls++;
+    ctx->counters[1]++;
+    OSB_REQUIRE(!(hess && !with_h), OSB_PANIC_NO_HESSIAN, "Hessian not available in the oracle");
+    int rc = fn(user, x, n, d_f, g, hess, (void*)ctx->stream);
+    OSB_REQUIRE(rc == 0, OSB_ABNORMAL_TERMINATION, "user device functor returned an error");
+  }
+};
+Objective* make_user_objective(Ctx* ctx, int64_t n, osb_device_eval_fn fn, void* user, bool with_h) {
+  return new UserObjective(ctx, n, fn, user, with_h);
+}
+
+Objective* make_logistic_generated(Ctx*, int64_t, int64_t, double) {
+  throw Error(OSB_ERR_UNSUPPORTED, "logistic regression objective: not built yet");
+}
+
+}  // namespace osb

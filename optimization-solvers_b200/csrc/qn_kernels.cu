@@ -1,0 +1,254 @@
+// qn_kernels.cu — the dense quasi-Newton hot path on the device-resident inverse-Hessian
+// approximation H (row-major, leading dimension ld = n rounded up to 16 doubles, zero padded).
+//
+// Replaces, per outer iteration of the reference:
+//   compute_direction          d = (-H) g                     src/quasi_newton/bfgs.rs:43-48
+//   update_next_iterate        two dense n^3 GEMMs            src/quasi_newton/bfgs.rs:115-124
+//                              (dfp.rs:115-120, broyden.rs:115-118, sr1_b.rs:143-146)
+// with the algebraically equal O(n^2) schedule:
+//   pass 1  qn_gemv_kernel     h = H y                        reads  n^2 * 8 B
+//   pass 2  qn_update_kernel   H <- H + rank-2(s, h) and, in the same read-modify-write,
+//                              u = H' g_new                   reads + writes n^2 * 8 B
+// so one iteration moves 3 * n^2 * 8 B of HBM traffic.  Both kernels are HBM-bound streaming
+// kernels: 128-bit coalesced loads with no L1 allocation, R rows per CTA tile so that the O(n)
+// vectors are re-read from L1/L2 only once per R rows, fused-multiply-add only in the dot
+// accumulators, warp-shuffle + fixed-order cross-warp reduction (deterministic; a row's sum is
+// formed entirely inside one CTA, so the result does not depend on the grid or on the number of
+// GPUs the rows are sharded over).
+#include "engine.cuh"
+
+namespace osb {
+
+constexpr int QN_T = 512;          // threads per CTA
+constexpr int QN_R = 8;            // rows per tile
+constexpr int QN_CHUNK = QN_T * 2; // columns per sweep step (one 16-byte vector per thread)
+
+int64_t qn_ld(int64_t n) { return (n + 15) / 16 * 16; }
+// H is allocated with its row count rounded up to a whole tile (zero rows), so that the kernels
+// need neither row clamping nor store guards; vectors are allocated with ld entries (zero padded).
+int64_t qn_rows_padded(int64_t nrows) { return (nrows + QN_R - 1) / QN_R * QN_R; }
+
+__device__ __forceinline__ void tile_reduce_store(double (&acc)[QN_R], double (*red)[QN_T / 32], double* out, int64_t row_base,
+                                                  int64_t r0, int64_t nrows) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = 0; r < QN_R; ++r) {
+    double v = warp_sum(acc[r]);
+    if (lane == 0) red[r][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < QN_R) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < QN_T / 32; ++w) v = v + red[threadIdx.x][w];
+    if (r0 + threadIdx.x < nrows) out[row_base + r0 + threadIdx.x] = v;
+  }
+  __syncthreads();
+}
+
+// ---- pass 1: out = H v ---------------------------------------------------------------------
+__global__ void __launch_bounds__(QN_T, 2)
+qn_gemv_kernel(const double* __restrict__ H, int64_t ld, int64_t nrows, int64_t row0, const DevState* __restrict__ st,
+               const double* __restrict__ v, double* __restrict__ out, const double* __restrict__ v_skip,
+               double* __restrict__ out_skip) {
+  if (st != nullptr) {
+    if (st->done) return;
+    if (st->skip) {  // bfgs.rs:106-112: H unchanged; only the next direction's u = H g is needed
+      v = v_skip;
+      out = out_skip;
+    }
+  }
+  if (v == nullptr) return;
+  __shared__ double red[QN_R][QN_T / 32];
+  const int64_t ntiles = (nrows + QN_R - 1) / QN_R;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r0 = tile * QN_R;
+    double acc[QN_R];
+#pragma unroll
+    for (int r = 0; r < QN_R; ++r) acc[r] = 0.0;
+    const double* __restrict__ base = H + r0 * ld;
+    for (int col = 2 * threadIdx.x; col < (int)ld; col += QN_CHUNK) {
+      const double2 vv = *reinterpret_cast<const double2*>(v + col);
+      double2 hv[QN_R];
+#pragma unroll
+      for (int r = 0; r < QN_R; ++r) hv[r] = ld_stream_nc(base + r * ld + col);
+#pragma unroll
+      for (int r = 0; r < QN_R; ++r) {
+        acc[r] = fma(hv[r].x, vv.x, acc[r]);
+        acc[r] = fma(hv[r].y, vv.y, acc[r]);
+      }
+    }
+    tile_reduce_store(acc, red, out, row0, r0, nrows);
+  }
+}
+
+void qn_launch_gemv(Ctx* ctx, const double* H, int64_t ld, int64_t nrows, int64_t row0, const DevState* st, const double* v,
+                    double* out, const double* v_skip, double* out_skip, int variant) {
+  (void)variant;
+  int64_t ntiles = (nrows + QN_R - 1) / QN_R;
+  int grid = (int)std::min<int64_t>(ntiles, (int64_t)ctx->num_sms * 2);
+  // rows are addressed relative to the local block; `out` is indexed by global row (row0 + local row)
+  qn_gemv_kernel<<<grid, QN_T, 0, ctx->stream>>>(H, ld, nrows, row0, st, v, out, v_skip, out_skip);
+  ctx->counters[0]++;
+}
+
+// ---- Broyden: out[j] = sum_i H_ij s_i  (column sums; two deterministic stages) -------------
+constexpr int GT_T = 256, GT_ROWS = 64;
+__global__ void __launch_bounds__(GT_T) qn_gemvT_stage1(const double* __restrict__ H, int64_t ld, int64_t nrows, int64_t row0,
+                                                        const DevState* __restrict__ st, const double* __restrict__ s,
+                                                        double* __restrict__ partial) {
+  if (st != nullptr && (st->done || st->skip)) return;
+  const int64_t col = ((int64_t)blockIdx.x * GT_T + threadIdx.x) * 2;
+  if (col >= ld) return;
+  const int64_t rb = (int64_t)blockIdx.y * GT_ROWS;
+  const int64_t re = rb + GT_ROWS < nrows ? rb + GT_ROWS : nrows;
+  double a0 = 0.0, a1 = 0.0;
+  for (int64_t i = rb; i < re; ++i) {
+    const double si = s[row0 + i];
+    const double2 hv = ld_stream_nc(H + i * ld + col);
+    a0 = fma(hv.x, si, a0);
+    a1 = fma(hv.y, si, a1);
+  }
+  *reinterpret_cast<double2*>(partial + (int64_t)blockIdx.y * ld + col) = make_double2(a0, a1);
+}
+__global__ void __launch_bounds__(GT_T) qn_gemvT_stage2(int64_t ld, int64_t nsplit, const DevState* __restrict__ st,
+                                                        const double* __restrict__ partial, double* __restrict__ out) {
+  if (st != nullptr && (st->done || st->skip)) return;
+  const int64_t col = (int64_t)blockIdx.x * GT_T + threadIdx.x;
+  if (col >= ld) return;
+  double a = 0.0;
+  for (int64_t k = 0; k < nsplit; ++k) a = a + partial[k * ld + col];
+  out[col] = a;
+}
+void qn_launch_gemvT(Ctx* ctx, const double* H, int64_t ld, int64_t nrows, int64_t row0, const DevState* st, const double* s,
+                     double* out, double* scratch) {
+  int64_t nsplit = (nrows + GT_ROWS - 1) / GT_ROWS;
+  dim3 g1((unsigned)((ld / 2 + GT_T - 1) / GT_T), (unsigned)nsplit);
+  qn_gemvT_stage1<<<g1, GT_T, 0, ctx->stream>>>(H, ld, nrows, row0, st, s, scratch);
+  qn_gemvT_stage2<<<(unsigned)((ld + GT_T - 1) / GT_T), GT_T, 0, ctx->stream>>>(ld, nsplit, st, scratch, out);
+  ctx->counters[0] += 2;
+}
+
+// ---- update coefficients -------------------------------------------------------------------
+// BFGS  (bfgs.rs:115-124)     H' = H - rho (s h^T + h s^T) + (rho^2 y.h + rho) s s^T,  rho = 1/(y.s), h = H y
+// DFP   (dfp.rs:115-120)      H' = H + s s^T/(s.y) - h h^T/(y.h)
+// SR1   (sr1_b.rs:143-146)    H' = H + p p^T/(p.y),            p = s - h
+// Broyden (broyden.rs:115-118) H' = H + p v^T/(s.y),           p = s - h, v = H^T s
+// Divisions by the scalar denominators are applied as multiplications by their reciprocals
+// (<= 1 ulp per term away from the reference's elementwise division; documented in DESIGN.md).
+__global__ void __launch_bounds__(1024) qn_coef_kernel(int kind, int64_t n, DevState* st, const double* __restrict__ s,
+                                                       const double* __restrict__ y, const double* __restrict__ h,
+                                                       double* __restrict__ p_out) {
+  if (st->done || st->skip) return;
+  __shared__ double smem[2 * 32];
+  double acc[2] = {0.0, 0.0};
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double yi = y[i], hi = h[i];
+    acc[0] = fma(yi, hi, acc[0]);
+    if (kind == QN_SR1 || kind == QN_BROYDEN) {
+      const double pi = s[i] - hi;
+      p_out[i] = pi;
+      acc[1] = fma(pi, yi, acc[1]);
+    }
+  }
+  RedOps<2> ops{{RED_SUM, RED_SUM}};
+  cta_reduce<2>(acc, ops, smem);
+  if (threadIdx.x == 0) {
+    const double yh = acc[0], ys = st->ys;
+    st->yh = yh;
+    if (kind == QN_BFGS) {
+      const double rho = 1.0 / ys;
+      st->c0 = rho * rho * yh + rho;
+      st->c1 = -rho;
+      st->c2 = 0.0;
+    } else if (kind == QN_DFP) {
+      st->c0 = 1.0 / ys;
+      st->c1 = 0.0;
+      st->c2 = -1.0 / yh;
+    } else if (kind == QN_SR1) {
+      st->c0 = 1.0 / acc[1];
+      st->c1 = st->c2 = 0.0;
+    } else {
+      st->c0 = 1.0 / ys;
+      st->c1 = st->c2 = 0.0;
+    }
+  }
+}
+void qn_launch_coef(Ctx* ctx, int kind, int64_t n, DevState* st, const double* s, const double* y, const double* h,
+                    double* p_out) {
+  qn_coef_kernel<<<1, 1024, 0, ctx->stream>>>(kind, n, st, s, y, h, p_out);
+  ctx->counters[0]++;
+}
+
+// ---- pass 2: fused rank-2 read-modify-write + u = H' g -------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(QN_T, 1)
+qn_update_kernel(double* __restrict__ H, int64_t ld, int64_t nrows, int64_t row0, const DevState* __restrict__ st,
+                 const double* __restrict__ p, const double* __restrict__ q, const double* __restrict__ rv,
+                 const double* __restrict__ g, double* __restrict__ u_out) {
+  if (st->done || st->skip) return;
+  const double c0 = st->c0, c1 = st->c1, c2 = st->c2;
+  __shared__ double red[QN_R][QN_T / 32];
+  __shared__ double2 rowpq[QN_R];
+  const int64_t ntiles = (nrows + QN_R - 1) / QN_R;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r0 = tile * QN_R;
+    double acc[QN_R];
+#pragma unroll
+    for (int r = 0; r < QN_R; ++r) acc[r] = 0.0;
+    // per-row scalars (p_i, q_i) are CTA-uniform: kept in shared memory and read as broadcasts
+    if (threadIdx.x < QN_R)
+      rowpq[threadIdx.x] = make_double2(p[row0 + r0 + threadIdx.x],
+                                        (KIND == QN_BFGS || KIND == QN_DFP) ? q[row0 + r0 + threadIdx.x] : 0.0);
+    __syncthreads();
+    double* __restrict__ base = H + r0 * ld;
+    for (int col = 2 * threadIdx.x; col < (int)ld; col += QN_CHUNK) {
+      const double2 gj = *reinterpret_cast<const double2*>(g + col);
+      double2 pj = make_double2(0.0, 0.0), qj = make_double2(0.0, 0.0);
+      if (KIND != QN_BROYDEN) pj = *reinterpret_cast<const double2*>(p + col);
+      if (KIND == QN_BFGS || KIND == QN_DFP) qj = *reinterpret_cast<const double2*>(q + col);
+      if (KIND == QN_BROYDEN) pj = *reinterpret_cast<const double2*>(rv + col);  // column vector v = H^T s
+      double2 hv[QN_R];
+#pragma unroll
+      for (int r = 0; r < QN_R; ++r) hv[r] = ld_stream(base + r * ld + col);
+#pragma unroll
+      for (int r = 0; r < QN_R; ++r) {
+        double2 hn;
+        const double2 pq = rowpq[r];
+        const double pi = pq.x, qi = pq.y;
+        if (KIND == QN_BFGS) {
+          // symmetric in (row, col): products are commutative and the cross term is a plain sum
+          const double cx = pi * qj.x + qi * pj.x, cy = pi * qj.y + qi * pj.y;
+          hn.x = fma(c0, pi * pj.x, fma(c1, cx, hv[r].x));
+          hn.y = fma(c0, pi * pj.y, fma(c1, cy, hv[r].y));
+        } else if (KIND == QN_DFP) {
+          hn.x = fma(c2, qi * qj.x, fma(c0, pi * pj.x, hv[r].x));
+          hn.y = fma(c2, qi * qj.y, fma(c0, pi * pj.y, hv[r].y));
+        } else {  // SR1: p p^T ; Broyden: p v^T
+          hn.x = fma(c0, pi * pj.x, hv[r].x);
+          hn.y = fma(c0, pi * pj.y, hv[r].y);
+        }
+        acc[r] = fma(hn.x, gj.x, acc[r]);
+        acc[r] = fma(hn.y, gj.y, acc[r]);
+        st_stream(base + r * ld + col, hn);
+      }
+    }
+    tile_reduce_store(acc, red, u_out, row0, r0, nrows);
+  }
+}
+
+void qn_launch_update(Ctx* ctx, int kind, double* H, int64_t ld, int64_t nrows, int64_t row0, const DevState* st,
+                      const double* p, const double* q, const double* r, const double* g, double* u_out, int variant) {
+  (void)variant;
+  int64_t ntiles = (nrows + QN_R - 1) / QN_R;
+  int grid = (int)std::min<int64_t>(ntiles, (int64_t)ctx->num_sms);
+  switch (kind) {
+    case QN_BFGS: qn_update_kernel<QN_BFGS><<<grid, QN_T, 0, ctx->stream>>>(H, ld, nrows, row0, st, p, q, r, g, u_out); break;
+    case QN_DFP: qn_update_kernel<QN_DFP><<<grid, QN_T, 0, ctx->stream>>>(H, ld, nrows, row0, st, p, q, r, g, u_out); break;
+    case QN_SR1: qn_update_kernel<QN_SR1><<<grid, QN_T, 0, ctx->stream>>>(H, ld, nrows, row0, st, p, q, r, g, u_out); break;
+    default: qn_update_kernel<QN_BROYDEN><<<grid, QN_T, 0, ctx->stream>>>(H, ld, nrows, row0, st, p, q, r, g, u_out); break;
+  }
+  ctx->counters[0]++;
+}
+
+}  // namespace osb

@@ -1,0 +1,381 @@
+"""GPU (-m gpu): parity of the CUDA path (through the C ABI) with the CPU oracle on the same inputs.
+
+Protocol:
+  * the reference's own unit tests / examples: same status, iteration count, termination reason,
+    iterates within 1e-9 relative;
+  * convex problems at sizes the oracle finishes in seconds, free-running: same, against the
+    FAITHFUL oracle (the reference's O(n^3) triple product);
+  * Rosenbrock (chaotic in the rounding): lock-step — every iteration starts from
+    the same state — plus a short free-running horizon against the oracle's rank-2 form;
+  * elementwise work (gradients, projections, active sets): bit-exact;
+  * BASELINE.json's full size (n = 16384): size-independent properties (exact symmetry of H,
+    the secant equation H+ y = s, Armijo decrease, engine-vs-engine agreement).
+Tolerance for floating point: 1e-9 relative (BASELINE.json north_star).
+"""
+import numpy as np
+import pytest
+
+from problems import INF, X0_TESTS, bfgs_example_3d, quad2
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+def run(m, solver, ls, oracle, mi, ml):
+    try:
+        solver.minimize(ls, oracle, mi, ml)
+        return "Ok"
+    except m.SolverError as e:
+        return type(e).__name__
+
+
+def close(a, b, rtol=RTOL, atol=1e-12):
+    a, b = np.asarray(a), np.asarray(b)
+    scale = max(1.0, float(np.max(np.abs(b)))) if b.size else 1.0
+    return bool(np.all(np.abs(a - b) <= atol + rtol * scale))
+
+
+def both(osb, orc, script):
+    """Run the same script against the oracle and the CUDA library."""
+    return script(orc), script(osb)
+
+
+def rosen_x0(n, problem=0):
+    # (-1.2, 1, ...) + int16(h(3, problem, i)) * 2^-16, replayed with the oracle's hash via numpy
+    def splitmix64(x):
+        x = (x + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+        return x ^ (x >> 31)
+    out = np.empty(n)
+    for i in range(n):
+        h = splitmix64(3 ^ ((problem * 0x9E3779B97F4A7C15 + i) & 0xFFFFFFFFFFFFFFFF))
+        v = h & 0xFFFF
+        v = v - 65536 if v >= 32768 else v
+        out[i] = (-1.2 if i % 2 == 0 else 1.0) + v * 2.0 ** -16
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+def test_examples_quadratic_rs_exact_on_gpu(osb):
+    # examples/quadratic.rs:43 assert_eq!(eval.f(), &0.0) — through the device dense-quadratic functor
+    obj = osb.DenseQuadratic(np.eye(2))
+    s = osb.BFGS(1e-6, [1.0, 1.0])
+    s.minimize(osb.MoreThuente.default(), obj, 100, 10)
+    assert s.k() == 2 and s.termination_reason() == "grad_tol"
+    assert obj(s.x()).f() == 0.0 and np.all(s.x() == 0.0)
+
+
+CASES = [
+    # name, solver ctor, line search ctor, oracle fn, tol, x0, bounds, iters
+    ("bfgs_example", "BFGS", "mt", bfgs_example_3d, 1e-8, [1.0, 1.0, 1.0], None, (50, 20)),
+    ("bfgs_mt", "BFGS", "mt", quad2(1.0, True), 1e-12, X0_TESTS, None, (1000, 100000)),
+    ("bfgs_bt", "BFGS", "bt", quad2(1.0, True), 1e-12, X0_TESTS, None, (1000, 100000)),
+    ("dfp_mt", "DFP", "mt", quad2(1.0, True), 1e-12, X0_TESTS, None, (1000, 100000)),
+    ("broyden_bt", "Broyden", "bt", quad2(1.0, True), 1e-12, X0_TESTS, None, (1000, 100000)),
+    ("bfgs_gamma", "BFGS", "bt", quad2(30.0), 1e-9, X0_TESTS, None, (200, 100)),
+    ("dfp_gamma", "DFP", "bt", quad2(30.0), 1e-9, X0_TESTS, None, (200, 100)),
+    ("broyden_gamma", "Broyden", "bt", quad2(30.0), 1e-9, X0_TESTS, None, (200, 100)),
+    ("bfgs_b", "BFGSB", "btb", quad2(999.0), 1e-12, X0_TESTS, ([-INF, -INF], [INF, INF]), (10000, 1000)),
+    ("dfp_b", "DFPB", "btb", quad2(1.0), 1e-12, X0_TESTS, ([-INF, -INF], [INF, INF]), (10000, 1000)),
+    ("broyden_b", "BroydenB", "btb", quad2(1.0), 1e-12, X0_TESTS, ([-INF, -INF], [INF, INF]), (10000, 1000)),
+    ("sr1_b", "SR1B", "btb", quad2(1.0), 1e-12, X0_TESTS, ([-INF, -INF], [INF, INF]), (10000, 1000)),
+    ("sr1_b_gamma", "SR1B", "mt", quad2(7.0), 1e-10, X0_TESTS, ([-500.0, -500.0], [500.0, 500.0]), (100, 50)),
+    ("bfgs_b_box", "BFGSB", "mt", quad2(7.0, True), 1e-10, X0_TESTS, ([0.5, -3.0], [400.0, 0.25]), (100, 50)),
+    ("gd_mt", "GradientDescent", "mt", quad2(90.0), 1e-12, X0_TESTS, None, (1000, 100)),
+    ("gd_bt_maxiter", "GradientDescent", "bt", quad2(90.0), 1e-12, X0_TESTS, None, (1000, 100)),
+    ("pgd", "ProjectedGradientDescent", "btb", quad2(999.0), 1e-6, X0_TESTS, ([-INF, -INF], [INF, INF]), (10000, 1000)),
+    ("pgd_box_mtb", "ProjectedGradientDescent", "mtb", quad2(9.0, True), 1e-8, X0_TESTS, ([0.0, -4.0], [300.0, 0.5]), (500, 50)),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_reference_unit_tests_through_gpu(osb, orc, case):
+    name, cls, lsk, fn, tol, x0, bounds, (mi, ml) = case
+
+    def script(m):
+        if lsk == "mt":
+            ls = m.MoreThuente.default()
+        elif lsk == "bt":
+            ls = m.BackTracking(1e-4, 0.5)
+        elif lsk == "btb":
+            ls = m.BackTrackingB(1e-4, 0.5, *bounds)
+        else:
+            ls = m.MoreThuenteB(2).with_lower_bound(bounds[0]).with_upper_bound(bounds[1])
+        s = getattr(m, cls)(tol, x0, *bounds) if bounds else getattr(m, cls)(tol, x0)
+        st = run(m, s, ls, fn, mi, ml)
+        aset = s.active_set() if bounds else None
+        return st, s.k(), s.termination_reason(), s.x(), s.s_norm(), s.y_norm(), aset
+
+    ref, got = both(osb, orc, script)
+    assert got[0] == ref[0], (got[0], ref[0])
+    assert got[1] == ref[1], ("iterations", got[1], ref[1])
+    assert got[2] == ref[2], ("reason", got[2], ref[2])
+    assert close(got[3], ref[3]), (got[3], ref[3])
+    if ref[4] is not None:
+        assert close(got[4], ref[4]) and close(got[5], ref[5])
+    if ref[6] is not None:
+        assert np.array_equal(got[6], ref[6])  # bit-exact active set
+
+
+def test_spectral_and_newton_unit_tests_through_gpu(osb, orc):
+    lb, ub = [-1.0, 47.0], [INF, INF]
+
+    def spg(m):
+        s = m.SpectralProjectedGradient(1e-12, X0_TESTS, quad2(1e9), lb, ub)  # spg.rs:151-204
+        st = run(m, s, m.GLLQuadratic(1e-4, 10), quad2(1e9), 10000, 1000)
+        return st, s.k(), s.termination_reason(), s.x(), s.active_set(), s.lambda_()
+
+    ref, got = both(osb, orc, spg)
+    assert got[:3] == ref[:3] and np.array_equal(got[3], ref[3]) and np.array_equal(got[4], ref[4])
+    assert got[1] == 3 and np.all(got[3] == np.array([0.0, 47.0]))
+
+    def newton(m, lsk):
+        qh = quad2(1222.0, with_hessian=True, FE=m.FuncEvalMultivariate)
+        s = m.Newton(1e-8, [1.0, 1.0])
+        ls = m.MoreThuente.default() if lsk == "mt" else m.BackTracking(1e-4, 0.5)
+        orac = m.HostOracle(qh, True) if m is orc else m.HostOracle(qh, 2, True)
+        st = run(m, s, ls, orac, 1000, 100)
+        return st, s.k(), s.termination_reason(), s.x(), s.decrement_squared()
+
+    for lsk in ("mt", "bt"):
+        ref, got = newton(orc, lsk), newton(osb, lsk)
+        assert got[:3] == ref[:3] == ("Ok", 2, "newton_decrement")
+        assert close(got[3], ref[3]) and close(got[4], ref[4], atol=1e-20)
+
+    def pn(m, cls):
+        qh = quad2(999.0 if cls == "ProjectedNewton" else 1e9, with_hessian=True, FE=m.FuncEvalMultivariate)
+        orac = m.HostOracle(qh, True) if m is orc else m.HostOracle(qh, 2, True)
+        if cls == "ProjectedNewton":
+            s = m.ProjectedNewton(1e-6, X0_TESTS, [-INF, -INF], ub)  # projected_newton.rs:147-198
+            ls = m.BackTrackingB(1e-4, 0.5, [-INF, -INF], ub)
+        else:
+            s = m.SpectralProjectedNewton(1e-12, X0_TESTS, orac, lb, ub)  # spn.rs:156-210
+            ls = m.GLLQuadratic(1e-4, 10)
+        st = run(m, s, ls, orac, 10000, 1000)
+        return st, s.k(), s.termination_reason(), s.x()
+
+    for cls in ("ProjectedNewton", "SpectralProjectedNewton"):
+        ref, got = pn(orc, cls), pn(osb, cls)
+        assert got[:3] == ref[:3], (cls, got[:3], ref[:3])
+        assert close(got[3], ref[3], atol=1e-9)
+
+
+def test_line_search_unit_tests_through_gpu(osb):
+    # backtracking.rs:63-113, morethuente.rs:303-352, morethuente_b.rs:330-379
+    f = quad2(90.0)
+    for ls in (osb.BackTracking(1e-4, 0.5), osb.MoreThuente.default(), osb.MoreThuenteB(2)):
+        x, k = np.array(X0_TESTS), 1
+        orac = osb.HostOracle(f, 2)
+        while 1000 > k:
+            val, g = f(x)
+            if g @ g < 1e-12:
+                break
+            d = -g
+            x = x + ls.compute_step_len(x, d, orac, 1000) * d
+            k += 1
+        assert abs(x[0]) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------
+def test_objective_functors_match_oracle(osb, orc):
+    rng = np.random.default_rng(3)
+    n = 4096
+    x = rng.standard_normal(n)
+    a, b = osb.ExtendedRosenbrock(n)(x), orc.ExtendedRosenbrock()(x)
+    assert np.array_equal(a.g(), b.g())                 # elementwise: bit-exact
+    assert abs(a.f() - b.f()) <= 1e-13 * abs(b.f())     # summation order only
+    a, b = osb.SeparableQuadratic.generated(n)(x), orc.SeparableQuadratic.generated(n)(x)
+    assert np.array_equal(a.g(), b.g()) and abs(a.f() - b.f()) <= 1e-13 * abs(b.f())
+    for shifted in (False, True):
+        oa, ob = osb.DenseQuadratic.generated(512, shifted), orc.DenseQuadratic.generated(512, shifted)
+        assert np.array_equal(oa.x0, ob.x0)
+        xx = rng.standard_normal(512)
+        a, b = oa(xx), ob(xx)
+        assert close(a.g(), b.g(), rtol=1e-13) and abs(a.f() - b.f()) <= 1e-12 * abs(b.f())
+        if not shifted:
+            assert close(a.hessian() @ xx, a.g(), rtol=1e-12)  # Hessian 2A: (2A) x == g
+
+
+@pytest.mark.parametrize("kind", ["BFGS", "DFP", "Broyden", "SR1B"])
+def test_one_update_lockstep_vs_oracle_rank2(osb, orc, kind):
+    """Same (x, H) in, one iteration out: the fused rank-2 kernel against the oracle's rank-2 form and
+    against the reference's dense triple product (faithful form)."""
+    n = 96
+    rng = np.random.default_rng(5)
+    B = rng.standard_normal((n, n)) * 0.05
+    H0 = np.eye(n) + (B + B.T) * (0.5 if kind != "Broyden" else 1.0) + (B if kind == "Broyden" else 0.0)
+    x0 = rosen_x0(n, 1)
+    out = {}
+    for tag, m, form in (("gpu", osb, None), ("rank2", orc, "rank2"), ("faithful", orc, "faithful")):
+        args = (1e-10, x0) if kind != "SR1B" else (1e-10, x0, np.full(n, -50.0), np.full(n, 50.0))
+        s = getattr(m, kind)(*args)
+        if form:
+            s.set_update_form(form)
+        s.set_approx_inv_hessian(H0)
+        obj = m.ExtendedRosenbrock(n) if m is osb else m.ExtendedRosenbrock()
+        st = run(m, s, m.BackTracking(1e-4, 0.5), obj, 1, 30)
+        assert st == "MaxIterReached"
+        out[tag] = (s.x(), s.approx_inv_hessian(), s.s_norm(), s.y_norm())
+    for ref in ("rank2", "faithful"):
+        assert close(out["gpu"][0], out[ref][0])
+        assert close(out["gpu"][1], out[ref][1]), (kind, ref, np.max(np.abs(out["gpu"][1] - out[ref][1])))
+        assert close(out["gpu"][2], out[ref][2]) and close(out["gpu"][3], out[ref][3])
+
+
+@pytest.mark.parametrize("kind,ls", [("BFGS", "bt"), ("DFP", "bt"), ("BFGS", "mt"), ("Broyden", "bt")])
+def test_free_running_convex_vs_faithful_oracle(osb, orc, kind, ls):
+    """Dense SPD quadratic (the C2 generator at n = 192), free-running against the reference's own
+    O(n^3) update: same iteration count, termination reason, iterates and objective within 1e-9."""
+    n = 192
+
+    def script(m):
+        obj = m.DenseQuadratic.generated(n, True)
+        s = getattr(m, kind)(1e-6, obj.x0)
+        lsearch = m.BackTracking(1e-4, 0.5) if ls == "bt" else m.MoreThuente.default()
+        st = run(m, s, lsearch, obj, 400, 40)
+        return st, s.k(), s.termination_reason(), s.x(), obj(s.x()).f()
+
+    ref, got = both(osb, orc, script)
+    assert got[:3] == ref[:3], (got[:3], ref[:3])
+    assert close(got[3], ref[3]) and abs(got[4] - ref[4]) <= RTOL * abs(ref[4])
+
+
+def test_gd_dense_quadratic_vs_oracle(osb, orc):
+    # C2 at n = 256: GradientDescent + BackTracking(1e-4, 0.5), tol 1e-6
+    def script(m):
+        obj = m.DenseQuadratic.generated(256, True)
+        s = m.GradientDescent(1e-6, obj.x0)
+        st = run(m, s, m.BackTracking(1e-4, 0.5), obj, 1000, 100)
+        return st, s.k(), s.termination_reason(), s.x()
+
+    ref, got = both(osb, orc, script)
+    assert got[:3] == ref[:3] and close(got[3], ref[3])
+
+
+def test_spg_box_active_set_bit_exact(osb, orc):
+    # C5b at n = 2^14: SPG on the separable box quadratic; active-set bitmaps compared bit-for-bit
+    n = 1 << 14
+    lb, ub = np.full(n, -1.0), np.full(n, 1.0)
+    for lsk in ("gll", "bt"):
+        def script(m):
+            obj = m.SeparableQuadratic.generated(n)
+            s = m.SpectralProjectedGradient(1e-6, np.zeros(n), obj, lb, ub)
+            ls = m.GLLQuadratic(1e-4, 10) if lsk == "gll" else m.BackTracking(1e-4, 0.5)
+            st = run(m, s, ls, obj, 500, 50)
+            return st, s.k(), s.termination_reason(), s.x(), s.active_set()
+
+        ref, got = both(osb, orc, script)
+        assert got[:3] == ref[:3], (got[:3], ref[:3])
+        assert np.array_equal(got[4], ref[4])
+        assert close(got[3], ref[3])
+        assert 0.3 < np.mean(got[4] != 0) < 0.7
+
+
+def test_rosenbrock_lockstep_and_short_horizon(osb, orc):
+    """Rosenbrock n = 64 from a perturbed start.  (a) free-running for 12 iterations against the
+    oracle's rank-2 form; (b) lock-step: re-synchronise the oracle to the device state before every
+    iteration for 40 iterations and compare one iteration out."""
+    n = 64
+    x0 = rosen_x0(n, 7)
+    K = 12
+    g_s = osb.BFGS(1e-8, x0)
+    assert run(osb, g_s, osb.BackTracking(1e-4, 0.5), osb.ExtendedRosenbrock(n), K, 20) == "MaxIterReached"
+    o_s = orc.BFGS(1e-8, x0).set_update_form("rank2")
+    assert run(orc, o_s, orc.BackTracking(1e-4, 0.5), orc.ExtendedRosenbrock(), K, 20) == "MaxIterReached"
+    assert close(g_s.x(), o_s.x(), rtol=1e-9)
+    assert close(g_s.approx_inv_hessian(), o_s.approx_inv_hessian(), rtol=1e-8)
+    # lock-step
+    g_s = osb.BFGS(1e-8, x0)
+    obj_g, obj_o = osb.ExtendedRosenbrock(n), orc.ExtendedRosenbrock()
+    ls_g, ls_o = osb.BackTracking(1e-4, 0.5), orc.BackTracking(1e-4, 0.5)
+    for it in range(40):
+        xs, Hs = g_s.x(), g_s.approx_inv_hessian()
+        assert np.array_equal(Hs, Hs.T)  # the fused update keeps H exactly symmetric
+        o_s = orc.BFGS(1e-8, xs).set_update_form("faithful")
+        o_s.set_approx_inv_hessian(Hs)
+        g_s.clear_norms()
+        st_g = run(osb, g_s, ls_g, obj_g, 1, 20)
+        st_o = run(orc, o_s, ls_o, obj_o, 1, 20)
+        assert st_g == st_o
+        assert close(g_s.x(), o_s.x()), it
+        assert close(g_s.approx_inv_hessian(), o_s.approx_inv_hessian()), it
+        assert close(g_s.s_norm(), o_s.s_norm()) and close(g_s.y_norm(), o_s.y_norm())
+
+
+def test_device_engine_matches_host_engine(osb):
+    """The device-resident control engine (single-CTA line search, predicated H passes, no host
+    round trip) against the host-driven engine on the same kernels."""
+    n = 2048
+    x0 = rosen_x0(n, 11)
+    res = []
+    for engine in (1, 2):
+        for lsk in ("bt", "mt"):
+            s = osb.BFGS(1e-8, x0).set_option("engine", engine)
+            ls = osb.BackTracking(1e-4, 0.5) if lsk == "bt" else osb.MoreThuente.default()
+            st = run(osb, s, ls, osb.ExtendedRosenbrock(n), 25, 20)
+            res.append((engine, lsk, st, s.k(), s.termination_reason(), s.x(), s.s_norm(), s.y_norm()))
+    for lsk in ("bt", "mt"):
+        a = [r for r in res if r[1] == lsk]
+        assert a[0][2:5] == a[1][2:5], (a[0][2:5], a[1][2:5])
+        assert close(a[0][5], a[1][5], rtol=1e-9), lsk
+    # full convergence on the separable quadratic (convex): identical counts and reasons
+    n = 4096
+    out = []
+    for engine in (1, 2):
+        obj = osb.SeparableQuadratic.generated(n)
+        s = osb.DFP(1e-7, np.zeros(n)).set_option("engine", engine)
+        st = run(osb, s, osb.BackTracking(1e-4, 0.5), obj, 300, 30)
+        out.append((st, s.k(), s.termination_reason(), s.x()))
+    assert out[0][:3] == out[1][:3] and out[0][0] == "Ok"
+    assert close(out[0][3], out[1][3])
+
+
+def test_device_engine_vs_oracle_convex(osb, orc):
+    # separable quadratic, BFGS/DFP/SR1B through the device-resident engine vs the faithful oracle
+    n = 96
+    for kind in ("BFGS", "DFP", "BFGSB"):
+        def script(m):
+            obj = m.SeparableQuadratic.generated(n)
+            args = (1e-7, np.zeros(n)) if kind != "BFGSB" else (1e-7, np.zeros(n), np.full(n, -1.0), np.full(n, 1.0))
+            s = getattr(m, kind)(*args)
+            if m is osb:
+                s.set_option("engine", 2)
+            st = run(m, s, m.BackTracking(1e-4, 0.5), obj, 300, 30)
+            return st, s.k(), s.termination_reason(), s.x()
+
+        ref, got = both(osb, orc, script)
+        assert got[:3] == ref[:3], (kind, got[:3], ref[:3])
+        assert close(got[3], ref[3])
+
+
+def test_full_size_properties_n16384(osb):
+    """BASELINE.json config C3 at full size: dense BFGS, extended Rosenbrock, n = 16384."""
+    n = 16384
+    x0 = rosen_x0(n, 0)
+    s = osb.BFGS(1e-8, x0).set_option("engine", 2)
+    obj = osb.ExtendedRosenbrock(n)
+    f0 = obj(x0).f()
+    assert run(osb, s, osb.BackTracking(1e-4, 0.5), obj, 6, 20) == "MaxIterReached"
+    assert s.k() == 6
+    x6 = s.x()
+    f6 = obj(x6).f()
+    assert f6 < f0  # Armijo decrease
+    H = s.approx_inv_hessian()
+    assert np.array_equal(H, H.T)  # exact symmetry of the fused rank-2 update
+    # secant equation of the last update: H+ y = s  (y, s recovered from one more oracle evaluation pair)
+    s2 = osb.BFGS(1e-8, x6).set_option("engine", 1)
+    s2.set_approx_inv_hessian(H)
+    g6 = obj(x6).g()
+    assert run(osb, s2, osb.BackTracking(1e-4, 0.5), obj, 1, 20) == "MaxIterReached"
+    x7 = s2.x()
+    yv = obj(x7).g() - g6
+    sv = x7 - x6
+    H7 = s2.approx_inv_hessian()
+    assert close(H7 @ yv, sv, rtol=1e-9, atol=1e-12 * np.linalg.norm(sv))
+    # device-resident engine == host-driven engine from the same state
+    s3 = osb.BFGS(1e-8, x6).set_option("engine", 2)
+    s3.set_approx_inv_hessian(H)
+    assert run(osb, s3, osb.BackTracking(1e-4, 0.5), obj, 1, 20) == "MaxIterReached"
+    assert close(s3.x(), x7, rtol=1e-12)
+    assert close(s3.approx_inv_hessian(), H7, rtol=1e-12)
