@@ -272,6 +272,11 @@ void Solver::prof_collect() {
 
 void Solver::qn_after_step() {
   const DevState* st = d_state;
+  if (n <= QN_SMALL_N && ctx->world == 1) {  // reference operation order, bit-for-bit (qn_small.cu)
+    qn_small_step(ctx, qn_kind, n, ld, H.p, d_state, s.p, y.p, g.p, u.p);
+    u_valid = true;
+    return;
+  }
   // pass 1: h = H y   (skip: u = H g_new, H unchanged — bfgs.rs:106-112)
   prof_mark();
   qn_launch_gemv(ctx, H.p, ld, nrows, row0, st, y.p, h.p, g.p, u.p, qn_variant);
@@ -339,7 +344,8 @@ int Solver::minimize_host(LineSearch* ls, Objective* obj, int64_t max_iter, int6
       u_valid = false;
     }
     if (is_qn && !u_valid) {
-      qn_launch_gemv(ctx, H.p, ld, nrows, row0, nullptr, g.p, u.p, nullptr, nullptr, qn_variant);
+      if (n <= QN_SMALL_N && ctx->world == 1) qn_small_gemv(ctx, n, ld, H.p, g.p, u.p);
+      else qn_launch_gemv(ctx, H.p, ld, nrows, row0, nullptr, g.p, u.p, nullptr, nullptr, qn_variant);
       if (ctx->world > 1) ctx->all_gather_inplace(u.p, nrows);
       u_valid = true;
     }
@@ -463,7 +469,8 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
     u_valid = false;
   }
   if (!u_valid) {
-    qn_launch_gemv(ctx, H.p, ld, nrows, row0, nullptr, g.p, u.p, nullptr, nullptr, qn_variant);
+    if (n <= QN_SMALL_N && ctx->world == 1) qn_small_gemv(ctx, n, ld, H.p, g.p, u.p);
+    else qn_launch_gemv(ctx, H.p, ld, nrows, row0, nullptr, g.p, u.p, nullptr, nullptr, qn_variant);
     if (ctx->world > 1) ctx->all_gather_inplace(u.p, nrows);
     u_valid = true;
   }

@@ -149,6 +149,11 @@ void qn_launch_coef(Ctx* ctx, int kind, int64_t n, DevState* st, const double* s
 void qn_launch_update(Ctx* ctx, int kind, double* H, int64_t ld, int64_t nrows, int64_t row0, const DevState* st,
                       const double* p, const double* q, const double* r, const double* g, double* u_out, int variant);
 int64_t qn_ld(int64_t n);
+// n <= QN_SMALL_N: single-thread replay of the reference's own operation order (qn_small.cu)
+constexpr int64_t QN_SMALL_N = 5;
+void qn_small_step(Ctx* ctx, int kind, int64_t n, int64_t ld, double* H, DevState* st, const double* s, const double* y,
+                   const double* g, double* u);
+void qn_small_gemv(Ctx* ctx, int64_t n, int64_t ld, const double* H, const double* g, double* u);
 int64_t qn_rows_padded(int64_t nrows);
 
 // ---- solver -------------------------------------------------------------------------------

@@ -68,7 +68,7 @@ struct FunctorObjective : Objective {
 #pragma unroll
       for (int j = 0; j < Fn::BS; ++j) {
         gt[i0 + j] = gb[j];
-        acc[1] = fma(gb[j], db[j], acc[1]);
+        acc[1] = acc[1] + gb[j] * db[j];
       }
       acc[0] = acc[0] + fb;
     };
@@ -138,9 +138,9 @@ struct DenseQuadratic : Objective {
     const double* bb = shifted ? b.p : nullptr;
     auto f = [=] __device__(int64_t i, double(&acc)[2]) {
       const double xi = x[i], axi = ax[i];
-      acc[0] = fma(xi, axi, acc[0]);
+      acc[0] = acc[0] + xi * axi;
       if (bb) {
-        acc[1] = fma(bb[i], xi, acc[1]);
+        acc[1] = acc[1] + bb[i] * xi;
         g[i] = 2.0 * (axi - bb[i]);
       } else {
         g[i] = 2.0 * axi;

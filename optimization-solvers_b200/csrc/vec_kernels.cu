@@ -27,7 +27,7 @@ void vec_axpy_project(Ctx* ctx, int64_t n, const double* x, const double* d, dou
 }
 
 void vec_dot(Ctx* ctx, int64_t n, const double* a, const double* b, double* d_out) {
-  auto f = [=] __device__(int64_t i, double(&acc)[1]) { acc[0] = fma(a[i], b[i], acc[0]); };
+  auto f = [=] __device__(int64_t i, double(&acc)[1]) { acc[0] = acc[0] + a[i] * b[i]; };
   launch_mapreduce<1>(ctx, f, n, RedOps<1>{{RED_SUM}}, d_out);
 }
 
@@ -45,7 +45,7 @@ void vec_neg(Ctx* ctx, int64_t n, const double* a, double* out, const double* g,
   auto f = [=] __device__(int64_t i, double(&acc)[1]) {
     const double di = -a[i];
     out[i] = di;
-    acc[0] = fma(g[i], di, acc[0]);
+    acc[0] = acc[0] + g[i] * di;
   };
   launch_mapreduce<1>(ctx, f, n, RedOps<1>{{RED_SUM}}, d_gd0);
 }
@@ -60,7 +60,7 @@ void vec_projected_direction(Ctx* ctx, int64_t n, const double* x, const double*
     v = fmin(fmax(v, lb[i]), ub[i]);
     const double di = v - xi;
     d[i] = di;
-    acc[0] = fma(g[i], di, acc[0]);
+    acc[0] = acc[0] + g[i] * di;
     double cand;  // morethuente_b.rs:185-197
     if (di > 0.0) cand = (ub[i] - xi) / di;
     else if (di < 0.0) cand = (lb[i] - xi) / di;
@@ -85,7 +85,7 @@ void vec_tmax_candidate(Ctx* ctx, int64_t n, const double* x, const double* d, c
 }
 
 void vec_conv_gnorm2(Ctx* ctx, int64_t n, const double* g, double* d_out) {
-  auto f = [=] __device__(int64_t i, double(&acc)[1]) { acc[0] = fma(g[i], g[i], acc[0]); };
+  auto f = [=] __device__(int64_t i, double(&acc)[1]) { acc[0] = acc[0] + g[i] * g[i]; };
   launch_mapreduce<1>(ctx, f, n, RedOps<1>{{RED_SUM}}, d_out);
 }
 // gradient_descent.rs:46-53: fold from -inf with NaN-dropping max
@@ -111,9 +111,9 @@ void vec_sy(Ctx* ctx, int64_t n, const double* xn, const double* x, const double
     const double yi = gn[i] - g[i];
     s[i] = si;
     y[i] = yi;
-    acc[0] = fma(si, si, acc[0]);
-    acc[1] = fma(yi, yi, acc[1]);
-    acc[2] = fma(yi, si, acc[2]);
+    acc[0] = acc[0] + si * si;
+    acc[1] = acc[1] + yi * yi;
+    acc[2] = acc[2] + yi * si;
   };
   launch_mapreduce<4>(ctx, f, n, RedOps<4>{{RED_SUM, RED_SUM, RED_SUM, RED_SUM}}, d_out4);
 }
