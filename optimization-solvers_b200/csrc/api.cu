@@ -343,6 +343,7 @@ int osb_solver_set_option(osb_solver* s, const char* name, int64_t value) {
   if (nm == "engine") S(s)->engine = (int)value;
   else if (nm == "record_trace") S(s)->record_trace = (int)value;
   else if (nm == "qn_kernel") S(s)->qn_variant = (int)value;
+  else if (nm == "head_kernel") S(s)->head_variant = (int)value;
   else if (nm == "profile_kernels") S(s)->profile_kernels = (int)value;
   else throw Error(OSB_ERROR_INPUT_PARAMS, "unknown option " + nm);
   return OSB_OK;

@@ -35,6 +35,8 @@ Ctx::Ctx(int dev) : device(dev) {
   OSB_CUDA(cudaMalloc(&red_partials, sizeof(double) * 8 * red_max_grid));
   OSB_CUDA(cudaMalloc(&red_ticket, sizeof(unsigned int)));
   OSB_CUDA(cudaMemsetAsync(red_ticket, 0, sizeof(unsigned int), stream));
+  OSB_CUDA(cudaMalloc(&gemv_ticket, sizeof(unsigned int)));
+  OSB_CUDA(cudaMemsetAsync(gemv_ticket, 0, sizeof(unsigned int), stream));
   OSB_CUDA(cudaMalloc(&d_dummy, sizeof(double) * 8));
   OSB_CUDA(cudaHostAlloc(&h_pinned, sizeof(double) * 4096, cudaHostAllocDefault));
   OSB_CUDA(cudaStreamSynchronize(stream));
@@ -44,6 +46,7 @@ Ctx::~Ctx() {
   if (stream) cudaStreamSynchronize(stream);
   cudaFree(red_partials);
   cudaFree(red_ticket);
+  cudaFree(gemv_ticket);
   cudaFree(d_dummy);
   cudaFreeHost(h_pinned);
   if (stream) cudaStreamDestroy(stream);
@@ -278,15 +281,17 @@ void Solver::qn_after_step() {
     return;
   }
   // pass 1: h = H y   (skip: u = H g_new, H unchanged — bfgs.rs:106-112)
+  const bool fuse_coef = ctx->world == 1;  // sharded: y.h needs the all-gathered h
+  QNCoefArgs ca{ctx->gemv_ticket, qn_kind, n, s.p, y.p, pvec.p};
   prof_mark();
-  qn_launch_gemv(ctx, H.p, ld, nrows, row0, st, y.p, h.p, g.p, u.p, qn_variant);
+  qn_launch_gemv(ctx, H.p, ld, nrows, row0, st, y.p, h.p, g.p, u.p, qn_variant, fuse_coef ? &ca : nullptr);
   prof_mark();
   if (ctx->world > 1) {
     ctx->all_gather_inplace(h.p, nrows);
     ctx->all_gather_inplace(u.p, nrows);
   }
   if (qn_kind == QN_BROYDEN) qn_launch_gemvT(ctx, H.p, ld, nrows, row0, st, s.p, vvec.p, scratch.p);
-  qn_launch_coef(ctx, qn_kind, n, d_state, s.p, y.p, h.p, pvec.p);
+  if (!fuse_coef) qn_launch_coef(ctx, qn_kind, n, d_state, s.p, y.p, h.p, pvec.p);
   const double* p = (qn_kind == QN_BFGS || qn_kind == QN_DFP) ? s.p : pvec.p;
   // pass 2: fused rank-2 read-modify-write + u = H' g_new
   prof_mark();
@@ -500,7 +505,7 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
   for (int64_t it = 0; it < max_iter && !stop; ++it) {
     qn_device_launch_head(ctx, obj->functor_kind(), obj->functor_ptr(0), obj->functor_ptr(1), bounded, d_ls, n, tol, max_ls,
                           d_state, x.p, g.p, d.p, xt.p, gt.p, s.p, y.p, u.p, bounded ? lb.p : nullptr, bounded ? ub.p : nullptr,
-                          ls_bounded ? ls->lb.p : nullptr, ls_bounded ? ls->ub.p : nullptr);
+                          ls_bounded ? ls->lb.p : nullptr, ls_bounded ? ls->ub.p : nullptr, head_variant);
     qn_after_step();
     if ((it + 1) % POLL == 0) {
       if (pending[slot]) {  // bound the run-ahead: wait for the older snapshot of this slot

@@ -47,6 +47,7 @@ struct Ctx {
   // reduction scratch
   double* red_partials = nullptr;
   unsigned int* red_ticket = nullptr;
+  unsigned int* gemv_ticket = nullptr;
   int red_max_grid = 0;
   // counters: launches, objective evals, ls trials, host syncs, collectives
   int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -137,8 +138,17 @@ struct LineSearch {
 enum QNKind : int { QN_BFGS = 0, QN_DFP = 1, QN_BROYDEN = 2, QN_SR1 = 3 };
 // out = H v over the local row block.  `sel` chooses the operand at run time ON DEVICE from
 // DevState.skip: skip ? (v_skip -> out_skip) : (v -> out); a null `st` means unconditional (v -> out).
+// optional epilogue of the gemv launch (single GPU): the last CTA computes y.h and c0..c2
+struct QNCoefArgs {
+  unsigned int* ticket;  // null => no fused epilogue
+  int kind;
+  int64_t n;
+  const double* s;
+  const double* y;
+  double* p_out;
+};
 void qn_launch_gemv(Ctx* ctx, const double* H, int64_t ld, int64_t nrows, int64_t row0, const DevState* st, const double* v,
-                    double* out, const double* v_skip, double* out_skip, int variant);
+                    double* out, const double* v_skip, double* out_skip, int variant, const QNCoefArgs* coef = nullptr);
 // out[j] = sum_i H_ij s_i over the local row block (Broyden's H^T s), two-stage deterministic
 void qn_launch_gemvT(Ctx* ctx, const double* H, int64_t ld, int64_t nrows, int64_t row0, const DevState* st,
                      const double* s, double* out, double* scratch);
@@ -172,6 +182,7 @@ struct Solver {
   int engine = 0;
   int record_trace = 0;
   int qn_variant = 0;
+  int head_variant = 0;  // 0 = cluster head, 1 = single-CTA smem head, 2 = generic single-CTA head
   // state vectors (device)
   DBuf x, g, d, xt, gt, s, y, lb, ub, w;
   bool bounded = false;
@@ -246,7 +257,7 @@ void state_finish_sy(Ctx*, DevState* st, double tol);
 void qn_device_launch_head(Ctx* ctx, int functor_kind, const double* fn_a, const double* fn_b, bool bounded,
                            LSParams* d_ls, int64_t n, double tol, int64_t max_ls, DevState* st, double* x, double* g,
                            double* d, double* xt, double* gt, double* s, double* y, const double* u, const double* lb,
-                           const double* ub, const double* ls_lb, const double* ls_ub);
+                           const double* ub, const double* ls_lb, const double* ls_ub, int head_variant);
 
 // batched (batched.cu)
 int batched_bfgs_rosenbrock(Ctx* ctx, int64_t n, int64_t np, const double* x0_host, bool generated, int64_t problem0,

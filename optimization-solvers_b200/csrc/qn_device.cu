@@ -12,6 +12,8 @@
 // The O(n) vectors (128 KiB each at n = 16384) live in L2; at that size one CTA is the right
 // shape: a trial is ~2 us, whereas a multi-CTA launch per trial costs more in launch latency
 // than the arithmetic.  All later launches of the iteration read DevState.done / .skip.
+#include <cooperative_groups.h>
+
 #include "engine.cuh"
 #include "functors.cuh"
 
@@ -174,6 +176,438 @@ qn_head_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol, int64_t
   }
 }
 
+// ---- fast head: n <= HEADF_T * HEADF_EPT -------------------------------------------------------
+// x_k is staged once in shared memory (128 KiB at n = 16384) and d_k lives in registers, so a
+// line-search trial touches no global memory at all: it is FP64 arithmetic on the block functor
+// plus one CTA reduction (~1 us), however many trials the search needs.  Only the accepted point
+// is written back (x, g, s, y).
+constexpr int HEADF_T = 512;
+constexpr int HEADF_EPT = 32;  // elements per thread
+
+template <class Fn, bool BOUNDED>
+__global__ void __launch_bounds__(HEADF_T, 1)
+qn_head_fast_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol, int64_t max_ls, DevState* __restrict__ st,
+                    double* __restrict__ x, double* __restrict__ g, double* __restrict__ s, double* __restrict__ y,
+                    const double* __restrict__ u, const double* __restrict__ lb, const double* __restrict__ ub,
+                    const double* __restrict__ ls_lb, const double* __restrict__ ls_ub) {
+  constexpr int BS = Fn::BS;
+  constexpr int KPT = HEADF_EPT / BS;  // blocks per thread
+  extern __shared__ double sx[];       // n doubles: x_k
+  __shared__ double smem[4 * 32];
+  const RedOps<3> sum3{{RED_SUM, RED_SUM, RED_SUM}};
+  const RedOps<4> sum4{{RED_SUM, RED_SUM, RED_SUM, RED_SUM}};
+  if (st->done) return;
+  const int tid = threadIdx.x;
+  const int nb = (int)(n / BS);
+  const double f0 = st->f;
+  if (is_bad(f0)) {  // ls_solver.rs:37-40
+    if (tid == 0) {
+      st->done = 1;
+      st->status = OSB_OUT_OF_DOMAIN;
+    }
+    return;
+  }
+  int why = OSB_REASON_NONE;
+  if (st->has_s && st->s_norm < tol) why = OSB_REASON_S_NORM;        // bfgs.rs:67-69
+  else if (st->has_y && st->y_norm < tol) why = OSB_REASON_Y_NORM;   // bfgs.rs:70-72
+  if (why != OSB_REASON_NONE) {
+    if (tid == 0) {
+      st->done = 1;
+      st->status = OSB_OK;
+      st->reason = why;
+    }
+    return;
+  }
+  // ---- stage x, form d in registers, ||g||^2 and g.d
+  double dreg[KPT][BS];
+  const bool need_tmax = lsp->kind == LS_MORETHUENTE_B;
+  double tm = INFINITY;
+  {
+    double acc[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < KPT; ++k) {
+      const int b = tid + k * HEADF_T;
+#pragma unroll
+      for (int j = 0; j < BS; ++j) {
+        dreg[k][j] = 0.0;
+        if (b < nb) {
+          const int i = b * BS + j;
+          const double xi = x[i], gi = g[i], ui = u[i];
+          double di;
+          if (BOUNDED) di = fmin(fmax(xi - ui, lb[i]), ub[i]) - xi;  // bfgs_b.rs:72-75
+          else di = -ui;                                             // bfgs.rs:47
+          sx[i] = xi;
+          dreg[k][j] = di;
+          acc[0] = acc[0] + gi * gi;
+          acc[1] = acc[1] + gi * di;
+          if (need_tmax) {  // morethuente_b.rs:185-197
+            double cand;
+            if (di > 0.0) cand = (ls_ub[i] - xi) / di;
+            else if (di < 0.0) cand = (ls_lb[i] - xi) / di;
+            else cand = INFINITY;
+            tm = fmin(cand, tm);
+          }
+        }
+      }
+    }
+    cta_reduce<3>(acc, sum3, smem);
+    if (sqrt(acc[0]) < tol) {  // bfgs.rs:74
+      if (tid == 0) {
+        st->done = 1;
+        st->status = OSB_OK;
+        st->reason = OSB_REASON_GRAD_TOL;
+      }
+      return;
+    }
+    // gd0 kept in acc[1]
+    tm = need_tmax ? tm : INFINITY;
+    double gd0 = acc[1];
+    double tmaxc = INFINITY;
+    if (need_tmax) {
+      double mm[1] = {tm};
+      cta_reduce<1>(mm, RedOps<1>{{RED_MIN}}, smem);
+      tmaxc = mm[0];
+    }
+    // ---- compute_step_len: every thread runs the automaton on CTA-reduced (identical) scalars
+    LSParams p = *lsp;
+    LSMachine m;
+    m.begin(p, f0, gd0, max_ls, tmaxc);
+    int evals = 0;
+    while (!m.done) {
+      const double t = m.request(p);
+      const bool proj = m.wants_projection(p);
+      double a3[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+      for (int k = 0; k < KPT; ++k) {
+        const int b = tid + k * HEADF_T;
+        if (b < nb) {
+          double xb[BS], gb[BS];
+#pragma unroll
+          for (int j = 0; j < BS; ++j) {
+            const int i = b * BS + j;
+            const double xi = sx[i];
+            const double td = t * dreg[k][j];
+            double v = xi + td;
+            if (proj) v = fmin(fmax(v, ls_lb[i]), ls_ub[i]);  // backtracking_b.rs:65-67
+            xb[j] = v;
+            const double df = v - xi;
+            a3[2] = a3[2] + df * df;
+          }
+          const double fb = fn.block((int64_t)b * BS, xb, gb);
+#pragma unroll
+          for (int j = 0; j < BS; ++j) a3[1] = a3[1] + gb[j] * dreg[k][j];
+          a3[0] = a3[0] + fb;
+        }
+      }
+      cta_reduce<3>(a3, sum3, smem);
+      m.feed(p, a3[0], a3[1], a3[2]);
+      ++evals;
+    }
+    const double t = m.result;
+    // ---- update_next_iterate: next = x + t d (ls_solver.rs:60); oracle(next) (bfgs.rs:98); s, y, norms
+    double a4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < KPT; ++k) {
+      const int b = tid + k * HEADF_T;
+      if (b < nb) {
+        double xb[BS], gb[BS];
+#pragma unroll
+        for (int j = 0; j < BS; ++j) {
+          const double td = t * dreg[k][j];
+          xb[j] = sx[b * BS + j] + td;
+        }
+        const double fb = fn.block((int64_t)b * BS, xb, gb);
+        a4[3] = a4[3] + fb;
+#pragma unroll
+        for (int j = 0; j < BS; ++j) {
+          const int i = b * BS + j;
+          const double si = xb[j] - sx[i];
+          const double yi = gb[j] - g[i];
+          s[i] = si;
+          y[i] = yi;
+          x[i] = xb[j];
+          g[i] = gb[j];
+          a4[0] = a4[0] + si * si;
+          a4[1] = a4[1] + yi * yi;
+          a4[2] = a4[2] + yi * si;
+        }
+      }
+    }
+    cta_reduce<4>(a4, sum4, smem);
+    if (tid == 0) {
+      st->f = a4[3];
+      st->ft = a4[3];
+      st->gd0 = gd0;
+      st->ss = a4[0];
+      st->yy = a4[1];
+      st->ys = a4[2];
+      const double sn = sqrt(a4[0]), yn = sqrt(a4[1]);
+      st->s_norm = sn;
+      st->y_norm = yn;
+      st->has_s = 1;
+      st->has_y = 1;
+      st->skip = (sn < tol || yn < tol) ? 1 : 0;  // bfgs.rs:106-112
+      st->t_last = t;
+      st->k += 1;
+      st->ls_evals += evals + 1;
+      *lsp = p;
+    }
+  }
+}
+
+template <class Fn>
+static bool launch_head_fast(Ctx* ctx, Fn fn, bool bounded, LSParams* d_ls, int64_t n, double tol, int64_t max_ls, DevState* st,
+                             double* x, double* g, double* s, double* y, const double* u, const double* lb, const double* ub,
+                             const double* ls_lb, const double* ls_ub) {
+  if (n > (int64_t)HEADF_T * HEADF_EPT) return false;
+  const size_t smem = sizeof(double) * (size_t)n;
+  static bool attr_set[2] = {false, false};
+  if (bounded) {
+    if (!attr_set[1]) {
+      OSB_CUDA(cudaFuncSetAttribute(qn_head_fast_kernel<Fn, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set[1] = true;
+    }
+    qn_head_fast_kernel<Fn, true><<<1, HEADF_T, smem, ctx->stream>>>(fn, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub);
+  } else {
+    if (!attr_set[0]) {
+      OSB_CUDA(cudaFuncSetAttribute(qn_head_fast_kernel<Fn, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set[0] = true;
+    }
+    qn_head_fast_kernel<Fn, false><<<1, HEADF_T, smem, ctx->stream>>>(fn, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub);
+  }
+  ctx->counters[0]++;
+  return true;
+}
+
+// ---- cluster head: the same head on a thread-block cluster of 8 CTAs ---------------------------
+// One SM's FP64 pipe bounds a trial of the single-CTA head (~9 us per trial at n = 16384, measured
+// with ncu); a cluster of 8 CTAs holds x_k and d_k entirely in registers (EPT elements per
+// thread), evaluates a trial in well under a microsecond and reduces across the cluster through
+// distributed shared memory (one barrier.cluster per reduction, double-buffered partials, rank-
+// ordered sum => every CTA sees the same bits).
+namespace cg = cooperative_groups;
+constexpr int HC_CTAS = 8;
+constexpr int HC_T = 512;
+
+template <int K>
+__device__ __forceinline__ void cluster_reduce(cg::cluster_group& cluster, double (&acc)[K], const RedOps<K>& ops, double* smem_cta,
+                                               double* part /* 2 x 8 */, double* res /* 8 */, int& phase) {
+  cta_reduce<K>(acc, ops, smem_cta);
+  double* mine = part + (phase & 1) * 8;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) mine[k] = acc[k];
+  }
+  cluster.sync();
+  if (threadIdx.x == 0) {
+    double v[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = red_identity(ops.op[k]);
+    for (int r = 0; r < HC_CTAS; ++r) {
+      const double* remote = cluster.map_shared_rank(mine, r);
+#pragma unroll
+      for (int k = 0; k < K; ++k) v[k] = red_combine(ops.op[k], v[k], remote[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) res[k] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) acc[k] = res[k];
+  phase += 1;
+}
+
+template <class Fn, bool BOUNDED, int EPT>
+__global__ void __cluster_dims__(HC_CTAS, 1, 1) __launch_bounds__(HC_T, 1)
+qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol, int64_t max_ls, DevState* __restrict__ st,
+                       double* __restrict__ x, double* __restrict__ g, double* __restrict__ s, double* __restrict__ y,
+                       const double* __restrict__ u, const double* __restrict__ lb, const double* __restrict__ ub,
+                       const double* __restrict__ ls_lb, const double* __restrict__ ls_ub) {
+  constexpr int BS = Fn::BS;
+  constexpr int KPT = EPT / BS;
+  constexpr int NT = HC_CTAS * HC_T;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ double smem_cta[4 * 32];
+  __shared__ double part[16];
+  __shared__ double res[8];
+  const RedOps<3> sum3{{RED_SUM, RED_SUM, RED_SUM}};
+  const RedOps<4> sum4{{RED_SUM, RED_SUM, RED_SUM, RED_SUM}};
+  if (st->done) return;
+  const int gt = (int)cluster.block_rank() * HC_T + threadIdx.x;
+  const bool leader = gt == 0;
+  const int nb = (int)(n / BS);
+  const double f0 = st->f;
+  if (is_bad(f0)) {  // ls_solver.rs:37-40
+    if (leader) {
+      st->done = 1;
+      st->status = OSB_OUT_OF_DOMAIN;
+    }
+    return;
+  }
+  int why = OSB_REASON_NONE;
+  if (st->has_s && st->s_norm < tol) why = OSB_REASON_S_NORM;        // bfgs.rs:67-69
+  else if (st->has_y && st->y_norm < tol) why = OSB_REASON_Y_NORM;   // bfgs.rs:70-72
+  if (why != OSB_REASON_NONE) {
+    if (leader) {
+      st->done = 1;
+      st->status = OSB_OK;
+      st->reason = why;
+    }
+    return;
+  }
+  int phase = 0;
+  double xreg[KPT][BS], dreg[KPT][BS], greg[KPT][BS];
+  const bool need_tmax = lsp->kind == LS_MORETHUENTE_B;
+  double tm = INFINITY;
+  double acc[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < KPT; ++k) {
+    const int b = gt + k * NT;
+#pragma unroll
+    for (int j = 0; j < BS; ++j) {
+      xreg[k][j] = dreg[k][j] = greg[k][j] = 0.0;
+      if (b < nb) {
+        const int i = b * BS + j;
+        const double xi = x[i], gi = g[i], ui = u[i];
+        double di;
+        if (BOUNDED) di = fmin(fmax(xi - ui, lb[i]), ub[i]) - xi;  // bfgs_b.rs:72-75
+        else di = -ui;                                             // bfgs.rs:47
+        xreg[k][j] = xi;
+        dreg[k][j] = di;
+        greg[k][j] = gi;
+        acc[0] = acc[0] + gi * gi;
+        acc[1] = acc[1] + gi * di;
+        if (need_tmax) {  // morethuente_b.rs:185-197
+          double cand;
+          if (di > 0.0) cand = (ls_ub[i] - xi) / di;
+          else if (di < 0.0) cand = (ls_lb[i] - xi) / di;
+          else cand = INFINITY;
+          tm = fmin(cand, tm);
+        }
+      }
+    }
+  }
+  cluster_reduce<3>(cluster, acc, sum3, smem_cta, part, res, phase);
+  if (sqrt(acc[0]) < tol) {  // bfgs.rs:74
+    if (leader) {
+      st->done = 1;
+      st->status = OSB_OK;
+      st->reason = OSB_REASON_GRAD_TOL;
+    }
+    cluster.sync();  // peers may still be reading this CTA's partials
+    return;
+  }
+  const double gd0 = acc[1];
+  double tmaxc = INFINITY;
+  if (need_tmax) {
+    double mm[1] = {tm};
+    cluster_reduce<1>(cluster, mm, RedOps<1>{{RED_MIN}}, smem_cta, part, res, phase);
+    tmaxc = mm[0];
+  }
+  LSParams p = *lsp;
+  LSMachine m;
+  m.begin(p, f0, gd0, max_ls, tmaxc);
+  int evals = 0;
+  while (!m.done) {
+    const double t = m.request(p);
+    const bool proj = m.wants_projection(p);
+    double a3[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < KPT; ++k) {
+      const int b = gt + k * NT;
+      if (b < nb) {
+        double xb[BS], gb[BS];
+#pragma unroll
+        for (int j = 0; j < BS; ++j) {
+          const double td = t * dreg[k][j];
+          double v = xreg[k][j] + td;
+          if (proj) v = fmin(fmax(v, ls_lb[b * BS + j]), ls_ub[b * BS + j]);  // backtracking_b.rs:65-67
+          xb[j] = v;
+          const double df = v - xreg[k][j];
+          a3[2] = a3[2] + df * df;
+        }
+        const double fb = fn.block((int64_t)b * BS, xb, gb);
+#pragma unroll
+        for (int j = 0; j < BS; ++j) a3[1] = a3[1] + gb[j] * dreg[k][j];
+        a3[0] = a3[0] + fb;
+      }
+    }
+    cluster_reduce<3>(cluster, a3, sum3, smem_cta, part, res, phase);
+    m.feed(p, a3[0], a3[1], a3[2]);
+    ++evals;
+  }
+  const double t = m.result;
+  // ---- next = x + t d (ls_solver.rs:60); oracle(next) (bfgs.rs:98); s, y, norms, y.s
+  double a4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < KPT; ++k) {
+    const int b = gt + k * NT;
+    if (b < nb) {
+      double xb[BS], gb[BS];
+#pragma unroll
+      for (int j = 0; j < BS; ++j) {
+        const double td = t * dreg[k][j];
+        xb[j] = xreg[k][j] + td;
+      }
+      const double fb = fn.block((int64_t)b * BS, xb, gb);
+      a4[3] = a4[3] + fb;
+#pragma unroll
+      for (int j = 0; j < BS; ++j) {
+        const int i = b * BS + j;
+        const double si = xb[j] - xreg[k][j];
+        const double yi = gb[j] - greg[k][j];
+        s[i] = si;
+        y[i] = yi;
+        x[i] = xb[j];
+        g[i] = gb[j];
+        a4[0] = a4[0] + si * si;
+        a4[1] = a4[1] + yi * yi;
+        a4[2] = a4[2] + yi * si;
+      }
+    }
+  }
+  cluster_reduce<4>(cluster, a4, sum4, smem_cta, part, res, phase);
+  if (leader) {
+    st->f = a4[3];
+    st->ft = a4[3];
+    st->gd0 = gd0;
+    st->ss = a4[0];
+    st->yy = a4[1];
+    st->ys = a4[2];
+    const double sn = sqrt(a4[0]), yn = sqrt(a4[1]);
+    st->s_norm = sn;
+    st->y_norm = yn;
+    st->has_s = 1;
+    st->has_y = 1;
+    st->skip = (sn < tol || yn < tol) ? 1 : 0;  // bfgs.rs:106-112
+    st->t_last = t;
+    st->k += 1;
+    st->ls_evals += evals + 1;
+    *lsp = p;
+  }
+  cluster.sync();  // keep every CTA's shared memory alive until all peers have read it
+}
+
+template <class Fn>
+static bool launch_head_cluster(Ctx* ctx, Fn fn, bool bounded, LSParams* d_ls, int64_t n, double tol, int64_t max_ls, DevState* st,
+                                double* x, double* g, double* s, double* y, const double* u, const double* lb, const double* ub,
+                                const double* ls_lb, const double* ls_ub) {
+  constexpr int NT = HC_CTAS * HC_T;
+  if (n > (int64_t)NT * 16) return false;
+#define OSB_HC_LAUNCH(B, E) \
+  qn_head_cluster_kernel<Fn, B, E><<<HC_CTAS, HC_T, 0, ctx->stream>>>(fn, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub)
+  if (n <= (int64_t)NT * 4) {
+    if (bounded) OSB_HC_LAUNCH(true, 4);
+    else OSB_HC_LAUNCH(false, 4);
+  } else {
+    if (bounded) OSB_HC_LAUNCH(true, 16);
+    else OSB_HC_LAUNCH(false, 16);
+  }
+#undef OSB_HC_LAUNCH
+  ctx->counters[0]++;
+  return true;
+}
+
 template <class Fn>
 static void launch_head(Ctx* ctx, Fn fn, bool bounded, LSParams* d_ls, int64_t n, double tol, int64_t max_ls, DevState* st,
                         double* x, double* g, double* d, double* xt, double* gt, double* s, double* y, const double* u,
@@ -188,13 +622,17 @@ static void launch_head(Ctx* ctx, Fn fn, bool bounded, LSParams* d_ls, int64_t n
 void qn_device_launch_head(Ctx* ctx, int functor_kind, const double* fn_a, const double* fn_b, bool bounded, LSParams* d_ls,
                            int64_t n, double tol, int64_t max_ls, DevState* st, double* x, double* g, double* d, double* xt,
                            double* gt, double* s, double* y, const double* u, const double* lb, const double* ub,
-                           const double* ls_lb, const double* ls_ub) {
+                           const double* ls_lb, const double* ls_ub, int head_variant) {
   if (functor_kind == FN_ROSENBROCK) {
+    if (head_variant == 0 && launch_head_cluster(ctx, RosenbrockFn{}, bounded, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub)) return;
+    if (head_variant <= 1 && launch_head_fast(ctx, RosenbrockFn{}, bounded, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub)) return;
     launch_head(ctx, RosenbrockFn{}, bounded, d_ls, n, tol, max_ls, st, x, g, d, xt, gt, s, y, u, lb, ub, ls_lb, ls_ub);
   } else if (functor_kind == FN_SEPQUAD) {
     SepQuadFn fn;
     fn.c = fn_a;
     fn.a = fn_b;
+    if (head_variant == 0 && launch_head_cluster(ctx, fn, bounded, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub)) return;
+    if (head_variant <= 1 && launch_head_fast(ctx, fn, bounded, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub)) return;
     launch_head(ctx, fn, bounded, d_ls, n, tol, max_ls, st, x, g, d, xt, gt, s, y, u, lb, ub, ls_lb, ls_ub);
   } else {
     throw Error(OSB_ERR_UNSUPPORTED, "objective has no block functor for the device-resident engine");

@@ -42,24 +42,33 @@ __device__ __forceinline__ void tile_reduce_store(double (&acc)[QN_R], double (*
 #pragma unroll
     for (int w = 0; w < QN_T / 32; ++w) v = v + red[threadIdx.x][w];
     if (r0 + threadIdx.x < nrows) out[row_base + r0 + threadIdx.x] = v;
+    __threadfence();  // the fused coefficient epilogue of another CTA may read this row sum
   }
   __syncthreads();
 }
 
+template <int NTHREADS>
+__device__ __forceinline__ void qn_coef_body(int kind, int64_t n, DevState* st, const double* __restrict__ s,
+                                             const double* __restrict__ y, const double* h, double* __restrict__ p_out,
+                                             double* smem);
+
 // ---- pass 1: out = H v ---------------------------------------------------------------------
 __global__ void __launch_bounds__(QN_T, 2)
-qn_gemv_kernel(const double* __restrict__ H, int64_t ld, int64_t nrows, int64_t row0, const DevState* __restrict__ st,
-               const double* __restrict__ v, double* __restrict__ out, const double* __restrict__ v_skip,
-               double* __restrict__ out_skip) {
+qn_gemv_kernel(const double* __restrict__ H, int64_t ld, int64_t nrows, int64_t row0, DevState* st,
+               const double* __restrict__ v, double* out, const double* __restrict__ v_skip,
+               double* __restrict__ out_skip, QNCoefArgs ca) {
+  bool fuse_coef = ca.ticket != nullptr;
   if (st != nullptr) {
     if (st->done) return;
     if (st->skip) {  // bfgs.rs:106-112: H unchanged; only the next direction's u = H g is needed
       v = v_skip;
       out = out_skip;
+      fuse_coef = false;
     }
   }
   if (v == nullptr) return;
   __shared__ double red[QN_R][QN_T / 32];
+  __shared__ bool is_last;
   const int64_t ntiles = (nrows + QN_R - 1) / QN_R;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t r0 = tile * QN_R;
@@ -80,15 +89,30 @@ qn_gemv_kernel(const double* __restrict__ H, int64_t ld, int64_t nrows, int64_t 
     }
     tile_reduce_store(acc, red, out, row0, r0, nrows);
   }
+  if (!fuse_coef) return;
+  // fused epilogue (single GPU): the last CTA to finish owns the complete h and computes y.h and the
+  // update coefficients, saving a launch on the critical path
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(ca.ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  qn_coef_body<QN_T>(ca.kind, ca.n, st, ca.s, ca.y, out, ca.p_out, &red[0][0]);
+  if (threadIdx.x == 0) *ca.ticket = 0u;
 }
 
 void qn_launch_gemv(Ctx* ctx, const double* H, int64_t ld, int64_t nrows, int64_t row0, const DevState* st, const double* v,
-                    double* out, const double* v_skip, double* out_skip, int variant) {
+                    double* out, const double* v_skip, double* out_skip, int variant, const QNCoefArgs* coef) {
   (void)variant;
   int64_t ntiles = (nrows + QN_R - 1) / QN_R;
   int grid = (int)std::min<int64_t>(ntiles, (int64_t)ctx->num_sms * 2);
+  QNCoefArgs ca{};
+  if (coef) ca = *coef;
   // rows are addressed relative to the local block; `out` is indexed by global row (row0 + local row)
-  qn_gemv_kernel<<<grid, QN_T, 0, ctx->stream>>>(H, ld, nrows, row0, st, v, out, v_skip, out_skip);
+  qn_gemv_kernel<<<grid, QN_T, 0, ctx->stream>>>(H, ld, nrows, row0, const_cast<DevState*>(st), v, out, v_skip, out_skip, ca);
   ctx->counters[0]++;
 }
 
@@ -136,13 +160,12 @@ void qn_launch_gemvT(Ctx* ctx, const double* H, int64_t ld, int64_t nrows, int64
 // Broyden (broyden.rs:115-118) H' = H + p v^T/(s.y),           p = s - h, v = H^T s
 // Divisions by the scalar denominators are applied as multiplications by their reciprocals
 // (<= 1 ulp per term away from the reference's elementwise division; documented in DESIGN.md).
-__global__ void __launch_bounds__(1024) qn_coef_kernel(int kind, int64_t n, DevState* st, const double* __restrict__ s,
-                                                       const double* __restrict__ y, const double* __restrict__ h,
-                                                       double* __restrict__ p_out) {
-  if (st->done || st->skip) return;
-  __shared__ double smem[2 * 32];
+template <int NTHREADS>
+__device__ __forceinline__ void qn_coef_body(int kind, int64_t n, DevState* st, const double* __restrict__ s,
+                                             const double* __restrict__ y, const double* h, double* __restrict__ p_out,
+                                             double* smem) {
   double acc[2] = {0.0, 0.0};
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int64_t i = threadIdx.x; i < n; i += NTHREADS) {
     const double yi = y[i], hi = h[i];
     acc[0] = fma(yi, hi, acc[0]);
     if (kind == QN_SR1 || kind == QN_BROYDEN) {
@@ -173,6 +196,14 @@ __global__ void __launch_bounds__(1024) qn_coef_kernel(int kind, int64_t n, DevS
       st->c1 = st->c2 = 0.0;
     }
   }
+}
+
+__global__ void __launch_bounds__(1024) qn_coef_kernel(int kind, int64_t n, DevState* st, const double* __restrict__ s,
+                                                       const double* __restrict__ y, const double* __restrict__ h,
+                                                       double* __restrict__ p_out) {
+  if (st->done || st->skip) return;
+  __shared__ double smem[2 * 32];
+  qn_coef_body<1024>(kind, n, st, s, y, h, p_out, smem);
 }
 void qn_launch_coef(Ctx* ctx, int kind, int64_t n, DevState* st, const double* s, const double* y, const double* h,
                     double* p_out) {

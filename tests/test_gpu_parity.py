@@ -314,16 +314,25 @@ def test_device_engine_matches_host_engine(osb):
     x0 = rosen_x0(n, 11)
     res = []
     for engine in (1, 2):
-        for lsk in ("bt", "mt"):
-            s = osb.BFGS(1e-8, x0).set_option("engine", engine)
-            ls = osb.BackTracking(1e-4, 0.5) if lsk == "bt" else osb.MoreThuente.default()
-            # BFGS + the reference's More-Thuente diverges on Rosenbrock: 4 iterations only
-            st = run(osb, s, ls, osb.ExtendedRosenbrock(n), 25 if lsk == "bt" else 4, 20)
-            res.append((engine, lsk, st, s.k(), s.termination_reason(), s.x(), s.s_norm(), s.y_norm()))
-    for lsk in ("bt", "mt"):
-        a = [r for r in res if r[1] == lsk]
-        assert a[0][2:5] == a[1][2:5], (a[0][2:5], a[1][2:5])
-        assert close(a[0][5], a[1][5], rtol=1e-9), lsk
+        s = osb.BFGS(1e-8, x0).set_option("engine", engine)
+        st = run(osb, s, osb.BackTracking(1e-4, 0.5), osb.ExtendedRosenbrock(n), 25, 20)
+        res.append((st, s.k(), s.termination_reason(), s.x(), s.s_norm(), s.y_norm()))
+    assert res[0][:3] == res[1][:3], (res[0][:3], res[1][:3])
+    assert close(res[0][3], res[1][3], rtol=1e-9)
+    # More-Thuente (and the bounded searches) on a convex problem: BFGS + the reference's More-Thuente
+    # diverges on Rosenbrock, where no two summation orders stay together
+    n = 1024
+    lbv, ubv = np.full(n, -1.5), np.full(n, 1.5)
+    for mk in (lambda: osb.MoreThuente.default(), lambda: osb.MoreThuenteB(n).with_lower_bound(lbv).with_upper_bound(ubv),
+               lambda: osb.BackTrackingB(1e-4, 0.5, lbv, ubv), lambda: osb.GLLQuadratic(1e-4, 5)):
+        out = []
+        for engine in (1, 2):
+            obj = osb.SeparableQuadratic.generated(n)
+            s = osb.BFGSB(1e-7, np.zeros(n), lbv, ubv).set_option("engine", engine)
+            st = run(osb, s, mk(), obj, 200, 30)
+            out.append((st, s.k(), s.termination_reason(), s.x(), s.active_set()))
+        assert out[0][:3] == out[1][:3], (out[0][:3], out[1][:3])
+        assert close(out[0][3], out[1][3]) and np.array_equal(out[0][4], out[1][4])
     # full convergence on the separable quadratic (convex): identical counts and reasons
     n = 4096
     out = []
