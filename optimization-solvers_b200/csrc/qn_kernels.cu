@@ -198,16 +198,18 @@ __device__ __forceinline__ void qn_coef_body(int kind, int64_t n, DevState* st, 
   }
 }
 
-__global__ void __launch_bounds__(1024) qn_coef_kernel(int kind, int64_t n, DevState* st, const double* __restrict__ s,
+// standalone launch (row-sharded H: y.h needs the all-gathered h).  Same thread count as the fused
+// epilogue, hence the same summation order: results are bit-identical for every number of GPUs.
+__global__ void __launch_bounds__(QN_T) qn_coef_kernel(int kind, int64_t n, DevState* st, const double* __restrict__ s,
                                                        const double* __restrict__ y, const double* __restrict__ h,
                                                        double* __restrict__ p_out) {
   if (st->done || st->skip) return;
   __shared__ double smem[2 * 32];
-  qn_coef_body<1024>(kind, n, st, s, y, h, p_out, smem);
+  qn_coef_body<QN_T>(kind, n, st, s, y, h, p_out, smem);
 }
 void qn_launch_coef(Ctx* ctx, int kind, int64_t n, DevState* st, const double* s, const double* y, const double* h,
                     double* p_out) {
-  qn_coef_kernel<<<1, 1024, 0, ctx->stream>>>(kind, n, st, s, y, h, p_out);
+  qn_coef_kernel<<<1, QN_T, 0, ctx->stream>>>(kind, n, st, s, y, h, p_out);
   ctx->counters[0]++;
 }
 

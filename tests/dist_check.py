@@ -1,0 +1,59 @@
+"""Multi-GPU check (run under torchrun on a GPU box, one process per GPU):
+row-block sharded BFGS/DFP must reproduce the single-GPU result BIT-FOR-BIT (a row's dot product is
+formed inside one CTA whatever the sharding; every O(n) vector and scalar is replicated).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_check.py
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from test_gpu_parity import rosen_x0
+    osb = importlib.import_module("optimization-solvers_b200")
+    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    uid = [osb.Context.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    ctx = osb.Context(lr, rank, world, uid[0])
+    solo = osb.Context(lr)
+    ok = True
+    for kind, n, iters in (("BFGS", 2048, 40), ("DFP", 1024, 25), ("BFGS", 16384, 12)):
+        x0 = rosen_x0(n, 5)
+        res = []
+        for c in (ctx, solo):
+            s = getattr(osb, kind)(1e-8, x0, ctx=c).set_option("engine", 2)
+            try:
+                s.minimize(osb.BackTracking(1e-4, 0.5), osb.ExtendedRosenbrock(n, ctx=c), iters, 20)
+            except osb.MaxIterReached:
+                pass
+            H = s.approx_inv_hessian()
+            res.append((s.k(), s.x(), s.s_norm(), H))
+            s.close()
+        rows = slice(rank * n // world, (rank + 1) * n // world)
+        same = (res[0][0] == res[1][0] and np.array_equal(res[0][1], res[1][1]) and res[0][2] == res[1][2]
+                and np.array_equal(res[0][3][rows], res[1][3][rows]))
+        print("rank %d %s n=%d k=%d bit-identical to single GPU: %s" % (rank, kind, n, res[0][0], same), flush=True)
+        ok &= bool(same)
+    t = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    dist.barrier()
+    dist.destroy_process_group()
+    if int(t.item()) != 1:
+        raise SystemExit("dist_check FAILED")
+    if rank == 0:
+        print("dist_check ok")
+
+
+if __name__ == "__main__":
+    main()
