@@ -13,6 +13,7 @@ typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
 enum { ncclFloat64 = 8 };
+enum { ncclSum = 0 };
 
 struct NcclApi {
   void* handle = nullptr;
@@ -20,6 +21,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -33,6 +35,7 @@ static NcclApi& nccl() {
     api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
     api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
     api.AllGather = (decltype(api.AllGather))dlsym(api.handle, "ncclAllGather");
+    api.AllReduce = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
     api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
     if (!api.GetUniqueId || !api.CommInitRank || !api.AllGather) throw Error(OSB_ERR_NCCL, "libnccl is missing required symbols");
   }
@@ -72,6 +75,13 @@ void Ctx::all_gather_inplace(double* buf, int64_t count) {
   if (world <= 1) return;
   OSB_NCCL(nccl().AllGather(buf + (int64_t)rank * count, buf, (size_t)count, ncclFloat64, (ncclComm_t)nccl_comm, stream));
   counters[4]++;
+}
+
+// in-place sum over ranks (sample-sharded logistic regression: loss, gradient, Hessian)
+void ctx_all_reduce_sum(Ctx* ctx, double* buf, int64_t count) {
+  if (ctx->world <= 1) return;
+  OSB_NCCL(nccl().AllReduce(buf, buf, (size_t)count, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+  ctx->counters[4]++;
 }
 
 }  // namespace osb

@@ -113,12 +113,241 @@ int newton_solve(Ctx* ctx, int64_t n, int64_t ld, const double* hess, double* ch
   return OSB_OK;
 }
 
-// placeholders until the blocked DMMA path lands
-int chol_blocked_factor(Ctx*, int64_t, int64_t, const double*, double*, int*) {
-  throw Error(OSB_ERR_UNSUPPORTED, "blocked Cholesky (n > 256) not built yet");
+// ---- blocked right-looking Cholesky (n > CHOL_SMALL_MAX) -----------------------------------
+// per block column k: POTRF of the 64x64 diagonal block in shared memory, TRSM of the panel below
+// (one thread per row, the row held in registers), SYRK update of the trailing lower triangle with
+// 64x64 register-tiled output tiles.  n^3/3 flops in total — three orders of magnitude below the
+// Hessian assembly of the logistic config, so plain FP64 FMA is the right tool here.
+constexpr int CB = 64;
+
+__global__ void __launch_bounds__(256) chol_copy_lower_kernel(int64_t n, int64_t ld, const double* __restrict__ A, double* __restrict__ L) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n * ld; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / ld, j = e % ld;
+    L[e] = (j <= i && j < n) ? A[e] : 0.0;
+  }
 }
-void chol_blocked_solve(Ctx*, int64_t, int64_t, const double*, const double*, double*, const int*) {
-  throw Error(OSB_ERR_UNSUPPORTED, "blocked Cholesky (n > 256) not built yet");
+
+__global__ void __launch_bounds__(256) chol_potrf_block_kernel(int64_t n, int64_t ld, double* __restrict__ L, int64_t k0, int* __restrict__ fail) {
+  __shared__ double T[CB][CB + 1];
+  __shared__ int s_fail;
+  if (*fail) return;
+  const int nb = (int)(n - k0 < CB ? n - k0 : CB);
+  const int tid = threadIdx.x;
+  if (tid == 0) s_fail = 0;
+  for (int e = tid; e < nb * nb; e += 256) {
+    const int i = e / nb, j = e % nb;
+    T[i][j] = (j <= i) ? L[(k0 + i) * ld + k0 + j] : 0.0;
+  }
+  __syncthreads();
+  for (int j = 0; j < nb; ++j) {
+    if (tid == 0) {
+      const double d = T[j][j];
+      if (d != 0.0 && d >= 0.0) T[j][j] = sqrt(d);
+      else s_fail = 1;
+    }
+    __syncthreads();
+    if (s_fail) {
+      if (tid == 0) *fail = 1;
+      return;
+    }
+    const double dj = T[j][j];
+    for (int i = j + 1 + tid; i < nb; i += 256) T[i][j] = T[i][j] / dj;
+    __syncthreads();
+    const int mrem = nb - j - 1;
+    for (int e = tid; e < mrem * mrem; e += 256) {
+      const int i = j + 1 + e / mrem, k = j + 1 + e % mrem;
+      if (k <= i) T[i][k] = (-T[k][j]) * T[i][j] + T[i][k];
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < nb * nb; e += 256) {
+    const int i = e / nb, j = e % nb;
+    if (j <= i) L[(k0 + i) * ld + k0 + j] = T[i][j];
+  }
+}
+
+// panel rows i >= k0 + nb: L[i, k0:k0+nb] <- A[i, k0:k0+nb] L11^{-T}
+__global__ void __launch_bounds__(128) chol_trsm_kernel(int64_t n, int64_t ld, double* __restrict__ L, int64_t k0, const int* __restrict__ fail) {
+  __shared__ double T[CB][CB + 1];
+  if (*fail) return;
+  const int nb = (int)(n - k0 < CB ? n - k0 : CB);
+  for (int e = threadIdx.x; e < nb * nb; e += 128) {
+    const int i = e / nb, j = e % nb;
+    T[i][j] = (j <= i) ? L[(k0 + i) * ld + k0 + j] : 0.0;
+  }
+  __syncthreads();
+  const int64_t i = k0 + nb + (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (i >= n) return;
+  double xr[CB];
+  double* row = L + i * ld + k0;
+#pragma unroll
+  for (int c = 0; c < CB; ++c) xr[c] = c < nb ? row[c] : 0.0;
+#pragma unroll
+  for (int c = 0; c < CB; ++c) {
+    if (c < nb) {
+      double v = xr[c];
+#pragma unroll
+      for (int p = 0; p < c; ++p) v = fma(-xr[p], T[c][p], v);
+      xr[c] = v / T[c][c];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CB; ++c)
+    if (c < nb) row[c] = xr[c];
+}
+
+// trailing update, lower-triangular 64x64 tiles: A[i][j] -= sum_p L[i][k0+p] L[j][k0+p]
+__global__ void __launch_bounds__(256) chol_syrk_kernel(int64_t n, int64_t ld, double* __restrict__ L, int64_t k0, int nb, int64_t t0,
+                                                        const int* __restrict__ fail) {
+  constexpr int PH = 32;  // the 64-wide panel is consumed in two halves (48 KB static shared memory limit)
+  __shared__ double Pi[CB][PH + 2];
+  __shared__ double Pj[CB][PH + 2];
+  if (*fail) return;
+  int t = blockIdx.x, ti = 0;
+  while (t > ti) {
+    t -= ti + 1;
+    ++ti;
+  }
+  const int tj = t;
+  const int64_t i0 = t0 + (int64_t)ti * CB, j0 = t0 + (int64_t)tj * CB;
+  const int tid = threadIdx.x;
+  const int tr = (tid / 16) * 4, tc = (tid % 16) * 4;
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+  for (int ph = 0; ph < CB; ph += PH) {
+    for (int e = tid; e < CB * PH; e += 256) {
+      const int r = e / PH, p = e % PH;
+      Pi[r][p] = (i0 + r < n && ph + p < nb) ? L[(i0 + r) * ld + k0 + ph + p] : 0.0;
+      Pj[r][p] = (j0 + r < n && ph + p < nb) ? L[(j0 + r) * ld + k0 + ph + p] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int p = 0; p < PH; ++p) {
+      double av[4], bv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) av[a] = Pi[tr + a][p];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) bv[b] = Pj[tc + b][p];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int64_t i = i0 + tr + a, j = j0 + tc + b;
+      if (i < n && j < n && j <= i) L[i * ld + j] = L[i * ld + j] - acc[a][b];
+    }
+}
+
+int chol_blocked_factor(Ctx* ctx, int64_t n, int64_t ld, const double* hess, double* chol, int* d_fail) {
+  cudaStream_t st = ctx->stream;
+  OSB_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), st));
+  chol_copy_lower_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(n, ld, hess, chol);
+  ctx->counters[0]++;
+  for (int64_t k0 = 0; k0 < n; k0 += CB) {
+    const int nb = (int)(n - k0 < CB ? n - k0 : CB);
+    chol_potrf_block_kernel<<<1, 256, 0, st>>>(n, ld, chol, k0, d_fail);
+    const int64_t rem = n - k0 - nb;
+    ctx->counters[0]++;
+    if (rem <= 0) break;
+    chol_trsm_kernel<<<(unsigned)((rem + 127) / 128), 128, 0, st>>>(n, ld, chol, k0, d_fail);
+    const int nt = (int)((rem + CB - 1) / CB);
+    chol_syrk_kernel<<<(unsigned)(nt * (nt + 1) / 2), 256, 0, st>>>(n, ld, chol, k0, nb, k0 + nb, d_fail);
+    ctx->counters[0] += 2;
+  }
+  return OSB_OK;
+}
+
+// blocked triangular solves: L y = rhs (forward), L^T w = y (backward)
+__global__ void __launch_bounds__(CB) chol_fwd_diag_kernel(int64_t n, int64_t ld, const double* __restrict__ L, double* __restrict__ b, int64_t k0,
+                                                           const int* __restrict__ fail) {
+  if (*fail) return;
+  __shared__ double y[CB];
+  const int nb = (int)(n - k0 < CB ? n - k0 : CB);
+  const int t = threadIdx.x;
+  if (t < nb) y[t] = b[k0 + t];
+  __syncthreads();
+  for (int c = 0; c < nb; ++c) {
+    if (t == c) y[c] = y[c] / L[(k0 + c) * ld + k0 + c];
+    __syncthreads();
+    if (t > c && t < nb) y[t] = (-y[c]) * L[(k0 + t) * ld + k0 + c] + y[t];
+    __syncthreads();
+  }
+  if (t < nb) b[k0 + t] = y[t];
+}
+__global__ void __launch_bounds__(128) chol_fwd_update_kernel(int64_t n, int64_t ld, const double* __restrict__ L, double* __restrict__ b, int64_t k0,
+                                                              int nb, const int* __restrict__ fail) {
+  if (*fail) return;
+  __shared__ double y[CB];
+  if (threadIdx.x < nb) y[threadIdx.x] = b[k0 + threadIdx.x];
+  __syncthreads();
+  const int64_t i = k0 + nb + (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (i >= n) return;
+  const double* row = L + i * ld + k0;
+  double acc = 0.0;
+  for (int p = 0; p < nb; ++p) acc = fma(row[p], y[p], acc);
+  b[i] = b[i] - acc;
+}
+__global__ void __launch_bounds__(CB) chol_bwd_diag_kernel(int64_t n, int64_t ld, const double* __restrict__ L, double* __restrict__ b, int64_t k0,
+                                                           const int* __restrict__ fail) {
+  if (*fail) return;
+  __shared__ double y[CB];
+  const int nb = (int)(n - k0 < CB ? n - k0 : CB);
+  const int t = threadIdx.x;
+  if (t < nb) y[t] = b[k0 + t];
+  __syncthreads();
+  for (int c = nb - 1; c >= 0; --c) {
+    if (t == c) y[c] = y[c] / L[(k0 + c) * ld + k0 + c];
+    __syncthreads();
+    if (t < c) y[t] = y[t] - L[(k0 + c) * ld + k0 + t] * y[c];
+    __syncthreads();
+  }
+  if (t < nb) b[k0 + t] = y[t];
+}
+__global__ void __launch_bounds__(128) chol_bwd_update_kernel(int64_t n, int64_t ld, const double* __restrict__ L, double* __restrict__ b, int64_t k0,
+                                                              int nb, const int* __restrict__ fail) {
+  if (*fail) return;
+  __shared__ double y[CB];
+  if (threadIdx.x < nb) y[threadIdx.x] = b[k0 + threadIdx.x];
+  __syncthreads();
+  const int64_t j = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (j >= k0) return;
+  double acc = 0.0;
+  for (int p = 0; p < nb; ++p) acc = fma(L[(k0 + p) * ld + j], y[p], acc);
+  b[j] = b[j] - acc;
+}
+
+void chol_blocked_solve(Ctx* ctx, int64_t n, int64_t ld, const double* chol, const double* rhs, double* out, const int* d_fail) {
+  cudaStream_t st = ctx->stream;
+  if (out != rhs) OSB_CUDA(cudaMemcpyAsync(out, rhs, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+  for (int64_t k0 = 0; k0 < n; k0 += CB) {
+    const int nb = (int)(n - k0 < CB ? n - k0 : CB);
+    chol_fwd_diag_kernel<<<1, CB, 0, st>>>(n, ld, chol, out, k0, d_fail);
+    const int64_t rem = n - k0 - nb;
+    ctx->counters[0]++;
+    if (rem > 0) {
+      chol_fwd_update_kernel<<<(unsigned)((rem + 127) / 128), 128, 0, st>>>(n, ld, chol, out, k0, nb, d_fail);
+      ctx->counters[0]++;
+    }
+  }
+  const int64_t last = ((n - 1) / CB) * CB;
+  for (int64_t k0 = last; k0 >= 0; k0 -= CB) {
+    const int nb = (int)(n - k0 < CB ? n - k0 : CB);
+    chol_bwd_diag_kernel<<<1, CB, 0, st>>>(n, ld, chol, out, k0, d_fail);
+    ctx->counters[0]++;
+    if (k0 > 0) {
+      chol_bwd_update_kernel<<<(unsigned)((k0 + 127) / 128), 128, 0, st>>>(n, ld, chol, out, k0, nb, d_fail);
+      ctx->counters[0]++;
+    }
+  }
 }
 
 }  // namespace osb

@@ -244,8 +244,4 @@ Objective* make_user_objective(Ctx* ctx, int64_t n, osb_device_eval_fn fn, void*
   return new UserObjective(ctx, n, fn, user, with_h);
 }
 
-Objective* make_logistic_generated(Ctx*, int64_t, int64_t, double) {
-  throw Error(OSB_ERR_UNSUPPORTED, "logistic regression objective: not built yet");
-}
-
 }  // namespace osb

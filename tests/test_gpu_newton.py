@@ -1,0 +1,103 @@
+"""GPU (-m gpu): Newton family (src/newton/mod.rs, projected_newton.rs, spn.rs) on the synthetic logistic
+regression of BASELINE.json configs[4] and on dense quadratics: DMMA Hessian assembly, blocked Cholesky."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+def close(a, b, rtol=RTOL, atol=1e-12):
+    a, b = np.asarray(a), np.asarray(b)
+    scale = max(1.0, float(np.max(np.abs(b))))
+    return bool(np.all(np.abs(a - b) <= atol + rtol * scale))
+
+
+def run(m, solver, ls, oracle, mi, ml):
+    try:
+        solver.minimize(ls, oracle, mi, ml)
+        return "Ok"
+    except m.SolverError as e:
+        return type(e).__name__
+
+
+@pytest.mark.parametrize("m,n", [(512, 64), (300, 200), (1000, 130)])
+def test_logistic_objective_matches_oracle(osb, orc, m, n):
+    # f, g (two passes over X) and the DMMA Hessian X^T D X + lambda I, tiles with ragged edges included
+    rng = np.random.default_rng(m + n)
+    w = rng.standard_normal(n) * 0.3
+    a = osb.LogisticRegression.generated(m, n, 1.0)(w)
+    b = orc.LogisticRegression.generated(m, n, 1.0)(w)
+    assert abs(a.f() - b.f()) <= 1e-12 * abs(b.f())
+    assert close(a.g(), b.g(), rtol=1e-12)
+    assert close(a.hessian(), b.hessian(), rtol=1e-12)
+    assert np.array_equal(a.hessian(), a.hessian().T)
+
+
+@pytest.mark.parametrize("ls", ["bt", "mt"])
+def test_newton_logistic_vs_oracle(osb, orc, ls):
+    m_, n = 2048, 64
+
+    def script(m):
+        obj = m.LogisticRegression.generated(m_, n, 1.0)
+        s = m.Newton(1e-8, np.zeros(n))
+        lsearch = m.BackTracking(1e-4, 0.5) if ls == "bt" else m.MoreThuente.default()
+        st = run(m, s, lsearch, obj, 50, 20)
+        return st, s.k(), s.termination_reason(), s.x(), s.decrement_squared()
+
+    ref, got = script(orc), script(osb)
+    assert got[:3] == ref[:3], (got[:3], ref[:3])
+    assert ref[0] == "Ok" and ref[2] == "newton_decrement"
+    assert close(got[3], ref[3]) and close(got[4], ref[4], atol=1e-18)
+
+
+def test_projected_and_spectral_newton_logistic_vs_oracle(osb, orc):
+    m_, n = 1024, 48
+    lb, ub = np.full(n, -0.05), np.full(n, 0.05)
+    for cls in ("ProjectedNewton", "SpectralProjectedNewton"):
+        def script(m):
+            obj = m.LogisticRegression.generated(m_, n, 1.0)
+            if cls == "ProjectedNewton":
+                s = m.ProjectedNewton(1e-7, np.zeros(n), lb, ub)
+                lsearch = m.BackTrackingB(1e-4, 0.5, lb, ub)
+            else:
+                s = m.SpectralProjectedNewton(1e-7, np.zeros(n), obj, lb, ub)
+                lsearch = m.GLLQuadratic(1e-4, 10)
+            st = run(m, s, lsearch, obj, 12, 30)
+            return st, s.k(), s.termination_reason(), s.x(), s.active_set()
+
+        ref, got = script(orc), script(osb)
+        assert got[:3] == ref[:3], (cls, got[:3], ref[:3])
+        assert close(got[3], ref[3])
+        assert np.array_equal(got[4], ref[4])
+
+
+@pytest.mark.parametrize("n", [300, 1000, 2050])
+def test_blocked_cholesky_newton_step(osb, n):
+    # one full Newton step on a dense SPD quadratic lands on the minimiser: x1 = x0 - (2A)^-1 g(x0) = A^-1 b
+    obj = osb.DenseQuadratic.generated(n, True)
+    s = osb.Newton(1e-30, obj.x0)
+    assert run(osb, s, osb.NoSearch(), obj, 1, 1) == "MaxIterReached"
+    x1 = s.x()
+    g1 = obj(x1).g()
+    g0 = obj(obj.x0).g()
+    assert np.max(np.abs(g1)) <= 1e-11 * np.max(np.abs(g0))
+    H = obj(obj.x0).hessian()
+    ref = obj.x0 - np.linalg.solve(H, g0)
+    assert close(x1, ref, rtol=1e-11)
+    assert s.decrement_squared() is not None and s.decrement_squared() > 0
+
+
+def test_not_spd_is_reported_like_the_reference_panic(osb):
+    # projected_newton.rs:75 `.cholesky().unwrap()` panics on a non-SPD Hessian
+    H = np.array([[1.0, 0.0], [0.0, -1.0]])
+
+    def orac(x):
+        return osb.FuncEvalMultivariate(0.5 * x @ H @ x, H @ x).with_hessian(H)
+    s = osb.ProjectedNewton(1e-8, [1.0, 1.0], [-5.0, -5.0], [5.0, 5.0])
+    with pytest.raises(osb.ReferencePanic):
+        s.minimize(osb.BackTrackingB(1e-4, 0.5, [-5.0, -5.0], [5.0, 5.0]), osb.HostOracle(orac, 2, True), 5, 5)
+    # missing Hessian: newton/mod.rs:34 `.expect("Hessian not available in the oracle")`
+    s = osb.Newton(1e-8, [1.0, 1.0])
+    with pytest.raises(osb.ReferencePanic):
+        s.minimize(osb.NoSearch(), osb.ExtendedRosenbrock(2), 5, 5)
