@@ -1,0 +1,77 @@
+"""CPU, world_size 2 over gloo: the host-side logic of the N > 1 path — rendezvous, broadcast of the
+128-byte communicator id, and the row / problem / sample partitions (they must tile the index space
+exactly, whatever the rank count).  The data path itself (NCCL all-gather inside the CUDA library) is
+covered on the GPU box by tests/dist_check.py."""
+import importlib.util
+import os
+import socket
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _load_dist():
+    spec = importlib.util.spec_from_file_location("osb_dist", os.path.join(ROOT, "optimization-solvers_b200", "dist.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import torch.distributed as dist
+    d = _load_dist()
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    payload = bytes(range(128)) if rank == 0 else None
+    got = d.broadcast_bytes(payload)
+    rows = d.shard_rows(16384, rank, world)
+    probs = d.shard_problems(262144 + 3, rank, world)
+    samp = d.shard_samples(1 << 20, rank, world)
+    allr = [None] * world
+    dist.all_gather_object(allr, (rows, probs, samp, got == bytes(range(128)), d.env_rank_world()))
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        q.put(allr)
+
+
+def test_partitions_and_id_broadcast_world2():
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world = 2
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    allr = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[3] for r in allr)
+    assert [r[4][0] for r in allr] == [0, 1]
+    # partitions tile the index space
+    assert allr[0][0] == (0, 8192) and allr[1][0] == (8192, 8192)
+    p = [r[1] for r in allr]
+    assert p[0][0] == 0 and p[0][0] + p[0][1] == p[1][0] and p[1][0] + p[1][1] == 262144 + 3
+    assert allr[0][2] == (0, 1 << 19) and allr[1][2] == (1 << 19, 1 << 19)
+
+
+def test_partition_rules():
+    d = _load_dist()
+    for world in (1, 2, 4, 8):
+        spans = [d.shard_rows(16384, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and sum(s[1] for s in spans) == 16384
+        assert all(spans[i][0] + spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+        pr = [d.shard_problems(1000, r, world) for r in range(world)]
+        assert sum(c for _, c in pr) == 1000 and all(pr[i][0] + pr[i][1] == pr[i + 1][0] for i in range(world - 1))
+    with pytest.raises(ValueError):
+        d.shard_rows(100, 0, 8)
+    with pytest.raises(ValueError):
+        d.shard_samples(10, 0, 4)
