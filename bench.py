@@ -160,6 +160,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--n", type=int, default=N_DIM, help="problem dimension (the benchmark line is only valid at 16384)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--schedule", default="lazy", choices=["lazy", "eager"],
+                    help="lazy: one read-modify-write of H per iteration (2 n^2 8 B); eager: h = H y then fused update (3 n^2 8 B)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -194,7 +196,8 @@ def main():
     x0 = rosen_x0(n, 0)
     obj = osb.ExtendedRosenbrock(n, ctx=ctx)
     ls = osb.BackTracking(1e-4, 0.5)
-    solver = osb.BFGS(TOL, x0, ctx=ctx).set_option("engine", 2)
+    lazy = args.schedule == "lazy"
+    solver = osb.BFGS(TOL, x0, ctx=ctx).set_option("engine", 2).set_option("qn_schedule", 1 if lazy else 0)
 
     def run_steps(k):
         try:
@@ -233,15 +236,19 @@ def main():
     rows_local = n // world
     upd_bytes = 2.0 * rows_local * n * 8.0  # read H + write H' (local row block); O(n) vectors excluded
     gemv_bytes = 1.0 * rows_local * n * 8.0
+    iter_bytes = (2.0 if lazy else 3.0) * rows_local * n * 8.0
     peak, peak_src = hbm_peak()
     ach = upd_bytes / (kt["update_ms"] * 1e-3) / 1e9 if kt["update_ms"] > 0 else None
-    roofline = {"bound": "hbm", "kernel": "qn_update_kernel<BFGS> (fused rank-2 RMW + u = H' g)", "achieved": ach,
+    kname = ("qn_lazy_kernel<BFGS> (pending rank-2 RMW + h = H y + w = H g in one pass)" if lazy
+             else "qn_update_kernel<BFGS> (fused rank-2 RMW + u = H' g)")
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": ach,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": (ach / peak) if ach else None,
                 "traffic": ncu_traffic(), "algorithmic_bytes_per_launch": upd_bytes, "ms_per_launch": kt["update_ms"],
-                "gemv_kernel": {"achieved": gemv_bytes / (kt["gemv_ms"] * 1e-3) / 1e9 if kt["gemv_ms"] > 0 else None,
-                                "ms_per_launch": kt["gemv_ms"], "algorithmic_bytes_per_launch": gemv_bytes},
-                "iteration_bytes": 3.0 * rows_local * n * 8.0,
-                "iteration_frac_of_peak": (3.0 * rows_local * n * 8.0 / (ms / args.steps * 1e-3) / 1e9) / peak}
+                "gemv_kernel": None if lazy else {
+                    "achieved": gemv_bytes / (kt["gemv_ms"] * 1e-3) / 1e9 if kt["gemv_ms"] > 0 else None,
+                    "ms_per_launch": kt["gemv_ms"], "algorithmic_bytes_per_launch": gemv_bytes},
+                "iteration_bytes": iter_bytes,
+                "iteration_frac_of_peak": (iter_bytes / (ms / args.steps * 1e-3) / 1e9) / peak}
 
     # ---- end to end through the public API with HOST buffers: construction from a pinned host x0 (H2D),
     # minimize with a per-iteration host callback that reads the iterate back (D2H), final x() (D2H)
@@ -274,7 +281,7 @@ def main():
         # sharded: the public API call itself (host x0 in, host x out), wall clock, max over ranks
         barrier()
         t0 = time.perf_counter()
-        s2 = osb.BFGS(TOL, x0, ctx=ctx).set_option("engine", 2)
+        s2 = osb.BFGS(TOL, x0, ctx=ctx).set_option("engine", 2).set_option("qn_schedule", 1 if lazy else 0)
         try:
             s2.minimize(osb.BackTracking(1e-4, 0.5), obj, args.steps, MAX_LS)
         except osb.MaxIterReached:
@@ -301,6 +308,7 @@ def main():
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "n": n, "line_search": "BackTracking(1e-4,0.5)", "tol": TOL,
                            "max_iter_line_search": MAX_LS, "engine": "device-resident control",
+                           "schedule": "lazy: 1 RMW pass of H per iteration (2 n^2 8 B)" if lazy else "eager: gemv + fused update (3 n^2 8 B)",
                            "l2": "inputs larger than L2 (H = %.2f GiB per GPU, streamed every step)" % (rows_local * n * 8 / 2 ** 30),
                            "parallelism": "row-block sharded H over %d GPU(s), NCCL all-gather of h and u" % world},
                 "roofline": roofline, "cpu_baseline": cb_line, "e2e": e2e,

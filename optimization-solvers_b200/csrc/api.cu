@@ -343,6 +343,7 @@ int osb_solver_set_option(osb_solver* s, const char* name, int64_t value) {
   if (nm == "engine") S(s)->engine = (int)value;
   else if (nm == "record_trace") S(s)->record_trace = (int)value;
   else if (nm == "qn_kernel") S(s)->qn_variant = (int)value;
+  else if (nm == "qn_schedule") S(s)->qn_schedule = (int)value;
   else if (nm == "head_kernel") S(s)->head_variant = (int)value;
   else if (nm == "profile_kernels") S(s)->profile_kernels = (int)value;
   else throw Error(OSB_ERROR_INPUT_PARAMS, "unknown option " + nm);
@@ -415,6 +416,7 @@ int osb_solver_inv_hessian(osb_solver* s, double* out) {
   Solver* p = S(s);
   OSB_REQUIRE(p->is_qn, OSB_ERROR_INPUT_PARAMS, "not a quasi-Newton solver");
   p->ctx->use();
+  p->flush_pending();
   // local row block [row0, row0 + nrows)
   OSB_CUDA(cudaMemcpy2DAsync(out + p->row0 * p->n, p->n * sizeof(double), p->H.p, p->ld * sizeof(double), p->n * sizeof(double),
                              p->nrows, cudaMemcpyDeviceToHost, p->ctx->stream));
@@ -427,6 +429,7 @@ int osb_solver_set_inv_hessian(osb_solver* s, const double* in) {
   Solver* p = S(s);
   OSB_REQUIRE(p->is_qn, OSB_ERROR_INPUT_PARAMS, "not a quasi-Newton solver");
   p->ctx->use();
+  p->flush_pending();
   OSB_CUDA(cudaMemcpy2DAsync(p->H.p, p->ld * sizeof(double), in + p->row0 * p->n, p->n * sizeof(double), p->n * sizeof(double),
                              p->nrows, cudaMemcpyHostToDevice, p->ctx->stream));
   p->ctx->sync();

@@ -143,7 +143,7 @@ Solver::Solver(Ctx* c, int kind_, int64_t n_, double tol_, const double* x0, con
     H.zero(st);
     set_identity_kernel<<<ctx->red_grid(nrows), RED_THREADS, 0, st>>>(H.p, ld, nrows, row0);  // bfgs.rs:30-33
     ctx->counters[0]++;
-    for (DBuf* b : {&u, &h, &pvec, &vvec}) {
+    for (DBuf* b : {&u, &h, &pvec, &vvec, &wv, &ps, &ph}) {
       b->alloc(ld);
       b->zero(st);
     }
@@ -273,10 +273,35 @@ void Solver::prof_collect() {
   prof_events.clear();
 }
 
+// lazy schedule: the stored matrix lags the true H by one rank-2 update; apply it (predicated on the device flag)
+void Solver::flush_pending() {
+  if (!lazy_used) return;
+  qn_launch_flush(ctx, qn_kind, H.p, ld, nrows, row0, d_state, ps.p, ph.p);
+  lazy_used = false;
+}
+
 void Solver::qn_after_step() {
   const DevState* st = d_state;
   if (n <= QN_SMALL_N && ctx->world == 1) {  // reference operation order, bit-for-bit (qn_small.cu)
     qn_small_step(ctx, qn_kind, n, ld, H.p, d_state, s.p, y.p, g.p, u.p);
+    u_valid = true;
+    return;
+  }
+  if (qn_schedule == 1 && (qn_kind == QN_BFGS || qn_kind == QN_DFP)) {
+    // ONE read-modify-write per iteration (2 n^2 8 B): pending update + h = H y + w = H g, epilogue forms u
+    QNLazyArgs a{H.p, ld, nrows, row0, n, d_state, ps.p, ph.p, y.p, g.p, s.p, h.p, wv.p, u.p, ps.p, ph.p,
+                 ctx->world == 1 ? ctx->gemv_ticket : nullptr, qn_kind};
+    prof_mark();
+    prof_mark();
+    prof_mark();
+    qn_launch_lazy(ctx, a);
+    prof_mark();
+    if (ctx->world > 1) {
+      ctx->all_gather_inplace(h.p, nrows);
+      ctx->all_gather_inplace(wv.p, nrows);
+      qn_launch_lazy_epilogue(ctx, a);
+    }
+    lazy_used = true;
     u_valid = true;
     return;
   }
@@ -332,6 +357,7 @@ int Solver::minimize(LineSearch* ls, Objective* obj, int64_t max_iter, int64_t m
 }
 
 int Solver::minimize_host(LineSearch* ls, Objective* obj, int64_t max_iter, int64_t max_ls, osb_callback_fn cb, void* user) {
+  if (is_qn) flush_pending();
   k = 0;  // ls_solver.rs:74
   reason = OSB_REASON_NONE;
   trace.clear();
@@ -464,6 +490,7 @@ int Solver::minimize_host(LineSearch* ls, Objective* obj, int64_t max_iter, int6
 }
 
 int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, int64_t max_ls) {
+  if (qn_schedule != 1) flush_pending();
   k = 0;
   reason = OSB_REASON_NONE;
   trace.clear();
@@ -474,6 +501,7 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
     u_valid = false;
   }
   if (!u_valid) {
+    flush_pending();  // u = H g needs the exact H
     if (n <= QN_SMALL_N && ctx->world == 1) qn_small_gemv(ctx, n, ld, H.p, g.p, u.p);
     else qn_launch_gemv(ctx, H.p, ld, nrows, row0, nullptr, g.p, u.p, nullptr, nullptr, qn_variant);
     if (ctx->world > 1) ctx->all_gather_inplace(u.p, nrows);

@@ -27,6 +27,7 @@ struct DevState {
   double yh, sp2;
   double s_norm, y_norm;
   double c0, c1, c2;  // rank-2 update coefficients (kind-specific, see qn_kernels.cu)
+  double pc0, pc1, pc2;  // lazy schedule: coefficients of the update that is still PENDING on the stored matrix
   double t_last;
   long long k;
   int has_s, has_y;
@@ -35,7 +36,7 @@ struct DevState {
   int status;  // OSB_* status when done
   int reason;  // OSB_REASON_*
   int ls_evals;
-  int pad;
+  int pending;  // lazy schedule: stored matrix = H - rank2(ps, ph; pc0..pc2) still to be applied
 };
 
 struct Ctx {
@@ -158,6 +159,30 @@ void qn_launch_coef(Ctx* ctx, int kind, int64_t n, DevState* st, const double* s
 // fused: H <- H + rank-2(kind; p, q, r; c0..c2) and u = H' g over the local row block
 void qn_launch_update(Ctx* ctx, int kind, double* H, int64_t ld, int64_t nrows, int64_t row0, const DevState* st,
                       const double* p, const double* q, const double* r, const double* g, double* u_out, int variant);
+// lazy (2-pass-less) schedule: ONE read-modify-write per iteration — applies the pending update while
+// computing h = H y and w = H g with the updated rows; the epilogue forms the new pending update and u.
+struct QNLazyArgs {
+  double* M;            // stored matrix (local row block)
+  int64_t ld, nrows, row0, n;
+  DevState* st;
+  const double* ps;     // pending p (= s of the previous iteration)
+  const double* ph;     // pending q (= h of the previous iteration)
+  const double* y;
+  const double* g;      // new gradient
+  const double* s;      // new s
+  double* h;            // out: H y
+  double* w;            // out: H g
+  double* u;            // out (epilogue): H+ g
+  double* ps_out;       // epilogue: ps <- s
+  double* ph_out;       // epilogue: ph <- h
+  unsigned int* ticket; // null => no fused epilogue (sharded: separate launch after the all-gather)
+  int kind;
+};
+void qn_launch_lazy(Ctx* ctx, const QNLazyArgs& a);
+void qn_launch_lazy_epilogue(Ctx* ctx, const QNLazyArgs& a);
+// apply a pending update to the stored matrix (getters, engine switches)
+void qn_launch_flush(Ctx* ctx, int kind, double* M, int64_t ld, int64_t nrows, int64_t row0, DevState* st, const double* ps,
+                     const double* ph);
 int64_t qn_ld(int64_t n);
 // n <= QN_SMALL_N: single-thread replay of the reference's own operation order (qn_small.cu)
 constexpr int64_t QN_SMALL_N = 5;
@@ -191,6 +216,10 @@ struct Solver {
   int qn_kind = QN_BFGS;
   int64_t ld = 0, row0 = 0, nrows = 0;  // local row block of H
   DBuf H, u, h, pvec, vvec, scratch;
+  DBuf wv, ps, ph;        // lazy schedule: w = H g, pending p and q
+  int qn_schedule = 0;    // 0 = eager (h = H y, then fused update: 3 n^2 8 B), 1 = lazy (one RMW: 2 n^2 8 B)
+  bool lazy_used = false;
+  void flush_pending();
   // Newton family
   DBuf hess, chol;
   bool has_dec = false;

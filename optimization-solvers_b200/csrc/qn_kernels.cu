@@ -270,6 +270,220 @@ qn_update_kernel(double* __restrict__ H, int64_t ld, int64_t nrows, int64_t row0
   }
 }
 
+// ---- lazy schedule -------------------------------------------------------------------------
+// Stored matrix M = H_k minus the update of iteration k-1 (pending).  One read-modify-write:
+//     M_ij <- M_ij + pc0 p_i p_j + pc1 (p_i q_j + q_i p_j) + pc2 q_i q_j      (now M = H_k exactly)
+//     h_i = sum_j M_ij y_j ,  w_i = sum_j M_ij g_j
+// The update of iteration k, H_{k+1} = H_k + rank2(s, h; c), is NOT applied: it becomes the new pending
+// update, and the next direction needs only u = H_{k+1} g = w + s (c0 s.g + c1 h.g) + h (c1 s.g + c2 h.g),
+// an O(n) epilogue.  HBM traffic per iteration: 2 n^2 8 B instead of 3 n^2 8 B.
+template <int KIND>
+__device__ __forceinline__ void lazy_epilogue_body(const QNLazyArgs& a, double* smem) {
+  DevState* st = a.st;
+  const int64_t n = a.n;
+  if (st->skip) {  // bfgs.rs:106-112: no new update; the stored matrix is now exact
+    for (int64_t i = threadIdx.x; i < n; i += QN_T) a.u[i] = a.w[i];
+    if (threadIdx.x == 0) {
+      st->pending = 0;
+      st->pc0 = st->pc1 = st->pc2 = 0.0;
+    }
+    return;
+  }
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int64_t i = threadIdx.x; i < n; i += QN_T) {
+    const double hi = a.h[i], gi = a.g[i];
+    acc[0] = fma(a.y[i], hi, acc[0]);  // y.h
+    acc[1] = fma(a.s[i], gi, acc[1]);  // s.g
+    acc[2] = fma(hi, gi, acc[2]);      // h.g
+  }
+  RedOps<3> ops{{RED_SUM, RED_SUM, RED_SUM}};
+  cta_reduce<3>(acc, ops, smem);
+  const double yh = acc[0], sg = acc[1], hg = acc[2], ys = st->ys;
+  double c0, c1, c2;
+  if (KIND == QN_BFGS) {
+    const double rho = 1.0 / ys;
+    c0 = rho * rho * yh + rho;
+    c1 = -rho;
+    c2 = 0.0;
+  } else {  // DFP
+    c0 = 1.0 / ys;
+    c1 = 0.0;
+    c2 = -1.0 / yh;
+  }
+  const double ca = c0 * sg + c1 * hg, cb = c1 * sg + c2 * hg;
+  for (int64_t i = threadIdx.x; i < n; i += QN_T) {
+    const double si = a.s[i], hi = a.h[i];
+    a.u[i] = a.w[i] + (si * ca + hi * cb);
+    a.ps_out[i] = si;
+    a.ph_out[i] = hi;
+  }
+  if (threadIdx.x == 0) {
+    st->yh = yh;
+    st->c0 = c0;
+    st->c1 = c1;
+    st->c2 = c2;
+    st->pc0 = c0;
+    st->pc1 = c1;
+    st->pc2 = c2;
+    st->pending = 1;
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(QN_T, 1) qn_lazy_kernel(QNLazyArgs a) {
+  DevState* st = a.st;
+  if (st->done) return;
+  const double c0 = st->pc0, c1 = st->pc1, c2 = st->pc2;
+  __shared__ double red[2 * QN_R][QN_T / 32];
+  __shared__ double2 rowpq[QN_R];
+  __shared__ bool is_last;
+  const int64_t ld = a.ld, nrows = a.nrows, row0 = a.row0;
+  const double* __restrict__ p = a.ps;
+  const double* __restrict__ q = a.ph;
+  const double* __restrict__ yv = a.y;
+  const double* __restrict__ gv = a.g;
+  const int64_t ntiles = (nrows + QN_R - 1) / QN_R;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r0 = tile * QN_R;
+    double ah[QN_R], aw[QN_R];
+#pragma unroll
+    for (int r = 0; r < QN_R; ++r) ah[r] = aw[r] = 0.0;
+    if (threadIdx.x < QN_R) rowpq[threadIdx.x] = make_double2(p[row0 + r0 + threadIdx.x], q[row0 + r0 + threadIdx.x]);
+    __syncthreads();
+    double* __restrict__ base = a.M + r0 * ld;
+    for (int col = 2 * threadIdx.x; col < (int)ld; col += QN_CHUNK) {
+      const double2 gj = *reinterpret_cast<const double2*>(gv + col);
+      const double2 yj = *reinterpret_cast<const double2*>(yv + col);
+      const double2 pj = *reinterpret_cast<const double2*>(p + col);
+      const double2 qj = *reinterpret_cast<const double2*>(q + col);
+      double2 hv[QN_R];
+#pragma unroll
+      for (int r = 0; r < QN_R; ++r) hv[r] = ld_stream(base + r * ld + col);
+#pragma unroll
+      for (int r = 0; r < QN_R; ++r) {
+        const double2 pq = rowpq[r];
+        const double pi = pq.x, qi = pq.y;
+        double2 hn;
+        if (KIND == QN_BFGS) {
+          const double cx = pi * qj.x + qi * pj.x, cy = pi * qj.y + qi * pj.y;
+          hn.x = fma(c0, pi * pj.x, fma(c1, cx, hv[r].x));
+          hn.y = fma(c0, pi * pj.y, fma(c1, cy, hv[r].y));
+        } else {
+          hn.x = fma(c2, qi * qj.x, fma(c0, pi * pj.x, hv[r].x));
+          hn.y = fma(c2, qi * qj.y, fma(c0, pi * pj.y, hv[r].y));
+        }
+        ah[r] = fma(hn.x, yj.x, ah[r]);
+        ah[r] = fma(hn.y, yj.y, ah[r]);
+        aw[r] = fma(hn.x, gj.x, aw[r]);
+        aw[r] = fma(hn.y, gj.y, aw[r]);
+        st_stream(base + r * ld + col, hn);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < QN_R; ++r) {
+      const double v1 = warp_sum(ah[r]), v2 = warp_sum(aw[r]);
+      if (lane == 0) {
+        red[r][warp] = v1;
+        red[QN_R + r][warp] = v2;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * QN_R) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < QN_T / 32; ++w) v = v + red[threadIdx.x][w];
+      const int r = threadIdx.x % QN_R;
+      if (r0 + r < nrows) {
+        if (threadIdx.x < QN_R) a.h[row0 + r0 + r] = v;
+        else a.w[row0 + r0 + r] = v;
+      }
+      __threadfence();
+    }
+    __syncthreads();
+  }
+  if (a.ticket == nullptr) return;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(a.ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  lazy_epilogue_body<KIND>(a, &red[0][0]);
+  if (threadIdx.x == 0) *a.ticket = 0u;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(QN_T) qn_lazy_epilogue_kernel(QNLazyArgs a) {
+  if (a.st->done) return;
+  __shared__ double smem[3 * 32];
+  lazy_epilogue_body<KIND>(a, smem);
+}
+
+void qn_launch_lazy(Ctx* ctx, const QNLazyArgs& a) {
+  int64_t ntiles = (a.nrows + QN_R - 1) / QN_R;
+  int grid = (int)std::min<int64_t>(ntiles, (int64_t)ctx->num_sms);
+  if (a.kind == QN_BFGS) qn_lazy_kernel<QN_BFGS><<<grid, QN_T, 0, ctx->stream>>>(a);
+  else qn_lazy_kernel<QN_DFP><<<grid, QN_T, 0, ctx->stream>>>(a);
+  ctx->counters[0]++;
+}
+void qn_launch_lazy_epilogue(Ctx* ctx, const QNLazyArgs& a) {
+  if (a.kind == QN_BFGS) qn_lazy_epilogue_kernel<QN_BFGS><<<1, QN_T, 0, ctx->stream>>>(a);
+  else qn_lazy_epilogue_kernel<QN_DFP><<<1, QN_T, 0, ctx->stream>>>(a);
+  ctx->counters[0]++;
+}
+
+// apply the pending update only (no products): M <- M + rank2(ps, ph; pc*)
+template <int KIND>
+__global__ void __launch_bounds__(QN_T, 1) qn_flush_kernel(double* __restrict__ M, int64_t ld, int64_t nrows, int64_t row0, DevState* st,
+                                                          const double* __restrict__ p, const double* __restrict__ q) {
+  if (!st->pending) return;
+  const double c0 = st->pc0, c1 = st->pc1, c2 = st->pc2;
+  __shared__ double2 rowpq[QN_R];
+  const int64_t ntiles = (nrows + QN_R - 1) / QN_R;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r0 = tile * QN_R;
+    __syncthreads();
+    if (threadIdx.x < QN_R) rowpq[threadIdx.x] = make_double2(p[row0 + r0 + threadIdx.x], q[row0 + r0 + threadIdx.x]);
+    __syncthreads();
+    double* __restrict__ base = M + r0 * ld;
+    for (int col = 2 * threadIdx.x; col < (int)ld; col += QN_CHUNK) {
+      const double2 pj = *reinterpret_cast<const double2*>(p + col);
+      const double2 qj = *reinterpret_cast<const double2*>(q + col);
+#pragma unroll
+      for (int r = 0; r < QN_R; ++r) {
+        const double2 pq = rowpq[r];
+        const double pi = pq.x, qi = pq.y;
+        double2 hv = ld_stream(base + r * ld + col), hn;
+        if (KIND == QN_BFGS) {
+          const double cx = pi * qj.x + qi * pj.x, cy = pi * qj.y + qi * pj.y;
+          hn.x = fma(c0, pi * pj.x, fma(c1, cx, hv.x));
+          hn.y = fma(c0, pi * pj.y, fma(c1, cy, hv.y));
+        } else {
+          hn.x = fma(c2, qi * qj.x, fma(c0, pi * pj.x, hv.x));
+          hn.y = fma(c2, qi * qj.y, fma(c0, pi * pj.y, hv.y));
+        }
+        st_stream(base + r * ld + col, hn);
+      }
+    }
+  }
+}
+__global__ void qn_clear_pending_kernel(DevState* st) {
+  st->pending = 0;
+  st->pc0 = st->pc1 = st->pc2 = 0.0;
+}
+void qn_launch_flush(Ctx* ctx, int kind, double* M, int64_t ld, int64_t nrows, int64_t row0, DevState* st, const double* ps,
+                     const double* ph) {
+  int64_t ntiles = (nrows + QN_R - 1) / QN_R;
+  int grid = (int)std::min<int64_t>(ntiles, (int64_t)ctx->num_sms);
+  if (kind == QN_BFGS) qn_flush_kernel<QN_BFGS><<<grid, QN_T, 0, ctx->stream>>>(M, ld, nrows, row0, st, ps, ph);
+  else qn_flush_kernel<QN_DFP><<<grid, QN_T, 0, ctx->stream>>>(M, ld, nrows, row0, st, ps, ph);
+  qn_clear_pending_kernel<<<1, 1, 0, ctx->stream>>>(st);
+  ctx->counters[0] += 2;
+}
+
 void qn_launch_update(Ctx* ctx, int kind, double* H, int64_t ld, int64_t nrows, int64_t row0, const DevState* st,
                       const double* p, const double* q, const double* r, const double* g, double* u_out, int variant) {
   (void)variant;
