@@ -160,6 +160,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--n", type=int, default=N_DIM, help="problem dimension (the benchmark line is only valid at 16384)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL all-gathers instead of the fused peer-memory exchange")
     ap.add_argument("--schedule", default="lazy", choices=["lazy", "eager"],
                     help="lazy: one read-modify-write of H per iteration (2 n^2 8 B); eager: h = H y then fused update (3 n^2 8 B)")
     args = ap.parse_args()
@@ -183,6 +184,8 @@ def main():
         uid = [osb.Context.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx = osb.Context(local_rank, rank, world, uid[0])
+        if not args.no_p2p:
+            ctx.connect_peers()  # CUDA IPC: fused NVLink all-gather inside the lazy kernel
     else:
         ctx = osb.Context(local_rank)
     osb.set_default_context(ctx)
@@ -310,7 +313,9 @@ def main():
                            "max_iter_line_search": MAX_LS, "engine": "device-resident control",
                            "schedule": "lazy: 1 RMW pass of H per iteration (2 n^2 8 B)" if lazy else "eager: gemv + fused update (3 n^2 8 B)",
                            "l2": "inputs larger than L2 (H = %.2f GiB per GPU, streamed every step)" % (rows_local * n * 8 / 2 ** 30),
-                           "parallelism": "row-block sharded H over %d GPU(s), NCCL all-gather of h and u" % world},
+                           "parallelism": "row-block sharded H over %d GPU(s); exchange: %s" % (
+                               world, "none" if world == 1 else ("NCCL all-gather of the h / w slices" if (args.no_p2p or not lazy)
+                                                                 else "peer-memory all-gather fused into the lazy kernel (NVLink stores + flags)"))},
                 "roofline": roofline, "cpu_baseline": cb_line, "e2e": e2e,
                 "gpu_launches": int(c1["launches"] - c0["launches"]),
                 "ls_trials_per_step": (c1["ls_trials"] - c0["ls_trials"]) / args.steps,

@@ -82,6 +82,12 @@ int osb_ctx_create(int device, osb_ctx** out);
  * by osb_nccl_unique_id() on rank 0 and broadcast by the caller (torch.distributed, MPI, ...). */
 int osb_nccl_unique_id(void* out128);
 int osb_ctx_create_dist(int device, int rank, int world, const void* nccl_unique_id, osb_ctx** out);
+/* Peer-memory exchange (optional, world > 1): every rank exports the 64-byte CUDA IPC handle of its exchange
+ * region, the caller all-gathers the handles (rank order, 64 bytes each) and every rank connects.  The
+ * lazy quasi-Newton pass then all-gathers its row sums with NVLink peer stores fused into the kernel
+ * instead of NCCL calls. */
+int osb_ctx_ipc_handle(osb_ctx* ctx, void* out64);
+int osb_ctx_ipc_connect(osb_ctx* ctx, const void* handles_world_x_64);
 void osb_ctx_destroy(osb_ctx* ctx);
 int osb_ctx_rank(const osb_ctx* ctx);
 int osb_ctx_world(const osb_ctx* ctx);
@@ -180,6 +186,10 @@ int osb_minimize(osb_solver* s, osb_linesearch* ls, osb_objective* obj, int64_t 
  *   "engine"        0 = auto (device-resident control when solver/line search/objective allow it),
  *                   1 = host-driven control only, 2 = device-resident only (error if unsupported)
  *   "record_trace"  1 = keep per-iteration (f, t, s_norm, y_norm) for osb_solver_trace
+ *   "qn_schedule"   0 = eager (h = H y, then fused update: 3 n^2 8 B per iteration),
+ *                   1 = lazy (one read-modify-write per iteration: 2 n^2 8 B; BFGS/DFP, device engine)
+ *   "use_p2p"       lazy schedule on an IPC-connected multi-GPU context: 1 = fused peer-memory all-gather (default), 0 = NCCL
+ *   "head_kernel"   device engine head: 0 = 8-CTA cluster (default), 1 = single CTA + shared memory, 2 = generic
  *   "qn_kernel"     dense quasi-Newton kernel variant: 0 = default, see DESIGN.md
  *   "profile_kernels" 1 = bracket the two H passes with CUDA events (osb_solver_kernel_timing) */
 int osb_solver_set_option(osb_solver* s, const char* name, int64_t value);

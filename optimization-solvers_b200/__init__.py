@@ -53,6 +53,7 @@ def lib():
             "osb_last_error_string": (C.c_char_p, []), "osb_version": (C.c_char_p, []),
             "osb_ctx_create": (ci, [ci, pp]), "osb_nccl_unique_id": (ci, [_vp]),
             "osb_ctx_create_dist": (ci, [ci, ci, ci, _vp, pp]), "osb_ctx_destroy": (None, [_vp]),
+            "osb_ctx_ipc_handle": (ci, [_vp, _vp]), "osb_ctx_ipc_connect": (ci, [_vp, _vp]),
             "osb_ctx_rank": (ci, [_vp]), "osb_ctx_world": (ci, [_vp]), "osb_ctx_synchronize": (ci, [_vp]),
             "osb_ctx_stream": (_vp, [_vp]), "osb_ctx_counters": (ci, [_vp, C.POINTER(i64)]),
             "osb_objective_create_dense_quadratic": (ci, [_vp, i64, _dp, _dp, pp]),
@@ -284,6 +285,26 @@ class Context:
         buf = C.create_string_buffer(128)
         _check(lib().osb_nccl_unique_id(buf))
         return bytes(buf.raw)
+
+    def ipc_handle(self):
+        buf = C.create_string_buffer(64)
+        _check(lib().osb_ctx_ipc_handle(self.handle, buf))
+        return bytes(buf.raw)
+
+    def ipc_connect(self, handles):
+        """handles: list of the 64-byte IPC handles of all ranks, in rank order."""
+        blob = b"".join(handles)
+        buf = C.create_string_buffer(blob, len(blob))
+        _check(lib().osb_ctx_ipc_connect(self.handle, buf))
+
+    def connect_peers(self):
+        """All-gather the IPC handles over torch.distributed and connect (fused NVLink all-gather)."""
+        import torch.distributed as dist
+        mine = self.ipc_handle()
+        allh = [None] * dist.get_world_size()
+        dist.all_gather_object(allh, mine)
+        self.ipc_connect(allh)
+        dist.barrier()
 
     def rank(self):
         return lib().osb_ctx_rank(self.handle)

@@ -8,6 +8,9 @@ const std::string& get_last_error();
 void nccl_unique_id(void* out128);
 void ctx_init_dist(Ctx* ctx, int rank, int world, const void* uid);
 void ctx_destroy_dist(Ctx* ctx);
+void ctx_ipc_export(Ctx* ctx, void* out64);
+void ctx_ipc_connect(Ctx* ctx, const void* handles);
+void ctx_ipc_close(Ctx* ctx);
 }  // namespace osb
 
 using namespace osb;
@@ -64,9 +67,22 @@ int osb_ctx_create_dist(int device, int rank, int world, const void* uid, osb_ct
   return OSB_OK;
   OSB_CATCH
 }
+int osb_ctx_ipc_handle(osb_ctx* ctx, void* out64) {
+  OSB_TRY
+  ctx_ipc_export(C(ctx), out64);
+  return OSB_OK;
+  OSB_CATCH
+}
+int osb_ctx_ipc_connect(osb_ctx* ctx, const void* handles) {
+  OSB_TRY
+  ctx_ipc_connect(C(ctx), handles);
+  return OSB_OK;
+  OSB_CATCH
+}
 void osb_ctx_destroy(osb_ctx* ctx) {
   if (!ctx) return;
   try {
+    ctx_ipc_close(C(ctx));
     ctx_destroy_dist(C(ctx));
   } catch (...) {
   }
@@ -344,6 +360,7 @@ int osb_solver_set_option(osb_solver* s, const char* name, int64_t value) {
   else if (nm == "record_trace") S(s)->record_trace = (int)value;
   else if (nm == "qn_kernel") S(s)->qn_variant = (int)value;
   else if (nm == "qn_schedule") S(s)->qn_schedule = (int)value;
+  else if (nm == "use_p2p") S(s)->use_p2p = (int)value;
   else if (nm == "head_kernel") S(s)->head_variant = (int)value;
   else if (nm == "profile_kernels") S(s)->profile_kernels = (int)value;
   else throw Error(OSB_ERROR_INPUT_PARAMS, "unknown option " + nm);

@@ -77,6 +77,56 @@ void Ctx::all_gather_inplace(double* buf, int64_t count) {
   counters[4]++;
 }
 
+// ---- peer-memory exchange region (CUDA IPC) -----------------------------------------------------
+static size_t xchg_bytes(int world) { return sizeof(double) * 4 * (size_t)XCHG_LD + sizeof(unsigned long long) * (size_t)(world + 8); }
+
+void ctx_ipc_export(Ctx* ctx, void* out64) {
+  ctx->use();
+  if (!ctx->xchg) {
+    OSB_CUDA(cudaMalloc(&ctx->xchg, xchg_bytes(ctx->world)));
+    OSB_CUDA(cudaMemset(ctx->xchg, 0, xchg_bytes(ctx->world)));
+    OSB_CUDA(cudaMalloc(&ctx->d_seq, sizeof(unsigned long long)));
+    OSB_CUDA(cudaMemset(ctx->d_seq, 0, sizeof(unsigned long long)));
+  }
+  cudaIpcMemHandle_t h;
+  OSB_CUDA(cudaIpcGetMemHandle(&h, ctx->xchg));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  std::memcpy(out64, &h, 64);
+}
+
+void ctx_ipc_connect(Ctx* ctx, const void* handles) {
+  ctx->use();
+  OSB_REQUIRE(ctx->xchg != nullptr, OSB_ERROR_INPUT_PARAMS, "call osb_ctx_ipc_handle first");
+  std::vector<double*> ptrs(ctx->world, nullptr);
+  for (int r = 0; r < ctx->world; ++r) {
+    if (r == ctx->rank) {
+      ptrs[r] = ctx->xchg;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, (const char*)handles + 64 * r, 64);
+    void* p = nullptr;
+    OSB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->peer_opened.push_back(p);
+    ptrs[r] = (double*)p;
+  }
+  OSB_CUDA(cudaMalloc(&ctx->d_peers, sizeof(double*) * ctx->world));
+  OSB_CUDA(cudaMemcpy(ctx->d_peers, ptrs.data(), sizeof(double*) * ctx->world, cudaMemcpyHostToDevice));
+  ctx->p2p_ready = true;
+}
+
+void ctx_ipc_close(Ctx* ctx) {
+  for (void* p : ctx->peer_opened) cudaIpcCloseMemHandle(p);
+  ctx->peer_opened.clear();
+  if (ctx->d_peers) cudaFree(ctx->d_peers);
+  if (ctx->xchg) cudaFree(ctx->xchg);
+  if (ctx->d_seq) cudaFree(ctx->d_seq);
+  ctx->d_peers = nullptr;
+  ctx->xchg = nullptr;
+  ctx->d_seq = nullptr;
+  ctx->p2p_ready = false;
+}
+
 // in-place sum over ranks (sample-sharded logistic regression: loss, gradient, Hessian)
 void ctx_all_reduce_sum(Ctx* ctx, double* buf, int64_t count) {
   if (ctx->world <= 1) return;

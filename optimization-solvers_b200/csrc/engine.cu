@@ -289,14 +289,17 @@ void Solver::qn_after_step() {
   }
   if (qn_schedule == 1 && (qn_kind == QN_BFGS || qn_kind == QN_DFP)) {
     // ONE read-modify-write per iteration (2 n^2 8 B): pending update + h = H y + w = H g, epilogue forms u
+    const bool p2p = ctx->world > 1 && ctx->p2p_ready && ld <= XCHG_LD && use_p2p;
     QNLazyArgs a{H.p, ld, nrows, row0, n, d_state, ps.p, ph.p, y.p, g.p, s.p, h.p, wv.p, u.p, ps.p, ph.p,
-                 ctx->world == 1 ? ctx->gemv_ticket : nullptr, qn_kind};
+                 (ctx->world == 1 || p2p) ? ctx->gemv_ticket : nullptr, qn_kind,
+                 p2p ? ctx->d_peers : nullptr, ctx->d_seq, ctx->world, ctx->rank};
     prof_mark();
     prof_mark();
     prof_mark();
     qn_launch_lazy(ctx, a);
     prof_mark();
-    if (ctx->world > 1) {
+    if (p2p) ctx->counters[4]++;  // one fused exchange
+    if (ctx->world > 1 && !p2p) {
       ctx->all_gather_inplace(h.p, nrows);
       ctx->all_gather_inplace(wv.p, nrows);
       qn_launch_lazy_epilogue(ctx, a);

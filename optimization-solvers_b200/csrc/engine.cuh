@@ -45,6 +45,13 @@ struct Ctx {
   int num_sms = 148;
   int rank = 0, world = 1;
   void* nccl_comm = nullptr;
+  // peer-memory exchange region (CUDA IPC): the fused all-gather of the lazy quasi-Newton pass writes
+  // its row sums straight into every peer's region over NVLink and synchronises with flags
+  double* xchg = nullptr;            // local region: 4 vectors of XCHG_LD doubles, then `world` 64-bit flags
+  double** d_peers = nullptr;        // device array[world] of region base pointers (own entry = xchg)
+  unsigned long long* d_seq = nullptr;  // exchange sequence number (device)
+  bool p2p_ready = false;
+  std::vector<void*> peer_opened;
   // reduction scratch
   double* red_partials = nullptr;
   unsigned int* red_ticket = nullptr;
@@ -161,6 +168,7 @@ void qn_launch_update(Ctx* ctx, int kind, double* H, int64_t ld, int64_t nrows, 
                       const double* p, const double* q, const double* r, const double* g, double* u_out, int variant);
 // lazy (2-pass-less) schedule: ONE read-modify-write per iteration — applies the pending update while
 // computing h = H y and w = H g with the updated rows; the epilogue forms the new pending update and u.
+constexpr int64_t XCHG_LD = 65536;  // capacity (doubles) of one exchanged vector
 struct QNLazyArgs {
   double* M;            // stored matrix (local row block)
   int64_t ld, nrows, row0, n;
@@ -177,6 +185,10 @@ struct QNLazyArgs {
   double* ph_out;       // epilogue: ph <- h
   unsigned int* ticket; // null => no fused epilogue (sharded: separate launch after the all-gather)
   int kind;
+  // fused peer-memory all-gather (world > 1 with an IPC-connected context); null => NCCL path
+  double* const* peers;
+  unsigned long long* seq;
+  int world, rank;
 };
 void qn_launch_lazy(Ctx* ctx, const QNLazyArgs& a);
 void qn_launch_lazy_epilogue(Ctx* ctx, const QNLazyArgs& a);
@@ -219,6 +231,7 @@ struct Solver {
   DBuf wv, ps, ph;        // lazy schedule: w = H g, pending p and q
   int qn_schedule = 0;    // 0 = eager (h = H y, then fused update: 3 n^2 8 B), 1 = lazy (one RMW: 2 n^2 8 B)
   bool lazy_used = false;
+  int use_p2p = 1;        // lazy schedule, world > 1: fused peer-memory all-gather when the context is IPC-connected
   void flush_pending();
   // Newton family
   DBuf hess, chol;

@@ -391,9 +391,9 @@ constexpr int HC_T = 512;
 
 template <int K>
 __device__ __forceinline__ void cluster_reduce(cg::cluster_group& cluster, double (&acc)[K], const RedOps<K>& ops, double* smem_cta,
-                                               double* part /* 2 x 8 */, double* res /* 8 */, int& phase) {
+                                               double* part /* 2 x 16 */, double* res /* 16 */, int& phase) {
   cta_reduce<K>(acc, ops, smem_cta);
-  double* mine = part + (phase & 1) * 8;
+  double* mine = part + (phase & 1) * 16;
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int k = 0; k < K; ++k) mine[k] = acc[k];
@@ -427,11 +427,15 @@ qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol,
   constexpr int KPT = EPT / BS;
   constexpr int NT = HC_CTAS * HC_T;
   cg::cluster_group cluster = cg::this_cluster();
-  __shared__ double smem_cta[4 * 32];
-  __shared__ double part[16];
-  __shared__ double res[8];
+  constexpr int SPEC = 4;  // backtracking trials evaluated per reduction round (speculatively)
+  __shared__ double smem_cta[3 * SPEC * 32];
+  __shared__ double part[32];
+  __shared__ double res[16];
   const RedOps<3> sum3{{RED_SUM, RED_SUM, RED_SUM}};
   const RedOps<4> sum4{{RED_SUM, RED_SUM, RED_SUM, RED_SUM}};
+  RedOps<3 * SPEC> sumS;
+#pragma unroll
+  for (int q = 0; q < 3 * SPEC; ++q) sumS.op[q] = RED_SUM;
   if (st->done) return;
   const int gt = (int)cluster.block_rank() * HC_T + threadIdx.x;
   const bool leader = gt == 0;
@@ -509,8 +513,53 @@ qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol,
   m.begin(p, f0, gd0, max_ls, tmaxc);
   int evals = 0;
   while (!m.done) {
-    const double t = m.request(p);
     const bool proj = m.wants_projection(p);
+    if (p.kind == LS_BACKTRACKING || p.kind == LS_BACKTRACKING_B) {
+      // Backtracking visits t, t*beta, t*beta^2, ... whatever the outcome of a trial (backtracking.rs:37-55
+      // multiplies by beta on both the NaN and the rejection branch), so SPEC consecutive trials are
+      // evaluated in one sweep and one cluster reduction, then fed to the automaton in order.  The
+      // objective has no side effects: the extra evaluations change nothing but the latency.
+      double ts[SPEC];
+      ts[0] = m.request(p);
+#pragma unroll
+      for (int q = 1; q < SPEC; ++q) ts[q] = ts[q - 1] * p.beta;
+      double aS[3 * SPEC];
+#pragma unroll
+      for (int q = 0; q < 3 * SPEC; ++q) aS[q] = 0.0;
+#pragma unroll
+      for (int k = 0; k < KPT; ++k) {
+        const int b = gt + k * NT;
+        if (b < nb) {
+#pragma unroll
+          for (int q = 0; q < SPEC; ++q) {
+            double xb[BS], gb[BS];
+#pragma unroll
+            for (int j = 0; j < BS; ++j) {
+              const double td = ts[q] * dreg[k][j];
+              double v = xreg[k][j] + td;
+              if (proj) v = fmin(fmax(v, ls_lb[b * BS + j]), ls_ub[b * BS + j]);  // backtracking_b.rs:65-67
+              xb[j] = v;
+              const double df = v - xreg[k][j];
+              aS[3 * q + 2] = aS[3 * q + 2] + df * df;
+            }
+            const double fb = fn.block((int64_t)b * BS, xb, gb);
+#pragma unroll
+            for (int j = 0; j < BS; ++j) aS[3 * q + 1] = aS[3 * q + 1] + gb[j] * dreg[k][j];
+            aS[3 * q] = aS[3 * q] + fb;
+          }
+        }
+      }
+      cluster_reduce<3 * SPEC>(cluster, aS, sumS, smem_cta, part, res, phase);
+#pragma unroll
+      for (int q = 0; q < SPEC; ++q) {
+        if (!m.done && m.request(p) == ts[q]) {
+          m.feed(p, aS[3 * q], aS[3 * q + 1], aS[3 * q + 2]);
+          ++evals;
+        }
+      }
+      continue;
+    }
+    const double t = m.request(p);
     double a3[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int k = 0; k < KPT; ++k) {

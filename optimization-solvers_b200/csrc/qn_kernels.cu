@@ -270,6 +270,15 @@ qn_update_kernel(double* __restrict__ H, int64_t ld, int64_t nrows, int64_t row0
   }
 }
 
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // ---- lazy schedule -------------------------------------------------------------------------
 // Stored matrix M = H_k minus the update of iteration k-1 (pending).  One read-modify-write:
 //     M_ij <- M_ij + pc0 p_i p_j + pc1 (p_i q_j + q_i p_j) + pc2 q_i q_j      (now M = H_k exactly)
@@ -344,6 +353,8 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_kernel(QNLazyArgs a) {
   const double* __restrict__ gv = a.g;
   const int64_t ntiles = (nrows + QN_R - 1) / QN_R;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned long long seq = a.peers != nullptr ? *a.seq + 1ULL : 0ULL;  // this exchange's sequence number
+  const int par = (int)(seq & 1ULL);
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t r0 = tile * QN_R;
     double ah[QN_R], aw[QN_R];
@@ -395,10 +406,18 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_kernel(QNLazyArgs a) {
       for (int w = 0; w < QN_T / 32; ++w) v = v + red[threadIdx.x][w];
       const int r = threadIdx.x % QN_R;
       if (r0 + r < nrows) {
-        if (threadIdx.x < QN_R) a.h[row0 + r0 + r] = v;
-        else a.w[row0 + r0 + r] = v;
+        if (a.peers != nullptr) {
+          // fused all-gather: the row sum goes straight into every rank's exchange region (NVLink peer
+          // stores); `par` double-buffers the region across iterations
+          const int64_t off = (int64_t)(par * 2 + (threadIdx.x < QN_R ? 0 : 1)) * XCHG_LD + row0 + r0 + r;
+          for (int pr = 0; pr < a.world; ++pr) a.peers[pr][off] = v;
+        } else {
+          if (threadIdx.x < QN_R) a.h[row0 + r0 + r] = v;
+          else a.w[row0 + r0 + r] = v;
+        }
       }
-      __threadfence();
+      if (a.peers != nullptr) __threadfence_system();
+      else __threadfence();
     }
     __syncthreads();
   }
@@ -411,6 +430,28 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_kernel(QNLazyArgs a) {
   __syncthreads();
   if (!is_last) return;
   __threadfence();
+  if (a.peers != nullptr) {
+    // every local CTA has pushed its rows to all peers: publish "rank `a.rank` reached `seq`" on every
+    // rank, then wait until all ranks have published the same sequence number here
+    __threadfence_system();
+    unsigned long long* myflags = reinterpret_cast<unsigned long long*>(a.peers[a.rank] + 4 * XCHG_LD);
+    if (threadIdx.x < a.world) {
+      unsigned long long* f = reinterpret_cast<unsigned long long*>(a.peers[threadIdx.x] + 4 * XCHG_LD) + a.rank;
+      st_release_sys(f, seq);
+      while (ld_acquire_sys(myflags + threadIdx.x) < seq) {
+      }
+    }
+    __syncthreads();
+    QNLazyArgs b = a;
+    b.h = a.peers[a.rank] + (int64_t)(par * 2 + 0) * XCHG_LD;
+    b.w = a.peers[a.rank] + (int64_t)(par * 2 + 1) * XCHG_LD;
+    lazy_epilogue_body<KIND>(b, &red[0][0]);
+    if (threadIdx.x == 0) {
+      *a.seq = seq;
+      *a.ticket = 0u;
+    }
+    return;
+  }
   lazy_epilogue_body<KIND>(a, &red[0][0]);
   if (threadIdx.x == 0) *a.ticket = 0u;
 }

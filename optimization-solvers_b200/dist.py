@@ -52,4 +52,6 @@ def make_context(osb, backend_init=True):
     if backend_init and not dist.is_initialized():
         dist.init_process_group("nccl")
     uid = broadcast_bytes(osb.Context.nccl_unique_id() if rank == 0 else None)
-    return osb.Context(local_rank, rank, world, uid)
+    ctx = osb.Context(local_rank, rank, world, uid)
+    ctx.connect_peers()
+    return ctx

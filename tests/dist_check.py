@@ -26,13 +26,18 @@ def main():
     uid = [osb.Context.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     ctx = osb.Context(lr, rank, world, uid[0])
+    ctx.connect_peers()  # CUDA IPC exchange regions: fused NVLink all-gather in the lazy pass
     solo = osb.Context(lr)
     ok = True
-    for kind, n, iters in (("BFGS", 2048, 40), ("DFP", 1024, 25), ("BFGS", 16384, 12)):
+    # (kind, n, iterations, schedule 0 = eager / 1 = lazy, use_p2p)
+    for kind, n, iters, sched, p2p in (("BFGS", 2048, 40, 0, 0), ("DFP", 1024, 25, 0, 0), ("BFGS", 16384, 12, 0, 0),
+                                       ("BFGS", 2048, 40, 1, 0), ("BFGS", 2048, 40, 1, 1), ("DFP", 1024, 25, 1, 1),
+                                       ("BFGS", 16384, 12, 1, 1)):
         x0 = rosen_x0(n, 5)
         res = []
         for c in (ctx, solo):
-            s = getattr(osb, kind)(1e-8, x0, ctx=c).set_option("engine", 2)
+            s = getattr(osb, kind)(1e-8, x0, ctx=c).set_option("engine", 2).set_option("qn_schedule", sched)
+            s.set_option("use_p2p", p2p)
             try:
                 s.minimize(osb.BackTracking(1e-4, 0.5), osb.ExtendedRosenbrock(n, ctx=c), iters, 20)
             except osb.MaxIterReached:
@@ -43,7 +48,8 @@ def main():
         rows = slice(rank * n // world, (rank + 1) * n // world)
         same = (res[0][0] == res[1][0] and np.array_equal(res[0][1], res[1][1]) and res[0][2] == res[1][2]
                 and np.array_equal(res[0][3][rows], res[1][3][rows]))
-        print("rank %d %s n=%d k=%d bit-identical to single GPU: %s" % (rank, kind, n, res[0][0], same), flush=True)
+        print("rank %d %s n=%d k=%d schedule=%d p2p=%d bit-identical to single GPU: %s"
+              % (rank, kind, n, res[0][0], sched, p2p, same), flush=True)
         ok &= bool(same)
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
