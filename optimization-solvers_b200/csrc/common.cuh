@@ -66,6 +66,27 @@ __device__ __forceinline__ double2 ld_stream_nc(const double* p) {  // read-only
 __device__ __forceinline__ void st_stream(double* p, double2 v) {
   asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
+// L2 evict-first policy for the H stream: 4 GB pass through L2 every iteration and would otherwise evict
+// what is re-used across launches (the O(n) vectors and, notably, the instruction lines of the small
+// head kernel, whose cold start is bound by instruction fetch).
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ double2 ld_stream_ef(const double* p, unsigned long long pol) {
+  double2 v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ double2 ld_stream_nc_ef(const double* p, unsigned long long pol) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_stream_ef(double* p, double2 v, unsigned long long pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, o);

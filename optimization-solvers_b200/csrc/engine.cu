@@ -536,7 +536,7 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
   for (int64_t it = 0; it < max_iter && !stop; ++it) {
     qn_device_launch_head(ctx, obj->functor_kind(), obj->functor_ptr(0), obj->functor_ptr(1), bounded, d_ls, n, tol, max_ls,
                           d_state, x.p, g.p, d.p, xt.p, gt.p, s.p, y.p, u.p, bounded ? lb.p : nullptr, bounded ? ub.p : nullptr,
-                          ls_bounded ? ls->lb.p : nullptr, ls_bounded ? ls->ub.p : nullptr, head_variant);
+                          ls_bounded ? ls->lb.p : nullptr, ls_bounded ? ls->ub.p : nullptr, head_variant, ls->p.kind);
     qn_after_step();
     if ((it + 1) % POLL == 0) {
       if (pending[slot]) {  // bound the run-ahead: wait for the older snapshot of this slot

@@ -299,7 +299,7 @@ void state_finish_sy(Ctx*, DevState* st, double tol);
 void qn_device_launch_head(Ctx* ctx, int functor_kind, const double* fn_a, const double* fn_b, bool bounded,
                            LSParams* d_ls, int64_t n, double tol, int64_t max_ls, DevState* st, double* x, double* g,
                            double* d, double* xt, double* gt, double* s, double* y, const double* u, const double* lb,
-                           const double* ub, const double* ls_lb, const double* ls_ub, int head_variant);
+                           const double* ub, const double* ls_lb, const double* ls_ub, int head_variant, int ls_kind);
 
 // batched (batched.cu)
 int batched_bfgs_rosenbrock(Ctx* ctx, int64_t n, int64_t np, const double* x0_host, bool generated, int64_t problem0,

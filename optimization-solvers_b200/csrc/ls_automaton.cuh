@@ -58,6 +58,9 @@ struct LSMachine {
   }
 
   // `tmax_candidate`: MoreThuenteB's feasible step bound (morethuente_b.rs:185-197), ignored otherwise.
+  // FK >= 0 fixes the line-search kind at compile time (device head kernels are specialised per kind so
+  // that each carries only its own automaton: a cold, large kernel body is bound by instruction fetch)
+  template <int FK = -1>
   HD void begin(LSParams& p, double f0_, double gd0_, int64_t max_iter_, double tmax_candidate) {
     f0 = f0_;
     gd0 = gd0_;
@@ -69,7 +72,7 @@ struct LSMachine {
     interval_converged = false;
     phase = MT_EVAL_T;
     f_max = f0_;
-    switch (p.kind) {
+    switch (FK >= 0 ? FK : p.kind) {
       case LS_NOSEARCH:
         finish(1.0, false);
         return;
@@ -111,7 +114,8 @@ struct LSMachine {
     return t;
   }
   // BackTrackingB evaluates the objective at the PROJECTED trial (backtracking_b.rs:65-67)
-  HD bool wants_projection(const LSParams& p) const { return p.kind == LS_BACKTRACKING_B; }
+  template <int FK = -1>
+  HD bool wants_projection(const LSParams& p) const { return (FK >= 0 ? FK : p.kind) == LS_BACKTRACKING_B; }
 
   static HD double cubic_minimizer(double ta, double tb, double f_ta, double f_tb, double g_ta, double g_tb) {
     double s = 3. * (f_tb - f_ta) / (tb - ta);  // morethuente.rs:103
@@ -149,18 +153,20 @@ struct LSMachine {
     if (i >= max_iter) finish(t, false);  // :295-296
   }
 
+  template <int FK = -1>
   HD void feed(LSParams& p, double f_t, double gd_t, double dn) {
-    switch (p.kind) {
+    const int kind = FK >= 0 ? FK : p.kind;
+    switch (kind) {
       case LS_BACKTRACKING:
       case LS_BACKTRACKING_B: {
         if (is_bad(f_t)) {  // backtracking.rs:37-41: shrink, do NOT count the iteration
           t *= p.beta;
           return;
         }
-        bool ok = (p.kind == LS_BACKTRACKING) ? (f_t - f0 <= p.c1 * t * gd0)        // line_search/mod.rs:35
+        bool ok = (kind == LS_BACKTRACKING) ? (f_t - f0 <= p.c1 * t * gd0)        // line_search/mod.rs:35
                                               : (f_t - f0 <= (-p.c1 / t) * dn);     // backtracking_b.rs:33
         if (ok) {
-          finish(t, p.kind == LS_BACKTRACKING);
+          finish(t, kind == LS_BACKTRACKING);
           return;
         }
         t *= p.beta;

@@ -389,53 +389,100 @@ namespace cg = cooperative_groups;
 constexpr int HC_CTAS = 8;
 constexpr int HC_T = 512;
 
-template <int K>
-__device__ __forceinline__ void cluster_reduce(cg::cluster_group& cluster, double (&acc)[K], const RedOps<K>& ops, double* smem_cta,
-                                               double* part /* 2 x 16 */, double* res /* 16 */, int& phase) {
-  cta_reduce<K>(acc, ops, smem_cta);
-  double* mine = part + (phase & 1) * 16;
+// Sum-reductions with a run-time value count and ROLLED loops: the head kernel is launched cold on 8 SMs
+// every iteration, its cost is instruction fetch, so its body is kept small and loopy on purpose (ncu:
+// the fully unrolled variant spent 169k cycles to retire ~2k instructions per scheduler, stalled on
+// "no instruction").
+__device__ __noinline__ void cta_sum_rt(double* acc, int K, double* smem /* K x 32 */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  __syncthreads();
+#pragma unroll 1
+  for (int k = 0; k < K; ++k) {
+    const double v = warp_sum(acc[k]);
+    if (lane == 0) smem[k * 32 + warp] = v;
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int k = 0; k < K; ++k) {
+    double v = 0.0;
+#pragma unroll 1
+    for (int w = 0; w < nwarp; ++w) v = v + smem[k * 32 + w];
+    acc[k] = v;
+  }
+}
+
+__device__ __noinline__ void cluster_sum_rt(double* acc, int K, double* smem_cta, double* part /* 2 x 16 */, double* res /* 16 */,
+                                            double* gat /* 16 x HC_CTAS */, int* phase) {
+  cg::cluster_group cluster = cg::this_cluster();
+  cta_sum_rt(acc, K, smem_cta);
+  double* mine = part + (*phase & 1) * 16;
   if (threadIdx.x == 0) {
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < K; ++k) mine[k] = acc[k];
   }
   cluster.sync();
-  if (threadIdx.x == 0) {
-    double v[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) v[k] = red_identity(ops.op[k]);
-    for (int r = 0; r < HC_CTAS; ++r) {
-      const double* remote = cluster.map_shared_rank(mine, r);
-#pragma unroll
-      for (int k = 0; k < K; ++k) v[k] = red_combine(ops.op[k], v[k], remote[k]);
-    }
-#pragma unroll
-    for (int k = 0; k < K; ++k) res[k] = v[k];
+  // K * HC_CTAS remote values are fetched by as many threads in parallel (one DSMEM round trip in total),
+  // then folded in rank order from local shared memory => identical bits in every CTA
+  if (threadIdx.x < K * HC_CTAS) {
+    const int k = threadIdx.x / HC_CTAS, r = threadIdx.x % HC_CTAS;
+    const double* remote = cluster.map_shared_rank(mine, r);
+    gat[k * HC_CTAS + r] = remote[k];
   }
   __syncthreads();
-#pragma unroll
+  if (threadIdx.x < K) {
+    double v = 0.0;
+#pragma unroll 1
+    for (int r = 0; r < HC_CTAS; ++r) v = v + gat[threadIdx.x * HC_CTAS + r];
+    res[threadIdx.x] = v;
+  }
+  __syncthreads();
+#pragma unroll 1
   for (int k = 0; k < K; ++k) acc[k] = res[k];
-  phase += 1;
+  *phase += 1;
 }
 
-template <class Fn, bool BOUNDED, int EPT>
+__device__ __noinline__ double cluster_min_rt(double v, double* smem_cta, double* part, double* res, double* gat, int* phase) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  v = warp_min(v);
+  if (lane == 0) smem_cta[warp] = v;
+  __syncthreads();
+  double m = INFINITY;
+#pragma unroll 1
+  for (int w = 0; w < nwarp; ++w) m = fmin(m, smem_cta[w]);
+  double* mine = part + (*phase & 1) * 16;
+  if (threadIdx.x == 0) mine[0] = m;
+  cluster.sync();
+  if (threadIdx.x < HC_CTAS) gat[threadIdx.x] = cluster.map_shared_rank(mine, threadIdx.x)[0];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double r = INFINITY;
+#pragma unroll 1
+    for (int q = 0; q < HC_CTAS; ++q) r = fmin(r, gat[q]);
+    res[0] = r;
+  }
+  __syncthreads();
+  *phase += 1;
+  return res[0];
+}
+
+template <class Fn, bool BOUNDED, int EPT, int LSK>
 __global__ void __cluster_dims__(HC_CTAS, 1, 1) __launch_bounds__(HC_T, 1)
 qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol, int64_t max_ls, DevState* __restrict__ st,
                        double* __restrict__ x, double* __restrict__ g, double* __restrict__ s, double* __restrict__ y,
                        const double* __restrict__ u, const double* __restrict__ lb, const double* __restrict__ ub,
-                       const double* __restrict__ ls_lb, const double* __restrict__ ls_ub) {
+                       const double* __restrict__ ls_lb, const double* __restrict__ ls_ub, int spec_on) {
   constexpr int BS = Fn::BS;
   constexpr int KPT = EPT / BS;
   constexpr int NT = HC_CTAS * HC_T;
-  cg::cluster_group cluster = cg::this_cluster();
   constexpr int SPEC = 4;  // backtracking trials evaluated per reduction round (speculatively)
+  constexpr bool IS_BT = LSK == LS_BACKTRACKING || LSK == LS_BACKTRACKING_B;
+  cg::cluster_group cluster = cg::this_cluster();
   __shared__ double smem_cta[3 * SPEC * 32];
   __shared__ double part[32];
   __shared__ double res[16];
-  const RedOps<3> sum3{{RED_SUM, RED_SUM, RED_SUM}};
-  const RedOps<4> sum4{{RED_SUM, RED_SUM, RED_SUM, RED_SUM}};
-  RedOps<3 * SPEC> sumS;
-#pragma unroll
-  for (int q = 0; q < 3 * SPEC; ++q) sumS.op[q] = RED_SUM;
+  __shared__ double gat[16 * HC_CTAS];
   if (st->done) return;
   const int gt = (int)cluster.block_rank() * HC_T + threadIdx.x;
   const bool leader = gt == 0;
@@ -461,9 +508,10 @@ qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol,
   }
   int phase = 0;
   double xreg[KPT][BS], dreg[KPT][BS], greg[KPT][BS];
-  const bool need_tmax = lsp->kind == LS_MORETHUENTE_B;
+  constexpr bool need_tmax = LSK == LS_MORETHUENTE_B;
   double tm = INFINITY;
-  double acc[3] = {0.0, 0.0, 0.0};
+  double acc[3 * SPEC];
+  acc[0] = acc[1] = acc[2] = 0.0;
 #pragma unroll
   for (int k = 0; k < KPT; ++k) {
     const int b = gt + k * NT;
@@ -491,7 +539,7 @@ qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol,
       }
     }
   }
-  cluster_reduce<3>(cluster, acc, sum3, smem_cta, part, res, phase);
+  cluster_sum_rt(acc, 2, smem_cta, part, res, gat, &phase);
   if (sqrt(acc[0]) < tol) {  // bfgs.rs:74
     if (leader) {
       st->done = 1;
@@ -503,91 +551,62 @@ qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol,
   }
   const double gd0 = acc[1];
   double tmaxc = INFINITY;
-  if (need_tmax) {
-    double mm[1] = {tm};
-    cluster_reduce<1>(cluster, mm, RedOps<1>{{RED_MIN}}, smem_cta, part, res, phase);
-    tmaxc = mm[0];
-  }
+  if (need_tmax) tmaxc = cluster_min_rt(tm, smem_cta, part, res, gat, &phase);
   LSParams p = *lsp;
   LSMachine m;
-  m.begin(p, f0, gd0, max_ls, tmaxc);
+  m.template begin<LSK>(p, f0, gd0, max_ls, tmaxc);
   int evals = 0;
+  // Backtracking visits t, t*beta, t*beta^2, ... whatever the outcome of a trial (backtracking.rs:37-55
+  // multiplies by beta on both the NaN and the rejection branch), so up to SPEC consecutive trials are
+  // evaluated in one sweep and ONE cluster reduction, then fed to the automaton in order.  The objective
+  // has no side effects: the extra evaluations change nothing but the latency.
+  const int nspec = (IS_BT && spec_on) ? SPEC : 1;
   while (!m.done) {
-    const bool proj = m.wants_projection(p);
-    if (p.kind == LS_BACKTRACKING || p.kind == LS_BACKTRACKING_B) {
-      // Backtracking visits t, t*beta, t*beta^2, ... whatever the outcome of a trial (backtracking.rs:37-55
-      // multiplies by beta on both the NaN and the rejection branch), so SPEC consecutive trials are
-      // evaluated in one sweep and one cluster reduction, then fed to the automaton in order.  The
-      // objective has no side effects: the extra evaluations change nothing but the latency.
-      double ts[SPEC];
-      ts[0] = m.request(p);
+    constexpr bool proj = LSK == LS_BACKTRACKING_B;
+    double ts[SPEC];
+    ts[0] = m.request(p);
 #pragma unroll
-      for (int q = 1; q < SPEC; ++q) ts[q] = ts[q - 1] * p.beta;
-      double aS[3 * SPEC];
-#pragma unroll
-      for (int q = 0; q < 3 * SPEC; ++q) aS[q] = 0.0;
+    for (int q = 1; q < SPEC; ++q) ts[q] = ts[q - 1] * p.beta;
+#pragma unroll 1
+    for (int q = 0; q < nspec; ++q) {
+      const double t = ts[q];
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0;
 #pragma unroll
       for (int k = 0; k < KPT; ++k) {
         const int b = gt + k * NT;
         if (b < nb) {
+          double xb[BS], gb[BS];
 #pragma unroll
-          for (int q = 0; q < SPEC; ++q) {
-            double xb[BS], gb[BS];
-#pragma unroll
-            for (int j = 0; j < BS; ++j) {
-              const double td = ts[q] * dreg[k][j];
-              double v = xreg[k][j] + td;
-              if (proj) v = fmin(fmax(v, ls_lb[b * BS + j]), ls_ub[b * BS + j]);  // backtracking_b.rs:65-67
-              xb[j] = v;
-              const double df = v - xreg[k][j];
-              aS[3 * q + 2] = aS[3 * q + 2] + df * df;
-            }
-            const double fb = fn.block((int64_t)b * BS, xb, gb);
-#pragma unroll
-            for (int j = 0; j < BS; ++j) aS[3 * q + 1] = aS[3 * q + 1] + gb[j] * dreg[k][j];
-            aS[3 * q] = aS[3 * q] + fb;
+          for (int j = 0; j < BS; ++j) {
+            const double td = t * dreg[k][j];
+            double v = xreg[k][j] + td;
+            if (proj) v = fmin(fmax(v, ls_lb[b * BS + j]), ls_ub[b * BS + j]);  // backtracking_b.rs:65-67
+            xb[j] = v;
+            const double df = v - xreg[k][j];
+            a2 = a2 + df * df;
           }
-        }
-      }
-      cluster_reduce<3 * SPEC>(cluster, aS, sumS, smem_cta, part, res, phase);
+          const double fb = fn.block((int64_t)b * BS, xb, gb);
 #pragma unroll
-      for (int q = 0; q < SPEC; ++q) {
-        if (!m.done && m.request(p) == ts[q]) {
-          m.feed(p, aS[3 * q], aS[3 * q + 1], aS[3 * q + 2]);
-          ++evals;
+          for (int j = 0; j < BS; ++j) a1 = a1 + gb[j] * dreg[k][j];
+          a0 = a0 + fb;
         }
       }
-      continue;
+      acc[3 * q] = a0;
+      acc[3 * q + 1] = a1;
+      acc[3 * q + 2] = a2;
     }
-    const double t = m.request(p);
-    double a3[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-    for (int k = 0; k < KPT; ++k) {
-      const int b = gt + k * NT;
-      if (b < nb) {
-        double xb[BS], gb[BS];
-#pragma unroll
-        for (int j = 0; j < BS; ++j) {
-          const double td = t * dreg[k][j];
-          double v = xreg[k][j] + td;
-          if (proj) v = fmin(fmax(v, ls_lb[b * BS + j]), ls_ub[b * BS + j]);  // backtracking_b.rs:65-67
-          xb[j] = v;
-          const double df = v - xreg[k][j];
-          a3[2] = a3[2] + df * df;
-        }
-        const double fb = fn.block((int64_t)b * BS, xb, gb);
-#pragma unroll
-        for (int j = 0; j < BS; ++j) a3[1] = a3[1] + gb[j] * dreg[k][j];
-        a3[0] = a3[0] + fb;
+    cluster_sum_rt(acc, 3 * nspec, smem_cta, part, res, gat, &phase);
+#pragma unroll 1
+    for (int q = 0; q < nspec; ++q) {
+      if (!m.done && m.request(p) == ts[q]) {
+        m.template feed<LSK>(p, acc[3 * q], acc[3 * q + 1], acc[3 * q + 2]);
+        ++evals;
       }
     }
-    cluster_reduce<3>(cluster, a3, sum3, smem_cta, part, res, phase);
-    m.feed(p, a3[0], a3[1], a3[2]);
-    ++evals;
   }
   const double t = m.result;
   // ---- next = x + t d (ls_solver.rs:60); oracle(next) (bfgs.rs:98); s, y, norms, y.s
-  double a4[4] = {0.0, 0.0, 0.0, 0.0};
+  acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
 #pragma unroll
   for (int k = 0; k < KPT; ++k) {
     const int b = gt + k * NT;
@@ -599,7 +618,7 @@ qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol,
         xb[j] = xreg[k][j] + td;
       }
       const double fb = fn.block((int64_t)b * BS, xb, gb);
-      a4[3] = a4[3] + fb;
+      acc[3] = acc[3] + fb;
 #pragma unroll
       for (int j = 0; j < BS; ++j) {
         const int i = b * BS + j;
@@ -609,21 +628,21 @@ qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol,
         y[i] = yi;
         x[i] = xb[j];
         g[i] = gb[j];
-        a4[0] = a4[0] + si * si;
-        a4[1] = a4[1] + yi * yi;
-        a4[2] = a4[2] + yi * si;
+        acc[0] = acc[0] + si * si;
+        acc[1] = acc[1] + yi * yi;
+        acc[2] = acc[2] + yi * si;
       }
     }
   }
-  cluster_reduce<4>(cluster, a4, sum4, smem_cta, part, res, phase);
+  cluster_sum_rt(acc, 4, smem_cta, part, res, gat, &phase);
   if (leader) {
-    st->f = a4[3];
-    st->ft = a4[3];
+    st->f = acc[3];
+    st->ft = acc[3];
     st->gd0 = gd0;
-    st->ss = a4[0];
-    st->yy = a4[1];
-    st->ys = a4[2];
-    const double sn = sqrt(a4[0]), yn = sqrt(a4[1]);
+    st->ss = acc[0];
+    st->yy = acc[1];
+    st->ys = acc[2];
+    const double sn = sqrt(acc[0]), yn = sqrt(acc[1]);
     st->s_norm = sn;
     st->y_norm = yn;
     st->has_s = 1;
@@ -637,22 +656,32 @@ qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol,
   cluster.sync();  // keep every CTA's shared memory alive until all peers have read it
 }
 
+template <class Fn, int LSK>
+static void launch_head_cluster_k(Ctx* ctx, Fn fn, bool bounded, LSParams* d_ls, int64_t n, double tol, int64_t max_ls, DevState* st,
+                                  double* x, double* g, double* s, double* y, const double* u, const double* lb, const double* ub,
+                                  const double* ls_lb, const double* ls_ub, int spec_on) {
+  if (bounded)
+    qn_head_cluster_kernel<Fn, true, 4, LSK><<<HC_CTAS, HC_T, 0, ctx->stream>>>(fn, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub, spec_on);
+  else
+    qn_head_cluster_kernel<Fn, false, 4, LSK><<<HC_CTAS, HC_T, 0, ctx->stream>>>(fn, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub, spec_on);
+}
+
 template <class Fn>
-static bool launch_head_cluster(Ctx* ctx, Fn fn, bool bounded, LSParams* d_ls, int64_t n, double tol, int64_t max_ls, DevState* st,
-                                double* x, double* g, double* s, double* y, const double* u, const double* lb, const double* ub,
-                                const double* ls_lb, const double* ls_ub) {
+static bool launch_head_cluster(Ctx* ctx, Fn fn, bool bounded, LSParams* d_ls, int ls_kind, int64_t n, double tol, int64_t max_ls,
+                                DevState* st, double* x, double* g, double* s, double* y, const double* u, const double* lb,
+                                const double* ub, const double* ls_lb, const double* ls_ub, int spec_on) {
   constexpr int NT = HC_CTAS * HC_T;
-  if (n > (int64_t)NT * 16) return false;
-#define OSB_HC_LAUNCH(B, E) \
-  qn_head_cluster_kernel<Fn, B, E><<<HC_CTAS, HC_T, 0, ctx->stream>>>(fn, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub)
-  if (n <= (int64_t)NT * 4) {
-    if (bounded) OSB_HC_LAUNCH(true, 4);
-    else OSB_HC_LAUNCH(false, 4);
-  } else {
-    if (bounded) OSB_HC_LAUNCH(true, 16);
-    else OSB_HC_LAUNCH(false, 16);
+  if (n > (int64_t)NT * 4) return false;
+#define OSB_HC(K) launch_head_cluster_k<Fn, K>(ctx, fn, bounded, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub, spec_on)
+  switch (ls_kind) {
+    case LS_BACKTRACKING: OSB_HC(LS_BACKTRACKING); break;
+    case LS_BACKTRACKING_B: OSB_HC(LS_BACKTRACKING_B); break;
+    case LS_MORETHUENTE: OSB_HC(LS_MORETHUENTE); break;
+    case LS_MORETHUENTE_B: OSB_HC(LS_MORETHUENTE_B); break;
+    case LS_GLL: OSB_HC(LS_GLL); break;
+    default: OSB_HC(LS_NOSEARCH); break;
   }
-#undef OSB_HC_LAUNCH
+#undef OSB_HC
   ctx->counters[0]++;
   return true;
 }
@@ -671,16 +700,16 @@ static void launch_head(Ctx* ctx, Fn fn, bool bounded, LSParams* d_ls, int64_t n
 void qn_device_launch_head(Ctx* ctx, int functor_kind, const double* fn_a, const double* fn_b, bool bounded, LSParams* d_ls,
                            int64_t n, double tol, int64_t max_ls, DevState* st, double* x, double* g, double* d, double* xt,
                            double* gt, double* s, double* y, const double* u, const double* lb, const double* ub,
-                           const double* ls_lb, const double* ls_ub, int head_variant) {
+                           const double* ls_lb, const double* ls_ub, int head_variant, int ls_kind) {
   if (functor_kind == FN_ROSENBROCK) {
-    if (head_variant == 0 && launch_head_cluster(ctx, RosenbrockFn{}, bounded, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub)) return;
+    if ((head_variant == 0 || head_variant == 3) && launch_head_cluster(ctx, RosenbrockFn{}, bounded, d_ls, ls_kind, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub, head_variant == 0)) return;
     if (head_variant <= 1 && launch_head_fast(ctx, RosenbrockFn{}, bounded, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub)) return;
     launch_head(ctx, RosenbrockFn{}, bounded, d_ls, n, tol, max_ls, st, x, g, d, xt, gt, s, y, u, lb, ub, ls_lb, ls_ub);
   } else if (functor_kind == FN_SEPQUAD) {
     SepQuadFn fn;
     fn.c = fn_a;
     fn.a = fn_b;
-    if (head_variant == 0 && launch_head_cluster(ctx, fn, bounded, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub)) return;
+    if ((head_variant == 0 || head_variant == 3) && launch_head_cluster(ctx, fn, bounded, d_ls, ls_kind, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub, head_variant == 0)) return;
     if (head_variant <= 1 && launch_head_fast(ctx, fn, bounded, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub)) return;
     launch_head(ctx, fn, bounded, d_ls, n, tol, max_ls, st, x, g, d, xt, gt, s, y, u, lb, ub, ls_lb, ls_ub);
   } else {

@@ -67,6 +67,7 @@ qn_gemv_kernel(const double* __restrict__ H, int64_t ld, int64_t nrows, int64_t 
     }
   }
   if (v == nullptr) return;
+  const unsigned long long pol = l2_evict_first_policy();
   __shared__ double red[QN_R][QN_T / 32];
   __shared__ bool is_last;
   const int64_t ntiles = (nrows + QN_R - 1) / QN_R;
@@ -80,7 +81,7 @@ qn_gemv_kernel(const double* __restrict__ H, int64_t ld, int64_t nrows, int64_t 
       const double2 vv = *reinterpret_cast<const double2*>(v + col);
       double2 hv[QN_R];
 #pragma unroll
-      for (int r = 0; r < QN_R; ++r) hv[r] = ld_stream_nc(base + r * ld + col);
+      for (int r = 0; r < QN_R; ++r) hv[r] = ld_stream_nc_ef(base + r * ld + col, pol);
 #pragma unroll
       for (int r = 0; r < QN_R; ++r) {
         acc[r] = fma(hv[r].x, vv.x, acc[r]);
@@ -221,6 +222,7 @@ qn_update_kernel(double* __restrict__ H, int64_t ld, int64_t nrows, int64_t row0
                  const double* __restrict__ g, double* __restrict__ u_out) {
   if (st->done || st->skip) return;
   const double c0 = st->c0, c1 = st->c1, c2 = st->c2;
+  const unsigned long long pol = l2_evict_first_policy();
   __shared__ double red[QN_R][QN_T / 32];
   __shared__ double2 rowpq[QN_R];
   const int64_t ntiles = (nrows + QN_R - 1) / QN_R;
@@ -243,7 +245,7 @@ qn_update_kernel(double* __restrict__ H, int64_t ld, int64_t nrows, int64_t row0
       if (KIND == QN_BROYDEN) pj = *reinterpret_cast<const double2*>(rv + col);  // column vector v = H^T s
       double2 hv[QN_R];
 #pragma unroll
-      for (int r = 0; r < QN_R; ++r) hv[r] = ld_stream(base + r * ld + col);
+      for (int r = 0; r < QN_R; ++r) hv[r] = ld_stream_ef(base + r * ld + col, pol);
 #pragma unroll
       for (int r = 0; r < QN_R; ++r) {
         double2 hn;
@@ -263,7 +265,7 @@ qn_update_kernel(double* __restrict__ H, int64_t ld, int64_t nrows, int64_t row0
         }
         acc[r] = fma(hn.x, gj.x, acc[r]);
         acc[r] = fma(hn.y, gj.y, acc[r]);
-        st_stream(base + r * ld + col, hn);
+        st_stream_ef(base + r * ld + col, hn, pol);
       }
     }
     tile_reduce_store(acc, red, u_out, row0, r0, nrows);
@@ -343,6 +345,7 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_kernel(QNLazyArgs a) {
   DevState* st = a.st;
   if (st->done) return;
   const double c0 = st->pc0, c1 = st->pc1, c2 = st->pc2;
+  const unsigned long long pol = l2_evict_first_policy();
   __shared__ double red[2 * QN_R][QN_T / 32];
   __shared__ double2 rowpq[QN_R];
   __shared__ bool is_last;
@@ -370,7 +373,7 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_kernel(QNLazyArgs a) {
       const double2 qj = *reinterpret_cast<const double2*>(q + col);
       double2 hv[QN_R];
 #pragma unroll
-      for (int r = 0; r < QN_R; ++r) hv[r] = ld_stream(base + r * ld + col);
+      for (int r = 0; r < QN_R; ++r) hv[r] = ld_stream_ef(base + r * ld + col, pol);
 #pragma unroll
       for (int r = 0; r < QN_R; ++r) {
         const double2 pq = rowpq[r];
@@ -388,7 +391,7 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_kernel(QNLazyArgs a) {
         ah[r] = fma(hn.y, yj.y, ah[r]);
         aw[r] = fma(hn.x, gj.x, aw[r]);
         aw[r] = fma(hn.y, gj.y, aw[r]);
-        st_stream(base + r * ld + col, hn);
+        st_stream_ef(base + r * ld + col, hn, pol);
       }
     }
 #pragma unroll
@@ -406,18 +409,10 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_kernel(QNLazyArgs a) {
       for (int w = 0; w < QN_T / 32; ++w) v = v + red[threadIdx.x][w];
       const int r = threadIdx.x % QN_R;
       if (r0 + r < nrows) {
-        if (a.peers != nullptr) {
-          // fused all-gather: the row sum goes straight into every rank's exchange region (NVLink peer
-          // stores); `par` double-buffers the region across iterations
-          const int64_t off = (int64_t)(par * 2 + (threadIdx.x < QN_R ? 0 : 1)) * XCHG_LD + row0 + r0 + r;
-          for (int pr = 0; pr < a.world; ++pr) a.peers[pr][off] = v;
-        } else {
-          if (threadIdx.x < QN_R) a.h[row0 + r0 + r] = v;
-          else a.w[row0 + r0 + r] = v;
-        }
+        if (threadIdx.x < QN_R) a.h[row0 + r0 + r] = v;
+        else a.w[row0 + r0 + r] = v;
       }
-      if (a.peers != nullptr) __threadfence_system();
-      else __threadfence();
+      __threadfence();
     }
     __syncthreads();
   }
@@ -431,9 +426,20 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_kernel(QNLazyArgs a) {
   if (!is_last) return;
   __threadfence();
   if (a.peers != nullptr) {
-    // every local CTA has pushed its rows to all peers: publish "rank `a.rank` reached `seq`" on every
-    // rank, then wait until all ranks have published the same sequence number here
+    // fused all-gather: this rank's slices of h and w are complete locally; push them into every rank's
+    // exchange region in one burst of NVLink peer stores (`par` double-buffers the region across
+    // iterations), publish "rank `a.rank` reached `seq`" on every rank, then wait until all ranks have
+    // published the same sequence number here
+    for (int pr = 0; pr < a.world; ++pr) {
+      double* dst_h = a.peers[pr] + (int64_t)(par * 2 + 0) * XCHG_LD + row0;
+      double* dst_w = a.peers[pr] + (int64_t)(par * 2 + 1) * XCHG_LD + row0;
+      for (int64_t i = 2 * threadIdx.x; i < nrows; i += 2 * QN_T) {
+        *reinterpret_cast<double2*>(dst_h + i) = *reinterpret_cast<const double2*>(a.h + row0 + i);
+        *reinterpret_cast<double2*>(dst_w + i) = *reinterpret_cast<const double2*>(a.w + row0 + i);
+      }
+    }
     __threadfence_system();
+    __syncthreads();
     unsigned long long* myflags = reinterpret_cast<unsigned long long*>(a.peers[a.rank] + 4 * XCHG_LD);
     if (threadIdx.x < a.world) {
       unsigned long long* f = reinterpret_cast<unsigned long long*>(a.peers[threadIdx.x] + 4 * XCHG_LD) + a.rank;
