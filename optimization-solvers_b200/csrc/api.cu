@@ -14,6 +14,7 @@ void ctx_ipc_close(Ctx* ctx);
 }  // namespace osb
 
 using namespace osb;
+namespace osb { extern long long* g_head_tdbg; }
 
 #define OSB_TRY try {
 #define OSB_CATCH                                  \
@@ -361,7 +362,13 @@ int osb_solver_set_option(osb_solver* s, const char* name, int64_t value) {
   else if (nm == "qn_kernel") S(s)->qn_variant = (int)value;
   else if (nm == "qn_schedule") S(s)->qn_schedule = (int)value;
   else if (nm == "use_p2p") S(s)->use_p2p = (int)value;
-  else if (nm == "head_kernel") S(s)->head_variant = (int)value;
+  else if (nm == "head_debug") {
+    if (value && !g_head_tdbg) {
+      OSB_CUDA(cudaMalloc(&g_head_tdbg, 32 * sizeof(long long)));
+      OSB_CUDA(cudaMemset(g_head_tdbg, 0, 32 * sizeof(long long)));
+    }
+    if (!value) g_head_tdbg = nullptr;
+  } else if (nm == "head_kernel") S(s)->head_variant = (int)value;
   else if (nm == "profile_kernels") S(s)->profile_kernels = (int)value;
   else throw Error(OSB_ERROR_INPUT_PARAMS, "unknown option " + nm);
   return OSB_OK;
@@ -483,6 +490,12 @@ int osb_solver_kernel_timing(const osb_solver* s, double out[3]) {
   out[0] = S(s)->prof_ms[0];
   out[1] = S(s)->prof_ms[1];
   out[2] = S(s)->prof_ms[2];
+  return OSB_OK;
+}
+int osb_debug_head_stamps(long long out[32]) {
+  if (!g_head_tdbg) return OSB_ERROR_INPUT_PARAMS;
+  cudaDeviceSynchronize();
+  cudaMemcpy(out, g_head_tdbg, 32 * sizeof(long long), cudaMemcpyDeviceToHost);
   return OSB_OK;
 }
 int osb_solver_last_timing(const osb_solver* s, double* ms, int64_t* iters) {

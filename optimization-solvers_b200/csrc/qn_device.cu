@@ -389,56 +389,47 @@ namespace cg = cooperative_groups;
 constexpr int HC_CTAS = 8;
 constexpr int HC_T = 512;
 
-// Sum-reductions with a run-time value count and ROLLED loops: the head kernel is launched cold on 8 SMs
-// every iteration, its cost is instruction fetch, so its body is kept small and loopy on purpose (ncu:
-// the fully unrolled variant spent 169k cycles to retire ~2k instructions per scheduler, stalled on
-// "no instruction").
-__device__ __noinline__ void cta_sum_rt(double* acc, int K, double* smem /* K x 32 */) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
-  __syncthreads();
-#pragma unroll 1
-  for (int k = 0; k < K; ++k) {
-    const double v = warp_sum(acc[k]);
-    if (lane == 0) smem[k * 32 + warp] = v;
-  }
-  __syncthreads();
-#pragma unroll 1
-  for (int k = 0; k < K; ++k) {
-    double v = 0.0;
-#pragma unroll 1
-    for (int w = 0; w < nwarp; ++w) v = v + smem[k * 32 + w];
-    acc[k] = v;
-  }
-}
-
-__device__ __noinline__ void cluster_sum_rt(double* acc, int K, double* smem_cta, double* part /* 2 x 16 */, double* res /* 16 */,
-                                            double* gat /* 16 x HC_CTAS */, int* phase) {
+// Cluster-wide sum of K <= 12 accumulators, result in all threads of all CTAs, ~1.5k cycles whatever K:
+//   1. warp shuffle trees for the K values (independent chains, interleaved);
+//   2. the K x 16 warp partials are folded by K x 16 threads with a 16-lane segmented shuffle tree;
+//   3. one barrier.cluster; the K x 8 CTA partials are fetched through DSMEM by K x 8 threads in parallel
+//      and folded with an 8-lane segmented tree.
+// Every tree has a fixed shape, so all CTAs (and all ranks of a sharded run) obtain identical bits.
+// (An earlier variant let every thread fold the 16 warp partials sequentially from shared memory:
+//  clock64 stamps showed 17.7k cycles per reduction at K = 12, two thirds of the head kernel.)
+template <int K>
+__device__ __forceinline__ void cluster_sum(double (&acc)[K], double* smem_cta /* K x 16 */, double* part /* 2 x 16 */,
+                                            double* res /* 16 */, int& phase) {
+  static_assert(K <= 12 && HC_T == 512, "layout below assumes 16 warps and K <= 12");
   cg::cluster_group cluster = cg::this_cluster();
-  cta_sum_rt(acc, K, smem_cta);
-  double* mine = part + (*phase & 1) * 16;
-  if (threadIdx.x == 0) {
-#pragma unroll 1
-    for (int k = 0; k < K; ++k) mine[k] = acc[k];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) acc[k] = warp_sum(acc[k]);
+  __syncthreads();  // smem_cta / res may still be read from the previous call
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) smem_cta[k * 16 + warp] = acc[k];
+  }
+  __syncthreads();
+  double* mine = part + (phase & 1) * 16;
+  if (threadIdx.x < ((K * 16 + 31) / 32) * 32) {  // thread = k * 16 + w ; whole warps execute the shuffles
+    double v = threadIdx.x < K * 16 ? smem_cta[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, o, 16);
+    if (threadIdx.x < K * 16 && (threadIdx.x & 15) == 0) mine[threadIdx.x >> 4] = v;
   }
   cluster.sync();
-  // K * HC_CTAS remote values are fetched by as many threads in parallel (one DSMEM round trip in total),
-  // then folded in rank order from local shared memory => identical bits in every CTA
-  if (threadIdx.x < K * HC_CTAS) {
-    const int k = threadIdx.x / HC_CTAS, r = threadIdx.x % HC_CTAS;
-    const double* remote = cluster.map_shared_rank(mine, r);
-    gat[k * HC_CTAS + r] = remote[k];
+  if (threadIdx.x < ((K * HC_CTAS + 31) / 32) * 32) {  // thread = k * 8 + r
+    const int k = threadIdx.x >> 3, r = threadIdx.x & 7;
+    double v = threadIdx.x < K * HC_CTAS ? cluster.map_shared_rank(mine, r)[k] : 0.0;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, o, 8);
+    if (threadIdx.x < K * HC_CTAS && r == 0) res[k] = v;
   }
   __syncthreads();
-  if (threadIdx.x < K) {
-    double v = 0.0;
-#pragma unroll 1
-    for (int r = 0; r < HC_CTAS; ++r) v = v + gat[threadIdx.x * HC_CTAS + r];
-    res[threadIdx.x] = v;
-  }
-  __syncthreads();
-#pragma unroll 1
+#pragma unroll
   for (int k = 0; k < K; ++k) acc[k] = res[k];
-  *phase += 1;
+  phase += 1;
 }
 
 __device__ __noinline__ double cluster_min_rt(double v, double* smem_cta, double* part, double* res, double* gat, int* phase) {
@@ -472,10 +463,13 @@ __global__ void __cluster_dims__(HC_CTAS, 1, 1) __launch_bounds__(HC_T, 1)
 qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol, int64_t max_ls, DevState* __restrict__ st,
                        double* __restrict__ x, double* __restrict__ g, double* __restrict__ s, double* __restrict__ y,
                        const double* __restrict__ u, const double* __restrict__ lb, const double* __restrict__ ub,
-                       const double* __restrict__ ls_lb, const double* __restrict__ ls_ub, int spec_on) {
+                       const double* __restrict__ ls_lb, const double* __restrict__ ls_ub, int spec_on, long long* tdbg) {
   constexpr int BS = Fn::BS;
   constexpr int KPT = EPT / BS;
   constexpr int NT = HC_CTAS * HC_T;
+  int tslot = 0;
+#define OSB_TS() do { if (tdbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && tslot < 30) tdbg[tslot++] = clock64(); } while (0)
+  OSB_TS();
   constexpr int SPEC = 4;  // backtracking trials evaluated per reduction round (speculatively)
   constexpr bool IS_BT = LSK == LS_BACKTRACKING || LSK == LS_BACKTRACKING_B;
   cg::cluster_group cluster = cg::this_cluster();
@@ -510,8 +504,8 @@ qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol,
   double xreg[KPT][BS], dreg[KPT][BS], greg[KPT][BS];
   constexpr bool need_tmax = LSK == LS_MORETHUENTE_B;
   double tm = INFINITY;
-  double acc[3 * SPEC];
-  acc[0] = acc[1] = acc[2] = 0.0;
+  double acc[4];
+  acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
 #pragma unroll
   for (int k = 0; k < KPT; ++k) {
     const int b = gt + k * NT;
@@ -539,7 +533,14 @@ qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol,
       }
     }
   }
-  cluster_sum_rt(acc, 2, smem_cta, part, res, gat, &phase);
+  OSB_TS();
+  {
+    double a2[2] = {acc[0], acc[1]};
+    cluster_sum<2>(a2, smem_cta, part, res, phase);
+    acc[0] = a2[0];
+    acc[1] = a2[1];
+  }
+  OSB_TS();
   if (sqrt(acc[0]) < tol) {  // bfgs.rs:74
     if (leader) {
       st->done = 1;
@@ -555,51 +556,53 @@ qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol,
   LSParams p = *lsp;
   LSMachine m;
   m.template begin<LSK>(p, f0, gd0, max_ls, tmaxc);
+  OSB_TS();
   int evals = 0;
   // Backtracking visits t, t*beta, t*beta^2, ... whatever the outcome of a trial (backtracking.rs:37-55
   // multiplies by beta on both the NaN and the rejection branch), so up to SPEC consecutive trials are
   // evaluated in one sweep and ONE cluster reduction, then fed to the automaton in order.  The objective
   // has no side effects: the extra evaluations change nothing but the latency.
-  const int nspec = (IS_BT && spec_on) ? SPEC : 1;
-  while (!m.done) {
+  (void)spec_on;
+  constexpr int NSPEC = IS_BT ? SPEC : 1;  // everything below is unrolled over NSPEC: arrays stay in registers
+  while (!m.done) {                        // (local memory misses L1 after every barrier.cluster, which invalidates it)
     constexpr bool proj = LSK == LS_BACKTRACKING_B;
-    double ts[SPEC];
+    double ts[NSPEC];
     ts[0] = m.request(p);
 #pragma unroll
-    for (int q = 1; q < SPEC; ++q) ts[q] = ts[q - 1] * p.beta;
-#pragma unroll 1
-    for (int q = 0; q < nspec; ++q) {
-      const double t = ts[q];
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (int q = 1; q < NSPEC; ++q) ts[q] = ts[q - 1] * p.beta;
+    double aS[3 * NSPEC];
 #pragma unroll
-      for (int k = 0; k < KPT; ++k) {
-        const int b = gt + k * NT;
-        if (b < nb) {
+    for (int q = 0; q < 3 * NSPEC; ++q) aS[q] = 0.0;
+#pragma unroll
+    for (int k = 0; k < KPT; ++k) {
+      const int b = gt + k * NT;
+      if (b < nb) {
+#pragma unroll
+        for (int q = 0; q < NSPEC; ++q) {
           double xb[BS], gb[BS];
 #pragma unroll
           for (int j = 0; j < BS; ++j) {
-            const double td = t * dreg[k][j];
+            const double td = ts[q] * dreg[k][j];
             double v = xreg[k][j] + td;
             if (proj) v = fmin(fmax(v, ls_lb[b * BS + j]), ls_ub[b * BS + j]);  // backtracking_b.rs:65-67
             xb[j] = v;
             const double df = v - xreg[k][j];
-            a2 = a2 + df * df;
+            aS[3 * q + 2] = aS[3 * q + 2] + df * df;
           }
           const double fb = fn.block((int64_t)b * BS, xb, gb);
 #pragma unroll
-          for (int j = 0; j < BS; ++j) a1 = a1 + gb[j] * dreg[k][j];
-          a0 = a0 + fb;
+          for (int j = 0; j < BS; ++j) aS[3 * q + 1] = aS[3 * q + 1] + gb[j] * dreg[k][j];
+          aS[3 * q] = aS[3 * q] + fb;
         }
       }
-      acc[3 * q] = a0;
-      acc[3 * q + 1] = a1;
-      acc[3 * q + 2] = a2;
     }
-    cluster_sum_rt(acc, 3 * nspec, smem_cta, part, res, gat, &phase);
-#pragma unroll 1
-    for (int q = 0; q < nspec; ++q) {
+    OSB_TS();
+    cluster_sum<3 * NSPEC>(aS, smem_cta, part, res, phase);
+    OSB_TS();
+#pragma unroll
+    for (int q = 0; q < NSPEC; ++q) {
       if (!m.done && m.request(p) == ts[q]) {
-        m.template feed<LSK>(p, acc[3 * q], acc[3 * q + 1], acc[3 * q + 2]);
+        m.template feed<LSK>(p, aS[3 * q], aS[3 * q + 1], aS[3 * q + 2]);
         ++evals;
       }
     }
@@ -634,7 +637,9 @@ qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol,
       }
     }
   }
-  cluster_sum_rt(acc, 4, smem_cta, part, res, gat, &phase);
+  OSB_TS();
+  cluster_sum<4>(acc, smem_cta, part, res, phase);
+  OSB_TS();
   if (leader) {
     st->f = acc[3];
     st->ft = acc[3];
@@ -651,19 +656,26 @@ qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol,
     st->t_last = t;
     st->k += 1;
     st->ls_evals += evals + 1;
-    *lsp = p;
+    // only GLLQuadratic.f_previous and MoreThuenteB.t_max persist across outer iterations
+    if (LSK == LS_GLL || LSK == LS_MORETHUENTE_B) *lsp = p;
   }
+  OSB_TS();
   cluster.sync();  // keep every CTA's shared memory alive until all peers have read it
+  OSB_TS();
+  if (tdbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) tdbg[31] = tslot;
+#undef OSB_TS
 }
+
+long long* g_head_tdbg = nullptr;  // debug: device buffer of 32 clock64 stamps (option "head_debug")
 
 template <class Fn, int LSK>
 static void launch_head_cluster_k(Ctx* ctx, Fn fn, bool bounded, LSParams* d_ls, int64_t n, double tol, int64_t max_ls, DevState* st,
                                   double* x, double* g, double* s, double* y, const double* u, const double* lb, const double* ub,
                                   const double* ls_lb, const double* ls_ub, int spec_on) {
   if (bounded)
-    qn_head_cluster_kernel<Fn, true, 4, LSK><<<HC_CTAS, HC_T, 0, ctx->stream>>>(fn, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub, spec_on);
+    qn_head_cluster_kernel<Fn, true, 4, LSK><<<HC_CTAS, HC_T, 0, ctx->stream>>>(fn, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub, spec_on, g_head_tdbg);
   else
-    qn_head_cluster_kernel<Fn, false, 4, LSK><<<HC_CTAS, HC_T, 0, ctx->stream>>>(fn, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub, spec_on);
+    qn_head_cluster_kernel<Fn, false, 4, LSK><<<HC_CTAS, HC_T, 0, ctx->stream>>>(fn, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub, spec_on, g_head_tdbg);
 }
 
 template <class Fn>
