@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--n", type=int, default=N_DIM, help="problem dimension (the benchmark line is only valid at 16384)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--head", type=int, default=0, help="device-engine head variant (0 cluster+speculation, 3 cluster, 1 single CTA)")
+    ap.add_argument("--qn-kernel", type=int, default=0, help="lazy-pass kernel: 0 = register-staged LDG, 1 = TMA-staged (cp.async.bulk + mbarrier)")
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL all-gathers instead of the fused peer-memory exchange")
     ap.add_argument("--schedule", default="lazy", choices=["lazy", "eager"],
                     help="lazy: one read-modify-write of H per iteration (2 n^2 8 B); eager: h = H y then fused update (3 n^2 8 B)")
@@ -203,6 +204,7 @@ def main():
     lazy = args.schedule == "lazy"
     solver = osb.BFGS(TOL, x0, ctx=ctx).set_option("engine", 2).set_option("qn_schedule", 1 if lazy else 0)
     solver.set_option("head_kernel", args.head)
+    solver.set_option("qn_kernel", args.qn_kernel)
 
     def run_steps(k):
         try:

@@ -14,7 +14,7 @@ void ctx_ipc_close(Ctx* ctx);
 }  // namespace osb
 
 using namespace osb;
-namespace osb { extern long long* g_head_tdbg; }
+namespace osb { extern long long* g_head_tdbg; void exp_launch(Ctx* ctx, int which, double* M, double* N, int64_t total_doubles); }
 
 #define OSB_TRY try {
 #define OSB_CATCH                                  \
@@ -552,7 +552,7 @@ int osb_bench_qn_kernel(osb_ctx* ctxh, int which, int64_t n, int reps, int varia
     ctx->sync();
   }
   if (which == 2) scratch.alloc(((n + 63) / 64) * ld);
-  if (which == 3) H2.alloc(qn_rows_padded(n) * ld);
+  if (which == 3 || which >= 10) H2.alloc(qn_rows_padded(n) * ld);
   cudaEvent_t e0, e1;
   OSB_CUDA(cudaEventCreate(&e0));
   OSB_CUDA(cudaEventCreate(&e1));
@@ -560,6 +560,7 @@ int osb_bench_qn_kernel(osb_ctx* ctxh, int which, int64_t n, int reps, int varia
     if (which == 0) qn_launch_gemv(ctx, H.p, ld, n, 0, st, a.p, out.p, b.p, out.p, variant);
     else if (which == 1) qn_launch_update(ctx, QN_BFGS, H.p, ld, n, 0, st, a.p, b.p, c.p, c.p, out.p, variant);
     else if (which == 2) qn_launch_gemvT(ctx, H.p, ld, n, 0, st, a.p, out.p, scratch.p);
+    else if (which >= 10) exp_launch(ctx, which, H.p, H2.p, n * ld);
     else OSB_CUDA(cudaMemcpyAsync(H2.p, H.p, sizeof(double) * (size_t)(n * ld), cudaMemcpyDeviceToDevice, ctx->stream));
   };
   for (int i = 0; i < 3; ++i) run();

@@ -296,7 +296,7 @@ void Solver::qn_after_step() {
     prof_mark();
     prof_mark();
     prof_mark();
-    qn_launch_lazy(ctx, a);
+    qn_launch_lazy(ctx, a, qn_variant);
     prof_mark();
     if (p2p) ctx->counters[4]++;  // one fused exchange
     if (ctx->world > 1 && !p2p) {

@@ -190,7 +190,7 @@ struct QNLazyArgs {
   unsigned long long* seq;
   int world, rank;
 };
-void qn_launch_lazy(Ctx* ctx, const QNLazyArgs& a);
+void qn_launch_lazy(Ctx* ctx, const QNLazyArgs& a, int variant = 0);
 void qn_launch_lazy_epilogue(Ctx* ctx, const QNLazyArgs& a);
 // apply a pending update to the stored matrix (getters, engine switches)
 void qn_launch_flush(Ctx* ctx, int kind, double* M, int64_t ld, int64_t nrows, int64_t row0, DevState* st, const double* ps,

@@ -293,7 +293,7 @@ __device__ __forceinline__ void lazy_epilogue_body(const QNLazyArgs& a, double* 
   DevState* st = a.st;
   const int64_t n = a.n;
   if (st->skip) {  // bfgs.rs:106-112: no new update; the stored matrix is now exact
-    for (int64_t i = threadIdx.x; i < n; i += QN_T) a.u[i] = a.w[i];
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) a.u[i] = a.w[i];
     if (threadIdx.x == 0) {
       st->pending = 0;
       st->pc0 = st->pc1 = st->pc2 = 0.0;
@@ -301,7 +301,7 @@ __device__ __forceinline__ void lazy_epilogue_body(const QNLazyArgs& a, double* 
     return;
   }
   double acc[3] = {0.0, 0.0, 0.0};
-  for (int64_t i = threadIdx.x; i < n; i += QN_T) {
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
     const double hi = a.h[i], gi = a.g[i];
     acc[0] = fma(a.y[i], hi, acc[0]);  // y.h
     acc[1] = fma(a.s[i], gi, acc[1]);  // s.g
@@ -322,7 +322,7 @@ __device__ __forceinline__ void lazy_epilogue_body(const QNLazyArgs& a, double* 
     c2 = -1.0 / yh;
   }
   const double ca = c0 * sg + c1 * hg, cb = c1 * sg + c2 * hg;
-  for (int64_t i = threadIdx.x; i < n; i += QN_T) {
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
     const double si = a.s[i], hi = a.h[i];
     a.u[i] = a.w[i] + (si * ca + hi * cb);
     a.ps_out[i] = si;
@@ -462,6 +462,234 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_kernel(QNLazyArgs a) {
   if (threadIdx.x == 0) *a.ticket = 0u;
 }
 
+// ---- lazy pass, TMA-staged variant (qn_kernel = 1) ----------------------------------------------
+// Same arithmetic as qn_lazy_kernel, different data movement: a producer thread streams row tiles of H
+// into a ring of shared-memory stages with bulk asynchronous copies (cp.async.bulk + mbarrier
+// complete_tx, SASS UBLKCP), so the bytes in flight per SM (3 stages x 64 KiB) no longer depend on
+// registers; 8 consumer warps read the stage with conflict-free 128-bit LDS, apply the pending update,
+// accumulate the two dot products for 16 rows per tile (the O(n) vectors are re-read once per 16 rows
+// instead of once per 8) and store the new rows straight to global memory.
+constexpr int TM_R = 16;              // rows per tile
+constexpr int TM_CW = 512;            // columns per stage (4 KiB per row segment)
+constexpr int TM_STAGES = 3;
+constexpr int TM_CONS = 256;          // consumer threads: one column pair each
+constexpr int TM_T = TM_CONS + 32;    // + producer warp
+constexpr size_t TM_SMEM = (size_t)TM_STAGES * TM_R * TM_CW * sizeof(double) + 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(TM_T, 1) qn_lazy_tma_kernel(QNLazyArgs a) {
+  DevState* st = a.st;
+  if (st->done) return;
+  extern __shared__ __align__(128) unsigned char tm_smem[];
+  double* stage = reinterpret_cast<double*>(tm_smem);                          // TM_STAGES x TM_R x TM_CW
+  uint64_t* full = reinterpret_cast<uint64_t*>(tm_smem + (size_t)TM_STAGES * TM_R * TM_CW * sizeof(double));
+  uint64_t* empty = full + TM_STAGES;
+  __shared__ double red[2 * TM_R][TM_CONS / 32];
+  __shared__ double2 rowpq[TM_R];
+  __shared__ bool is_last;
+  const double c0 = st->pc0, c1 = st->pc1, c2 = st->pc2;
+  const unsigned long long pol = l2_evict_first_policy();
+  const int64_t ld = a.ld, nrows = a.nrows, row0 = a.row0;
+  const double* __restrict__ p = a.ps;
+  const double* __restrict__ q = a.ph;
+  const double* __restrict__ yv = a.y;
+  const double* __restrict__ gv = a.g;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned long long seq = a.peers != nullptr ? *a.seq + 1ULL : 0ULL;
+  const int par = (int)(seq & 1ULL);
+  if (tid == 0) {
+    for (int s_ = 0; s_ < TM_STAGES; ++s_) {
+      mbar_init(&full[s_], 1);
+      mbar_init(&empty[s_], TM_CONS / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int64_t ntiles = (nrows + TM_R - 1) / TM_R;  // H is allocated with rows padded to a multiple of 8; TM_R = 16 needs a guard
+  const int nchunks = (int)((ld + TM_CW - 1) / TM_CW);
+  if (warp == TM_CONS / 32) {
+    // ===== producer warp: lane 0 streams (tile, chunk) stages; the warp stays converged for the barriers =====
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t r0 = tile * TM_R;
+      const int rows_here = (int)((nrows - r0) < TM_R ? (nrows - r0) : TM_R);
+      for (int c = 0; c < nchunks; ++c, ++it) {
+        if (lane == 0) {
+          const int s_ = it % TM_STAGES;
+          const uint32_t ph = (uint32_t)((it / TM_STAGES) & 1);
+          mbar_wait(&empty[s_], ph ^ 1u);  // fresh barrier: the wait for parity 1 passes immediately
+          const int cw = (int)((ld - (int64_t)c * TM_CW) < TM_CW ? (ld - (int64_t)c * TM_CW) : TM_CW);
+          const uint32_t bytes_row = (uint32_t)(cw * sizeof(double));
+          mbar_expect_tx(&full[s_], bytes_row * (uint32_t)rows_here);
+          double* dst = stage + (size_t)s_ * TM_R * TM_CW;
+          for (int r = 0; r < rows_here; ++r)
+            bulk_load(dst + (size_t)r * TM_CW, a.M + (r0 + r) * ld + (int64_t)c * TM_CW, bytes_row, &full[s_]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===== consumers =====
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t r0 = tile * TM_R;
+      const int rows_here = (int)((nrows - r0) < TM_R ? (nrows - r0) : TM_R);
+      double ah[TM_R], aw[TM_R];
+#pragma unroll
+      for (int r = 0; r < TM_R; ++r) ah[r] = aw[r] = 0.0;
+      asm volatile("bar.sync 1, %0;" ::"r"(TM_CONS));  // rowpq / red reuse across tiles
+      if (tid < TM_R) {
+        const bool ok = tid < rows_here;
+        rowpq[tid] = make_double2(ok ? p[row0 + r0 + tid] : 0.0, ok ? q[row0 + r0 + tid] : 0.0);
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(TM_CONS));
+      // the O(n) vectors come from L2 (they never survive in L1 next to the H stream): their loads are
+      // issued one chunk ahead so that the latency hides behind the previous chunk's arithmetic
+      double2 gn = make_double2(0.0, 0.0), yn = gn, pn = gn, qn = gn;
+      {
+        const int col0 = 2 * tid;
+        if (col0 < (int)ld) {
+          gn = *reinterpret_cast<const double2*>(gv + col0);
+          yn = *reinterpret_cast<const double2*>(yv + col0);
+          pn = *reinterpret_cast<const double2*>(p + col0);
+          qn = *reinterpret_cast<const double2*>(q + col0);
+        }
+      }
+      for (int c = 0; c < nchunks; ++c, ++it) {
+        const int s_ = it % TM_STAGES;
+        const uint32_t ph = (uint32_t)((it / TM_STAGES) & 1);
+        const int col = c * TM_CW + 2 * tid;
+        const bool colok = col < (int)ld;
+        const double2 gj = gn, yj = yn, pj = pn, qj = qn;
+        {
+          const int coln = col + TM_CW;
+          if (c + 1 < nchunks && coln < (int)ld) {
+            gn = *reinterpret_cast<const double2*>(gv + coln);
+            yn = *reinterpret_cast<const double2*>(yv + coln);
+            pn = *reinterpret_cast<const double2*>(p + coln);
+            qn = *reinterpret_cast<const double2*>(q + coln);
+          }
+        }
+        mbar_wait(&full[s_], ph);
+        const double* src = stage + (size_t)s_ * TM_R * TM_CW + 2 * tid;
+        if (colok) {
+#pragma unroll
+          for (int r = 0; r < TM_R; ++r) {
+            if (r < rows_here) {
+              const double2 hv = *reinterpret_cast<const double2*>(src + (size_t)r * TM_CW);
+              const double2 pq = rowpq[r];
+              const double pi = pq.x, qi = pq.y;
+              double2 hn;
+              if (KIND == QN_BFGS) {
+                const double cx = pi * qj.x + qi * pj.x, cy = pi * qj.y + qi * pj.y;
+                hn.x = fma(c0, pi * pj.x, fma(c1, cx, hv.x));
+                hn.y = fma(c0, pi * pj.y, fma(c1, cy, hv.y));
+              } else {
+                hn.x = fma(c2, qi * qj.x, fma(c0, pi * pj.x, hv.x));
+                hn.y = fma(c2, qi * qj.y, fma(c0, pi * pj.y, hv.y));
+              }
+              ah[r] = fma(hn.x, yj.x, ah[r]);
+              ah[r] = fma(hn.y, yj.y, ah[r]);
+              aw[r] = fma(hn.x, gj.x, aw[r]);
+              aw[r] = fma(hn.y, gj.y, aw[r]);
+              st_stream_ef(a.M + (r0 + r) * ld + col, hn, pol);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s_]);
+      }
+      // row sums of the tile: shuffle trees, then fixed-order cross-warp fold
+#pragma unroll
+      for (int r = 0; r < TM_R; ++r) {
+        const double v1 = warp_sum(ah[r]), v2 = warp_sum(aw[r]);
+        if (lane == 0) {
+          red[r][warp] = v1;
+          red[TM_R + r][warp] = v2;
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(TM_CONS));
+      if (tid < 2 * TM_R) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < TM_CONS / 32; ++w) v = v + red[tid][w];
+        const int r = tid % TM_R;
+        if (r < rows_here) {
+          if (tid < TM_R) a.h[row0 + r0 + r] = v;
+          else a.w[row0 + r0 + r] = v;
+        }
+        __threadfence();
+      }
+    }
+  }
+  __syncthreads();
+  if (a.ticket == nullptr) return;
+  if (tid == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(a.ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (a.peers != nullptr) {
+    for (int pr = 0; pr < a.world; ++pr) {
+      double* dst_h = a.peers[pr] + (int64_t)(par * 2 + 0) * XCHG_LD + row0;
+      double* dst_w = a.peers[pr] + (int64_t)(par * 2 + 1) * XCHG_LD + row0;
+      for (int64_t i = 2 * tid; i < nrows; i += 2 * TM_T) {
+        *reinterpret_cast<double2*>(dst_h + i) = *reinterpret_cast<const double2*>(a.h + row0 + i);
+        *reinterpret_cast<double2*>(dst_w + i) = *reinterpret_cast<const double2*>(a.w + row0 + i);
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    unsigned long long* myflags = reinterpret_cast<unsigned long long*>(a.peers[a.rank] + 4 * XCHG_LD);
+    if (tid < a.world) {
+      unsigned long long* f = reinterpret_cast<unsigned long long*>(a.peers[tid] + 4 * XCHG_LD) + a.rank;
+      st_release_sys(f, seq);
+      while (ld_acquire_sys(myflags + tid) < seq) {
+      }
+    }
+    __syncthreads();
+    QNLazyArgs b = a;
+    b.h = a.peers[a.rank] + (int64_t)(par * 2 + 0) * XCHG_LD;
+    b.w = a.peers[a.rank] + (int64_t)(par * 2 + 1) * XCHG_LD;
+    lazy_epilogue_body<KIND>(b, &red[0][0]);
+    if (tid == 0) {
+      *a.seq = seq;
+      *a.ticket = 0u;
+    }
+    return;
+  }
+  lazy_epilogue_body<KIND>(a, &red[0][0]);
+  if (tid == 0) *a.ticket = 0u;
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(QN_T) qn_lazy_epilogue_kernel(QNLazyArgs a) {
   if (a.st->done) return;
@@ -469,7 +697,21 @@ __global__ void __launch_bounds__(QN_T) qn_lazy_epilogue_kernel(QNLazyArgs a) {
   lazy_epilogue_body<KIND>(a, smem);
 }
 
-void qn_launch_lazy(Ctx* ctx, const QNLazyArgs& a) {
+void qn_launch_lazy(Ctx* ctx, const QNLazyArgs& a, int variant) {
+  if (variant == 1) {
+    static bool attr = false;
+    if (!attr) {
+      OSB_CUDA(cudaFuncSetAttribute(qn_lazy_tma_kernel<QN_BFGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM));
+      OSB_CUDA(cudaFuncSetAttribute(qn_lazy_tma_kernel<QN_DFP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM));
+      attr = true;
+    }
+    int64_t nt = (a.nrows + TM_R - 1) / TM_R;
+    int g = (int)std::min<int64_t>(nt, (int64_t)ctx->num_sms);
+    if (a.kind == QN_BFGS) qn_lazy_tma_kernel<QN_BFGS><<<g, TM_T, TM_SMEM, ctx->stream>>>(a);
+    else qn_lazy_tma_kernel<QN_DFP><<<g, TM_T, TM_SMEM, ctx->stream>>>(a);
+    ctx->counters[0]++;
+    return;
+  }
   int64_t ntiles = (a.nrows + QN_R - 1) / QN_R;
   int grid = (int)std::min<int64_t>(ntiles, (int64_t)ctx->num_sms);
   if (a.kind == QN_BFGS) qn_lazy_kernel<QN_BFGS><<<grid, QN_T, 0, ctx->stream>>>(a);

@@ -452,3 +452,18 @@ def test_lazy_schedule_dense_quadratic_full_loop(osb, orc):
         res.append((st, s.k(), s.termination_reason(), s.x()))
     assert res[0][:3] == res[1][:3] and res[0][0] == "Ok"
     assert close(res[0][3], res[1][3])
+
+
+def test_tma_staged_lazy_kernel_matches_register_staged(osb):
+    """qn_kernel = 1 (bulk async copies into a shared-memory ring, mbarrier pipeline) against qn_kernel = 0."""
+    for n in (1024, 2056, 16384):
+        x0 = rosen_x0(n, 31)
+        out = []
+        for variant in (0, 1):
+            s = osb.BFGS(1e-8, x0).set_option("engine", 2).set_option("qn_schedule", 1).set_option("qn_kernel", variant)
+            st = run(osb, s, osb.BackTracking(1e-4, 0.5), osb.ExtendedRosenbrock(n), 9, 20)
+            out.append((st, s.k(), s.x(), s.approx_inv_hessian() if n <= 2056 else None))
+        assert out[0][:2] == out[1][:2]
+        assert close(out[0][2], out[1][2], rtol=1e-10)
+        if n <= 2056:
+            assert close(out[0][3], out[1][3], rtol=1e-10)
