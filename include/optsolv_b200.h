@@ -241,6 +241,8 @@ int osb_batched_bfgs_rosenbrock_generated(osb_ctx* ctx, int64_t n, int64_t n_pro
  *   which = 0: h = H y (read n^2)   1: fused rank-2 update + u = H' g (read + write n^2)
  *           2: Broyden H^T s        3: plain device copy of H (cudaMemcpyAsync D2D) for calibration */
 int osb_bench_qn_kernel(osb_ctx* ctx, int which, int64_t n, int reps, int variant, double* ms_out);
+/* mean ms per launch of the DMMA Hessian assembly X^T D X of a logistic-regression objective (m n^2 MACs on the lower triangle) */
+int osb_bench_syrk(osb_ctx* ctx, osb_objective* logistic, int reps, double* ms_out);
 
 #ifdef __cplusplus
 }

@@ -97,6 +97,7 @@ def lib():
             "osb_batched_bfgs_rosenbrock_generated": (ci, [_vp, i64, i64, i64, dbl, i64, i64, dbl, dbl, _dp, _dp,
                                                            i32p, i32p, i32p, _dp]),
             "osb_bench_qn_kernel": (ci, [_vp, ci, i64, ci, ci, _dp]),
+            "osb_bench_syrk": (ci, [_vp, _vp, ci, _dp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -893,4 +894,12 @@ def bench_qn_kernel(which, n, reps=20, variant=0, ctx=None):
     ctx = ctx or default_context()
     ms = C.c_double()
     _check(lib().osb_bench_qn_kernel(ctx.handle, which, n, reps, variant, C.byref(ms)))
+    return ms.value
+
+
+def bench_syrk(logistic, reps=3, ctx=None):
+    """Mean ms/launch of the DMMA Hessian assembly of a LogisticRegression objective."""
+    ctx = ctx or default_context()
+    ms = C.c_double()
+    _check(lib().osb_bench_syrk(ctx.handle, logistic.handle, reps, C.byref(ms)))
     return ms.value

@@ -14,7 +14,7 @@ void ctx_ipc_close(Ctx* ctx);
 }  // namespace osb
 
 using namespace osb;
-namespace osb { extern long long* g_head_tdbg; void exp_launch(Ctx* ctx, int which, double* M, double* N, int64_t total_doubles); }
+namespace osb { double bench_syrk_dmma(Ctx* ctx, Objective* obj, int reps); extern long long* g_head_tdbg; void exp_launch(Ctx* ctx, int which, double* M, double* N, int64_t total_doubles); }
 
 #define OSB_TRY try {
 #define OSB_CATCH                                  \
@@ -521,6 +521,14 @@ int osb_batched_bfgs_rosenbrock_generated(osb_ctx* ctx, int64_t n, int64_t np, i
   C(ctx)->use();
   return batched_bfgs_rosenbrock(C(ctx), n, np, nullptr, true, problem0, tol, max_iter, max_ls, c1, beta, x_out, f_out, k_out,
                                  st_out, reason_out, ms_out);
+  OSB_CATCH
+}
+
+int osb_bench_syrk(osb_ctx* ctx, osb_objective* logistic, int reps, double* ms_out) {
+  OSB_TRY
+  C(ctx)->use();
+  *ms_out = bench_syrk_dmma(C(ctx), O(logistic), reps);
+  return OSB_OK;
   OSB_CATCH
 }
 

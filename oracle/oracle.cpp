@@ -28,6 +28,7 @@
 #include <memory>
 #include <string>
 #include <vector>
+#include <immintrin.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -177,25 +178,62 @@ static Mat matmul(const Mat& A, const Mat& B) {
   Mat C(A.r, B.c);
   const size_t n = A.r, kk = A.c, m = B.c;
   if (n > SMALL_DIM && m > SMALL_DIM && A.r > SMALL_DIM && A.c > SMALL_DIM) {
-#pragma omp parallel
-    {
-      std::vector<double> tmp(n);
-#pragma omp for schedule(static)
-      for (long jj = 0; jj < (long)m; ++jj) {
-        size_t j = (size_t)jj;
-        double* cj = C.col(j);
-        for (size_t k0 = 0; k0 < kk; k0 += KC) {
-          size_t k1 = std::min(kk, k0 + KC);
-          std::fill(tmp.begin(), tmp.end(), 0.0);
-          for (size_t k = k0; k < k1; ++k) {
-            const double* ak = A.col(k);
-            double b = B(k, j);
-            for (size_t i = 0; i < n; ++i) tmp[i] = __builtin_fma(ak[i], b, tmp[i]);
+    // register-blocked micro-kernel (8 x 6 block of C in 12 ymm accumulators), same per-element order as
+    // stated above: within a kc-panel an FMA chain over k ascending from 0, then C = first ? ab : C + ab.
+    // The blocking only changes WHICH elements are computed together, not the order of any element's sums.
+    const size_t MR = 8, NR = 6;
+    const size_t nblk = n / MR;  // full 8-row blocks; the remaining rows take the scalar path
+    std::vector<double> Ap(nblk * MR * KC);
+    for (size_t k0 = 0; k0 < kk; k0 += KC) {
+      const size_t k1 = std::min(kk, k0 + KC), kc = k1 - k0;
+      // pack the A panel: Ap[ib][k][0..8) contiguous (no cache-set conflicts in the micro-kernel)
+#pragma omp parallel for schedule(static)
+      for (long ib = 0; ib < (long)nblk; ++ib)
+        for (size_t k = 0; k < kc; ++k) {
+          const double* src = A.col(k0 + k) + (size_t)ib * MR;
+          double* dst = &Ap[((size_t)ib * KC + k) * MR];
+          for (size_t r = 0; r < MR; ++r) dst[r] = src[r];
+        }
+#pragma omp parallel for schedule(dynamic, 2)
+      for (long jb = 0; jb < (long)((m + NR - 1) / NR); ++jb) {
+        const size_t j0 = (size_t)jb * NR, jn = std::min(NR, m - j0);
+        size_t i_done = 0;
+        if (jn == NR) {
+          const double* bcol[NR];
+          for (size_t j = 0; j < NR; ++j) bcol[j] = &B.a[k0 + (j0 + j) * B.r];
+          for (size_t ib = 0; ib < nblk; ++ib) {
+            const double* ap = &Ap[(size_t)ib * KC * MR];
+            __m256d c[NR][2];
+            for (size_t j = 0; j < NR; ++j) c[j][0] = c[j][1] = _mm256_setzero_pd();
+            for (size_t k = 0; k < kc; ++k) {
+              const __m256d a0 = _mm256_loadu_pd(ap + k * MR), a1 = _mm256_loadu_pd(ap + k * MR + 4);
+              for (size_t j = 0; j < NR; ++j) {
+                const __m256d b = _mm256_broadcast_sd(bcol[j] + k);
+                c[j][0] = _mm256_fmadd_pd(a0, b, c[j][0]);
+                c[j][1] = _mm256_fmadd_pd(a1, b, c[j][1]);
+              }
+            }
+            for (size_t j = 0; j < NR; ++j) {
+              double* cj = C.col(j0 + j) + ib * MR;
+              if (k0 == 0) {
+                _mm256_storeu_pd(cj, c[j][0]);
+                _mm256_storeu_pd(cj + 4, c[j][1]);
+              } else {
+                _mm256_storeu_pd(cj, _mm256_add_pd(_mm256_loadu_pd(cj), c[j][0]));
+                _mm256_storeu_pd(cj + 4, _mm256_add_pd(_mm256_loadu_pd(cj + 4), c[j][1]));
+              }
+            }
           }
-          if (k0 == 0)
-            for (size_t i = 0; i < n; ++i) cj[i] = tmp[i];
-          else
-            for (size_t i = 0; i < n; ++i) cj[i] = cj[i] + tmp[i];
+          i_done = nblk * MR;
+        }
+        // edges: scalar, same order
+        for (size_t j = 0; j < jn; ++j) {
+          double* cj = C.col(j0 + j);
+          for (size_t i = i_done; i < n; ++i) {
+            double ab = 0.0;
+            for (size_t k = k0; k < k1; ++k) ab = __builtin_fma(A(i, k), B(k, j0 + j), ab);
+            cj[i] = (k0 == 0) ? ab : cj[i] + ab;
+          }
         }
       }
     }
