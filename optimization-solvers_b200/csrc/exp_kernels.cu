@@ -79,6 +79,11 @@ void exp_launch(Ctx* ctx, int which, double* M, double* N, int64_t total_doubles
     case 15: exp_copy_slab<8><<<sms * 2, 512, 0, ctx->stream>>>(M, N, t2, 1.0000001); break;
     case 16: exp_rmw_gridstride<8><<<sms * 16, 256, 0, ctx->stream>>>(M, t2, 1.0000001); break;
     case 17: exp_rmw_slab<16><<<sms, 512, 0, ctx->stream>>>(M, t2, 1.0000001); break;
+    case 18: exp_rmw_gridstride<8><<<sms * 2, 256, 0, ctx->stream>>>(M, t2, 1.0000001); break;
+    case 19: exp_rmw_gridstride<8><<<sms * 4, 256, 0, ctx->stream>>>(M, t2, 1.0000001); break;
+    case 20: exp_rmw_gridstride<16><<<sms * 4, 256, 0, ctx->stream>>>(M, t2, 1.0000001); break;
+    case 21: exp_rmw_gridstride<16><<<sms * 8, 256, 0, ctx->stream>>>(M, t2, 1.0000001); break;
+    case 22: exp_rmw_gridstride<4><<<sms * 16, 256, 0, ctx->stream>>>(M, t2, 1.0000001); break;
     default: break;
   }
   ctx->counters[0]++;

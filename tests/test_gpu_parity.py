@@ -463,7 +463,8 @@ def test_tma_staged_lazy_kernel_matches_register_staged(osb):
             s = osb.BFGS(1e-8, x0).set_option("engine", 2).set_option("qn_schedule", 1).set_option("qn_kernel", variant)
             st = run(osb, s, osb.BackTracking(1e-4, 0.5), osb.ExtendedRosenbrock(n), 9, 20)
             out.append((st, s.k(), s.x(), s.approx_inv_hessian() if n <= 2056 else None))
-        assert out[0][:2] == out[1][:2]
-        assert close(out[0][2], out[1][2], rtol=1e-10)
-        if n <= 2056:
-            assert close(out[0][3], out[1][3], rtol=1e-10)
+        for o in out[1:]:
+            assert out[0][:2] == o[:2]
+            assert close(out[0][2], o[2], rtol=1e-10)
+            if n <= 2056:
+                assert close(out[0][3], o[3], rtol=1e-10)
