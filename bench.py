@@ -261,12 +261,12 @@ def main():
     # minimize with a per-iteration host callback that reads the iterate back (D2H), final x() (D2H)
     e2e = None
     if world == 1:
-        k_e2e = min(args.steps, 50)
+        k_e2e = args.steps
         x0_pinned = torch.from_numpy(x0).pin_memory()
         xs = []
         barrier()
         t0 = time.perf_counter()
-        s2 = osb.BFGS(TOL, x0_pinned.numpy(), ctx=ctx)
+        s2 = osb.BFGS(TOL, x0_pinned.numpy(), ctx=ctx).set_option("qn_schedule", 1 if lazy else 0)
 
         def cb(s):
             xs.append(s.x()[0])

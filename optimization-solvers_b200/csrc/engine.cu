@@ -342,12 +342,12 @@ int Solver::minimize(LineSearch* ls, Objective* obj, int64_t max_iter, int64_t m
   OSB_REQUIRE(!kind_needs_hessian(kind) || obj->provides_hessian(), OSB_PANIC_NO_HESSIAN, "Hessian not available in the oracle");
   if ((ls->p.kind == LS_BACKTRACKING_B || ls->p.kind == LS_MORETHUENTE_B))
     OSB_REQUIRE(ls->n == n, OSB_ERROR_INPUT_PARAMS, "line-search bounds dimension does not match the solver");
-  bool dev_ok = device_engine_supported(ls, obj) && cb == nullptr && !record_trace;
+  bool dev_ok = device_engine_supported(ls, obj);
   OSB_REQUIRE(engine != 2 || dev_ok, OSB_ERR_UNSUPPORTED,
-              "device-resident engine needs a quasi-Newton solver, a block-functor objective, no callback and no trace");
+              "device-resident engine needs a quasi-Newton solver and a block-functor objective");
   OSB_CUDA(cudaEventRecord(ev0, ctx->stream));
   int rc;
-  if (dev_ok && engine != 1) rc = minimize_device(ls, obj, max_iter, max_ls);
+  if (dev_ok && engine != 1) rc = minimize_device(ls, obj, max_iter, max_ls, cb, user);
   else rc = minimize_host(ls, obj, max_iter, max_ls, cb, user);
   OSB_CUDA(cudaEventRecord(ev1, ctx->stream));
   OSB_CUDA(cudaEventSynchronize(ev1));
@@ -492,7 +492,7 @@ int Solver::minimize_host(LineSearch* ls, Objective* obj, int64_t max_iter, int6
   return OSB_MAX_ITER_REACHED;  // ls_solver.rs:109-110
 }
 
-int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, int64_t max_ls) {
+int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, int64_t max_ls, osb_callback_fn cb, void* user) {
   if (qn_schedule != 1) flush_pending();
   k = 0;
   reason = OSB_REASON_NONE;
@@ -538,6 +538,20 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
                           d_state, x.p, g.p, d.p, xt.p, gt.p, s.p, y.p, u.p, bounded ? lb.p : nullptr, bounded ? ub.p : nullptr,
                           ls_bounded ? ls->lb.p : nullptr, ls_bounded ? ls->ub.p : nullptr, head_variant, ls->p.kind);
     qn_after_step();
+    if (cb != nullptr || record_trace) {
+      // a host callback (ls_solver.rs:105-107) or a trace needs the state after every iteration: one
+      // synchronisation per outer iteration, still none inside the line search
+      const double f_before = h_state->f;
+      fetch_state();
+      if (h_state->done) break;  // the head found convergence at the start of this iteration: no k += 1, no callback
+      k = h_state->k;
+      has_s = has_y = true;
+      s_norm = h_state->s_norm;
+      y_norm = h_state->y_norm;
+      if (record_trace) trace.push_back(TraceRec{f_before, h_state->t_last, s_norm, y_norm});
+      if (cb) cb(user, reinterpret_cast<osb_solver*>(this));
+      continue;
+    }
     if ((it + 1) % POLL == 0) {
       if (pending[slot]) {  // bound the run-ahead: wait for the older snapshot of this slot
         OSB_CUDA(cudaEventSynchronize(sev[slot]));

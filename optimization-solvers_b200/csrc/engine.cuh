@@ -267,7 +267,7 @@ struct Solver {
 
  private:
   int minimize_host(LineSearch* ls, Objective* obj, int64_t max_iter, int64_t max_ls, osb_callback_fn cb, void* user);
-  int minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, int64_t max_ls);
+  int minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, int64_t max_ls, osb_callback_fn cb, void* user);
   bool device_engine_supported(const LineSearch* ls, const Objective* obj) const;
   void compute_conv_scalar(Objective* obj);
   int compute_direction(Objective* obj, LineSearch* ls);

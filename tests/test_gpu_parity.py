@@ -468,3 +468,28 @@ def test_tma_staged_lazy_kernel_matches_register_staged(osb):
             assert close(out[0][2], o[2], rtol=1e-10)
             if n <= 2056:
                 assert close(out[0][3], o[3], rtol=1e-10)
+
+
+def test_callback_and_trace_on_the_device_engine(osb):
+    """ls_solver.rs:104-107: the callback runs after k += 1 and sees the new iterate; the device engine honours it
+    with one synchronisation per outer iteration, and a callback run reproduces the callback-free run exactly."""
+    n = 2048
+    x0 = rosen_x0(n, 41)
+    ref = osb.BFGS(1e-8, x0).set_option("engine", 2).set_option("qn_schedule", 1)
+    run(osb, ref, osb.BackTracking(1e-4, 0.5), osb.ExtendedRosenbrock(n), 12, 20)
+    seen = []
+    s = osb.BFGS(1e-8, x0).set_option("engine", 2).set_option("qn_schedule", 1).record_trace(True)
+    try:
+        s.minimize(osb.BackTracking(1e-4, 0.5), osb.ExtendedRosenbrock(n), 12, 20, callback=lambda sv: seen.append((sv.k(), sv.x().copy())))
+    except osb.MaxIterReached:
+        pass
+    assert [k for k, _ in seen] == list(range(1, 13))
+    assert np.array_equal(seen[-1][1], ref.x()) and np.array_equal(s.x(), ref.x())
+    tr = s.trace()
+    assert len(tr["t"]) == 12 and np.all(np.diff(tr["f"]) < 0) and np.all(tr["t"] > 0)
+    # converging run: the callback count equals k (no callback for the iteration that detects convergence)
+    calls = []
+    obj = osb.SeparableQuadratic.generated(512)
+    s = osb.BFGS(1e-7, np.zeros(512)).set_option("engine", 2)
+    s.minimize(osb.BackTracking(1e-4, 0.5), obj, 300, 30, callback=lambda sv: calls.append(sv.k()))
+    assert len(calls) == s.k() and s.termination_reason() is not None
