@@ -125,8 +125,10 @@ int osb_objective_create_host(osb_ctx* ctx, int64_t n, osb_host_eval_fn fn, void
                               osb_objective** out);
 
 /* A user-supplied DEVICE functor: the callback must enqueue, on `stream` (a cudaStream_t), work
- * that reads d_x[n] and writes *d_f, d_g[n] and, if d_hess != NULL, d_hess[n*n] (device pointers).
- * It must not synchronise.  Returns 0 on success. */
+ * that reads d_x[n] and writes *d_f, d_g[n] and, if d_hess != NULL, the Hessian (device pointers).
+ * The Hessian buffer is row-major with leading dimension osb_hessian_ld(n) (n rounded up to 16
+ * doubles; the padding columns must be left zero).  It must not synchronise.  Returns 0 on success. */
+int64_t osb_hessian_ld(int64_t n);
 typedef int (*osb_device_eval_fn)(void* user, const double* d_x, int64_t n, double* d_f, double* d_g,
                                   double* d_hess, void* stream);
 int osb_objective_create_user(osb_ctx* ctx, int64_t n, osb_device_eval_fn fn, void* user, int with_hessian,

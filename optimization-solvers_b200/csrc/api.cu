@@ -128,6 +128,7 @@ int osb_objective_create_logistic_generated(osb_ctx* ctx, int64_t m, int64_t n, 
 int osb_objective_create_host(osb_ctx* ctx, int64_t n, osb_host_eval_fn fn, void* user, int with_h, osb_objective** out) {
   MAKE_OBJ(make_host_objective(C(ctx), n, fn, user, with_h != 0))
 }
+int64_t osb_hessian_ld(int64_t n) { return qn_ld(n); }
 int osb_objective_create_user(osb_ctx* ctx, int64_t n, osb_device_eval_fn fn, void* user, int with_h, osb_objective** out) {
   MAKE_OBJ(make_user_objective(C(ctx), n, fn, user, with_h != 0))
 }
