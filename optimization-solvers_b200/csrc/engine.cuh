@@ -189,6 +189,7 @@ struct QNLazyArgs {
   double* const* peers;
   unsigned long long* seq;
   int world, rank;
+  int tile_rows;  // filled by qn_launch_lazy
 };
 void qn_launch_lazy(Ctx* ctx, const QNLazyArgs& a, int variant = 0);
 void qn_launch_lazy_epilogue(Ctx* ctx, const QNLazyArgs& a);

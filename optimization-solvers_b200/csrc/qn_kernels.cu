@@ -25,11 +25,31 @@ constexpr int QN_CHUNK = QN_T * 2; // columns per sweep step (one 16-byte vector
 
 int64_t qn_ld(int64_t n) { return (n + 15) / 16 * 16; }
 // H is allocated with its row count rounded up to a whole tile (zero rows), so that the kernels
-// need neither row clamping nor store guards; vectors are allocated with ld entries (zero padded).
-int64_t qn_rows_padded(int64_t nrows) { return (nrows + QN_R - 1) / QN_R * QN_R; }
+// need no row clamping (a CTA's last, partial tile still LOADS whole tiles: hence the extra tile of slack);
+// vectors are allocated with ld entries (zero padded).
+int64_t qn_rows_padded(int64_t nrows) { return (nrows + QN_R - 1) / QN_R * QN_R + QN_R; }
+
+// Tile height: tiles of `rt` <= QN_R rows are dealt round-robin to the CTAs (round-robin keeps concurrently
+// running CTAs on ADJACENT rows, which the memory system rewards: profiles/r01_rmw_pattern_experiments.txt;
+// contiguous per-CTA row ranges were measured 2 % slower).  With rt = 8, 256 tiles on 148 CTAs (the 8-GPU
+// shard of n = 16384) take two full waves for 1.73 waves of work; rt = 7 gives 293 tiles = 1.98 waves.
+// The host picks the rt in 5..8 that minimises waves * rt.
+inline int qn_pick_tile_rows(int64_t nrows, int grid) {
+  int best = QN_R;
+  int64_t best_cost = -1;
+  for (int rt = QN_R; rt >= 5; --rt) {
+    const int64_t tiles = (nrows + rt - 1) / rt;
+    const int64_t cost = ((tiles + grid - 1) / grid) * rt;
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = rt;
+    }
+  }
+  return best;
+}
 
 __device__ __forceinline__ void tile_reduce_store(double (&acc)[QN_R], double (*red)[QN_T / 32], double* out, int64_t row_base,
-                                                  int64_t r0, int64_t nrows) {
+                                                  int64_t r0, int64_t rend) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int r = 0; r < QN_R; ++r) {
@@ -41,7 +61,7 @@ __device__ __forceinline__ void tile_reduce_store(double (&acc)[QN_R], double (*
     double v = 0.0;
 #pragma unroll
     for (int w = 0; w < QN_T / 32; ++w) v = v + red[threadIdx.x][w];
-    if (r0 + threadIdx.x < nrows) out[row_base + r0 + threadIdx.x] = v;
+    if (r0 + threadIdx.x < rend) out[row_base + r0 + threadIdx.x] = v;
     __threadfence();  // the fused coefficient epilogue of another CTA may read this row sum
   }
   __syncthreads();
@@ -56,7 +76,7 @@ __device__ __forceinline__ void qn_coef_body(int kind, int64_t n, DevState* st, 
 __global__ void __launch_bounds__(QN_T, 2)
 qn_gemv_kernel(const double* __restrict__ H, int64_t ld, int64_t nrows, int64_t row0, DevState* st,
                const double* __restrict__ v, double* out, const double* __restrict__ v_skip,
-               double* __restrict__ out_skip, QNCoefArgs ca) {
+               double* __restrict__ out_skip, QNCoefArgs ca, int rt) {
   bool fuse_coef = ca.ticket != nullptr;
   if (st != nullptr) {
     if (st->done) return;
@@ -70,9 +90,9 @@ qn_gemv_kernel(const double* __restrict__ H, int64_t ld, int64_t nrows, int64_t 
   const unsigned long long pol = l2_evict_first_policy();
   __shared__ double red[QN_R][QN_T / 32];
   __shared__ bool is_last;
-  const int64_t ntiles = (nrows + QN_R - 1) / QN_R;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t r0 = tile * QN_R;
+  for (int64_t r0 = (int64_t)blockIdx.x * rt; r0 < nrows; r0 += (int64_t)gridDim.x * rt) {
+    const int64_t re = r0 + rt < nrows ? r0 + rt : nrows;
+    const int rows_here = (int)(re - r0);
     double acc[QN_R];
 #pragma unroll
     for (int r = 0; r < QN_R; ++r) acc[r] = 0.0;
@@ -81,14 +101,14 @@ qn_gemv_kernel(const double* __restrict__ H, int64_t ld, int64_t nrows, int64_t 
       const double2 vv = *reinterpret_cast<const double2*>(v + col);
       double2 hv[QN_R];
 #pragma unroll
-      for (int r = 0; r < QN_R; ++r) hv[r] = ld_stream_nc_ef(base + r * ld + col, pol);
+      for (int r = 0; r < QN_R; ++r) hv[r] = r < rows_here ? ld_stream_nc_ef(base + r * ld + col, pol) : make_double2(0.0, 0.0);
 #pragma unroll
       for (int r = 0; r < QN_R; ++r) {
         acc[r] = fma(hv[r].x, vv.x, acc[r]);
         acc[r] = fma(hv[r].y, vv.y, acc[r]);
       }
     }
-    tile_reduce_store(acc, red, out, row0, r0, nrows);
+    tile_reduce_store(acc, red, out, row0, r0, re);
   }
   if (!fuse_coef) return;
   // fused epilogue (single GPU): the last CTA to finish owns the complete h and computes y.h and the
@@ -108,12 +128,12 @@ qn_gemv_kernel(const double* __restrict__ H, int64_t ld, int64_t nrows, int64_t 
 void qn_launch_gemv(Ctx* ctx, const double* H, int64_t ld, int64_t nrows, int64_t row0, const DevState* st, const double* v,
                     double* out, const double* v_skip, double* out_skip, int variant, const QNCoefArgs* coef) {
   (void)variant;
-  int64_t ntiles = (nrows + QN_R - 1) / QN_R;
-  int grid = (int)std::min<int64_t>(ntiles, (int64_t)ctx->num_sms * 2);
+  int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nrows + QN_R - 1) / QN_R, (int64_t)ctx->num_sms * 2));
+  const int rt = qn_pick_tile_rows(nrows, grid);
   QNCoefArgs ca{};
   if (coef) ca = *coef;
   // rows are addressed relative to the local block; `out` is indexed by global row (row0 + local row)
-  qn_gemv_kernel<<<grid, QN_T, 0, ctx->stream>>>(H, ld, nrows, row0, const_cast<DevState*>(st), v, out, v_skip, out_skip, ca);
+  qn_gemv_kernel<<<grid, QN_T, 0, ctx->stream>>>(H, ld, nrows, row0, const_cast<DevState*>(st), v, out, v_skip, out_skip, ca, rt);
   ctx->counters[0]++;
 }
 
@@ -219,22 +239,24 @@ template <int KIND>
 __global__ void __launch_bounds__(QN_T, 1)
 qn_update_kernel(double* __restrict__ H, int64_t ld, int64_t nrows, int64_t row0, const DevState* __restrict__ st,
                  const double* __restrict__ p, const double* __restrict__ q, const double* __restrict__ rv,
-                 const double* __restrict__ g, double* __restrict__ u_out) {
+                 const double* __restrict__ g, double* __restrict__ u_out, int rt) {
   if (st->done || st->skip) return;
   const double c0 = st->c0, c1 = st->c1, c2 = st->c2;
   const unsigned long long pol = l2_evict_first_policy();
   __shared__ double red[QN_R][QN_T / 32];
   __shared__ double2 rowpq[QN_R];
-  const int64_t ntiles = (nrows + QN_R - 1) / QN_R;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t r0 = tile * QN_R;
+  for (int64_t r0 = (int64_t)blockIdx.x * rt; r0 < nrows; r0 += (int64_t)gridDim.x * rt) {
+    const int64_t re = r0 + rt < nrows ? r0 + rt : nrows;
+    const int rows_here = (int)(re - r0);
     double acc[QN_R];
 #pragma unroll
     for (int r = 0; r < QN_R; ++r) acc[r] = 0.0;
     // per-row scalars (p_i, q_i) are CTA-uniform: kept in shared memory and read as broadcasts
-    if (threadIdx.x < QN_R)
-      rowpq[threadIdx.x] = make_double2(p[row0 + r0 + threadIdx.x],
-                                        (KIND == QN_BFGS || KIND == QN_DFP) ? q[row0 + r0 + threadIdx.x] : 0.0);
+    if (threadIdx.x < QN_R) {
+      const bool ok = (int)threadIdx.x < rows_here;
+      rowpq[threadIdx.x] = make_double2(ok ? p[row0 + r0 + threadIdx.x] : 0.0,
+                                        (ok && (KIND == QN_BFGS || KIND == QN_DFP)) ? q[row0 + r0 + threadIdx.x] : 0.0);
+    }
     __syncthreads();
     double* __restrict__ base = H + r0 * ld;
     for (int col = 2 * threadIdx.x; col < (int)ld; col += QN_CHUNK) {
@@ -245,7 +267,7 @@ qn_update_kernel(double* __restrict__ H, int64_t ld, int64_t nrows, int64_t row0
       if (KIND == QN_BROYDEN) pj = *reinterpret_cast<const double2*>(rv + col);  // column vector v = H^T s
       double2 hv[QN_R];
 #pragma unroll
-      for (int r = 0; r < QN_R; ++r) hv[r] = ld_stream_ef(base + r * ld + col, pol);
+      for (int r = 0; r < QN_R; ++r) hv[r] = r < rows_here ? ld_stream_ef(base + r * ld + col, pol) : make_double2(0.0, 0.0);
 #pragma unroll
       for (int r = 0; r < QN_R; ++r) {
         double2 hn;
@@ -265,10 +287,10 @@ qn_update_kernel(double* __restrict__ H, int64_t ld, int64_t nrows, int64_t row0
         }
         acc[r] = fma(hn.x, gj.x, acc[r]);
         acc[r] = fma(hn.y, gj.y, acc[r]);
-        st_stream_ef(base + r * ld + col, hn, pol);
+        if (r < rows_here) st_stream_ef(base + r * ld + col, hn, pol);
       }
     }
-    tile_reduce_store(acc, red, u_out, row0, r0, nrows);
+    tile_reduce_store(acc, red, u_out, row0, r0, re);
   }
 }
 
@@ -354,16 +376,20 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_kernel(QNLazyArgs a) {
   const double* __restrict__ q = a.ph;
   const double* __restrict__ yv = a.y;
   const double* __restrict__ gv = a.g;
-  const int64_t ntiles = (nrows + QN_R - 1) / QN_R;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned long long seq = a.peers != nullptr ? *a.seq + 1ULL : 0ULL;  // this exchange's sequence number
   const int par = (int)(seq & 1ULL);
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t r0 = tile * QN_R;
+  const int rt = a.tile_rows;
+  for (int64_t r0 = (int64_t)blockIdx.x * rt; r0 < nrows; r0 += (int64_t)gridDim.x * rt) {
+    const int64_t re = r0 + rt < nrows ? r0 + rt : nrows;
+    const int rows_here = (int)(re - r0);
     double ah[QN_R], aw[QN_R];
 #pragma unroll
     for (int r = 0; r < QN_R; ++r) ah[r] = aw[r] = 0.0;
-    if (threadIdx.x < QN_R) rowpq[threadIdx.x] = make_double2(p[row0 + r0 + threadIdx.x], q[row0 + r0 + threadIdx.x]);
+    if (threadIdx.x < QN_R) {
+      const bool ok = (int)threadIdx.x < rows_here;
+      rowpq[threadIdx.x] = make_double2(ok ? p[row0 + r0 + threadIdx.x] : 0.0, ok ? q[row0 + r0 + threadIdx.x] : 0.0);
+    }
     __syncthreads();
     double* __restrict__ base = a.M + r0 * ld;
     for (int col = 2 * threadIdx.x; col < (int)ld; col += QN_CHUNK) {
@@ -373,7 +399,7 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_kernel(QNLazyArgs a) {
       const double2 qj = *reinterpret_cast<const double2*>(q + col);
       double2 hv[QN_R];
 #pragma unroll
-      for (int r = 0; r < QN_R; ++r) hv[r] = ld_stream_ef(base + r * ld + col, pol);
+      for (int r = 0; r < QN_R; ++r) hv[r] = r < rows_here ? ld_stream_ef(base + r * ld + col, pol) : make_double2(0.0, 0.0);
 #pragma unroll
       for (int r = 0; r < QN_R; ++r) {
         const double2 pq = rowpq[r];
@@ -391,7 +417,7 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_kernel(QNLazyArgs a) {
         ah[r] = fma(hn.y, yj.y, ah[r]);
         aw[r] = fma(hn.x, gj.x, aw[r]);
         aw[r] = fma(hn.y, gj.y, aw[r]);
-        st_stream_ef(base + r * ld + col, hn, pol);
+        if (r < rows_here) st_stream_ef(base + r * ld + col, hn, pol);
       }
     }
 #pragma unroll
@@ -408,7 +434,7 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_kernel(QNLazyArgs a) {
 #pragma unroll
       for (int w = 0; w < QN_T / 32; ++w) v = v + red[threadIdx.x][w];
       const int r = threadIdx.x % QN_R;
-      if (r0 + r < nrows) {
+      if (r < rows_here) {
         if (threadIdx.x < QN_R) a.h[row0 + r0 + r] = v;
         else a.w[row0 + r0 + r] = v;
       }
@@ -697,7 +723,9 @@ __global__ void __launch_bounds__(QN_T) qn_lazy_epilogue_kernel(QNLazyArgs a) {
   lazy_epilogue_body<KIND>(a, smem);
 }
 
-void qn_launch_lazy(Ctx* ctx, const QNLazyArgs& a, int variant) {
+void qn_launch_lazy(Ctx* ctx, const QNLazyArgs& a_in, int variant) {
+  QNLazyArgs a = a_in;
+  a.tile_rows = qn_pick_tile_rows(a.nrows, (int)std::min<int64_t>((a.nrows + QN_R - 1) / QN_R, (int64_t)ctx->num_sms));
   if (variant == 1) {
     static bool attr = false;
     if (!attr) {
@@ -727,15 +755,18 @@ void qn_launch_lazy_epilogue(Ctx* ctx, const QNLazyArgs& a) {
 // apply the pending update only (no products): M <- M + rank2(ps, ph; pc*)
 template <int KIND>
 __global__ void __launch_bounds__(QN_T, 1) qn_flush_kernel(double* __restrict__ M, int64_t ld, int64_t nrows, int64_t row0, DevState* st,
-                                                          const double* __restrict__ p, const double* __restrict__ q) {
+                                                          const double* __restrict__ p, const double* __restrict__ q, int rt) {
   if (!st->pending) return;
   const double c0 = st->pc0, c1 = st->pc1, c2 = st->pc2;
   __shared__ double2 rowpq[QN_R];
-  const int64_t ntiles = (nrows + QN_R - 1) / QN_R;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t r0 = tile * QN_R;
+  for (int64_t r0 = (int64_t)blockIdx.x * rt; r0 < nrows; r0 += (int64_t)gridDim.x * rt) {
+    const int64_t re = r0 + rt < nrows ? r0 + rt : nrows;
+    const int rows_here = (int)(re - r0);
     __syncthreads();
-    if (threadIdx.x < QN_R) rowpq[threadIdx.x] = make_double2(p[row0 + r0 + threadIdx.x], q[row0 + r0 + threadIdx.x]);
+    if (threadIdx.x < QN_R) {
+      const bool ok = (int)threadIdx.x < rows_here;
+      rowpq[threadIdx.x] = make_double2(ok ? p[row0 + r0 + threadIdx.x] : 0.0, ok ? q[row0 + r0 + threadIdx.x] : 0.0);
+    }
     __syncthreads();
     double* __restrict__ base = M + r0 * ld;
     for (int col = 2 * threadIdx.x; col < (int)ld; col += QN_CHUNK) {
@@ -745,6 +776,7 @@ __global__ void __launch_bounds__(QN_T, 1) qn_flush_kernel(double* __restrict__ 
       for (int r = 0; r < QN_R; ++r) {
         const double2 pq = rowpq[r];
         const double pi = pq.x, qi = pq.y;
+        if (r >= rows_here) continue;
         double2 hv = ld_stream(base + r * ld + col), hn;
         if (KIND == QN_BFGS) {
           const double cx = pi * qj.x + qi * pj.x, cy = pi * qj.y + qi * pj.y;
@@ -767,8 +799,9 @@ void qn_launch_flush(Ctx* ctx, int kind, double* M, int64_t ld, int64_t nrows, i
                      const double* ph) {
   int64_t ntiles = (nrows + QN_R - 1) / QN_R;
   int grid = (int)std::min<int64_t>(ntiles, (int64_t)ctx->num_sms);
-  if (kind == QN_BFGS) qn_flush_kernel<QN_BFGS><<<grid, QN_T, 0, ctx->stream>>>(M, ld, nrows, row0, st, ps, ph);
-  else qn_flush_kernel<QN_DFP><<<grid, QN_T, 0, ctx->stream>>>(M, ld, nrows, row0, st, ps, ph);
+  const int rt = qn_pick_tile_rows(nrows, grid);
+  if (kind == QN_BFGS) qn_flush_kernel<QN_BFGS><<<grid, QN_T, 0, ctx->stream>>>(M, ld, nrows, row0, st, ps, ph, rt);
+  else qn_flush_kernel<QN_DFP><<<grid, QN_T, 0, ctx->stream>>>(M, ld, nrows, row0, st, ps, ph, rt);
   qn_clear_pending_kernel<<<1, 1, 0, ctx->stream>>>(st);
   ctx->counters[0] += 2;
 }
@@ -778,11 +811,12 @@ void qn_launch_update(Ctx* ctx, int kind, double* H, int64_t ld, int64_t nrows, 
   (void)variant;
   int64_t ntiles = (nrows + QN_R - 1) / QN_R;
   int grid = (int)std::min<int64_t>(ntiles, (int64_t)ctx->num_sms);
+  const int rt = qn_pick_tile_rows(nrows, grid);
   switch (kind) {
-    case QN_BFGS: qn_update_kernel<QN_BFGS><<<grid, QN_T, 0, ctx->stream>>>(H, ld, nrows, row0, st, p, q, r, g, u_out); break;
-    case QN_DFP: qn_update_kernel<QN_DFP><<<grid, QN_T, 0, ctx->stream>>>(H, ld, nrows, row0, st, p, q, r, g, u_out); break;
-    case QN_SR1: qn_update_kernel<QN_SR1><<<grid, QN_T, 0, ctx->stream>>>(H, ld, nrows, row0, st, p, q, r, g, u_out); break;
-    default: qn_update_kernel<QN_BROYDEN><<<grid, QN_T, 0, ctx->stream>>>(H, ld, nrows, row0, st, p, q, r, g, u_out); break;
+    case QN_BFGS: qn_update_kernel<QN_BFGS><<<grid, QN_T, 0, ctx->stream>>>(H, ld, nrows, row0, st, p, q, r, g, u_out, rt); break;
+    case QN_DFP: qn_update_kernel<QN_DFP><<<grid, QN_T, 0, ctx->stream>>>(H, ld, nrows, row0, st, p, q, r, g, u_out, rt); break;
+    case QN_SR1: qn_update_kernel<QN_SR1><<<grid, QN_T, 0, ctx->stream>>>(H, ld, nrows, row0, st, p, q, r, g, u_out, rt); break;
+    default: qn_update_kernel<QN_BROYDEN><<<grid, QN_T, 0, ctx->stream>>>(H, ld, nrows, row0, st, p, q, r, g, u_out, rt); break;
   }
   ctx->counters[0]++;
 }
