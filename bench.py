@@ -100,9 +100,9 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
+def ncu_traffic(lazy=True):
     """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
-    p = os.path.join(ROOT, "profiles", "qn_update_ncu_summary.json")
+    p = os.path.join(ROOT, "profiles", "qn_lazy_ncu_summary.json" if lazy else "qn_update_ncu_summary.json")
     if os.path.exists(p):
         try:
             return float(json.load(open(p))["dram_bytes_per_launch"])
@@ -250,7 +250,7 @@ def main():
              else "qn_update_kernel<BFGS> (fused rank-2 RMW + u = H' g)")
     roofline = {"bound": "hbm", "kernel": kname, "achieved": ach,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": (ach / peak) if ach else None,
-                "traffic": ncu_traffic(), "algorithmic_bytes_per_launch": upd_bytes, "ms_per_launch": kt["update_ms"],
+                "traffic": ncu_traffic(lazy) if world == 1 else None, "algorithmic_bytes_per_launch": upd_bytes, "ms_per_launch": kt["update_ms"],
                 "gemv_kernel": None if lazy else {
                     "achieved": gemv_bytes / (kt["gemv_ms"] * 1e-3) / 1e9 if kt["gemv_ms"] > 0 else None,
                     "ms_per_launch": kt["gemv_ms"], "algorithmic_bytes_per_launch": gemv_bytes},

@@ -435,14 +435,24 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_kernel(QNLazyArgs a) {
       for (int w = 0; w < QN_T / 32; ++w) v = v + red[threadIdx.x][w];
       const int r = threadIdx.x % QN_R;
       if (r < rows_here) {
-        if (threadIdx.x < QN_R) a.h[row0 + r0 + r] = v;
-        else a.w[row0 + r0 + r] = v;
+        if (a.peers != nullptr) {
+          // fused all-gather: the row sum goes straight into every rank's exchange region (NVLink peer stores,
+          // `par` double-buffers the region across iterations).  The stores are posted here and fenced ONCE per
+          // CTA below, so their latency overlaps with the streaming of the other CTAs.
+          const int64_t off = (int64_t)(par * 2 + (threadIdx.x < QN_R ? 0 : 1)) * XCHG_LD + row0 + r0 + r;
+          for (int pr = 0; pr < a.world; ++pr) a.peers[pr][off] = v;
+        } else {
+          if (threadIdx.x < QN_R) a.h[row0 + r0 + r] = v;
+          else a.w[row0 + r0 + r] = v;
+        }
       }
-      __threadfence();
+      if (a.peers == nullptr) __threadfence();
     }
     __syncthreads();
   }
   if (a.ticket == nullptr) return;
+  if (a.peers != nullptr && threadIdx.x < 2 * QN_R) __threadfence_system();  // this CTA's peer stores are performed
+  __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
     const unsigned int t = atomicAdd(a.ticket, 1u);
@@ -452,20 +462,9 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_kernel(QNLazyArgs a) {
   if (!is_last) return;
   __threadfence();
   if (a.peers != nullptr) {
-    // fused all-gather: this rank's slices of h and w are complete locally; push them into every rank's
-    // exchange region in one burst of NVLink peer stores (`par` double-buffers the region across
-    // iterations), publish "rank `a.rank` reached `seq`" on every rank, then wait until all ranks have
-    // published the same sequence number here
-    for (int pr = 0; pr < a.world; ++pr) {
-      double* dst_h = a.peers[pr] + (int64_t)(par * 2 + 0) * XCHG_LD + row0;
-      double* dst_w = a.peers[pr] + (int64_t)(par * 2 + 1) * XCHG_LD + row0;
-      for (int64_t i = 2 * threadIdx.x; i < nrows; i += 2 * QN_T) {
-        *reinterpret_cast<double2*>(dst_h + i) = *reinterpret_cast<const double2*>(a.h + row0 + i);
-        *reinterpret_cast<double2*>(dst_w + i) = *reinterpret_cast<const double2*>(a.w + row0 + i);
-      }
-    }
+    // every local CTA has pushed and fenced its rows: publish "rank `a.rank` reached `seq`" on every rank,
+    // then wait until all ranks have published the same sequence number here
     __threadfence_system();
-    __syncthreads();
     unsigned long long* myflags = reinterpret_cast<unsigned long long*>(a.peers[a.rank] + 4 * XCHG_LD);
     if (threadIdx.x < a.world) {
       unsigned long long* f = reinterpret_cast<unsigned long long*>(a.peers[threadIdx.x] + 4 * XCHG_LD) + a.rank;
