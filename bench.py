@@ -161,6 +161,8 @@ def main():
     ap.add_argument("--n", type=int, default=N_DIM, help="problem dimension (the benchmark line is only valid at 16384)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--head", type=int, default=0, help="device-engine head variant (0 cluster+speculation, 3 cluster, 1 single CTA)")
+    ap.add_argument("--storage", default="full", choices=["full", "sym"],
+                    help="sym: packed lower triangle of H (n^2 8 B per iteration; single GPU, lazy schedule)")
     ap.add_argument("--qn-kernel", type=int, default=0, help="lazy-pass kernel: 0 = register-staged LDG, 1 = TMA-staged (cp.async.bulk + mbarrier)")
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL all-gathers instead of the fused peer-memory exchange")
     ap.add_argument("--schedule", default="lazy", choices=["lazy", "eager"],
@@ -205,6 +207,8 @@ def main():
     solver = osb.BFGS(TOL, x0, ctx=ctx).set_option("engine", 2).set_option("qn_schedule", 1 if lazy else 0)
     solver.set_option("head_kernel", args.head)
     solver.set_option("qn_kernel", args.qn_kernel)
+    sym = lazy and args.storage == "sym" and world == 1
+    solver.set_option("qn_storage", 1 if sym else 0)
 
     def run_steps(k):
         try:
@@ -244,13 +248,16 @@ def main():
     upd_bytes = 2.0 * rows_local * n * 8.0  # read H + write H' (local row block); O(n) vectors excluded
     gemv_bytes = 1.0 * rows_local * n * 8.0
     iter_bytes = (2.0 if lazy else 3.0) * rows_local * n * 8.0
+    if sym:
+        upd_bytes = iter_bytes = 1.0 * n * n * 8.0  # read + write of the lower triangle
     peak, peak_src = hbm_peak()
     ach = upd_bytes / (kt["update_ms"] * 1e-3) / 1e9 if kt["update_ms"] > 0 else None
-    kname = ("qn_lazy_kernel<BFGS> (pending rank-2 RMW + h = H y + w = H g in one pass)" if lazy
+    kname = ("qn_lazy_sym_kernel<BFGS> + fold (packed lower triangle: pending rank-2 RMW + row and column sums)" if sym else
+             "qn_lazy_kernel<BFGS> (pending rank-2 RMW + h = H y + w = H g in one pass)" if lazy
              else "qn_update_kernel<BFGS> (fused rank-2 RMW + u = H' g)")
     roofline = {"bound": "hbm", "kernel": kname, "achieved": ach,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": (ach / peak) if ach else None,
-                "traffic": ncu_traffic(lazy) if world == 1 else None, "algorithmic_bytes_per_launch": upd_bytes, "ms_per_launch": kt["update_ms"],
+                "traffic": ncu_traffic(lazy) if (world == 1 and not sym) else None, "algorithmic_bytes_per_launch": upd_bytes, "ms_per_launch": kt["update_ms"],
                 "gemv_kernel": None if lazy else {
                     "achieved": gemv_bytes / (kt["gemv_ms"] * 1e-3) / 1e9 if kt["gemv_ms"] > 0 else None,
                     "ms_per_launch": kt["gemv_ms"], "algorithmic_bytes_per_launch": gemv_bytes},
@@ -324,7 +331,8 @@ def main():
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "n": n, "line_search": "BackTracking(1e-4,0.5)", "tol": TOL,
                            "max_iter_line_search": MAX_LS, "engine": "device-resident control",
-                           "schedule": "lazy: 1 RMW pass of H per iteration (2 n^2 8 B)" if lazy else "eager: gemv + fused update (3 n^2 8 B)",
+                           "schedule": "lazy + packed symmetric storage: 1 RMW pass of the lower triangle per iteration (n^2 8 B)" if sym else
+                           "lazy: 1 RMW pass of H per iteration (2 n^2 8 B)" if lazy else "eager: gemv + fused update (3 n^2 8 B)",
                            "l2": "inputs larger than L2 (H = %.2f GiB per GPU, streamed every step)" % (rows_local * n * 8 / 2 ** 30),
                            "parallelism": "row-block sharded H over %d GPU(s); exchange: %s" % (
                                world, "none" if world == 1 else ("NCCL all-gather of the h / w slices" if (args.no_p2p or not lazy)

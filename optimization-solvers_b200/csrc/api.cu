@@ -362,6 +362,7 @@ int osb_solver_set_option(osb_solver* s, const char* name, int64_t value) {
   else if (nm == "record_trace") S(s)->record_trace = (int)value;
   else if (nm == "qn_kernel") S(s)->qn_variant = (int)value;
   else if (nm == "qn_schedule") S(s)->qn_schedule = (int)value;
+  else if (nm == "qn_storage") S(s)->qn_storage = (int)value;
   else if (nm == "use_p2p") S(s)->use_p2p = (int)value;
   else if (nm == "head_debug") {
     if (value && !g_head_tdbg) {
@@ -455,6 +456,16 @@ int osb_solver_set_inv_hessian(osb_solver* s, const double* in) {
   OSB_REQUIRE(p->is_qn, OSB_ERROR_INPUT_PARAMS, "not a quasi-Newton solver");
   p->ctx->use();
   p->flush_pending();
+  {
+    bool sym = true;  // packed symmetric storage is only valid for a symmetric matrix
+    for (int64_t i = 0; i < p->n && sym; ++i)
+      for (int64_t j = 0; j < i; ++j)
+        if (in[i * p->n + j] != in[j * p->n + i]) {
+          sym = false;
+          break;
+        }
+    p->h_symmetric = sym;
+  }
   OSB_CUDA(cudaMemcpy2DAsync(p->H.p, p->ld * sizeof(double), in + p->row0 * p->n, p->n * sizeof(double), p->n * sizeof(double),
                              p->nrows, cudaMemcpyHostToDevice, p->ctx->stream));
   p->ctx->sync();

@@ -274,7 +274,15 @@ void Solver::prof_collect() {
 }
 
 // lazy schedule: the stored matrix lags the true H by one rank-2 update; apply it (predicated on the device flag)
+// packed symmetric copy -> full matrix (getters, engine / schedule switches)
+void Solver::sym_to_full() {
+  if (!sym_current) return;
+  qn_sym_unpack(ctx, Hsym.p, ld, n, H.p);
+  sym_current = false;
+}
+
 void Solver::flush_pending() {
+  sym_to_full();
   if (!lazy_used) return;
   qn_launch_flush(ctx, qn_kind, H.p, ld, nrows, row0, d_state, ps.p, ph.p);
   lazy_used = false;
@@ -287,7 +295,30 @@ void Solver::qn_after_step() {
     u_valid = true;
     return;
   }
+  if (qn_schedule == 1 && qn_storage == 1 && h_symmetric && ctx->world == 1 && (qn_kind == QN_BFGS || qn_kind == QN_DFP)) {
+    // packed symmetric storage: the pass moves n^2 * 8 B (read + write of the lower triangle).  A pending
+    // update means "the stored matrix lags by one rank-2 term": packing the lagging matrix keeps that meaning.
+    if (!sym_current) {
+      if (Hsym.p == nullptr) {
+        Hsym.alloc(qn_sym_doubles(n));
+        colpart.alloc((int64_t)qn_sym_grid(ctx, n) * 2 * ld);
+      }
+      qn_sym_pack(ctx, H.p, ld, n, Hsym.p);
+      sym_current = true;
+    }
+    QNLazyArgs a{nullptr, ld, nrows, row0, n, d_state, ps.p, ph.p, y.p, g.p, s.p, h.p, wv.p, u.p, ps.p, ph.p,
+                 ctx->gemv_ticket, qn_kind, nullptr, ctx->d_seq, 1, 0};
+    prof_mark();
+    prof_mark();
+    prof_mark();
+    qn_launch_lazy_sym(ctx, a, Hsym.p, colpart.p, n, ld);
+    prof_mark();
+    lazy_used = true;
+    u_valid = true;
+    return;
+  }
   if (qn_schedule == 1 && (qn_kind == QN_BFGS || qn_kind == QN_DFP)) {
+    sym_to_full();  // (the pending update, if any, now refers to the full matrix)
     // ONE read-modify-write per iteration (2 n^2 8 B): pending update + h = H y + w = H g, epilogue forms u
     const bool p2p = ctx->world > 1 && ctx->p2p_ready && ld <= XCHG_LD && use_p2p;
     QNLazyArgs a{H.p, ld, nrows, row0, n, d_state, ps.p, ph.p, y.p, g.p, s.p, h.p, wv.p, u.p, ps.p, ph.p,

@@ -193,6 +193,12 @@ struct QNLazyArgs {
 };
 void qn_launch_lazy(Ctx* ctx, const QNLazyArgs& a, int variant = 0);
 void qn_launch_lazy_epilogue(Ctx* ctx, const QNLazyArgs& a);
+// packed symmetric storage (lower triangle in 8-row tiles): one pass moves n^2 * 8 B
+int64_t qn_sym_doubles(int64_t n);
+int qn_sym_grid(Ctx* ctx, int64_t n);
+void qn_sym_pack(Ctx* ctx, const double* H, int64_t ld, int64_t n, double* P);
+void qn_sym_unpack(Ctx* ctx, const double* P, int64_t ld, int64_t n, double* H);
+void qn_launch_lazy_sym(Ctx* ctx, const QNLazyArgs& a, double* P, double* colpart, int64_t n, int64_t ld);
 // apply a pending update to the stored matrix (getters, engine switches)
 void qn_launch_flush(Ctx* ctx, int kind, double* M, int64_t ld, int64_t nrows, int64_t row0, DevState* st, const double* ps,
                      const double* ph);
@@ -232,6 +238,11 @@ struct Solver {
   DBuf wv, ps, ph;        // lazy schedule: w = H g, pending p and q
   int qn_schedule = 0;    // 0 = eager (h = H y, then fused update: 3 n^2 8 B), 1 = lazy (one RMW: 2 n^2 8 B)
   bool lazy_used = false;
+  int qn_storage = 0;     // 0 = full n x n, 1 = packed symmetric lower triangle (lazy schedule, BFGS/DFP, single GPU)
+  DBuf Hsym, colpart;     // packed matrix and per-CTA column partials
+  bool sym_current = false;  // the packed copy (not H) holds the current matrix
+  bool h_symmetric = true;   // false after set_inv_hessian with a non-symmetric matrix (then full storage is used)
+  void sym_to_full();
   int use_p2p = 1;        // lazy schedule, world > 1: fused peer-memory all-gather when the context is IPC-connected
   void flush_pending();
   // Newton family

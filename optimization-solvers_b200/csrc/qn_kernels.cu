@@ -715,6 +715,229 @@ __global__ void __launch_bounds__(TM_T, 1) qn_lazy_tma_kernel(QNLazyArgs a) {
   if (tid == 0) *a.ticket = 0u;
 }
 
+// ---- lazy pass on PACKED SYMMETRIC storage (qn_storage = 1) ---------------------------------------
+// BFGS / DFP keep H exactly symmetric (every update term is symmetric in (i, j)), so only the lower
+// triangle needs to live in HBM: the pass reads and writes n^2/2 elements, i.e. n^2 * 8 B of traffic per
+// iteration instead of 2 n^2 * 8 B.
+// Layout: row tiles of 8 rows; tile T (rows 8T .. 8T+7) stores, for each of its rows, the columns
+// 0 .. 8T+7 (the 8x8 diagonal block is stored in full), padded to a multiple of 16 doubles; tiles are
+// consecutive.  A stored element M_ij contributes to the row sum of i (as before) and — when it lies
+// strictly left of the diagonal block — to the row sum of j (M_ji = M_ij).  The second contribution is
+// a COLUMN sum: the thread that owns the column accumulates it over the 8 rows of the tile in
+// registers and adds it to a per-CTA partial vector (L2-resident, 148 x n x 2 doubles); a fold kernel
+// adds the per-CTA partials in CTA order (deterministic) to the row sums.
+__host__ __device__ inline int64_t sym_lpad(int64_t tile) { return 16 * (tile / 2) + 16; }  // roundup16(8 tile + 8)
+__host__ __device__ inline int64_t sym_tile_offset(int64_t tile) {                          // doubles before tile
+  const int64_t m = tile / 2;
+  int64_t cnt = 16 * m * (m + 1);      // sum of lpad over tiles < 2m
+  if (tile & 1) cnt += 16 * (m + 1);
+  return 8 * cnt;
+}
+int64_t qn_sym_doubles(int64_t n) { return sym_tile_offset((n + 7) / 8) + 8 * sym_lpad((n + 7) / 8); }
+
+struct QNSymArgs {
+  double* P;         // packed matrix
+  double* colpart;   // gridDim x 2 x ld per-CTA column partials (h then w)
+  int64_t n, ld;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(QN_T, 1) qn_lazy_sym_kernel(QNLazyArgs a, QNSymArgs sa) {
+  DevState* st = a.st;
+  if (st->done) return;
+  const double c0 = st->pc0, c1 = st->pc1, c2 = st->pc2;
+  const unsigned long long pol = l2_evict_first_policy();
+  __shared__ double red[2 * QN_R][QN_T / 32];
+  __shared__ double4 rowv[QN_R];  // p_i, q_i, y_i, g_i of the tile's rows
+  const int64_t n = sa.n, ld = sa.ld;
+  const double* __restrict__ p = a.ps;
+  const double* __restrict__ q = a.ph;
+  const double* __restrict__ yv = a.y;
+  const double* __restrict__ gv = a.g;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* __restrict__ cph = sa.colpart + (int64_t)blockIdx.x * 2 * ld;
+  double* __restrict__ cpw = cph + ld;
+  // zero this CTA's column partials (columns it will touch are a subset of [0, n))
+  for (int64_t j = 2 * threadIdx.x; j < ld; j += 2 * QN_T) {
+    *reinterpret_cast<double2*>(cph + j) = make_double2(0.0, 0.0);
+    *reinterpret_cast<double2*>(cpw + j) = make_double2(0.0, 0.0);
+  }
+  __syncthreads();
+  const int64_t ntiles = (n + QN_R - 1) / QN_R;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r0 = tile * QN_R;
+    const int rows_here = (int)((n - r0) < QN_R ? (n - r0) : QN_R);
+    const int64_t lpad = sym_lpad(tile);
+    const int ncols = (int)(r0 + QN_R < n ? r0 + QN_R : n);  // stored columns: 0 .. ncols-1
+    double ah[QN_R], aw[QN_R];
+#pragma unroll
+    for (int r = 0; r < QN_R; ++r) ah[r] = aw[r] = 0.0;
+    if (threadIdx.x < QN_R) {
+      const bool ok = (int)threadIdx.x < rows_here;
+      const int64_t i = r0 + threadIdx.x;
+      rowv[threadIdx.x] = ok ? make_double4(p[i], q[i], yv[i], gv[i]) : make_double4(0.0, 0.0, 0.0, 0.0);
+    }
+    __syncthreads();
+    double* __restrict__ base = sa.P + sym_tile_offset(tile);
+    for (int col = 2 * threadIdx.x; col < (int)lpad; col += QN_CHUNK) {
+      // element validity: columns >= ncols are padding (never stored, never updated)
+      const bool v0 = col < ncols, v1 = col + 1 < ncols;
+      if (!v0) continue;
+      const double2 gj = *reinterpret_cast<const double2*>(gv + col);
+      const double2 yj = *reinterpret_cast<const double2*>(yv + col);
+      const double2 pj = *reinterpret_cast<const double2*>(p + col);
+      const double2 qj = *reinterpret_cast<const double2*>(q + col);
+      double2 hv[QN_R];
+#pragma unroll
+      for (int r = 0; r < QN_R; ++r) hv[r] = r < rows_here ? ld_stream_ef(base + r * lpad + col, pol) : make_double2(0.0, 0.0);
+      // column contributions only strictly left of the diagonal block
+      const bool c0ok = col < (int)r0, c1ok = col + 1 < (int)r0;
+      double ch0 = 0.0, ch1 = 0.0, cw0 = 0.0, cw1 = 0.0;
+#pragma unroll
+      for (int r = 0; r < QN_R; ++r) {
+        if (r < rows_here) {
+          const double4 rv = rowv[r];
+          const double pi = rv.x, qi = rv.y;
+          double2 hn;
+          if (KIND == QN_BFGS) {
+            const double cx = pi * qj.x + qi * pj.x, cy = pi * qj.y + qi * pj.y;
+            hn.x = fma(c0, pi * pj.x, fma(c1, cx, hv[r].x));
+            hn.y = fma(c0, pi * pj.y, fma(c1, cy, hv[r].y));
+          } else {
+            hn.x = fma(c2, qi * qj.x, fma(c0, pi * pj.x, hv[r].x));
+            hn.y = fma(c2, qi * qj.y, fma(c0, pi * pj.y, hv[r].y));
+          }
+          if (!v1) hn.y = 0.0;
+          ah[r] = fma(hn.x, yj.x, ah[r]);
+          ah[r] = fma(hn.y, yj.y, ah[r]);
+          aw[r] = fma(hn.x, gj.x, aw[r]);
+          aw[r] = fma(hn.y, gj.y, aw[r]);
+          ch0 = fma(hn.x, rv.z, ch0);
+          ch1 = fma(hn.y, rv.z, ch1);
+          cw0 = fma(hn.x, rv.w, cw0);
+          cw1 = fma(hn.y, rv.w, cw1);
+          st_stream_ef(base + r * lpad + col, hn, pol);
+        }
+      }
+      if (c0ok) {
+        double2 oh = *reinterpret_cast<double2*>(cph + col), ow = *reinterpret_cast<double2*>(cpw + col);
+        oh.x += ch0;
+        ow.x += cw0;
+        if (c1ok) {
+          oh.y += ch1;
+          ow.y += cw1;
+        }
+        *reinterpret_cast<double2*>(cph + col) = oh;
+        *reinterpret_cast<double2*>(cpw + col) = ow;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < QN_R; ++r) {
+      const double v1s = warp_sum(ah[r]), v2s = warp_sum(aw[r]);
+      if (lane == 0) {
+        red[r][warp] = v1s;
+        red[QN_R + r][warp] = v2s;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * QN_R) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < QN_T / 32; ++w) v = v + red[threadIdx.x][w];
+      const int r = threadIdx.x % QN_R;
+      if (r < rows_here) {
+        if (threadIdx.x < QN_R) a.h[r0 + r] = v;
+        else a.w[r0 + r] = v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// h_j += sum over CTAs (in CTA order) of the column partials; then the O(n) epilogue (y.h, coefficients, u)
+template <int KIND>
+__global__ void __launch_bounds__(QN_T) qn_sym_fold_kernel(QNLazyArgs a, QNSymArgs sa, int nparts, unsigned int* ticket) {
+  DevState* st = a.st;
+  if (st->done) return;
+  __shared__ double smem[3 * 32];
+  __shared__ bool is_last;
+  const int64_t ld = sa.ld;
+  for (int64_t j = (int64_t)blockIdx.x * QN_T + threadIdx.x; j < sa.n; j += (int64_t)gridDim.x * QN_T) {
+    double sh = 0.0, sw = 0.0;
+    for (int c = 0; c < nparts; ++c) {
+      sh = sh + __ldcg(sa.colpart + ((int64_t)c * 2 + 0) * ld + j);
+      sw = sw + __ldcg(sa.colpart + ((int64_t)c * 2 + 1) * ld + j);
+    }
+    a.h[j] = a.h[j] + sh;
+    a.w[j] = a.w[j] + sw;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  lazy_epilogue_body<KIND>(a, smem);
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+
+// full (row-major, ld) <-> packed conversions
+__global__ void __launch_bounds__(256) qn_sym_pack_kernel(const double* __restrict__ H, int64_t ld, int64_t n, double* __restrict__ P) {
+  const int64_t ntiles = (n + QN_R - 1) / QN_R;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r0 = tile * QN_R, lpad = sym_lpad(tile);
+    const int64_t ncols = r0 + QN_R < n ? r0 + QN_R : n;
+    double* base = P + sym_tile_offset(tile);
+    for (int64_t e = threadIdx.x; e < QN_R * lpad; e += blockDim.x) {
+      const int64_t r = e / lpad, c = e % lpad;
+      base[e] = (r0 + r < n && c < ncols) ? H[(r0 + r) * ld + c] : 0.0;
+    }
+  }
+}
+__global__ void __launch_bounds__(256) qn_sym_unpack_kernel(const double* __restrict__ P, int64_t ld, int64_t n, double* __restrict__ H) {
+  const int64_t ntiles = (n + QN_R - 1) / QN_R;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r0 = tile * QN_R, lpad = sym_lpad(tile);
+    const int64_t ncols = r0 + QN_R < n ? r0 + QN_R : n;
+    const double* base = P + sym_tile_offset(tile);
+    for (int64_t e = threadIdx.x; e < QN_R * lpad; e += blockDim.x) {
+      const int64_t r = e / lpad, c = e % lpad;
+      if (r0 + r < n && c < ncols) {
+        const double v = base[e];
+        H[(r0 + r) * ld + c] = v;
+        if (c < r0) H[c * ld + r0 + r] = v;  // mirror (the diagonal block is stored in full)
+      }
+    }
+  }
+}
+
+void qn_sym_pack(Ctx* ctx, const double* H, int64_t ld, int64_t n, double* P) {
+  qn_sym_pack_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(H, ld, n, P);
+  ctx->counters[0]++;
+}
+void qn_sym_unpack(Ctx* ctx, const double* P, int64_t ld, int64_t n, double* H) {
+  qn_sym_unpack_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(P, ld, n, H);
+  ctx->counters[0]++;
+}
+int qn_sym_grid(Ctx* ctx, int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + QN_R - 1) / QN_R, (int64_t)ctx->num_sms)); }
+
+void qn_launch_lazy_sym(Ctx* ctx, const QNLazyArgs& a, double* P, double* colpart, int64_t n, int64_t ld) {
+  QNSymArgs sa{P, colpart, n, ld};
+  const int grid = qn_sym_grid(ctx, n);
+  const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>((n + QN_T - 1) / QN_T, (int64_t)ctx->num_sms));
+  if (a.kind == QN_BFGS) {
+    qn_lazy_sym_kernel<QN_BFGS><<<grid, QN_T, 0, ctx->stream>>>(a, sa);
+    qn_sym_fold_kernel<QN_BFGS><<<fgrid, QN_T, 0, ctx->stream>>>(a, sa, grid, a.ticket);
+  } else {
+    qn_lazy_sym_kernel<QN_DFP><<<grid, QN_T, 0, ctx->stream>>>(a, sa);
+    qn_sym_fold_kernel<QN_DFP><<<fgrid, QN_T, 0, ctx->stream>>>(a, sa, grid, a.ticket);
+  }
+  ctx->counters[0] += 2;
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(QN_T) qn_lazy_epilogue_kernel(QNLazyArgs a) {
   if (a.st->done) return;

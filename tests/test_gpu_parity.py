@@ -493,3 +493,56 @@ def test_callback_and_trace_on_the_device_engine(osb):
     s = osb.BFGS(1e-7, np.zeros(512)).set_option("engine", 2)
     s.minimize(osb.BackTracking(1e-4, 0.5), obj, 300, 30, callback=lambda sv: calls.append(sv.k()))
     assert len(calls) == s.k() and s.termination_reason() is not None
+
+
+@pytest.mark.parametrize("kind", ["BFGS", "DFP"])
+def test_packed_symmetric_storage_matches_full_storage(osb, orc, kind):
+    """qn_storage = 1: only the lower triangle of H lives in HBM (n^2 * 8 B per iteration); transposed
+    contributions are column sums folded deterministically.  Same trajectory as the full-storage lazy pass."""
+    for n in (8, 24, 250, 1000, 2056):
+        x0 = np.linspace(-1.0, 1.0, n)
+        out = []
+        for storage in (0, 1):
+            obj = osb.SeparableQuadratic.generated(n)
+            s = getattr(osb, kind)(1e-7, x0).set_option("engine", 2).set_option("qn_schedule", 1).set_option("qn_storage", storage)
+            st = run(osb, s, osb.BackTracking(1e-4, 0.5), obj, 12, 30)
+            H = s.approx_inv_hessian()
+            out.append((st, s.k(), s.x(), H))
+        assert out[0][:2] == out[1][:2], n
+        assert close(out[0][2], out[1][2], rtol=1e-10), n
+        assert close(out[0][3], out[1][3], rtol=1e-10), n
+        assert np.array_equal(out[1][3], out[1][3].T)
+    # free-running against the faithful oracle, and Rosenbrock against the full-storage run
+    n = 96
+
+    def script(m):
+        obj = m.SeparableQuadratic.generated(n)
+        s = getattr(m, kind)(1e-7, np.zeros(n))
+        if m is osb:
+            s.set_option("engine", 2).set_option("qn_schedule", 1).set_option("qn_storage", 1)
+        st = run(m, s, m.BackTracking(1e-4, 0.5), obj, 300, 30)
+        return st, s.k(), s.termination_reason(), s.x()
+
+    ref, got = both(osb, orc, script)
+    assert got[:3] == ref[:3] and close(got[3], ref[3])
+    n = 2048
+    x0 = rosen_x0(n, 51)
+    res = []
+    for storage in (0, 1):
+        s = getattr(osb, kind)(1e-8, x0).set_option("engine", 2).set_option("qn_schedule", 1).set_option("qn_storage", storage)
+        run(osb, s, osb.BackTracking(1e-4, 0.5), osb.ExtendedRosenbrock(n), 7, 20)
+        s.approx_inv_hessian()  # forces packed -> full -> (next call) packed again
+        s.clear_norms()
+        run(osb, s, osb.BackTracking(1e-4, 0.5), osb.ExtendedRosenbrock(n), 8, 20)
+        res.append((s.x(), s.approx_inv_hessian()))
+    assert close(res[0][0], res[1][0], rtol=1e-9) and close(res[0][1], res[1][1], rtol=1e-8)
+    # a non-symmetric user matrix disables the packed path (results must equal full storage exactly)
+    rng = np.random.default_rng(0)
+    Hn = np.eye(64) + 0.01 * rng.standard_normal((64, 64))
+    res = []
+    for storage in (0, 1):
+        s = getattr(osb, kind)(1e-8, rosen_x0(64, 3)).set_option("engine", 2).set_option("qn_schedule", 1).set_option("qn_storage", storage)
+        s.set_approx_inv_hessian(Hn)
+        run(osb, s, osb.BackTracking(1e-4, 0.5), osb.ExtendedRosenbrock(64), 5, 20)
+        res.append(s.x())
+    assert np.array_equal(res[0], res[1])
