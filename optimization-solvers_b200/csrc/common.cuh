@@ -63,6 +63,15 @@ __device__ __forceinline__ double2 ld_stream_nc(const double* p) {  // read-only
   asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
   return v;
 }
+// O(n) column vectors of the streaming kernels: an ordinary cached load, but volatile so that it keeps its program
+// position relative to the (volatile) H loads and stores.  The schedule "all loads of a column step, then the
+// arithmetic, then the stores" is what the measured bandwidth depends on; left free, the compiler rotated the loop
+// differently from build to build (0.73 ms vs 0.78 ms per pass at n = 16384 for unrelated source changes).
+__device__ __forceinline__ double2 ld_vec2(const double* p) {
+  double2 v;
+  asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ void st_stream(double* p, double2 v) {
   asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }

@@ -281,6 +281,25 @@ void Solver::sym_to_full() {
   sym_current = false;
 }
 
+HeadEpi Solver::head_epi() const {
+  if (!defer_epi) return HeadEpi{-1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  const double* h2 = nullptr;
+  const double* w2 = nullptr;
+  const double* h1 = h.p;
+  const double* w1 = wv.p;
+  if (epi_p2p) {  // qn_lazy_kernel's exchange buffers: parity * 2 + {h, w}
+    h1 = ctx->xchg;
+    w1 = ctx->xchg + XCHG_LD;
+    h2 = ctx->xchg + 2 * XCHG_LD;
+    w2 = ctx->xchg + 3 * XCHG_LD;
+  }
+  return HeadEpi{qn_kind, h1, w1, h2, w2, u.p, ps.p, ph.p};
+}
+void Solver::finish_epilogue() {
+  if (!defer_epi) return;
+  qn_launch_epilogue_cluster(ctx, head_epi(), n, d_state, s.p, y.p, g.p);
+}
+
 void Solver::flush_pending() {
   sym_to_full();
   if (!lazy_used) return;
@@ -308,10 +327,12 @@ void Solver::qn_after_step() {
     }
     QNLazyArgs a{nullptr, ld, nrows, row0, n, d_state, ps.p, ph.p, y.p, g.p, s.p, h.p, wv.p, u.p, ps.p, ph.p,
                  ctx->gemv_ticket, qn_kind, nullptr, ctx->d_seq, 1, 0};
+    a.defer_epi = defer_epi ? 1 : 0;
+    prof_mark();  // slot 0: the streaming pass, slot 1: the column fold + epilogue
+    qn_launch_lazy_sym(ctx, a, Hsym.p, colpart.p, n, ld, 0);
     prof_mark();
     prof_mark();
-    prof_mark();
-    qn_launch_lazy_sym(ctx, a, Hsym.p, colpart.p, n, ld);
+    qn_launch_lazy_sym(ctx, a, Hsym.p, colpart.p, n, ld, 1);
     prof_mark();
     lazy_used = true;
     u_valid = true;
@@ -324,6 +345,7 @@ void Solver::qn_after_step() {
     QNLazyArgs a{H.p, ld, nrows, row0, n, d_state, ps.p, ph.p, y.p, g.p, s.p, h.p, wv.p, u.p, ps.p, ph.p,
                  (ctx->world == 1 || p2p) ? ctx->gemv_ticket : nullptr, qn_kind,
                  p2p ? ctx->d_peers : nullptr, ctx->d_seq, ctx->world, ctx->rank};
+    a.defer_epi = (defer_epi && qn_variant == 0 && (ctx->world == 1 || p2p)) ? 1 : 0;
     prof_mark();
     prof_mark();
     prof_mark();
@@ -333,7 +355,9 @@ void Solver::qn_after_step() {
     if (ctx->world > 1 && !p2p) {
       ctx->all_gather_inplace(h.p, nrows);
       ctx->all_gather_inplace(wv.p, nrows);
-      qn_launch_lazy_epilogue(ctx, a);
+      // same arithmetic (cluster order) as the head's deferred epilogue: sharded runs stay bit-identical to one GPU
+      if (defer_epi) qn_launch_epilogue_cluster(ctx, head_epi(), n, d_state, s.p, y.p, g.p, true);
+      else qn_launch_lazy_epilogue(ctx, a);
     }
     lazy_used = true;
     u_valid = true;
@@ -564,12 +588,19 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
   int slot = 0;
   bool stop = false;
   const bool ls_bounded = ls->p.kind == LS_BACKTRACKING_B || ls->p.kind == LS_MORETHUENTE_B;
+  // lazy schedule + cluster head: the O(n) epilogue of the pass runs at the top of the next head (8 SMs instead of 1)
+  epi_p2p = ctx->world > 1 && ctx->p2p_ready && ld <= XCHG_LD && use_p2p;
+  static const bool no_defer = getenv("OSB_NO_DEFER") != nullptr;  // experiment switch
+  defer_epi = !no_defer && qn_schedule == 1 && (qn_kind == QN_BFGS || qn_kind == QN_DFP) && n > QN_SMALL_N &&
+              (qn_storage == 1 || qn_variant == 0) &&
+              qn_device_head_is_cluster(obj->functor_kind(), n, head_variant);
   for (int64_t it = 0; it < max_iter && !stop; ++it) {
     qn_device_launch_head(ctx, obj->functor_kind(), obj->functor_ptr(0), obj->functor_ptr(1), bounded, d_ls, n, tol, max_ls,
                           d_state, x.p, g.p, d.p, xt.p, gt.p, s.p, y.p, u.p, bounded ? lb.p : nullptr, bounded ? ub.p : nullptr,
-                          ls_bounded ? ls->lb.p : nullptr, ls_bounded ? ls->ub.p : nullptr, head_variant, ls->p.kind);
+                          ls_bounded ? ls->lb.p : nullptr, ls_bounded ? ls->ub.p : nullptr, head_variant, ls->p.kind, head_epi());
     qn_after_step();
     if (cb != nullptr || record_trace) {
+      finish_epilogue();  // the callback may read H or restart: leave no epilogue owed
       // a host callback (ls_solver.rs:105-107) or a trace needs the state after every iteration: one
       // synchronisation per outer iteration, still none inside the line search
       const double f_before = h_state->f;
@@ -603,6 +634,8 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
       }
     }
   }
+  finish_epilogue();
+  defer_epi = false;
   fetch_state();
   OSB_CUDA(cudaMemcpyAsync(&ls->p, d_ls, sizeof(LSParams), cudaMemcpyDeviceToHost, stm));
   ctx->sync();

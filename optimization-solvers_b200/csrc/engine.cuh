@@ -37,6 +37,8 @@ struct DevState {
   int reason;  // OSB_REASON_*
   int ls_evals;
   int pending;  // lazy schedule: stored matrix = H - rank2(ps, ph; pc0..pc2) still to be applied
+  int epi;      // lazy schedule: h = H y and w = H g are fresh and their O(n) epilogue is still owed (deferred to the next
+                // cluster head, or to qn_launch_epilogue_cluster when no head follows)
 };
 
 struct Ctx {
@@ -169,6 +171,18 @@ void qn_launch_update(Ctx* ctx, int kind, double* H, int64_t ld, int64_t nrows, 
 // lazy (2-pass-less) schedule: ONE read-modify-write per iteration — applies the pending update while
 // computing h = H y and w = H g with the updated rows; the epilogue forms the new pending update and u.
 constexpr int64_t XCHG_LD = 65536;  // capacity (doubles) of one exchanged vector
+// Deferred lazy-schedule epilogue, executed by the 8-CTA cluster head (a single CTA is bound by one SM's L2 port:
+// 1.3 MB of O(n) vectors took 16 us of a 450 us iteration at n = 16384).
+struct HeadEpi {
+  int kind;          // QN_BFGS / QN_DFP, or -1: the head never runs an epilogue
+  const double* h;   // H y
+  const double* w;   // H g
+  const double* h2;  // peer-memory exchange: h, w of the odd-parity exchange buffers (st->epi == 2), else null
+  const double* w2;
+  double* u_out;     // u = H+ g (also kept for getters)
+  double* ps_out;    // pending p <- s
+  double* ph_out;    // pending q <- h
+};
 struct QNLazyArgs {
   double* M;            // stored matrix (local row block)
   int64_t ld, nrows, row0, n;
@@ -190,6 +204,7 @@ struct QNLazyArgs {
   unsigned long long* seq;
   int world, rank;
   int tile_rows;  // filled by qn_launch_lazy
+  int defer_epi;  // 1 => do not run the epilogue in the pass: raise st->epi and let the cluster head do it on 8 SMs
 };
 void qn_launch_lazy(Ctx* ctx, const QNLazyArgs& a, int variant = 0);
 void qn_launch_lazy_epilogue(Ctx* ctx, const QNLazyArgs& a);
@@ -198,7 +213,7 @@ int64_t qn_sym_doubles(int64_t n);
 int qn_sym_grid(Ctx* ctx, int64_t n);
 void qn_sym_pack(Ctx* ctx, const double* H, int64_t ld, int64_t n, double* P);
 void qn_sym_unpack(Ctx* ctx, const double* P, int64_t ld, int64_t n, double* H);
-void qn_launch_lazy_sym(Ctx* ctx, const QNLazyArgs& a, double* P, double* colpart, int64_t n, int64_t ld);
+void qn_launch_lazy_sym(Ctx* ctx, const QNLazyArgs& a, double* P, double* colpart, int64_t n, int64_t ld, int phase);
 // apply a pending update to the stored matrix (getters, engine switches)
 void qn_launch_flush(Ctx* ctx, int kind, double* M, int64_t ld, int64_t nrows, int64_t row0, DevState* st, const double* ps,
                      const double* ph);
@@ -238,6 +253,10 @@ struct Solver {
   DBuf wv, ps, ph;        // lazy schedule: w = H g, pending p and q
   int qn_schedule = 0;    // 0 = eager (h = H y, then fused update: 3 n^2 8 B), 1 = lazy (one RMW: 2 n^2 8 B)
   bool lazy_used = false;
+  bool defer_epi = false;  // minimize_device with the cluster head: the lazy pass leaves its epilogue to the next head
+  bool epi_p2p = false;    // ... and h, w live in the peer-memory exchange buffers
+  HeadEpi head_epi() const;
+  void finish_epilogue();  // run an owed epilogue now (no head follows)
   int qn_storage = 0;     // 0 = full n x n, 1 = packed symmetric lower triangle (lazy schedule, BFGS/DFP, single GPU)
   DBuf Hsym, colpart;     // packed matrix and per-CTA column partials
   bool sym_current = false;  // the packed copy (not H) holds the current matrix
@@ -308,10 +327,14 @@ void vec_active_set(Ctx*, int64_t n, const double* x, const double* lb, const do
 void state_finish_sy(Ctx*, DevState* st, double tol);
 
 // device-resident engine (qn_device.cu)
+bool qn_device_head_is_cluster(int functor_kind, int64_t n, int head_variant);
+void qn_launch_epilogue_cluster(Ctx* ctx, const HeadEpi& e, int64_t n, DevState* st, const double* s, const double* y, const double* g,
+                                bool force = false);
 void qn_device_launch_head(Ctx* ctx, int functor_kind, const double* fn_a, const double* fn_b, bool bounded,
                            LSParams* d_ls, int64_t n, double tol, int64_t max_ls, DevState* st, double* x, double* g,
                            double* d, double* xt, double* gt, double* s, double* y, const double* u, const double* lb,
-                           const double* ub, const double* ls_lb, const double* ls_ub, int head_variant, int ls_kind);
+                           const double* ub, const double* ls_lb, const double* ls_ub, int head_variant, int ls_kind,
+                           const HeadEpi& epi);
 
 // batched (batched.cu)
 int batched_bfgs_rosenbrock(Ctx* ctx, int64_t n, int64_t np, const double* x0_host, bool generated, int64_t problem0,

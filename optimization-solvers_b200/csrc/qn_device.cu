@@ -458,12 +458,110 @@ __device__ __noinline__ double cluster_min_rt(double v, double* smem_cta, double
   return res[0];
 }
 
+// ---- deferred lazy-schedule epilogue on the cluster -------------------------------------------
+// y.h, s.g, h.g with element i = gt + k * NT (a mapping that does not depend on the functor's block size, so the
+// head and the stand-alone finisher add in the same order), then the coefficients of qn_kernels.cu's
+// lazy_epilogue_body.  Returns ca, cb of  u = w + (s ca + h cb); the leader publishes the coefficients.
+template <int EPT>
+__device__ __forceinline__ void cluster_epilogue_coefs(int kind, const double* __restrict__ hh, const double* s, const double* y,
+                                                       const double* g, int64_t n, DevState* st, bool leader, int gt,
+                                                       double* smem_cta, double* part, double* res, int& phase, double& ca,
+                                                       double& cb) {
+  constexpr int NT = HC_CTAS * HC_T;
+  double hv[EPT], gv[EPT], yv[EPT], sv[EPT];
+#pragma unroll
+  for (int k = 0; k < EPT; ++k) {
+    const int64_t i = gt + (int64_t)k * NT;
+    const bool ok = i < n;
+    hv[k] = ok ? __ldcg(hh + i) : 0.0;
+    gv[k] = ok ? g[i] : 0.0;
+    yv[k] = ok ? y[i] : 0.0;
+    sv[k] = ok ? s[i] : 0.0;
+  }
+  double e3[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < EPT; ++k) {
+    e3[0] = fma(yv[k], hv[k], e3[0]);  // y.h
+    e3[1] = fma(sv[k], gv[k], e3[1]);  // s.g
+    e3[2] = fma(hv[k], gv[k], e3[2]);  // h.g
+  }
+  cluster_sum<3>(e3, smem_cta, part, res, phase);
+  const double yh = e3[0], sg = e3[1], hg = e3[2], ys = st->ys;
+  double c0, c1, c2;
+  if (kind == QN_BFGS) {
+    const double rho = 1.0 / ys;
+    c0 = rho * rho * yh + rho;
+    c1 = -rho;
+    c2 = 0.0;
+  } else {  // DFP
+    c0 = 1.0 / ys;
+    c1 = 0.0;
+    c2 = -1.0 / yh;
+  }
+  ca = c0 * sg + c1 * hg;
+  cb = c1 * sg + c2 * hg;
+  if (leader) {
+    st->yh = yh;
+    st->c0 = c0;
+    st->c1 = c1;
+    st->c2 = c2;
+    st->pc0 = c0;
+    st->pc1 = c1;
+    st->pc2 = c2;
+    st->pending = 1;
+    st->epi = 0;
+  }
+}
+
+// stand-alone finisher: runs the owed epilogue when no head follows (end of minimize(), before a host callback)
+__global__ void __cluster_dims__(HC_CTAS, 1, 1) __launch_bounds__(HC_T, 1)
+qn_epilogue_cluster_kernel(HeadEpi e, int64_t n, DevState* __restrict__ st, const double* s, const double* y, const double* g, int force) {
+  constexpr int EPT = 4;
+  constexpr int NT = HC_CTAS * HC_T;
+  __shared__ double smem_cta[3 * 16];
+  __shared__ double part[32];
+  __shared__ double res[16];
+  // force: the caller has just completed h, w itself (NCCL all-gather) and nobody raised st->epi
+  const int epi = st->epi ? st->epi : ((force && !st->done) ? 1 : 0);
+  if (!epi) return;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int gt = (int)cluster.block_rank() * HC_T + threadIdx.x;
+  const bool leader = gt == 0;
+  const double* hh = epi == 2 ? e.h2 : e.h;
+  const double* ww = epi == 2 ? e.w2 : e.w;
+  const bool skip = st->skip != 0;
+  int phase = 0;
+  double ca = 0.0, cb = 0.0;
+  if (!skip) cluster_epilogue_coefs<EPT>(e.kind, hh, s, y, g, n, st, leader, gt, smem_cta, part, res, phase, ca, cb);
+  else if (leader) {  // bfgs.rs:106-112: no new update; the stored matrix is exact once the pending one is applied
+    st->pending = 0;
+    st->pc0 = st->pc1 = st->pc2 = 0.0;
+    st->epi = 0;
+  }
+#pragma unroll
+  for (int k = 0; k < EPT; ++k) {
+    const int64_t i = gt + (int64_t)k * NT;
+    if (i < n) {
+      const double wi = __ldcg(ww + i);
+      if (skip) {
+        e.u_out[i] = wi;
+      } else {
+        const double si = s[i], hi = __ldcg(hh + i);
+        e.u_out[i] = wi + (si * ca + hi * cb);
+        e.ps_out[i] = si;
+        e.ph_out[i] = hi;
+      }
+    }
+  }
+  cluster.sync();  // keep every CTA's shared memory alive until all peers have read it
+}
+
 template <class Fn, bool BOUNDED, int EPT, int LSK>
 __global__ void __cluster_dims__(HC_CTAS, 1, 1) __launch_bounds__(HC_T, 1)
 qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol, int64_t max_ls, DevState* __restrict__ st,
                        double* __restrict__ x, double* __restrict__ g, double* __restrict__ s, double* __restrict__ y,
                        const double* __restrict__ u, const double* __restrict__ lb, const double* __restrict__ ub,
-                       const double* __restrict__ ls_lb, const double* __restrict__ ls_ub, int spec_on, long long* tdbg) {
+                       const double* __restrict__ ls_lb, const double* __restrict__ ls_ub, int spec_on, long long* tdbg, HeadEpi epi) {
   constexpr int BS = Fn::BS;
   constexpr int KPT = EPT / BS;
   constexpr int NT = HC_CTAS * HC_T;
@@ -489,18 +587,25 @@ qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol,
     }
     return;
   }
+  int phase = 0;
+  // the lazy pass of the previous iteration left h = H y, w = H g and owes their O(n) epilogue (st->epi): do it here,
+  // on 8 SMs, before anything can terminate the run (the update it defines belongs to the iteration that has ended)
+  const int epi_flag = epi.kind >= 0 ? st->epi : 0;
+  const bool epi_skip = st->skip != 0;
+  const double* __restrict__ epi_h = epi_flag == 2 ? epi.h2 : epi.h;
+  const double* __restrict__ epi_w = epi_flag == 2 ? epi.w2 : epi.w;
+  double epi_ca = 0.0, epi_cb = 0.0;
+  if (epi_flag) {
+    if (!epi_skip) cluster_epilogue_coefs<EPT>(epi.kind, epi_h, s, y, g, n, st, leader, gt, smem_cta, part, res, phase, epi_ca, epi_cb);
+    else if (leader) {
+      st->pending = 0;
+      st->pc0 = st->pc1 = st->pc2 = 0.0;
+      st->epi = 0;
+    }
+  }
   int why = OSB_REASON_NONE;
   if (st->has_s && st->s_norm < tol) why = OSB_REASON_S_NORM;        // bfgs.rs:67-69
   else if (st->has_y && st->y_norm < tol) why = OSB_REASON_Y_NORM;   // bfgs.rs:70-72
-  if (why != OSB_REASON_NONE) {
-    if (leader) {
-      st->done = 1;
-      st->status = OSB_OK;
-      st->reason = why;
-    }
-    return;
-  }
-  int phase = 0;
   double xreg[KPT][BS], dreg[KPT][BS], greg[KPT][BS];
   constexpr bool need_tmax = LSK == LS_MORETHUENTE_B;
   double tm = INFINITY;
@@ -514,7 +619,22 @@ qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol,
       xreg[k][j] = dreg[k][j] = greg[k][j] = 0.0;
       if (b < nb) {
         const int i = b * BS + j;
-        const double xi = x[i], gi = g[i], ui = u[i];
+        const double xi = x[i], gi = g[i];
+        double ui;
+        if (epi_flag) {  // u = H+ g = w + (s ca + h cb); the vectors of the now pending update are saved
+          const double wi = __ldcg(epi_w + i);
+          if (epi_skip) {
+            ui = wi;
+          } else {
+            const double si = s[i], hi = __ldcg(epi_h + i);
+            ui = wi + (si * epi_ca + hi * epi_cb);
+            epi.ps_out[i] = si;
+            epi.ph_out[i] = hi;
+          }
+          epi.u_out[i] = ui;
+        } else {
+          ui = u[i];
+        }
         double di;
         if (BOUNDED) di = fmin(fmax(xi - ui, lb[i]), ub[i]) - xi;  // bfgs_b.rs:72-75
         else di = -ui;                                             // bfgs.rs:47
@@ -532,6 +652,15 @@ qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol,
         }
       }
     }
+  }
+  if (why != OSB_REASON_NONE) {
+    if (leader) {
+      st->done = 1;
+      st->status = OSB_OK;
+      st->reason = why;
+    }
+    cluster.sync();  // peers may still be reading this CTA's partials of the epilogue reduction
+    return;
   }
   OSB_TS();
   {
@@ -671,20 +800,20 @@ long long* g_head_tdbg = nullptr;  // debug: device buffer of 32 clock64 stamps 
 template <class Fn, int LSK>
 static void launch_head_cluster_k(Ctx* ctx, Fn fn, bool bounded, LSParams* d_ls, int64_t n, double tol, int64_t max_ls, DevState* st,
                                   double* x, double* g, double* s, double* y, const double* u, const double* lb, const double* ub,
-                                  const double* ls_lb, const double* ls_ub, int spec_on) {
+                                  const double* ls_lb, const double* ls_ub, int spec_on, const HeadEpi& epi) {
   if (bounded)
-    qn_head_cluster_kernel<Fn, true, 4, LSK><<<HC_CTAS, HC_T, 0, ctx->stream>>>(fn, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub, spec_on, g_head_tdbg);
+    qn_head_cluster_kernel<Fn, true, 4, LSK><<<HC_CTAS, HC_T, 0, ctx->stream>>>(fn, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub, spec_on, g_head_tdbg, epi);
   else
-    qn_head_cluster_kernel<Fn, false, 4, LSK><<<HC_CTAS, HC_T, 0, ctx->stream>>>(fn, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub, spec_on, g_head_tdbg);
+    qn_head_cluster_kernel<Fn, false, 4, LSK><<<HC_CTAS, HC_T, 0, ctx->stream>>>(fn, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub, spec_on, g_head_tdbg, epi);
 }
 
 template <class Fn>
 static bool launch_head_cluster(Ctx* ctx, Fn fn, bool bounded, LSParams* d_ls, int ls_kind, int64_t n, double tol, int64_t max_ls,
                                 DevState* st, double* x, double* g, double* s, double* y, const double* u, const double* lb,
-                                const double* ub, const double* ls_lb, const double* ls_ub, int spec_on) {
+                                const double* ub, const double* ls_lb, const double* ls_ub, int spec_on, const HeadEpi& epi) {
   constexpr int NT = HC_CTAS * HC_T;
   if (n > (int64_t)NT * 4) return false;
-#define OSB_HC(K) launch_head_cluster_k<Fn, K>(ctx, fn, bounded, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub, spec_on)
+#define OSB_HC(K) launch_head_cluster_k<Fn, K>(ctx, fn, bounded, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub, spec_on, epi)
   switch (ls_kind) {
     case LS_BACKTRACKING: OSB_HC(LS_BACKTRACKING); break;
     case LS_BACKTRACKING_B: OSB_HC(LS_BACKTRACKING_B); break;
@@ -709,19 +838,29 @@ static void launch_head(Ctx* ctx, Fn fn, bool bounded, LSParams* d_ls, int64_t n
   ctx->counters[0]++;
 }
 
+bool qn_device_head_is_cluster(int functor_kind, int64_t n, int head_variant) {
+  return (functor_kind == FN_ROSENBROCK || functor_kind == FN_SEPQUAD) && (head_variant == 0 || head_variant == 3) &&
+         n <= (int64_t)HC_CTAS * HC_T * 4;
+}
+void qn_launch_epilogue_cluster(Ctx* ctx, const HeadEpi& e, int64_t n, DevState* st, const double* s, const double* y, const double* g,
+                                bool force) {
+  qn_epilogue_cluster_kernel<<<HC_CTAS, HC_T, 0, ctx->stream>>>(e, n, st, s, y, g, force ? 1 : 0);
+  ctx->counters[0]++;
+}
+
 void qn_device_launch_head(Ctx* ctx, int functor_kind, const double* fn_a, const double* fn_b, bool bounded, LSParams* d_ls,
                            int64_t n, double tol, int64_t max_ls, DevState* st, double* x, double* g, double* d, double* xt,
                            double* gt, double* s, double* y, const double* u, const double* lb, const double* ub,
-                           const double* ls_lb, const double* ls_ub, int head_variant, int ls_kind) {
+                           const double* ls_lb, const double* ls_ub, int head_variant, int ls_kind, const HeadEpi& epi) {
   if (functor_kind == FN_ROSENBROCK) {
-    if ((head_variant == 0 || head_variant == 3) && launch_head_cluster(ctx, RosenbrockFn{}, bounded, d_ls, ls_kind, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub, head_variant == 0)) return;
+    if ((head_variant == 0 || head_variant == 3) && launch_head_cluster(ctx, RosenbrockFn{}, bounded, d_ls, ls_kind, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub, head_variant == 0, epi)) return;
     if (head_variant <= 1 && launch_head_fast(ctx, RosenbrockFn{}, bounded, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub)) return;
     launch_head(ctx, RosenbrockFn{}, bounded, d_ls, n, tol, max_ls, st, x, g, d, xt, gt, s, y, u, lb, ub, ls_lb, ls_ub);
   } else if (functor_kind == FN_SEPQUAD) {
     SepQuadFn fn;
     fn.c = fn_a;
     fn.a = fn_b;
-    if ((head_variant == 0 || head_variant == 3) && launch_head_cluster(ctx, fn, bounded, d_ls, ls_kind, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub, head_variant == 0)) return;
+    if ((head_variant == 0 || head_variant == 3) && launch_head_cluster(ctx, fn, bounded, d_ls, ls_kind, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub, head_variant == 0, epi)) return;
     if (head_variant <= 1 && launch_head_fast(ctx, fn, bounded, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub)) return;
     launch_head(ctx, fn, bounded, d_ls, n, tol, max_ls, st, x, g, d, xt, gt, s, y, u, lb, ub, ls_lb, ls_ub);
   } else {

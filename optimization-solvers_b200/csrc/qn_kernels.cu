@@ -15,6 +15,8 @@
 // accumulators, warp-shuffle + fixed-order cross-warp reduction (deterministic; a row's sum is
 // formed entirely inside one CTA, so the result does not depend on the grid or on the number of
 // GPUs the rows are sharded over).
+#include <cstdlib>
+
 #include "engine.cuh"
 
 namespace osb {
@@ -98,7 +100,7 @@ qn_gemv_kernel(const double* __restrict__ H, int64_t ld, int64_t nrows, int64_t 
     for (int r = 0; r < QN_R; ++r) acc[r] = 0.0;
     const double* __restrict__ base = H + r0 * ld;
     for (int col = 2 * threadIdx.x; col < (int)ld; col += QN_CHUNK) {
-      const double2 vv = *reinterpret_cast<const double2*>(v + col);
+      const double2 vv = ld_vec2(v + col);
       double2 hv[QN_R];
 #pragma unroll
       for (int r = 0; r < QN_R; ++r) hv[r] = r < rows_here ? ld_stream_nc_ef(base + r * ld + col, pol) : make_double2(0.0, 0.0);
@@ -260,11 +262,11 @@ qn_update_kernel(double* __restrict__ H, int64_t ld, int64_t nrows, int64_t row0
     __syncthreads();
     double* __restrict__ base = H + r0 * ld;
     for (int col = 2 * threadIdx.x; col < (int)ld; col += QN_CHUNK) {
-      const double2 gj = *reinterpret_cast<const double2*>(g + col);
+      const double2 gj = ld_vec2(g + col);
       double2 pj = make_double2(0.0, 0.0), qj = make_double2(0.0, 0.0);
-      if (KIND != QN_BROYDEN) pj = *reinterpret_cast<const double2*>(p + col);
-      if (KIND == QN_BFGS || KIND == QN_DFP) qj = *reinterpret_cast<const double2*>(q + col);
-      if (KIND == QN_BROYDEN) pj = *reinterpret_cast<const double2*>(rv + col);  // column vector v = H^T s
+      if (KIND != QN_BROYDEN) pj = ld_vec2(p + col);
+      if (KIND == QN_BFGS || KIND == QN_DFP) qj = ld_vec2(q + col);
+      if (KIND == QN_BROYDEN) pj = ld_vec2(rv + col);  // column vector v = H^T s
       double2 hv[QN_R];
 #pragma unroll
       for (int r = 0; r < QN_R; ++r) hv[r] = r < rows_here ? ld_stream_ef(base + r * ld + col, pol) : make_double2(0.0, 0.0);
@@ -311,23 +313,44 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 // update, and the next direction needs only u = H_{k+1} g = w + s (c0 s.g + c1 h.g) + h (c1 s.g + c2 h.g),
 // an O(n) epilogue.  HBM traffic per iteration: 2 n^2 8 B instead of 3 n^2 8 B.
 template <int KIND>
-__device__ __forceinline__ void lazy_epilogue_body(const QNLazyArgs& a, double* smem) {
+// (not inlined, and the kernels pass their __grid_constant__ parameter block by address: the streaming loops keep
+//  the whole register budget — inlined, this body cost qn_lazy_kernel 40 us per launch in spills and scheduling)
+__device__ __noinline__ void lazy_epilogue_body(const QNLazyArgs& a, const double* hsrc, const double* wsrc, double* smem) {
   DevState* st = a.st;
   const int64_t n = a.n;
   if (st->skip) {  // bfgs.rs:106-112: no new update; the stored matrix is now exact
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) a.u[i] = a.w[i];
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) a.u[i] = wsrc[i];
     if (threadIdx.x == 0) {
       st->pending = 0;
       st->pc0 = st->pc1 = st->pc2 = 0.0;
     }
     return;
   }
+  // One CTA walks the O(n) vectors out of L2: the loop is latency bound, so loads are issued in batches of EPI_U
+  // before any use (the stores of the second loop would otherwise serialise it: the pointers may alias as far as
+  // the compiler knows).  The order of the additions is unchanged: element i goes to thread i % blockDim.x, ascending.
+  constexpr int EPI_U = 8;
+  const int64_t bd = blockDim.x;
   double acc[3] = {0.0, 0.0, 0.0};
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const double hi = a.h[i], gi = a.g[i];
-    acc[0] = fma(a.y[i], hi, acc[0]);  // y.h
-    acc[1] = fma(a.s[i], gi, acc[1]);  // s.g
-    acc[2] = fma(hi, gi, acc[2]);      // h.g
+  for (int64_t i0 = threadIdx.x; i0 < n; i0 += bd * EPI_U) {
+    double hv[EPI_U], gv[EPI_U], yv[EPI_U], sv[EPI_U];
+#pragma unroll
+    for (int k = 0; k < EPI_U; ++k) {
+      const int64_t i = i0 + k * bd;
+      const bool ok = i < n;
+      hv[k] = ok ? __ldcg(hsrc + i) : 0.0;
+      gv[k] = ok ? __ldcg(a.g + i) : 0.0;
+      yv[k] = ok ? __ldcg(a.y + i) : 0.0;
+      sv[k] = ok ? __ldcg(a.s + i) : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < EPI_U; ++k) {
+      if (i0 + k * bd < n) {
+        acc[0] = fma(yv[k], hv[k], acc[0]);  // y.h
+        acc[1] = fma(sv[k], gv[k], acc[1]);  // s.g
+        acc[2] = fma(hv[k], gv[k], acc[2]);  // h.g
+      }
+    }
   }
   RedOps<3> ops{{RED_SUM, RED_SUM, RED_SUM}};
   cta_reduce<3>(acc, ops, smem);
@@ -344,11 +367,25 @@ __device__ __forceinline__ void lazy_epilogue_body(const QNLazyArgs& a, double* 
     c2 = -1.0 / yh;
   }
   const double ca = c0 * sg + c1 * hg, cb = c1 * sg + c2 * hg;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const double si = a.s[i], hi = a.h[i];
-    a.u[i] = a.w[i] + (si * ca + hi * cb);
-    a.ps_out[i] = si;
-    a.ph_out[i] = hi;
+  for (int64_t i0 = threadIdx.x; i0 < n; i0 += bd * EPI_U) {
+    double hv[EPI_U], sv[EPI_U], wv[EPI_U];
+#pragma unroll
+    for (int k = 0; k < EPI_U; ++k) {
+      const int64_t i = i0 + k * bd;
+      const bool ok = i < n;
+      hv[k] = ok ? __ldcg(hsrc + i) : 0.0;
+      sv[k] = ok ? __ldcg(a.s + i) : 0.0;
+      wv[k] = ok ? __ldcg(wsrc + i) : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < EPI_U; ++k) {
+      const int64_t i = i0 + k * bd;
+      if (i < n) {
+        a.u[i] = wv[k] + (sv[k] * ca + hv[k] * cb);
+        a.ps_out[i] = sv[k];
+        a.ph_out[i] = hv[k];
+      }
+    }
   }
   if (threadIdx.x == 0) {
     st->yh = yh;
@@ -362,8 +399,11 @@ __device__ __forceinline__ void lazy_epilogue_body(const QNLazyArgs& a, double* 
   }
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(QN_T, 1) qn_lazy_kernel(QNLazyArgs a) {
+// DEFER (compile time, = a.defer_epi): the epilogue is left to the next cluster head.  A run-time test of the flag
+// in this kernel was enough to push the streaming loop into spills (128 registers, 1 CTA of 512 threads per SM).
+// P2P (compile time, = P2P): the single-GPU instantiation carries no exchange state through the loop.
+template <int KIND, bool DEFER, bool P2P>
+__global__ void __launch_bounds__(QN_T, 1) qn_lazy_kernel(const __grid_constant__ QNLazyArgs a) {
   DevState* st = a.st;
   if (st->done) return;
   const double c0 = st->pc0, c1 = st->pc1, c2 = st->pc2;
@@ -377,7 +417,7 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_kernel(QNLazyArgs a) {
   const double* __restrict__ yv = a.y;
   const double* __restrict__ gv = a.g;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned long long seq = a.peers != nullptr ? *a.seq + 1ULL : 0ULL;  // this exchange's sequence number
+  const unsigned long long seq = P2P ? *a.seq + 1ULL : 0ULL;  // this exchange's sequence number
   const int par = (int)(seq & 1ULL);
   const int rt = a.tile_rows;
   for (int64_t r0 = (int64_t)blockIdx.x * rt; r0 < nrows; r0 += (int64_t)gridDim.x * rt) {
@@ -393,10 +433,10 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_kernel(QNLazyArgs a) {
     __syncthreads();
     double* __restrict__ base = a.M + r0 * ld;
     for (int col = 2 * threadIdx.x; col < (int)ld; col += QN_CHUNK) {
-      const double2 gj = *reinterpret_cast<const double2*>(gv + col);
-      const double2 yj = *reinterpret_cast<const double2*>(yv + col);
-      const double2 pj = *reinterpret_cast<const double2*>(p + col);
-      const double2 qj = *reinterpret_cast<const double2*>(q + col);
+      const double2 gj = ld_vec2(gv + col);
+      const double2 yj = ld_vec2(yv + col);
+      const double2 pj = ld_vec2(p + col);
+      const double2 qj = ld_vec2(q + col);
       double2 hv[QN_R];
 #pragma unroll
       for (int r = 0; r < QN_R; ++r) hv[r] = r < rows_here ? ld_stream_ef(base + r * ld + col, pol) : make_double2(0.0, 0.0);
@@ -435,7 +475,7 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_kernel(QNLazyArgs a) {
       for (int w = 0; w < QN_T / 32; ++w) v = v + red[threadIdx.x][w];
       const int r = threadIdx.x % QN_R;
       if (r < rows_here) {
-        if (a.peers != nullptr) {
+        if (P2P) {
           // fused all-gather: the row sum goes straight into every rank's exchange region (NVLink peer stores,
           // `par` double-buffers the region across iterations).  The stores are posted here and fenced ONCE per
           // CTA below, so their latency overlaps with the streaming of the other CTAs.
@@ -446,12 +486,16 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_kernel(QNLazyArgs a) {
           else a.w[row0 + r0 + r] = v;
         }
       }
-      if (a.peers == nullptr) __threadfence();
+      if (!P2P) __threadfence();
     }
     __syncthreads();
   }
+  if (DEFER && !P2P) {  // the next cluster head runs the epilogue; the kernel boundary orders h, w before it
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->epi = 1;
+    return;
+  }
   if (a.ticket == nullptr) return;
-  if (a.peers != nullptr && threadIdx.x < 2 * QN_R) __threadfence_system();  // this CTA's peer stores are performed
+  if (P2P && threadIdx.x < 2 * QN_R) __threadfence_system();  // this CTA's peer stores are performed
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -461,7 +505,7 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_kernel(QNLazyArgs a) {
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  if (a.peers != nullptr) {
+  if (P2P) {
     // every local CTA has pushed and fenced its rows: publish "rank `a.rank` reached `seq`" on every rank,
     // then wait until all ranks have published the same sequence number here
     __threadfence_system();
@@ -473,17 +517,24 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_kernel(QNLazyArgs a) {
       }
     }
     __syncthreads();
-    QNLazyArgs b = a;
-    b.h = a.peers[a.rank] + (int64_t)(par * 2 + 0) * XCHG_LD;
-    b.w = a.peers[a.rank] + (int64_t)(par * 2 + 1) * XCHG_LD;
-    lazy_epilogue_body<KIND>(b, &red[0][0]);
+    if (DEFER) {  // all ranks' rows have arrived in this rank's exchange buffers of parity `par`
+      if (threadIdx.x == 0) {
+        st->epi = 1 + par;
+        *a.seq = seq;
+        *a.ticket = 0u;
+      }
+      return;
+    }
+    if (!DEFER)
+      lazy_epilogue_body<KIND>(a, a.peers[a.rank] + (int64_t)(par * 2 + 0) * XCHG_LD,
+                               a.peers[a.rank] + (int64_t)(par * 2 + 1) * XCHG_LD, &red[0][0]);
     if (threadIdx.x == 0) {
       *a.seq = seq;
       *a.ticket = 0u;
     }
     return;
   }
-  lazy_epilogue_body<KIND>(a, &red[0][0]);
+  if (!DEFER) lazy_epilogue_body<KIND>(a, a.h, a.w, &red[0][0]);
   if (threadIdx.x == 0) *a.ticket = 0u;
 }
 
@@ -527,7 +578,7 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(TM_T, 1) qn_lazy_tma_kernel(QNLazyArgs a) {
+__global__ void __launch_bounds__(TM_T, 1) qn_lazy_tma_kernel(const __grid_constant__ QNLazyArgs a) {
   DevState* st = a.st;
   if (st->done) return;
   extern __shared__ __align__(128) unsigned char tm_smem[];
@@ -701,17 +752,15 @@ __global__ void __launch_bounds__(TM_T, 1) qn_lazy_tma_kernel(QNLazyArgs a) {
       }
     }
     __syncthreads();
-    QNLazyArgs b = a;
-    b.h = a.peers[a.rank] + (int64_t)(par * 2 + 0) * XCHG_LD;
-    b.w = a.peers[a.rank] + (int64_t)(par * 2 + 1) * XCHG_LD;
-    lazy_epilogue_body<KIND>(b, &red[0][0]);
+    lazy_epilogue_body<KIND>(a, a.peers[a.rank] + (int64_t)(par * 2 + 0) * XCHG_LD,
+                             a.peers[a.rank] + (int64_t)(par * 2 + 1) * XCHG_LD, &red[0][0]);
     if (tid == 0) {
       *a.seq = seq;
       *a.ticket = 0u;
     }
     return;
   }
-  lazy_epilogue_body<KIND>(a, &red[0][0]);
+  lazy_epilogue_body<KIND>(a, a.h, a.w, &red[0][0]);
   if (tid == 0) *a.ticket = 0u;
 }
 
@@ -741,14 +790,32 @@ struct QNSymArgs {
   int64_t n, ld;
 };
 
+// 16 per-thread values -> warp sums with 16 double shuffles (recursive halving) instead of 80; after the call
+// lane l holds the warp sum of value l >> 1.
+__device__ __forceinline__ double warp_sum16(double (&v)[16]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int hs = 8, o = 16; hs >= 1; hs >>= 1, o >>= 1) {
+    const bool upper = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < hs; ++i) {
+      const double send = upper ? v[i] : v[i + hs];
+      const double keep = upper ? v[i + hs] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(QN_T, 1) qn_lazy_sym_kernel(QNLazyArgs a, QNSymArgs sa) {
   DevState* st = a.st;
   if (st->done) return;
   const double c0 = st->pc0, c1 = st->pc1, c2 = st->pc2;
   const unsigned long long pol = l2_evict_first_policy();
-  __shared__ double red[2 * QN_R][QN_T / 32];
-  __shared__ double4 rowv[QN_R];  // p_i, q_i, y_i, g_i of the tile's rows
+  __shared__ double red2[2][QN_T / 32][16];  // double-buffered by tile parity: two barriers per tile instead of four
+  __shared__ double4 rowv2[2][QN_R];         // p_i, q_i, y_i, g_i of the tile's rows
+  int tpar = 0;
   const int64_t n = sa.n, ld = sa.ld;
   const double* __restrict__ p = a.ps;
   const double* __restrict__ q = a.ph;
@@ -763,8 +830,15 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_sym_kernel(QNLazyArgs a, QNSy
     *reinterpret_cast<double2*>(cpw + j) = make_double2(0.0, 0.0);
   }
   __syncthreads();
+  // Tile t has 8 (t + 1) stored columns: tiles are processed in PAIRS (t, ntiles - 1 - t) of equal total length,
+  // pairs dealt round-robin — a static (hence deterministic) assignment that balances the triangle to within
+  // one pair; plain round-robin leaves the CTA holding the longest tiles 7 % above the average.
   const int64_t ntiles = (n + QN_R - 1) / QN_R;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  const int64_t nhalf = (ntiles + 1) / 2;
+  for (int64_t pairi = blockIdx.x; pairi < nhalf; pairi += gridDim.x)
+  for (int side = 0; side < 2; ++side) {
+    const int64_t tile = side == 0 ? pairi : ntiles - 1 - pairi;
+    if (side == 1 && tile == pairi) continue;  // odd tile count: the middle tile only once
     const int64_t r0 = tile * QN_R;
     const int rows_here = (int)((n - r0) < QN_R ? (n - r0) : QN_R);
     const int64_t lpad = sym_lpad(tile);
@@ -772,21 +846,24 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_sym_kernel(QNLazyArgs a, QNSy
     double ah[QN_R], aw[QN_R];
 #pragma unroll
     for (int r = 0; r < QN_R; ++r) ah[r] = aw[r] = 0.0;
+    tpar ^= 1;
+    double4* rowv = rowv2[tpar];
+    double (*red)[16] = red2[tpar];
     if (threadIdx.x < QN_R) {
       const bool ok = (int)threadIdx.x < rows_here;
       const int64_t i = r0 + threadIdx.x;
       rowv[threadIdx.x] = ok ? make_double4(p[i], q[i], yv[i], gv[i]) : make_double4(0.0, 0.0, 0.0, 0.0);
     }
-    __syncthreads();
+    __syncthreads();  // (A) rowv[tpar] visible; also orders the previous tile's red[tpar^1] readers before its next reuse
     double* __restrict__ base = sa.P + sym_tile_offset(tile);
     for (int col = 2 * threadIdx.x; col < (int)lpad; col += QN_CHUNK) {
       // element validity: columns >= ncols are padding (never stored, never updated)
       const bool v0 = col < ncols, v1 = col + 1 < ncols;
       if (!v0) continue;
-      const double2 gj = *reinterpret_cast<const double2*>(gv + col);
-      const double2 yj = *reinterpret_cast<const double2*>(yv + col);
-      const double2 pj = *reinterpret_cast<const double2*>(p + col);
-      const double2 qj = *reinterpret_cast<const double2*>(q + col);
+      const double2 gj = ld_vec2(gv + col);
+      const double2 yj = ld_vec2(yv + col);
+      const double2 pj = ld_vec2(p + col);
+      const double2 qj = ld_vec2(q + col);
       double2 hv[QN_R];
 #pragma unroll
       for (int r = 0; r < QN_R; ++r) hv[r] = r < rows_here ? ld_stream_ef(base + r * lpad + col, pol) : make_double2(0.0, 0.0);
@@ -831,45 +908,90 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_sym_kernel(QNLazyArgs a, QNSy
         *reinterpret_cast<double2*>(cpw + col) = ow;
       }
     }
+    {
+      double v16[16];
 #pragma unroll
-    for (int r = 0; r < QN_R; ++r) {
-      const double v1s = warp_sum(ah[r]), v2s = warp_sum(aw[r]);
-      if (lane == 0) {
-        red[r][warp] = v1s;
-        red[QN_R + r][warp] = v2s;
+      for (int r = 0; r < QN_R; ++r) {
+        v16[r] = ah[r];
+        v16[QN_R + r] = aw[r];
       }
+      const double ws = warp_sum16(v16);
+      if ((lane & 1) == 0) red[warp][lane >> 1] = ws;
     }
-    __syncthreads();
+    __syncthreads();  // (B)
     if (threadIdx.x < 2 * QN_R) {
       double v = 0.0;
 #pragma unroll
-      for (int w = 0; w < QN_T / 32; ++w) v = v + red[threadIdx.x][w];
+      for (int w = 0; w < QN_T / 32; ++w) v = v + red[w][threadIdx.x];
       const int r = threadIdx.x % QN_R;
       if (r < rows_here) {
         if (threadIdx.x < QN_R) a.h[r0 + r] = v;
         else a.w[r0 + r] = v;
       }
     }
-    __syncthreads();
   }
 }
 
-// h_j += sum over CTAs (in CTA order) of the column partials; then the O(n) epilogue (y.h, coefficients, u)
+// h_j += sum over CTAs of the column partials (fixed shape: 4 groups of consecutive CTAs summed in order, then
+// ((g0 + g1) + (g2 + g3))); then the O(n) epilogue (y.h, coefficients, u) by the last CTA.
+// CTA = 8 warps = {h, w} x 4 groups, lane = column within a block of 32 columns: every load is a coalesced
+// 256-byte row of one partial vector, 512 CTAs keep all SMs busy (a one-thread-per-column version took 58 us).
+constexpr int FOLD_T = 512;   // = QN_T: the fused epilogue then adds in the same order as the full-storage kernel's
+constexpr int FOLD_G = FOLD_T / 64;  // groups of partial rows per vector
 template <int KIND>
-__global__ void __launch_bounds__(QN_T) qn_sym_fold_kernel(QNLazyArgs a, QNSymArgs sa, int nparts, unsigned int* ticket) {
+__global__ void __launch_bounds__(FOLD_T) qn_sym_fold_kernel(const __grid_constant__ QNLazyArgs a, QNSymArgs sa, int nparts, unsigned int* ticket) {
   DevState* st = a.st;
   if (st->done) return;
+  __shared__ double2 part[2][FOLD_G][32];
   __shared__ double smem[3 * 32];
   __shared__ bool is_last;
   const int64_t ld = sa.ld;
-  for (int64_t j = (int64_t)blockIdx.x * QN_T + threadIdx.x; j < sa.n; j += (int64_t)gridDim.x * QN_T) {
-    double sh = 0.0, sw = 0.0;
-    for (int c = 0; c < nparts; ++c) {
-      sh = sh + __ldcg(sa.colpart + ((int64_t)c * 2 + 0) * ld + j);
-      sw = sw + __ldcg(sa.colpart + ((int64_t)c * 2 + 1) * ld + j);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int vec = warp / FOLD_G, grp = warp % FOLD_G;
+  const int per = (nparts + FOLD_G - 1) / FOLD_G;
+  const int cb = grp * per, ce = (cb + per < nparts) ? cb + per : nparts;
+  // a warp reads 512 contiguous bytes of one partial row per load and keeps 8 loads in flight; the order of the
+  // additions is fixed by (nparts, 4 groups), not by timing
+  for (int64_t j0 = (int64_t)blockIdx.x * 64; j0 < sa.n; j0 += (int64_t)gridDim.x * 64) {
+    const int64_t j = j0 + 2 * lane;  // ld is a multiple of 8 and the pad columns of colpart are zero, so j + 1 < ld is readable
+    double2 acc = make_double2(0.0, 0.0);
+    if (j < sa.n) {
+      const double* src = sa.colpart + (int64_t)vec * ld + j;
+      int c = cb;
+      for (; c + 8 <= ce; c += 8) {
+        double2 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = __ldcg(reinterpret_cast<const double2*>(src + (int64_t)(c + k) * 2 * ld));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          acc.x = acc.x + v[k].x;
+          acc.y = acc.y + v[k].y;
+        }
+      }
+      for (; c < ce; ++c) {
+        const double2 v = __ldcg(reinterpret_cast<const double2*>(src + (int64_t)c * 2 * ld));
+        acc.x = acc.x + v.x;
+        acc.y = acc.y + v.y;
+      }
     }
-    a.h[j] = a.h[j] + sh;
-    a.w[j] = a.w[j] + sw;
+    __syncthreads();
+    part[vec][grp][lane] = acc;
+    __syncthreads();
+    if (grp == 0 && j < sa.n) {
+      double2 tot = part[vec][0][lane];
+#pragma unroll
+      for (int g = 1; g < FOLD_G; ++g) {
+        tot.x = tot.x + part[vec][g][lane].x;
+        tot.y = tot.y + part[vec][g][lane].y;
+      }
+      double* dst = vec == 0 ? a.h : a.w;
+      dst[j] = dst[j] + tot.x;
+      if (j + 1 < sa.n) dst[j + 1] = dst[j + 1] + tot.y;
+    }
+  }
+  if (a.defer_epi) {  // the next cluster head forms the coefficients and u on 8 SMs; the kernel boundary orders h, w before it
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->epi = 1;
+    return;
   }
   __threadfence();
   __syncthreads();
@@ -880,7 +1002,7 @@ __global__ void __launch_bounds__(QN_T) qn_sym_fold_kernel(QNLazyArgs a, QNSymAr
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  lazy_epilogue_body<KIND>(a, smem);
+  lazy_epilogue_body<KIND>(a, a.h, a.w, smem);
   if (threadIdx.x == 0) *ticket = 0u;
 }
 
@@ -924,25 +1046,25 @@ void qn_sym_unpack(Ctx* ctx, const double* P, int64_t ld, int64_t n, double* H) 
 }
 int qn_sym_grid(Ctx* ctx, int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + QN_R - 1) / QN_R, (int64_t)ctx->num_sms)); }
 
-void qn_launch_lazy_sym(Ctx* ctx, const QNLazyArgs& a, double* P, double* colpart, int64_t n, int64_t ld) {
+void qn_launch_lazy_sym(Ctx* ctx, const QNLazyArgs& a, double* P, double* colpart, int64_t n, int64_t ld, int phase) {
   QNSymArgs sa{P, colpart, n, ld};
   const int grid = qn_sym_grid(ctx, n);
-  const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>((n + QN_T - 1) / QN_T, (int64_t)ctx->num_sms));
-  if (a.kind == QN_BFGS) {
-    qn_lazy_sym_kernel<QN_BFGS><<<grid, QN_T, 0, ctx->stream>>>(a, sa);
-    qn_sym_fold_kernel<QN_BFGS><<<fgrid, QN_T, 0, ctx->stream>>>(a, sa, grid, a.ticket);
-  } else {
-    qn_lazy_sym_kernel<QN_DFP><<<grid, QN_T, 0, ctx->stream>>>(a, sa);
-    qn_sym_fold_kernel<QN_DFP><<<fgrid, QN_T, 0, ctx->stream>>>(a, sa, grid, a.ticket);
+  const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 63) / 64, (int64_t)ctx->num_sms * 2));
+  if (phase == 0) {  // the streaming pass over the packed triangle
+    if (a.kind == QN_BFGS) qn_lazy_sym_kernel<QN_BFGS><<<grid, QN_T, 0, ctx->stream>>>(a, sa);
+    else qn_lazy_sym_kernel<QN_DFP><<<grid, QN_T, 0, ctx->stream>>>(a, sa);
+  } else {  // fold of the per-CTA column partials + coefficient epilogue
+    if (a.kind == QN_BFGS) qn_sym_fold_kernel<QN_BFGS><<<fgrid, FOLD_T, 0, ctx->stream>>>(a, sa, grid, a.ticket);
+    else qn_sym_fold_kernel<QN_DFP><<<fgrid, FOLD_T, 0, ctx->stream>>>(a, sa, grid, a.ticket);
   }
-  ctx->counters[0] += 2;
+  ctx->counters[0] += 1;
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(QN_T) qn_lazy_epilogue_kernel(QNLazyArgs a) {
+__global__ void __launch_bounds__(QN_T) qn_lazy_epilogue_kernel(const __grid_constant__ QNLazyArgs a) {
   if (a.st->done) return;
   __shared__ double smem[3 * 32];
-  lazy_epilogue_body<KIND>(a, smem);
+  lazy_epilogue_body<KIND>(a, a.h, a.w, smem);
 }
 
 void qn_launch_lazy(Ctx* ctx, const QNLazyArgs& a_in, int variant) {
@@ -964,8 +1086,22 @@ void qn_launch_lazy(Ctx* ctx, const QNLazyArgs& a_in, int variant) {
   }
   int64_t ntiles = (a.nrows + QN_R - 1) / QN_R;
   int grid = (int)std::min<int64_t>(ntiles, (int64_t)ctx->num_sms);
-  if (a.kind == QN_BFGS) qn_lazy_kernel<QN_BFGS><<<grid, QN_T, 0, ctx->stream>>>(a);
-  else qn_lazy_kernel<QN_DFP><<<grid, QN_T, 0, ctx->stream>>>(a);
+  const bool p2p = a.peers != nullptr;
+#define OSB_LAZY(K, D, P) qn_lazy_kernel<K, D, P><<<grid, QN_T, 0, ctx->stream>>>(a)
+#define OSB_LAZY_K(K)                                  \
+  do {                                                 \
+    if (a.defer_epi) {                                 \
+      if (p2p) OSB_LAZY(K, true, true);                \
+      else OSB_LAZY(K, true, false);                   \
+    } else {                                           \
+      if (p2p) OSB_LAZY(K, false, true);               \
+      else OSB_LAZY(K, false, false);                  \
+    }                                                  \
+  } while (0)
+  if (a.kind == QN_BFGS) OSB_LAZY_K(QN_BFGS);
+  else OSB_LAZY_K(QN_DFP);
+#undef OSB_LAZY_K
+#undef OSB_LAZY
   ctx->counters[0]++;
 }
 void qn_launch_lazy_epilogue(Ctx* ctx, const QNLazyArgs& a) {
@@ -992,8 +1128,8 @@ __global__ void __launch_bounds__(QN_T, 1) qn_flush_kernel(double* __restrict__ 
     __syncthreads();
     double* __restrict__ base = M + r0 * ld;
     for (int col = 2 * threadIdx.x; col < (int)ld; col += QN_CHUNK) {
-      const double2 pj = *reinterpret_cast<const double2*>(p + col);
-      const double2 qj = *reinterpret_cast<const double2*>(q + col);
+      const double2 pj = ld_vec2(p + col);
+      const double2 qj = ld_vec2(q + col);
 #pragma unroll
       for (int r = 0; r < QN_R; ++r) {
         const double2 pq = rowpq[r];
