@@ -100,9 +100,10 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(lazy=True):
+def ncu_traffic(lazy=True, sym=False):
     """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
-    p = os.path.join(ROOT, "profiles", "qn_lazy_ncu_summary.json" if lazy else "qn_update_ncu_summary.json")
+    p = os.path.join(ROOT, "profiles", "qn_lazy_sym_ncu_summary.json" if sym else
+                     "qn_lazy_ncu_summary.json" if lazy else "qn_update_ncu_summary.json")
     if os.path.exists(p):
         try:
             return float(json.load(open(p))["dram_bytes_per_launch"])
@@ -161,8 +162,9 @@ def main():
     ap.add_argument("--n", type=int, default=N_DIM, help="problem dimension (the benchmark line is only valid at 16384)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--head", type=int, default=0, help="device-engine head variant (0 cluster+speculation, 3 cluster, 1 single CTA)")
-    ap.add_argument("--storage", default="full", choices=["full", "sym"],
-                    help="sym: packed lower triangle of H (n^2 8 B per iteration; single GPU, lazy schedule)")
+    ap.add_argument("--storage", default="auto", choices=["auto", "full", "sym"],
+                    help="sym: packed lower triangle of H (n^2 8 B per iteration; single GPU, lazy schedule); "
+                         "full: n x n row-major (row-block sharded over N GPUs); auto: sym on one GPU, full when sharded")
     ap.add_argument("--qn-kernel", type=int, default=0, help="lazy-pass kernel: 0 = register-staged LDG, 1 = TMA-staged (cp.async.bulk + mbarrier)")
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL all-gathers instead of the fused peer-memory exchange")
     ap.add_argument("--schedule", default="lazy", choices=["lazy", "eager"],
@@ -207,7 +209,7 @@ def main():
     solver = osb.BFGS(TOL, x0, ctx=ctx).set_option("engine", 2).set_option("qn_schedule", 1 if lazy else 0)
     solver.set_option("head_kernel", args.head)
     solver.set_option("qn_kernel", args.qn_kernel)
-    sym = lazy and args.storage == "sym" and world == 1
+    sym = lazy and args.storage in ("sym", "auto") and world == 1
     solver.set_option("qn_storage", 1 if sym else 0)
 
     def run_steps(k):
@@ -261,7 +263,7 @@ def main():
              else "qn_update_kernel<BFGS> (fused rank-2 RMW + u = H' g)")
     roofline = {"bound": "hbm", "kernel": kname, "achieved": ach,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": (ach / peak) if ach else None,
-                "traffic": ncu_traffic(lazy) if (world == 1 and not sym) else None, "algorithmic_bytes_per_launch": upd_bytes, "ms_per_launch": kt["update_ms"], "sym_parts": sym_parts,
+                "traffic": ncu_traffic(lazy, sym) if world == 1 else None, "algorithmic_bytes_per_launch": upd_bytes, "ms_per_launch": kt["update_ms"], "sym_parts": sym_parts,
                 "gemv_kernel": None if lazy else {
                     "achieved": gemv_bytes / (kt["gemv_ms"] * 1e-3) / 1e9 if kt["gemv_ms"] > 0 else None,
                     "ms_per_launch": kt["gemv_ms"], "algorithmic_bytes_per_launch": gemv_bytes},

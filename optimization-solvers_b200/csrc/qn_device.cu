@@ -397,19 +397,45 @@ constexpr int HC_T = 512;
 // Every tree has a fixed shape, so all CTAs (and all ranks of a sharded run) obtain identical bits.
 // (An earlier variant let every thread fold the 16 warp partials sequentially from shared memory:
 //  clock64 stamps showed 17.7k cycles per reduction at K = 12, two thirds of the head kernel.)
+// Warp sums of P (a power of two) values with P - 1 + log2(32 / P) double shuffles instead of 5 P (the head's
+// reductions were bound by the SM's shuffle throughput: 12 values x 5 steps x 16 warps).  Recursive halving: at
+// offset o a lane keeps half of its values and adds the partner's copies of them — the same pairs (l, l ^ o) at
+// the same levels as the plain butterfly, so the sums are bit-identical to warp_sum().  On return the lanes
+// [i * 32 / P, (i + 1) * 32 / P) all hold the total of value i.
+template <int P>
+__device__ __forceinline__ double warp_sum_multi(double (&v)[P]) {
+  static_assert(P == 1 || P == 2 || P == 4 || P == 8 || P == 16, "P must be a power of two <= 16");
+  const int lane = threadIdx.x & 31;
+  int o = 16;
+#pragma unroll
+  for (int hs = P / 2; hs >= 1; hs >>= 1, o >>= 1) {
+    const bool upper = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < hs; ++i) {
+      const double send = upper ? v[i] : v[i + hs];
+      const double keep = upper ? v[i + hs] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  double r = v[0];
+#pragma unroll
+  for (int oo = 16 / P; oo > 0; oo >>= 1) r = r + __shfl_xor_sync(0xffffffffu, r, oo);
+  return r;
+}
+
 template <int K>
 __device__ __forceinline__ void cluster_sum(double (&acc)[K], double* smem_cta /* K x 16 */, double* part /* 2 x 16 */,
                                             double* res /* 16 */, int& phase) {
   static_assert(K <= 12 && HC_T == 512, "layout below assumes 16 warps and K <= 12");
   cg::cluster_group cluster = cg::this_cluster();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int P = K <= 1 ? 1 : K <= 2 ? 2 : K <= 4 ? 4 : K <= 8 ? 8 : 16;
+  double vp[P];
 #pragma unroll
-  for (int k = 0; k < K; ++k) acc[k] = warp_sum(acc[k]);
+  for (int k = 0; k < P; ++k) vp[k] = k < K ? acc[k] : 0.0;
+  const double wsum = warp_sum_multi<P>(vp);
   __syncthreads();  // smem_cta / res may still be read from the previous call
-  if (lane == 0) {
-#pragma unroll
-    for (int k = 0; k < K; ++k) smem_cta[k * 16 + warp] = acc[k];
-  }
+  if (lane % (32 / P) == 0 && lane / (32 / P) < K) smem_cta[(lane / (32 / P)) * 16 + warp] = wsum;
   __syncthreads();
   double* mine = part + (phase & 1) * 16;
   if (threadIdx.x < ((K * 16 + 31) / 32) * 32) {  // thread = k * 16 + w ; whole warps execute the shuffles
@@ -603,6 +629,7 @@ qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol,
       st->epi = 0;
     }
   }
+  OSB_TS();
   int why = OSB_REASON_NONE;
   if (st->has_s && st->s_norm < tol) why = OSB_REASON_S_NORM;        // bfgs.rs:67-69
   else if (st->has_y && st->y_norm < tol) why = OSB_REASON_Y_NORM;   // bfgs.rs:70-72

@@ -4,7 +4,7 @@ import numpy as np
 osb=importlib.import_module("optimization-solvers_b200")
 from bench import rosen_x0
 n=16384
-s=osb.BFGS(1e-8, rosen_x0(n,0)).set_option("engine",2).set_option("qn_schedule",1).set_option("head_debug",1)
+s=osb.BFGS(1e-8, rosen_x0(n,0)).set_option("engine",2).set_option("qn_schedule",1).set_option("head_debug",1).set_option("qn_storage", int(os.environ.get("SYM","1")))
 obj=osb.ExtendedRosenbrock(n)
 L=osb.lib(); L.osb_debug_head_stamps.argtypes=[C.POINTER(C.c_longlong)]
 for it in (20, 1, 1, 1, 60, 1, 1):
