@@ -282,6 +282,7 @@ def main():
             barrier()
             t0 = time.perf_counter()
             s2 = osb.BFGS(TOL, x0_pinned.numpy(), ctx=ctx).set_option("qn_schedule", 1 if lazy else 0)
+            s2.set_option("qn_storage", 1 if sym else 0)
             t_c = time.perf_counter()
 
             def cb(s):
@@ -339,7 +340,9 @@ def main():
                            "max_iter_line_search": MAX_LS, "engine": "device-resident control",
                            "schedule": "lazy + packed symmetric storage: 1 RMW pass of the lower triangle per iteration (n^2 8 B)" if sym else
                            "lazy: 1 RMW pass of H per iteration (2 n^2 8 B)" if lazy else "eager: gemv + fused update (3 n^2 8 B)",
-                           "l2": "inputs larger than L2 (H = %.2f GiB per GPU, streamed every step)" % (rows_local * n * 8 / 2 ** 30),
+                           "storage": "packed lower triangle, 8-row tiles" if sym else "full n x n row-major",
+                           "l2": "inputs larger than L2 (H = %.2f GiB per GPU, streamed every step)" % (
+                               (n * (n + 8) / 2 if sym else rows_local * n) * 8 / 2 ** 30),
                            "parallelism": "row-block sharded H over %d GPU(s); exchange: %s" % (
                                world, "none" if world == 1 else ("NCCL all-gather of the h / w slices" if (args.no_p2p or not lazy)
                                                                  else "peer-memory all-gather fused into the lazy kernel (NVLink stores + flags)"))},
