@@ -88,6 +88,12 @@ int osb_ctx_create_dist(int device, int rank, int world, const void* nccl_unique
  * instead of NCCL calls. */
 int osb_ctx_ipc_handle(osb_ctx* ctx, void* out64);
 int osb_ctx_ipc_connect(osb_ctx* ctx, const void* handles_world_x_64);
+/* Index-range sharding of the O(n) solvers (world > 1): when on, GradientDescent / ProjectedGradientDescent /
+ * SpectralProjectedGradient created on this context own a contiguous SLICE of the variables (their n, x0, lb, ub are
+ * the local ones; objectives must be block-functor objectives created for the same slice), and every scalar of
+ * the path (f, g.d, s.y, s.s, the inf-norms of number.rs:27-31 and projected_gradient_descent.rs:76-83) is
+ * combined across ranks in rank order.  Replaces nothing in the reference (single-threaded); SURVEY 8e. */
+int osb_ctx_set_vector_sharding(osb_ctx* ctx, int on);
 void osb_ctx_destroy(osb_ctx* ctx);
 int osb_ctx_rank(const osb_ctx* ctx);
 int osb_ctx_world(const osb_ctx* ctx);
@@ -114,6 +120,8 @@ int osb_objective_create_dense_quadratic_generated(osb_ctx* ctx, int64_t n, int 
 int osb_objective_create_rosenbrock(osb_ctx* ctx, int64_t n, osb_objective** out);
 /* separable f = sum 0.5 c_i (x_i - a_i)^2 with hash-generated c, a (box-constrained SPG config) */
 int osb_objective_create_separable_quadratic_generated(osb_ctx* ctx, int64_t n, osb_objective** out);
+/* the slice [index0, index0 + n_local) of the same generated problem (index-range sharding) */
+int osb_objective_create_separable_quadratic_generated_shard(osb_ctx* ctx, int64_t n_local, int64_t index0, osb_objective** out);
 /* synthetic l2-regularised logistic regression, m samples x n features generated on device */
 int osb_objective_create_logistic_generated(osb_ctx* ctx, int64_t m, int64_t n, double lambda, osb_objective** out);
 

@@ -60,6 +60,8 @@ def lib():
             "osb_objective_create_dense_quadratic_generated": (ci, [_vp, i64, ci, _dp, pp]),
             "osb_objective_create_rosenbrock": (ci, [_vp, i64, pp]),
             "osb_objective_create_separable_quadratic_generated": (ci, [_vp, i64, pp]),
+            "osb_objective_create_separable_quadratic_generated_shard": (ci, [_vp, i64, i64, pp]),
+            "osb_ctx_set_vector_sharding": (ci, [_vp, ci]),
             "osb_objective_create_logistic_generated": (ci, [_vp, i64, i64, dbl, pp]),
             "osb_objective_create_host": (ci, [_vp, i64, HOST_EVAL, _vp, ci, pp]),
             "osb_objective_create_user": (ci, [_vp, i64, DEVICE_EVAL, _vp, ci, pp]),
@@ -307,6 +309,11 @@ class Context:
         self.ipc_connect(allh)
         dist.barrier()
 
+    def set_vector_sharding(self, on=True):
+        """Index-range sharding of GD / PGD / SPG over the ranks of this context (see include/optsolv_b200.h)."""
+        _check(lib().osb_ctx_set_vector_sharding(self.handle, 1 if on else 0))
+        return self
+
     def rank(self):
         return lib().osb_ctx_rank(self.handle)
 
@@ -469,6 +476,16 @@ class SeparableQuadratic(_Objective):
         self.ctx = ctx or default_context()
         h = _vp()
         _check(lib().osb_objective_create_separable_quadratic_generated(self.ctx.handle, n, C.byref(h)))
+        self.handle = h
+        return self
+
+    @classmethod
+    def generated_shard(cls, n_local, index0, ctx):
+        """Coordinates [index0, index0 + n_local) of the generated problem (index-range sharded SPG / PGD / GD)."""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        h = _vp()
+        _check(lib().osb_objective_create_separable_quadratic_generated_shard(self.ctx.handle, n_local, index0, C.byref(h)))
         self.handle = h
         return self
 

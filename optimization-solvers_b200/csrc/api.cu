@@ -98,6 +98,19 @@ int osb_ctx_synchronize(osb_ctx* ctx) {
   return OSB_OK;
   OSB_CATCH
 }
+int osb_ctx_set_vector_sharding(osb_ctx* ctx, int on) {
+  OSB_TRY
+  Ctx* c = C(ctx);
+  c->use();
+  OSB_REQUIRE(!on || c->world > 1, OSB_ERROR_INPUT_PARAMS, "index-range sharding needs a distributed context (osb_ctx_create_dist)");
+  if (on && !c->shard_scratch) {
+    OSB_CUDA(cudaMalloc(&c->shard_scratch, sizeof(double) * 8 * (size_t)c->world));
+    OSB_CUDA(cudaMemset(c->shard_scratch, 0, sizeof(double) * 8 * (size_t)c->world));
+  }
+  c->vec_sharded = on != 0;
+  return OSB_OK;
+  OSB_CATCH
+}
 void* osb_ctx_stream(osb_ctx* ctx) { return (void*)C(ctx)->stream; }
 int osb_ctx_counters(const osb_ctx* ctx, int64_t out[8]) {
   std::memcpy(out, C(ctx)->counters, sizeof(int64_t) * 8);
@@ -121,6 +134,9 @@ int osb_objective_create_dense_quadratic_generated(osb_ctx* ctx, int64_t n, int 
 int osb_objective_create_rosenbrock(osb_ctx* ctx, int64_t n, osb_objective** out) { MAKE_OBJ(make_rosenbrock(C(ctx), n)) }
 int osb_objective_create_separable_quadratic_generated(osb_ctx* ctx, int64_t n, osb_objective** out) {
   MAKE_OBJ(make_sepquad_generated(C(ctx), n))
+}
+int osb_objective_create_separable_quadratic_generated_shard(osb_ctx* ctx, int64_t n_local, int64_t index0, osb_objective** out) {
+  MAKE_OBJ(make_sepquad_generated(C(ctx), n_local, index0))
 }
 int osb_objective_create_logistic_generated(osb_ctx* ctx, int64_t m, int64_t n, double lambda, osb_objective** out) {
   MAKE_OBJ(make_logistic_generated(C(ctx), m, n, lambda))

@@ -48,6 +48,7 @@ Ctx::~Ctx() {
   cudaFree(red_ticket);
   cudaFree(gemv_ticket);
   cudaFree(d_dummy);
+  cudaFree(shard_scratch);
   cudaFreeHost(h_pinned);
   if (stream) cudaStreamDestroy(stream);
 }
@@ -102,6 +103,8 @@ Solver::Solver(Ctx* c, int kind_, int64_t n_, double tol_, const double* x0, con
   OSB_REQUIRE(n >= 1 && x0 != nullptr, OSB_ERROR_INPUT_PARAMS, "n >= 1 and x0 required");
   bounded = kind_is_bounded(kind);
   is_qn = kind_is_qn(kind);
+  OSB_REQUIRE(!ctx->vec_sharded || kind == OSB_GD || kind == OSB_PGD || kind == OSB_SPG, OSB_ERR_UNSUPPORTED,
+              "index-range sharding supports GradientDescent, ProjectedGradientDescent and SpectralProjectedGradient");
   OSB_REQUIRE(!bounded || (lb_h && ub_h), OSB_ERROR_INPUT_PARAMS, "bounded solver needs lower and upper bounds");
   ld = qn_ld(n);
   cudaStream_t st = ctx->stream;

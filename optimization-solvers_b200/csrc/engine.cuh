@@ -64,6 +64,11 @@ struct Ctx {
   // pinned staging for small transfers
   double* h_pinned = nullptr;  // 4096 doubles
   double* d_dummy = nullptr;   // 8 doubles: sink for reductions whose result is unused
+  // Index-range sharding of the O(n) solvers (GD / PGD / SPG with block-functor objectives, SURVEY 8e "SPG / PGD
+  // streaming"): every rank owns a contiguous slice of x, g, lb, ub; every map-reduce of the path then ends in an
+  // all-gather of the K per-rank values and a rank-ordered combine (same bits on every rank).
+  bool vec_sharded = false;
+  double* shard_scratch = nullptr;  // world x 8 doubles
 
   explicit Ctx(int dev);
   ~Ctx();
@@ -97,10 +102,34 @@ struct DBuf {
   void download(double* h, int64_t cnt, cudaStream_t s) const;
 };
 
+#ifdef __CUDACC__
+template <int K, class Fin>
+__global__ void shard_combine_kernel(Fin fin, RedOps<K> ops, const double* gathered, int world, double* out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double v[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    v[k] = red_identity(ops.op[k]);
+    for (int r = 0; r < world; ++r) v[k] = red_combine(ops.op[k], v[k], gathered[r * 8 + k]);
+  }
+  fin(v, out);
+}
+#endif
+
 template <int K, class F, class Fin>
 inline void launch_mapreduce_fin(Ctx* ctx, F f, Fin fin, int64_t count, RedOps<K> ops, double* out) {
   static_assert(K <= RED_THREADS / 32, "final fold uses one warp per output");
+  static_assert(K <= 8, "shard_scratch holds 8 values per rank");
   int grid = ctx->red_grid(count);
+  if (ctx->vec_sharded && ctx->world > 1) {
+    // local fold -> K raw values per rank -> all-gather -> rank-ordered combine + the caller's finalizer
+    mapreduce_kernel<K, F, FinStore><<<grid, RED_THREADS, 0, ctx->stream>>>(f, FinStore{}, count, ops, ctx->red_partials, ctx->red_ticket,
+                                                                           ctx->shard_scratch + ctx->rank * 8);
+    ctx->all_gather_inplace(ctx->shard_scratch, 8);
+    shard_combine_kernel<K, Fin><<<1, 32, 0, ctx->stream>>>(fin, ops, ctx->shard_scratch, ctx->world, out);
+    ctx->counters[0] += 2;
+    return;
+  }
   mapreduce_kernel<K, F, Fin><<<grid, RED_THREADS, 0, ctx->stream>>>(f, fin, count, ops, ctx->red_partials, ctx->red_ticket, out);
   ctx->counters[0]++;
 }
@@ -131,7 +160,7 @@ struct Objective {
 Objective* make_dense_quadratic(Ctx*, int64_t n, const double* A_host, const double* b_host);
 Objective* make_dense_quadratic_generated(Ctx*, int64_t n, bool shifted, double* x0_host);
 Objective* make_rosenbrock(Ctx*, int64_t n);
-Objective* make_sepquad_generated(Ctx*, int64_t n);
+Objective* make_sepquad_generated(Ctx*, int64_t n, int64_t index0 = 0);
 Objective* make_logistic_generated(Ctx*, int64_t m, int64_t n, double lambda);
 Objective* make_host_objective(Ctx*, int64_t n, osb_host_eval_fn fn, void* user, bool with_h);
 Objective* make_user_objective(Ctx*, int64_t n, osb_device_eval_fn fn, void* user, bool with_h);

@@ -81,17 +81,18 @@ Objective* make_rosenbrock(Ctx* ctx, int64_t n) {
   return new FunctorObjective<RosenbrockFn>(ctx, n, FN_ROSENBROCK);
 }
 
-__global__ void gen_sepquad_kernel(int64_t n, double* c, double* a) {
+__global__ void gen_sepquad_kernel(int64_t n, double* c, double* a, int64_t index0) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    c[i] = 1.0 + (double)(hash3(7, (uint64_t)i, 0) & 0xFF) / 16.0;
-    a[i] = (double)h16(8, (uint64_t)i, 0) * 6.103515625e-05;  // 2^-14
+    const uint64_t gi = (uint64_t)(index0 + i);  // global coordinate (index-range sharding: this rank holds [index0, index0 + n))
+    c[i] = 1.0 + (double)(hash3(7, gi, 0) & 0xFF) / 16.0;
+    a[i] = (double)h16(8, gi, 0) * 6.103515625e-05;  // 2^-14
   }
 }
-Objective* make_sepquad_generated(Ctx* ctx, int64_t n) {
+Objective* make_sepquad_generated(Ctx* ctx, int64_t n, int64_t index0) {
   auto* o = new FunctorObjective<SepQuadFn>(ctx, n, FN_SEPQUAD);
   o->pa.alloc(qn_ld(n));
   o->pb.alloc(qn_ld(n));
-  gen_sepquad_kernel<<<ctx->red_grid(n), RED_THREADS, 0, ctx->stream>>>(n, o->pa.p, o->pb.p);
+  gen_sepquad_kernel<<<ctx->red_grid(n), RED_THREADS, 0, ctx->stream>>>(n, o->pa.p, o->pb.p, index0);
   ctx->counters[0]++;
   o->fn.c = o->pa.p;
   o->fn.a = o->pb.p;
@@ -99,10 +100,10 @@ Objective* make_sepquad_generated(Ctx* ctx, int64_t n) {
 }
 
 // ---- dense quadratic ----------------------------------------------------------------------
-__global__ void gen_quad_kernel(int64_t n, int64_t ld, double sc, double* A) {
-  const int64_t total = n * ld;
+__global__ void gen_quad_kernel(int64_t n, int64_t ld, double sc, double* A, int64_t nrows, int64_t row0) {
+  const int64_t total = nrows * ld;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = e / ld, j = e % ld;
+    const int64_t i = row0 + e / ld, j = e % ld;
     double v = 0.0;
     if (j < n) {
       if (i == j) v = 2.0 + (double)(i % 7);
@@ -118,22 +119,33 @@ __global__ void scale_copy_kernel(int64_t total, const double* in, double* out, 
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) out[e] = sc * in[e];
 }
 
+// Multi-GPU: A is row-block sharded like H — rank p owns rows [p n/P, (p+1) n/P) — and x, g are
+// replicated; (A x)_p is all-gathered, then f and g are formed redundantly (and identically) on every rank.  A row's
+// dot product is formed inside one CTA whatever the sharding, so sharded runs are bit-identical to one GPU.
 struct DenseQuadratic : Objective {
   DBuf A, b, Ax;
-  int64_t ld;
+  int64_t ld, nrows, row0;
   bool shifted = false;
-  DenseQuadratic(Ctx* c, int64_t n_) : Objective(c, n_), ld(qn_ld(n_)) {
-    A.alloc(qn_rows_padded(n_) * ld);
+  DenseQuadratic(Ctx* c, int64_t n_) : Objective(c, n_), ld(qn_ld(n_)), nrows(n_), row0(0) {
+    OSB_REQUIRE(!c->vec_sharded, OSB_ERR_UNSUPPORTED, "index-range sharding applies to block-functor objectives only");
+    if (c->world > 1) {
+      OSB_REQUIRE(n_ % (c->world * 8) == 0, OSB_ERROR_INPUT_PARAMS, "row-sharded A needs n divisible by 8 * world");
+      nrows = n_ / c->world;
+      row0 = nrows * c->rank;
+    }
+    A.alloc(qn_rows_padded(nrows) * ld);
     A.zero(c->stream);
     Ax.alloc(ld);
     Ax.zero(c->stream);
   }
-  bool provides_hessian() const override { return true; }
+  bool provides_hessian() const override { return ctx->world == 1; }
   void eval(const double* x, double* d_f, double* g, double* hess) override {
     calls++;
     ctx->counters[1]++;
-    // one read of A yields A x, hence f and g  (n^2 * 8 B per evaluation)
-    qn_launch_gemv(ctx, A.p, ld, n, 0, nullptr, x, Ax.p, nullptr, nullptr, 0);
+    OSB_REQUIRE(hess == nullptr || ctx->world == 1, OSB_ERR_UNSUPPORTED, "the Hessian of a row-sharded quadratic is not assembled");
+    // one read of A yields A x, hence f and g  (n^2 * 8 B per evaluation, / world when sharded)
+    qn_launch_gemv(ctx, A.p, ld, nrows, row0, nullptr, x, Ax.p, nullptr, nullptr, 0);
+    if (ctx->world > 1) ctx->all_gather_inplace(Ax.p, nrows);
     const double* ax = Ax.p;
     const double* bb = shifted ? b.p : nullptr;
     auto f = [=] __device__(int64_t i, double(&acc)[2]) {
@@ -157,7 +169,7 @@ struct DenseQuadratic : Objective {
 
 Objective* make_dense_quadratic(Ctx* ctx, int64_t n, const double* A_host, const double* b_host) {
   auto* o = new DenseQuadratic(ctx, n);
-  OSB_CUDA(cudaMemcpy2DAsync(o->A.p, o->ld * sizeof(double), A_host, n * sizeof(double), n * sizeof(double), n,
+  OSB_CUDA(cudaMemcpy2DAsync(o->A.p, o->ld * sizeof(double), A_host + o->row0 * n, n * sizeof(double), n * sizeof(double), o->nrows,
                              cudaMemcpyHostToDevice, ctx->stream));
   if (b_host) {
     o->shifted = true;
@@ -174,7 +186,7 @@ Objective* make_dense_quadratic_generated(Ctx* ctx, int64_t n, bool shifted, dou
   int lg = 0;
   while (((int64_t)1 << lg) < n) ++lg;
   const double sc = std::ldexp(1.0, -(15 + lg));
-  gen_quad_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(n, o->ld, sc, o->A.p);
+  gen_quad_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(n, o->ld, sc, o->A.p, o->nrows, o->row0);
   ctx->counters[0]++;
   if (shifted) {
     std::vector<double> b(n);

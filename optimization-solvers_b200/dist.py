@@ -29,6 +29,16 @@ def shard_problems(n_problems, rank, world):
     return p0, count
 
 
+def shard_indices(n, rank, world, block=2):
+    """Contiguous coordinate range [i0, i0 + count) of an n-vector owned by `rank` (index-range sharded GD / PGD / SPG).
+    Ranges are multiples of `block` (the objective functor's block size: 2 for extended Rosenbrock) and equal-sized,
+    because the all-gather of the per-rank scalars assumes nothing about them but the rank order."""
+    if n % (block * world) != 0:
+        raise ValueError("index-range sharding needs n divisible by block * world (n=%d, block=%d, world=%d)" % (n, block, world))
+    count = n // world
+    return rank * count, count
+
+
 def shard_samples(m, rank, world):
     if m % world != 0:
         raise ValueError("sample count must divide by the number of ranks")

@@ -15,6 +15,12 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+def _second_uid(osb, dist, rank):
+    uid = [osb.Context.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    return uid[0]
+
+
 def main():
     import torch
     import torch.distributed as dist
@@ -51,6 +57,55 @@ def main():
         print("rank %d %s n=%d k=%d schedule=%d p2p=%d bit-identical to single GPU: %s"
               % (rank, kind, n, res[0][0], sched, p2p, same), flush=True)
         ok &= bool(same)
+    # ---- C2 shape: GradientDescent on a row-sharded dense quadratic (A row-block sharded, x / g replicated, all-gather
+    # of (A x)_p): bit-identical to one GPU
+    n = 4096
+    res = []
+    for c in (ctx, solo):
+        obj = osb.DenseQuadratic.generated(n, True, ctx=c)
+        s = osb.GradientDescent(1e-6, obj.x0, ctx=c)
+        try:
+            s.minimize(osb.BackTracking(1e-4, 0.5), obj, 400, 100)
+        except osb.MaxIterReached:
+            pass
+        res.append((s.k(), s.x(), s.f(), s.termination_reason()))
+        s.close()
+    same = res[0][0] == res[1][0] and np.array_equal(res[0][1], res[1][1]) and res[0][2] == res[1][2] and res[0][3] == res[1][3]
+    print("rank %d GD dense quadratic n=%d k=%d reason=%s row-sharded A bit-identical to single GPU: %s"
+          % (rank, n, res[0][0], res[0][3], same), flush=True)
+    ok &= bool(same)
+
+    # ---- C5b shape: SPG / PGD / GD with index-range sharded vectors (every scalar combined across ranks in rank order):
+    # same iteration count and termination reason, bit-exact active set, x and f to rounding of the summation order
+    from importlib import import_module
+    shard_indices = import_module("optimization-solvers_b200.dist").shard_indices
+    n = 1 << 20
+    i0, cnt = shard_indices(n, rank, world)
+    vctx = osb.Context(lr, rank, world, _second_uid(osb, dist, rank)).set_vector_sharding(True)
+    for name, mk_ls, tol in (("SPG+GLL", lambda: osb.GLLQuadratic(1e-4, 10), 1e-6), ("SPG+BackTracking", lambda: osb.BackTracking(1e-4, 0.5), 1e-5),
+                             ("PGD+BackTracking", lambda: osb.BackTracking(1e-4, 0.5), 1e-5)):
+        out = []
+        for c, nn, off in ((vctx, cnt, i0), (solo, n, 0)):
+            obj = (osb.SeparableQuadratic.generated_shard(nn, off, c) if c is vctx else osb.SeparableQuadratic.generated(nn, ctx=c))
+            lb, ub = np.full(nn, -1.0), np.full(nn, 1.0)
+            if name.startswith("SPG"):
+                s = osb.SpectralProjectedGradient(tol, np.zeros(nn), obj, lb, ub, ctx=c)
+            else:
+                s = osb.ProjectedGradientDescent(tol, np.zeros(nn), lb, ub, ctx=c)
+            try:
+                s.minimize(mk_ls(), obj, 500, 50)
+            except osb.MaxIterReached:
+                pass
+            out.append((s.k(), s.termination_reason(), s.x(), s.f(), s.active_set()))
+            s.close()
+        (k1, r1, x1, f1, a1), (k0, r0, x0_, f0, a0) = out
+        sl = slice(i0, i0 + cnt)
+        good = (k1 == k0 and r1 == r0 and np.array_equal(a1, a0[sl]) and abs(f1 - f0) <= 1e-12 * abs(f0)
+                and np.max(np.abs(x1 - x0_[sl])) <= 1e-9)
+        print("rank %d %s n=2^20 index-range sharded: k=%d/%d reason=%s/%s f rel diff %.2e max|dx| %.2e active sets equal %s -> %s"
+              % (rank, name, k1, k0, r1, r0, abs(f1 - f0) / abs(f0), np.max(np.abs(x1 - x0_[sl])), np.array_equal(a1, a0[sl]), good), flush=True)
+        ok &= bool(good)
+
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.barrier()

@@ -75,3 +75,52 @@ def test_partition_rules():
         d.shard_rows(100, 0, 8)
     with pytest.raises(ValueError):
         d.shard_samples(10, 0, 4)
+
+
+def test_index_range_sharding_rules():
+    """Index-range sharding of GD / PGD / SPG: equal contiguous ranges, whole functor blocks."""
+    d = _load_dist()
+    for world in (1, 2, 4, 8):
+        spans = [d.shard_indices(1 << 28, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and sum(c for _, c in spans) == 1 << 28
+        assert all(spans[i][0] + spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+        assert len({c for _, c in spans}) == 1 and spans[0][1] % 2 == 0
+    with pytest.raises(ValueError):
+        d.shard_indices(1002, 0, 4)  # 1002 / 4 is not a whole number of 2-blocks
+
+
+def test_rank_ordered_combine_matches_the_device_rule_world2(tmp_path):
+    """The cross-rank combine of the sharded reductions is 'fold the per-rank values in rank order' (sum, max, min):
+    two gloo ranks all-gather their partials and fold them; both obtain the same bits, equal to the sequential fold."""
+    import subprocess
+    import sys
+    code = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+rng = np.random.default_rng(7)
+parts = rng.standard_normal((world, 3)) * [1.0, 1e8, 1e-8]
+mine = torch.from_numpy(parts[rank].copy())
+allp = [torch.zeros(3, dtype=torch.float64) for _ in range(world)]
+dist.all_gather(allp, mine)
+def fold(ps):
+    s, mx, mn = 0.0, -np.inf, np.inf
+    for p in ps:
+        s = s + float(p[0]); mx = max(mx, float(p[1])); mn = min(mn, float(p[2]))
+    return s, mx, mn
+got = fold(allp)
+want = fold([torch.from_numpy(parts[r]) for r in range(world)])
+assert got == want, (got, want)
+res = [None] * world
+dist.all_gather_object(res, got)
+assert all(r == res[0] for r in res)
+dist.destroy_process_group()
+'''
+    script = tmp_path / "combine_worker.py"
+    script.write_text(code)
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stderr[-2000:]

@@ -2,6 +2,8 @@
 Prints one JSON object per config; results are copied to profiles/ by hand.
 
     python tools/bench_configs.py [c2] [c4] [c5a] [c5b] [--m 262144]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        tools/bench_configs.py c2 c5b        # C2 with A row-sharded, C5b with index-range sharded vectors
 """
 import importlib
 import json
@@ -21,6 +23,38 @@ except Exception:
     pass
 
 
+RANK, WORLD, LOCAL = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+_DIST = None
+
+
+def dist_ctx(vector_sharding=False):
+    """Per-rank library context under torchrun (a fresh NCCL communicator per call); the default context otherwise."""
+    global _DIST
+    if WORLD == 1:
+        return osb.default_context()
+    import torch
+    import torch.distributed as dist
+    if _DIST is None:
+        torch.cuda.set_device(LOCAL)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", LOCAL))
+        _DIST = dist
+    uid = [osb.Context.nccl_unique_id() if RANK == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    ctx = osb.Context(LOCAL, RANK, WORLD, uid[0])
+    if vector_sharding:
+        ctx.set_vector_sharding(True)
+    return ctx
+
+
+def max_over_ranks(v):
+    if WORLD == 1:
+        return v
+    import torch
+    t = torch.tensor([v], dtype=torch.float64, device="cuda")
+    _DIST.all_reduce(t, op=_DIST.ReduceOp.MAX)
+    return float(t.item())
+
+
 def run(solver, ls, obj, mi, ml):
     try:
         solver.minimize(ls, obj, mi, ml)
@@ -32,19 +66,21 @@ def run(solver, ls, obj, mi, ml):
 def c2():
     # GradientDescent + BackTracking(1e-4, 0.5), dense SPD quadratic n = 16384 (GEMV-bound: n^2 * 8 B per oracle call)
     n = 16384
-    obj = osb.DenseQuadratic.generated(n, True)
-    ctx = osb.default_context()
-    s = osb.GradientDescent(1e-6, obj.x0)
+    ctx = dist_ctx()
+    obj = osb.DenseQuadratic.generated(n, True, ctx=ctx)
+    s = osb.GradientDescent(1e-6, obj.x0, ctx=ctx)
     run(s, osb.BackTracking(1e-4, 0.5), obj, 3, 100)  # warm-up
-    s = osb.GradientDescent(1e-6, obj.x0)
+    s = osb.GradientDescent(1e-6, obj.x0, ctx=ctx)
     c0 = obj.calls()
     st = run(s, osb.BackTracking(1e-4, 0.5), obj, 1000, 100)
     ms, it = s.last_timing()
+    ms = max_over_ranks(ms)
     evals = obj.calls() - c0
-    return {"config": "C2 GD + BackTracking, dense SPD quadratic n=16384", "status": st, "iterations": it, "reason": s.termination_reason(),
+    return {"config": "C2 GD + BackTracking, dense SPD quadratic n=16384, A row-sharded over %d GPU(s)" % WORLD, "n_gpus": WORLD,
+            "status": st, "iterations": it, "reason": s.termination_reason(),
             "ms_total": ms, "iterations_per_s": it / ms * 1e3, "oracle_evals": evals, "evals_per_iteration": evals / max(it, 1),
             "bytes_per_eval": n * n * 8, "achieved_GBps": evals * n * n * 8 / (ms * 1e-3) / 1e9,
-            "frac_of_measured_hbm_peak": evals * n * n * 8 / (ms * 1e-3) / 1e9 / PEAK,
+            "frac_of_measured_hbm_peak": evals * n * n * 8 / (ms * 1e-3) / 1e9 / PEAK / WORLD,
             "note": "host-driven engine: one D2H fetch per trial is inside the time"}
 
 
@@ -83,20 +119,26 @@ def c5a(m):
 
 def c5b():
     n = 1 << 28
-    lb, ub = np.full(n, -1.0), np.full(n, 1.0)
+    ctx = dist_ctx(vector_sharding=True)
+    nl, i0 = n // WORLD, RANK * (n // WORLD)  # index-range sharding: this rank owns coordinates [i0, i0 + nl)
+    lb, ub = np.full(nl, -1.0), np.full(nl, 1.0)
     out = []
     for name, ls in (("GLLQuadratic(1e-4,10)", osb.GLLQuadratic(1e-4, 10)), ("BackTracking(1e-4,0.5)", osb.BackTracking(1e-4, 0.5))):
-        obj = osb.SeparableQuadratic.generated(n)
-        s = osb.SpectralProjectedGradient(1e-6 if "GLL" in name else 1e-5, np.zeros(n), obj, lb, ub)
+        obj = osb.SeparableQuadratic.generated_shard(nl, i0, ctx) if WORLD > 1 else osb.SeparableQuadratic.generated(n, ctx=ctx)
+        s = osb.SpectralProjectedGradient(1e-6 if "GLL" in name else 1e-5, np.zeros(nl), obj, lb, ub, ctx=ctx)
         st = run(s, ls, obj, 500, 50)
         ms, it = s.last_timing()
+        ms = max_over_ranks(ms)
         aset = s.active_set()
         evals = obj.calls()
+        act = float(np.mean(aset != 0))
+        if WORLD > 1:
+            act = max_over_ranks(act)  # (per-rank fractions are equal to 1e-4 on this problem; reported as the max)
         out.append({"line_search": name, "status": st, "iterations": it, "reason": s.termination_reason(), "ms_total": ms,
-                    "iterations_per_s": it / ms * 1e3, "oracle_evals": evals, "active_fraction": float(np.mean(aset != 0)),
+                    "iterations_per_s": it / ms * 1e3, "oracle_evals": evals, "active_fraction": act, "n_gpus": WORLD,
                     "vector_bytes": n * 8, "approx_vector_passes_per_iteration": 14,
                     "approx_GBps": it * 14 * n * 8 / (ms * 1e-3) / 1e9})
-    return {"config": "C5b SPG box-constrained separable quadratic n=2^28", "runs": out}
+    return {"config": "C5b SPG box-constrained separable quadratic n=2^28, vectors index-range sharded over %d GPU(s)" % WORLD, "runs": out}
 
 
 if __name__ == "__main__":
@@ -106,4 +148,8 @@ if __name__ == "__main__":
         m = int(sys.argv[sys.argv.index("--m") + 1])
     for w in which:
         r = {"c2": c2, "c4": c4, "c5b": c5b}[w]() if w != "c5a" else c5a(m)
-        print(json.dumps(r), flush=True)
+        if RANK == 0:
+            print(json.dumps(r), flush=True)
+    if _DIST is not None:
+        _DIST.barrier()
+        _DIST.destroy_process_group()
