@@ -63,7 +63,9 @@ enum {
   OSB_SR1B = 9,         /* src/quasi_newton/sr1_b.rs */
   OSB_NEWTON = 10,      /* src/newton/mod.rs */
   OSB_PROJ_NEWTON = 11, /* src/newton/projected_newton.rs */
-  OSB_SPN = 12          /* src/newton/spn.rs */
+  OSB_SPN = 12,         /* src/newton/spn.rs */
+  OSB_PNORM = 13        /* PnormDescent               src/steepest_descent/pnorm_descent.rs: direction
+                           -(inverse_p g); the matrix is set with osb_solver_set_inv_hessian (identity until then) */
 };
 
 typedef struct osb_ctx osb_ctx;
@@ -219,6 +221,7 @@ int osb_solver_clear_norms(osb_solver* s);                    /* s_norm = y_norm
 double osb_solver_lambda(const osb_solver* s);                /* SPG / SPN */
 double osb_solver_decrement_squared(const osb_solver* s);     /* Newton; NaN when None */
 int osb_solver_inv_hessian(osb_solver* s, double* out_host);  /* approx_inv_hessian(), row-major n*n */
+/* also PnormDescent::new's inverse_p (pnorm_descent.rs:23-30) / its getter inverse_p() */
 int osb_solver_set_inv_hessian(osb_solver* s, const double* in_host);
 /* one byte per coordinate: bit0 = (x_i == lb_i), bit1 = (x_i == ub_i) — exact compares, the
  * active-set definition of HasProjectedGradient::projected_gradient (src/ls_solver.rs:121-133) */

@@ -682,7 +682,7 @@ class NoSearch(_LS):
 
 # ---- solvers ----------------------------------------------------------------------------------
 _KIND = dict(GD=0, PGD=1, SPG=2, BFGS=3, DFP=4, BROYDEN=5, BFGSB=6, DFPB=7, BROYDENB=8, SR1B=9, NEWTON=10,
-             PROJ_NEWTON=11, SPN=12)
+             PROJ_NEWTON=11, SPN=12, PNORM=13)
 
 
 class _Solver:
@@ -878,6 +878,23 @@ SR1B = _mk("SR1B", "SR1B", bounded=True)
 Newton = _mk("Newton", "NEWTON", needs_h=True)
 ProjectedNewton = _mk("ProjectedNewton", "PROJ_NEWTON", bounded=True, needs_h=True)
 SpectralProjectedNewton = _mk("SpectralProjectedNewton", "SPN", needs_oracle=True, needs_h=True)
+
+
+class PnormDescent(_Solver):
+    """PnormDescent::new(grad_tol, x0, inverse_p) (src/steepest_descent/pnorm_descent.rs:23-30).  `inverse_p` is an
+    n x n array ([i, j] = row i, column j); the direction is -(inverse_p g) (pnorm_descent.rs:35), convergence is the
+    inf-norm test of GradientDescent (pnorm_descent.rs:52-58)."""
+    KIND = "PNORM"
+
+    def __init__(self, tol, x0, inverse_p, ctx=None):
+        _Solver.__init__(self, tol, x0, ctx=ctx)
+        P = np.ascontiguousarray(np.asarray(inverse_p, dtype=np.float64))
+        if P.shape != (self.n, self.n):
+            raise ErrorInputParams("inverse_p must be n x n")
+        self.set_approx_inv_hessian(P)
+
+    def inverse_p(self):
+        return self.approx_inv_hessian()
 
 
 # ---- batched mode -----------------------------------------------------------------------------

@@ -456,7 +456,7 @@ double osb_solver_decrement_squared(const osb_solver* s) { return S(s)->has_dec 
 int osb_solver_inv_hessian(osb_solver* s, double* out) {
   OSB_TRY
   Solver* p = S(s);
-  OSB_REQUIRE(p->is_qn, OSB_ERROR_INPUT_PARAMS, "not a quasi-Newton solver");
+  OSB_REQUIRE(p->is_qn || p->kind == OSB_PNORM, OSB_ERROR_INPUT_PARAMS, "solver holds no n x n matrix");
   p->ctx->use();
   p->flush_pending();
   // local row block [row0, row0 + nrows)
@@ -469,7 +469,7 @@ int osb_solver_inv_hessian(osb_solver* s, double* out) {
 int osb_solver_set_inv_hessian(osb_solver* s, const double* in) {
   OSB_TRY
   Solver* p = S(s);
-  OSB_REQUIRE(p->is_qn, OSB_ERROR_INPUT_PARAMS, "not a quasi-Newton solver");
+  OSB_REQUIRE(p->is_qn || p->kind == OSB_PNORM, OSB_ERROR_INPUT_PARAMS, "solver holds no n x n matrix");
   p->ctx->use();
   p->flush_pending();
   {

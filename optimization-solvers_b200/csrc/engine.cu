@@ -99,7 +99,7 @@ Solver::Solver(Ctx* c, int kind_, int64_t n_, double tol_, const double* x0, con
                Objective* obj0)
     : ctx(c), kind(kind_), n(n_), tol(tol_) {
   ctx->use();
-  OSB_REQUIRE(kind >= OSB_GD && kind <= OSB_SPN, OSB_ERROR_INPUT_PARAMS, "unknown solver kind");
+  OSB_REQUIRE(kind >= OSB_GD && kind <= OSB_PNORM, OSB_ERROR_INPUT_PARAMS, "unknown solver kind");
   OSB_REQUIRE(n >= 1 && x0 != nullptr, OSB_ERROR_INPUT_PARAMS, "n >= 1 and x0 required");
   bounded = kind_is_bounded(kind);
   is_qn = kind_is_qn(kind);
@@ -152,6 +152,22 @@ Solver::Solver(Ctx* c, int kind_, int64_t n_, double tol_, const double* x0, con
     }
     if (qn_kind == QN_BROYDEN) scratch.alloc(((nrows + 63) / 64) * ld);
   }
+  if (kind == OSB_PNORM) {  // pnorm_descent.rs:15-30: a constant n x n matrix, row-block sharded like H
+    if (ctx->world > 1) {
+      OSB_REQUIRE(n % (ctx->world * 8) == 0, OSB_ERROR_INPUT_PARAMS, "row-sharded inverse_p needs n divisible by 8 * world");
+      nrows = n / ctx->world;
+      row0 = nrows * ctx->rank;
+    } else {
+      nrows = n;
+      row0 = 0;
+    }
+    H.alloc(qn_rows_padded(nrows) * ld);
+    H.zero(st);
+    set_identity_kernel<<<ctx->red_grid(nrows), RED_THREADS, 0, st>>>(H.p, ld, nrows, row0);
+    ctx->counters[0]++;
+    u.alloc(ld);
+    u.zero(st);
+  }
   if (kind_needs_hessian(kind)) {
     hess.alloc(qn_rows_padded(n) * ld);
     hess.zero(st);
@@ -192,7 +208,7 @@ void Solver::push_state() {
 void Solver::compute_conv_scalar(Objective*) {
   double* out = &d_state->conv;
   if (is_qn) vec_conv_gnorm2(ctx, n, g.p, out);                        // bfgs.rs:74
-  else if (kind == OSB_GD) vec_conv_gmax(ctx, n, g.p, out);            // gradient_descent.rs:46-53
+  else if (kind == OSB_GD || kind == OSB_PNORM) vec_conv_gmax(ctx, n, g.p, out);  // gradient_descent.rs:46-53, pnorm_descent.rs:52-58
   else if (kind == OSB_NEWTON) return;                                 // newton/mod.rs:64-69 ignores the eval
   else vec_conv_pginf(ctx, n, x.p, g.p, lb.p, ub.p, out);              // projected_gradient_descent.rs:76-83
 }
@@ -205,6 +221,12 @@ int Solver::compute_direction(Objective*, LineSearch* ls) {
   switch (kind) {
     case OSB_GD:
       vec_neg(ctx, n, g.p, d.p, g.p, out3);  // gradient_descent.rs:29
+      break;
+    case OSB_PNORM:  // pnorm_descent.rs:35: (-inverse_p) g == -(inverse_p g), one read of the matrix
+      if (n <= QN_SMALL_N && ctx->world == 1) qn_small_gemv(ctx, n, ld, H.p, g.p, u.p);
+      else qn_launch_gemv(ctx, H.p, ld, nrows, row0, nullptr, g.p, u.p, nullptr, nullptr, 0);
+      if (ctx->world > 1) ctx->all_gather_inplace(u.p, nrows);
+      vec_neg(ctx, n, u.p, d.p, g.p, out3);
       break;
     case OSB_PGD:
       vec_projected_direction(ctx, n, x.p, g.p, 1.0, false, lb.p, ub.p, g.p, d.p, out3);  // projected_gradient_descent.rs:56-59
@@ -464,7 +486,7 @@ int Solver::minimize_host(LineSearch* ls, Objective* obj, int64_t max_iter, int6
       else if (is_qn) {
         if (sqrt(h_state->conv) < tol) { reason = OSB_REASON_GRAD_TOL; conv = true; }  // bfgs.rs:74
       } else if (rmax(0.0, h_state->conv) < tol) { reason = OSB_REASON_PROJ_GRAD_TOL; conv = true; }
-    } else if (kind == OSB_GD) {
+    } else if (kind == OSB_GD || kind == OSB_PNORM) {
       if (h_state->conv < tol) { reason = OSB_REASON_GRAD_TOL; conv = true; }
     } else if (kind == OSB_NEWTON) {
       if (has_dec && decrement_squared * 0.5 < tol) { reason = OSB_REASON_NEWTON_DECREMENT; conv = true; }

@@ -899,6 +899,14 @@ struct GradientDescent : Solver {  // gradient_descent.rs:24-79
   int compute_direction(const Eval& e, Vec& d) override { d = neg(e.g); return OK; }
 };
 
+struct PnormDescent : GradientDescent {  // pnorm_descent.rs:15-84 — steepest descent in the P-norm; same test and update as GD
+  Mat inverse_p;
+  int compute_direction(const Eval& e, Vec& d) override {
+    d = neg(gemv(inverse_p, e.g));  // pnorm_descent.rs:35  (-inverse_p) * g: every product and sum is negated exactly
+    return OK;
+  }
+};
+
 struct ProjectedGradientDescent : Solver, Bounded {  // projected_gradient_descent.rs:50-109
   bool has_converged(const Eval& e) override {
     if (infinity_norm(projected_gradient(x, e)) < tol) { reason = R_PROJ_GRAD; return true; }
@@ -1124,7 +1132,7 @@ using namespace orc;
 extern "C" {
 
 enum { ORC_GD = 0, ORC_PGD = 1, ORC_SPG = 2, ORC_BFGS = 3, ORC_DFP = 4, ORC_BROYDEN = 5, ORC_BFGSB = 6, ORC_DFPB = 7,
-       ORC_BROYDENB = 8, ORC_SR1B = 9, ORC_NEWTON = 10, ORC_PROJ_NEWTON = 11, ORC_SPN = 12 };
+       ORC_BROYDENB = 8, ORC_SR1B = 9, ORC_NEWTON = 10, ORC_PROJ_NEWTON = 11, ORC_SPN = 12, ORC_PNORM = 13 };
 
 void orc_set_threads(int t) {
 #ifdef _OPENMP
@@ -1225,6 +1233,7 @@ void* orc_solver_create(int kind, int64_t n, double tol, const double* x0, const
   Solver* s = nullptr;
   switch (kind) {
     case ORC_GD: { auto* p = new GradientDescent(); p->x = x; s = p; break; }
+    case ORC_PNORM: { auto* p = new PnormDescent(); p->x = x; p->inverse_p = Mat::identity((size_t)n); s = p; break; }
     case ORC_PGD: { auto* p = new ProjectedGradientDescent(); p->lb = l; p->ub = u; p->x = proj(); s = p; break; }
     case ORC_SPG: case ORC_SPN: {
       SpectralBase* p = kind == ORC_SPG ? (SpectralBase*)new SpectralProjectedGradient() : (SpectralBase*)new SpectralProjectedNewton();
@@ -1279,6 +1288,12 @@ int orc_solver_inv_hessian(void* s, double* out_rowmajor) {
   return 0;
 }
 int orc_solver_set_inv_hessian(void* s, const double* in_rowmajor) {
+  if (auto* pn = dynamic_cast<PnormDescent*>((Solver*)s)) {  // PnormDescent::new(tol, x0, inverse_p), pnorm_descent.rs:23-30
+    size_t n = pn->inverse_p.r;
+    for (size_t i = 0; i < n; ++i)
+      for (size_t j = 0; j < n; ++j) pn->inverse_p(i, j) = in_rowmajor[i * n + j];
+    return 0;
+  }
   auto* q = dynamic_cast<QuasiNewton*>((Solver*)s);
   if (!q) return -1;
   size_t n = q->H.r;

@@ -28,6 +28,7 @@ pub const OSB_SR1B: c_int = 9;
 pub const OSB_NEWTON: c_int = 10;
 pub const OSB_PROJ_NEWTON: c_int = 11;
 pub const OSB_SPN: c_int = 12;
+pub const OSB_PNORM: c_int = 13;
 
 pub type osb_host_eval_fn = unsafe extern "C" fn(user: *mut c_void, x: *const c_double, n: i64, f: *mut c_double,
                                                  g: *mut c_double, hess: *mut c_double) -> c_int;

@@ -255,6 +255,37 @@ def test_gd_dense_quadratic_vs_oracle(osb, orc):
     assert got[:3] == ref[:3] and close(got[3], ref[3])
 
 
+def test_pnorm_descent_vs_oracle(osb, orc):
+    # SURVEY 8f rank 2 — PnormDescent (pnorm_descent.rs): the reference's two unit tests (n = 2, bit-exact: the small-n
+    # GEMV replays nalgebra's column-axpy order) and a Jacobi-preconditioned dense quadratic at n = 256
+    P2 = [[1.0, 0.0], [0.0, 1.0 / 90.0]]
+    for mk_ls in (lambda m: m.MoreThuente.default(), lambda m: m.BackTracking(1e-4, 0.5)):
+        def script(m):
+            s = m.PnormDescent(1e-12, X0_TESTS, P2)
+            st = run(m, s, mk_ls(m), quad2(90.0), 1000, 100)
+            return st, s.k(), s.termination_reason(), s.x()
+        ref, got = both(osb, orc, script)
+        assert got[:3] == ref[:3] == ("Ok", 1, "grad_tol") and np.array_equal(got[3], ref[3])
+
+    n = 256
+
+    def script(m):
+        obj = m.DenseQuadratic.generated(n, True)
+        # P = diag(1 / (2 A_ii)) with A_ii = 2 + (i mod 7): the Jacobi preconditioner of f = x'Ax - 2b'x,
+        # plus a small symmetric off-diagonal term so that the GEMV is not trivially diagonal
+        i = np.arange(n)
+        P = np.diag(1.0 / (2.0 * (2.0 + (i % 7)))) + 2.0 ** -12 * np.cos(np.add.outer(i, i))
+        s = m.PnormDescent(1e-6, obj.x0, P)  # (1e-8 sits at the rounding floor of g = 2(Ax - b) for some P: the oracle itself stalls)
+        st = run(m, s, m.BackTracking(1e-4, 0.5), obj, 1000, 100)
+        return st, s.k(), s.termination_reason(), s.x(), P
+
+    ref, got = both(osb, orc, script)
+    assert got[:3] == ref[:3] and ref[0] == "Ok" and close(got[3], ref[3])
+    # the getter returns the matrix as set (pnorm_descent.rs derive_getters inverse_p())
+    s = osb.PnormDescent(1e-8, np.zeros(n), ref[4])
+    assert np.array_equal(s.inverse_p(), ref[4])
+
+
 def test_spg_box_active_set_bit_exact(osb, orc):
     # C5b at n = 2^14: SPG on the separable box quadratic; active-set bitmaps compared bit-for-bit
     n = 1 << 14

@@ -71,6 +71,21 @@ def test_gradient_descent_unit_tests(orc):
     assert s.k() == 1000 and abs(quad2(90.0)(s.x())[0]) < 1e-6
 
 
+def test_pnorm_descent_unit_tests(orc):
+    # pnorm_descent.rs:90-141 (MoreThuente) and :144-194 (BackTracking): inverse_p is the exact inverse Hessian of
+    # 0.5 (x0^2 + 90 x1^2), so one unit step lands on the minimiser exactly; both asserts |f| < 1e-6 hold
+    P = [[1.0, 0.0], [0.0, 1.0 / 90.0]]
+    for ls in (orc.MoreThuente.default(), orc.BackTracking(1e-4, 0.5)):
+        s = orc.PnormDescent(1e-12, X0_TESTS, P)
+        assert run(s, ls, quad2(90.0), 1000, 100, orc) == "Ok"
+        assert s.k() == 1 and s.termination_reason() == "grad_tol" and quad2(90.0)(s.x())[0] == 0.0
+    # with inverse_p = I the solver is GradientDescent (pnorm_descent.rs:9): same 6 iterations as gradient_descent.rs:86-130
+    s = orc.PnormDescent(1e-12, X0_TESTS, [[1.0, 0.0], [0.0, 1.0]])
+    g = orc.GradientDescent(1e-12, X0_TESTS)
+    assert run(s, orc.MoreThuente.default(), quad2(90.0), 1000, 100, orc) == run(g, orc.MoreThuente.default(), quad2(90.0), 1000, 100, orc)
+    assert s.k() == g.k() == 6 and (s.x() == g.x()).all()
+
+
 def test_projected_and_spectral_unit_tests(orc):
     lb, ub = [-INF, -INF], [INF, INF]
     s = orc.ProjectedGradientDescent(1e-6, X0_TESTS, lb, ub)  # projected_gradient_descent.rs:114-165
