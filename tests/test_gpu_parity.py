@@ -286,6 +286,25 @@ def test_pnorm_descent_vs_oracle(osb, orc):
     assert np.array_equal(s.inverse_p(), ref[4])
 
 
+@pytest.mark.parametrize("cls", ["BFGSB", "DFPB", "SR1B"])
+def test_bounded_quasi_newton_with_morethuente_b_vs_oracle(osb, orc, cls):
+    # the bounded quasi-Newton solvers with the bounded More-Thuente search (morethuente_b.rs), free
+    # running against the oracle on the convex separable box problem (short horizon: the projected iteration may cycle)
+    n = 256
+    lbv, ubv = np.full(n, -1.0), np.full(n, 1.0)
+
+    def script(m):
+        obj = m.SeparableQuadratic.generated(n)
+        s = getattr(m, cls)(1e-7, np.zeros(n), lbv, ubv)
+        ls = m.MoreThuenteB(n).with_lower_bound(lbv).with_upper_bound(ubv)
+        st = run(m, s, ls, obj, 6, 30)
+        return st, s.k(), s.termination_reason(), s.x(), s.active_set()
+
+    ref, got = both(osb, orc, script)
+    assert got[:3] == ref[:3], (got[:3], ref[:3])
+    assert close(got[3], ref[3]) and np.array_equal(got[4], ref[4])
+
+
 def test_spg_box_active_set_bit_exact(osb, orc):
     # C5b at n = 2^14: SPG on the separable box quadratic; active-set bitmaps compared bit-for-bit
     n = 1 << 14
