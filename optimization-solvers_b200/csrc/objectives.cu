@@ -203,34 +203,44 @@ Objective* make_dense_quadratic_generated(Ctx* ctx, int64_t n, bool shifted, dou
 }
 
 // ---- host closure (compatibility path) ----------------------------------------------------
+// Staging buffers are PINNED, so both copies are real asynchronous DMA transfers, and the call returns without waiting
+// for the upload: the next call's download of x is ordered after it on the same stream and is followed by the only
+// synchronisation of the path, which is also what makes the staging buffers safe to overwrite.
 struct HostObjective : Objective {
   osb_host_eval_fn fn;
   void* user;
   bool with_h;
-  std::vector<double> hx, hg, hh;
+  double* hx = nullptr;  // n
+  double* hg = nullptr;  // n + 1: gradient, then f
+  double* hh = nullptr;  // n * n when the closure provides the Hessian
   HostObjective(Ctx* c, int64_t n_, osb_host_eval_fn f, void* u, bool wh) : Objective(c, n_), fn(f), user(u), with_h(wh) {
-    hx.resize(n_);
-    hg.resize(n_);
-    if (wh) hh.resize(n_ * n_);
+    OSB_CUDA(cudaHostAlloc(&hx, sizeof(double) * (size_t)n_, cudaHostAllocDefault));
+    OSB_CUDA(cudaHostAlloc(&hg, sizeof(double) * (size_t)(n_ + 1), cudaHostAllocDefault));
+    if (wh) OSB_CUDA(cudaHostAlloc(&hh, sizeof(double) * (size_t)n_ * (size_t)n_, cudaHostAllocDefault));
+  }
+  ~HostObjective() override {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFreeHost(hx);
+    cudaFreeHost(hg);
+    cudaFreeHost(hh);
   }
   bool provides_hessian() const override { return with_h; }
   void eval(const double* x, double* d_f, double* g, double* hess) override {
     calls++;
     ctx->counters[1]++;
-    OSB_CUDA(cudaMemcpyAsync(hx.data(), x, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    OSB_CUDA(cudaMemcpyAsync(hx, x, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     ctx->sync();
     double f = NAN;
-    int got = fn(user, hx.data(), n, &f, hg.data(), (hess && with_h) ? hh.data() : nullptr);
+    int got = fn(user, hx, n, &f, hg, (hess && with_h) ? hh : nullptr);
     OSB_REQUIRE(!(hess && !got), OSB_PANIC_NO_HESSIAN, "Hessian not available in the oracle");
-    ctx->h_pinned[0] = f;
-    OSB_CUDA(cudaMemcpyAsync(d_f, ctx->h_pinned, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    OSB_CUDA(cudaMemcpyAsync(g, hg.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    hg[n] = f;
+    OSB_CUDA(cudaMemcpyAsync(d_f, hg + n, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    OSB_CUDA(cudaMemcpyAsync(g, hg, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     if (hess) {
       const int64_t ld = qn_ld(n);
-      OSB_CUDA(cudaMemcpy2DAsync(hess, ld * sizeof(double), hh.data(), n * sizeof(double), n * sizeof(double), n,
+      OSB_CUDA(cudaMemcpy2DAsync(hess, ld * sizeof(double), hh, n * sizeof(double), n * sizeof(double), n,
                                  cudaMemcpyHostToDevice, ctx->stream));
     }
-    ctx->sync();  // staging buffers are reused by the next call
   }
 };
 Objective* make_host_objective(Ctx* ctx, int64_t n, osb_host_eval_fn fn, void* user, bool with_h) {
