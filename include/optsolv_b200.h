@@ -96,6 +96,9 @@ int osb_ctx_ipc_connect(osb_ctx* ctx, const void* handles_world_x_64);
  * the path (f, g.d, s.y, s.s, the inf-norms of number.rs:27-31 and projected_gradient_descent.rs:76-83) is
  * combined across ranks in rank order.  Replaces nothing in the reference (single-threaded); SURVEY 8e. */
 int osb_ctx_set_vector_sharding(osb_ctx* ctx, int on);
+/* The n x n matrices of destroyed solvers are kept in a small per-device pool (at most 6 buffers / 6 GiB) and reused by
+ * the next solver of the same size; this returns them to the driver (context destruction does it too). */
+int osb_ctx_trim_memory(osb_ctx* ctx);
 void osb_ctx_destroy(osb_ctx* ctx);
 int osb_ctx_rank(const osb_ctx* ctx);
 int osb_ctx_world(const osb_ctx* ctx);

@@ -61,7 +61,7 @@ def lib():
             "osb_objective_create_rosenbrock": (ci, [_vp, i64, pp]),
             "osb_objective_create_separable_quadratic_generated": (ci, [_vp, i64, pp]),
             "osb_objective_create_separable_quadratic_generated_shard": (ci, [_vp, i64, i64, pp]),
-            "osb_ctx_set_vector_sharding": (ci, [_vp, ci]),
+            "osb_ctx_set_vector_sharding": (ci, [_vp, ci]), "osb_ctx_trim_memory": (ci, [_vp]),
             "osb_objective_create_logistic_generated": (ci, [_vp, i64, i64, dbl, pp]),
             "osb_objective_create_host": (ci, [_vp, i64, HOST_EVAL, _vp, ci, pp]),
             "osb_objective_create_user": (ci, [_vp, i64, DEVICE_EVAL, _vp, ci, pp]),
@@ -313,6 +313,10 @@ class Context:
         """Index-range sharding of GD / PGD / SPG over the ranks of this context (see include/optsolv_b200.h)."""
         _check(lib().osb_ctx_set_vector_sharding(self.handle, 1 if on else 0))
         return self
+
+    def trim_memory(self):
+        """Return the pooled n x n buffers of closed solvers to the driver."""
+        _check(lib().osb_ctx_trim_memory(self.handle))
 
     def rank(self):
         return lib().osb_ctx_rank(self.handle)

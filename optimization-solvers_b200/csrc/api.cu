@@ -111,6 +111,14 @@ int osb_ctx_set_vector_sharding(osb_ctx* ctx, int on) {
   return OSB_OK;
   OSB_CATCH
 }
+int osb_ctx_trim_memory(osb_ctx* ctx) {
+  OSB_TRY
+  C(ctx)->use();
+  C(ctx)->sync();
+  pool_trim(C(ctx)->device);
+  return OSB_OK;
+  OSB_CATCH
+}
 void* osb_ctx_stream(osb_ctx* ctx) { return (void*)C(ctx)->stream; }
 int osb_ctx_counters(const osb_ctx* ctx, int64_t out[8]) {
   std::memcpy(out, C(ctx)->counters, sizeof(int64_t) * 8);
@@ -376,6 +384,7 @@ int osb_solver_set_option(osb_solver* s, const char* name, int64_t value) {
   std::string nm(name);
   if (nm == "engine") S(s)->engine = (int)value;
   else if (nm == "record_trace") S(s)->record_trace = (int)value;
+  else if (nm == "callback_run_ahead") S(s)->callback_run_ahead = (int)value;
   else if (nm == "qn_kernel") S(s)->qn_variant = (int)value;
   else if (nm == "qn_schedule") S(s)->qn_schedule = (int)value;
   else if (nm == "qn_storage") S(s)->qn_storage = (int)value;
@@ -403,6 +412,10 @@ int osb_solver_termination_reason(const osb_solver* s) { return S(s)->reason; }
 int osb_solver_x(osb_solver* s, double* out) {
   OSB_TRY
   Solver* p = S(s);
+  if (p->cb_x_mirror) {  // inside a run-ahead callback: the snapshot of this iteration (the device is already one ahead)
+    std::memcpy(out, p->cb_x_mirror, sizeof(double) * (size_t)p->n);
+    return OSB_OK;
+  }
   p->ctx->use();
   p->x.download(out, p->n, p->ctx->stream);
   p->ctx->sync();
@@ -423,6 +436,10 @@ int osb_solver_set_x(osb_solver* s, const double* in) {
 int osb_solver_f(osb_solver* s, double* f_out) {
   OSB_TRY
   Solver* p = S(s);
+  if (p->cb_state_mirror) {
+    *f_out = p->cb_state_mirror->f;
+    return OSB_OK;
+  }
   p->ctx->use();
   p->fetch_state();
   *f_out = p->h_state->f;
@@ -459,6 +476,7 @@ int osb_solver_inv_hessian(osb_solver* s, double* out) {
   OSB_REQUIRE(p->is_qn || p->kind == OSB_PNORM, OSB_ERROR_INPUT_PARAMS, "solver holds no n x n matrix");
   p->ctx->use();
   p->flush_pending();
+  p->ensure_full();
   // local row block [row0, row0 + nrows)
   OSB_CUDA(cudaMemcpy2DAsync(out + p->row0 * p->n, p->n * sizeof(double), p->H.p, p->ld * sizeof(double), p->n * sizeof(double),
                              p->nrows, cudaMemcpyDeviceToHost, p->ctx->stream));
@@ -472,6 +490,7 @@ int osb_solver_set_inv_hessian(osb_solver* s, const double* in) {
   OSB_REQUIRE(p->is_qn || p->kind == OSB_PNORM, OSB_ERROR_INPUT_PARAMS, "solver holds no n x n matrix");
   p->ctx->use();
   p->flush_pending();
+  p->ensure_full();
   {
     bool sym = true;  // packed symmetric storage is only valid for a symmetric matrix
     for (int64_t i = 0; i < p->n && sym; ++i)

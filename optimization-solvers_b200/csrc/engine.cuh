@@ -96,6 +96,8 @@ struct DBuf {
   DBuf& operator=(const DBuf&) = delete;
   ~DBuf() { release(); }
   void alloc(int64_t n_);
+  // all buffers come from / return to the per-device pool (engine.cu); contents are NOT preserved or cleared
+  void alloc_pooled(int64_t n_);
   void release();
   void zero(cudaStream_t s);
   void upload(const double* h, int64_t cnt, cudaStream_t s);
@@ -241,6 +243,7 @@ void qn_launch_lazy_epilogue(Ctx* ctx, const QNLazyArgs& a);
 int64_t qn_sym_doubles(int64_t n);
 int qn_sym_grid(Ctx* ctx, int64_t n);
 void qn_sym_pack(Ctx* ctx, const double* H, int64_t ld, int64_t n, double* P);
+void qn_sym_set_identity(Ctx* ctx, int64_t n, double* P);
 void qn_sym_unpack(Ctx* ctx, const double* P, int64_t ld, int64_t n, double* H);
 void qn_launch_lazy_sym(Ctx* ctx, const QNLazyArgs& a, double* P, double* colpart, int64_t n, int64_t ld, int phase);
 // apply a pending update to the stored matrix (getters, engine switches)
@@ -269,6 +272,18 @@ struct Solver {
   // options
   int engine = 0;
   int record_trace = 0;
+  // callback_run_ahead = 1: the per-iteration callback / trace of the device-resident engine no longer stalls the device.
+  // After iteration k the control block and x_k+1 are copied into pinned snapshots, iteration k + 1 is enqueued, and
+  // only then is the callback for iteration k delivered; inside it x(), f(), k(), s_norm(), y_norm() read the
+  // snapshot.  Any other getter (or a mutation) inside the callback would see the solver one iteration ahead:
+  // hence an option and not the default.
+  int callback_run_ahead = 0;
+  LSParams* d_ls_buf = nullptr;      // device copy of the line-search parameters (minimize_device)
+  DevState* poll_snap = nullptr;     // 2 pinned slots of the polling snapshots
+  DevState* cb_snap = nullptr;       // 2 pinned slots
+  double* cb_xsnap = nullptr;        // 2 x ld doubles, pinned
+  const double* cb_x_mirror = nullptr;  // non-null while a run-ahead callback is being delivered
+  const DevState* cb_state_mirror = nullptr;
   int qn_variant = 0;
   int head_variant = 0;  // 0 = cluster head, 1 = single-CTA smem head, 2 = generic single-CTA head
   // state vectors (device)
@@ -282,6 +297,9 @@ struct Solver {
   DBuf wv, ps, ph;        // lazy schedule: w = H g, pending p and q
   int qn_schedule = 0;    // 0 = eager (h = H y, then fused update: 3 n^2 8 B), 1 = lazy (one RMW: 2 n^2 8 B)
   bool lazy_used = false;
+  bool H_virtual_identity = false;  // H = I and not materialised yet (large n: the 2 GiB buffer is allocated on first need;
+                                    // with packed storage it never is)
+  void ensure_full();               // materialise the full row-major H
   bool defer_epi = false;  // minimize_device with the cluster head: the lazy pass leaves its epilogue to the next head
   bool epi_p2p = false;    // ... and h, w live in the peer-memory exchange buffers
   HeadEpi head_epi() const;
@@ -370,6 +388,9 @@ int batched_bfgs_rosenbrock(Ctx* ctx, int64_t n, int64_t np, const double* x0_ho
                             double tol, int64_t max_iter, int64_t max_ls, double c1, double beta, double* x_out,
                             double* f_out, int32_t* k_out, int32_t* st_out, int32_t* reason_out, double* ms_out);
 
+void* pool_get(int kind, size_t bytes);            // kind 0 = device, 1 = pinned host
+void pool_put(int kind, size_t bytes, void* p);
+void pool_trim(int device);  // return every pooled buffer of the device to the driver
 void set_last_error(const std::string& s);
 
 }  // namespace osb

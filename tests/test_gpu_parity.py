@@ -549,6 +549,35 @@ def test_callback_and_trace_on_the_device_engine(osb):
     assert len(calls) == s.k() and s.termination_reason() is not None
 
 
+def test_run_ahead_callbacks_deliver_the_same_sequence(osb):
+    """callback_run_ahead = 1: the callback for iteration k is delivered from pinned snapshots while the device already
+    works on iteration k + 1.  The sequence of (k, x, f, s_norm) it sees, the trace and the final state are bit-identical
+    to the stalling delivery, for a run that hits max_iter and for one that converges (no callback for the iteration
+    that detects convergence)."""
+    def go(run_ahead, n, tol, obj_fn, x0, max_iter, storage):
+        seen = []
+        s = osb.BFGS(tol, x0).set_option("engine", 2).set_option("qn_schedule", 1).set_option("qn_storage", storage)
+        s.set_option("callback_run_ahead", run_ahead).record_trace(True)
+        st = "Ok"
+        try:
+            s.minimize(osb.BackTracking(1e-4, 0.5), obj_fn(n), max_iter, 30,
+                       callback=lambda sv: seen.append((sv.k(), sv.x().copy(), sv.f(), sv.s_norm(), sv.y_norm())))
+        except osb.MaxIterReached:
+            st = "MaxIterReached"
+        return st, s.k(), s.termination_reason(), s.x(), s.f(), seen, s.trace()
+
+    for (n, tol, obj_fn, x0, mi, storage) in ((2048, 1e-8, lambda n: osb.ExtendedRosenbrock(n), rosen_x0(2048, 43), 15, 1),
+                                               (512, 1e-7, lambda n: osb.SeparableQuadratic.generated(n), np.zeros(512), 300, 0)):
+        a = go(0, n, tol, obj_fn, x0, mi, storage)
+        b = go(1, n, tol, obj_fn, x0, mi, storage)
+        assert a[:3] == b[:3] and np.array_equal(a[3], b[3]) and a[4] == b[4]
+        assert len(a[5]) == len(b[5]) == a[1]
+        for (ka, xa, fa, sa, ya), (kb, xb, fb, sb, yb) in zip(a[5], b[5]):
+            assert ka == kb and np.array_equal(xa, xb) and fa == fb and sa == sb and ya == yb
+        for key in ("f", "t"):
+            assert np.array_equal(a[6][key], b[6][key])
+
+
 @pytest.mark.parametrize("kind", ["BFGS", "DFP"])
 def test_packed_symmetric_storage_matches_full_storage(osb, orc, kind):
     """qn_storage = 1: only the lower triangle of H lives in HBM (n^2 * 8 B per iteration); transposed
