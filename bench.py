@@ -163,8 +163,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--head", type=int, default=0, help="device-engine head variant (0 cluster+speculation, 3 cluster, 1 single CTA)")
     ap.add_argument("--storage", default="auto", choices=["auto", "full", "sym"],
-                    help="sym: packed lower triangle of H (n^2 8 B per iteration; single GPU, lazy schedule); "
-                         "full: n x n row-major (row-block sharded over N GPUs); auto: sym on one GPU, full when sharded")
+                    help="sym: packed lower triangle of H (n^2 8 B per iteration, lazy schedule; sharded by tile pairs over "
+                         "N GPUs with the peer-memory exchange); full: n x n row-major (row-block sharded); auto: sym "
+                         "whenever it is available (one GPU, or N GPUs with P2P)")
     ap.add_argument("--qn-kernel", type=int, default=0, help="lazy-pass kernel: 0 = register-staged LDG, 1 = TMA-staged (cp.async.bulk + mbarrier)")
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL all-gathers instead of the fused peer-memory exchange")
     ap.add_argument("--schedule", default="lazy", choices=["lazy", "eager"],
@@ -209,7 +210,7 @@ def main():
     solver = osb.BFGS(TOL, x0, ctx=ctx).set_option("engine", 2).set_option("qn_schedule", 1 if lazy else 0)
     solver.set_option("head_kernel", args.head)
     solver.set_option("qn_kernel", args.qn_kernel)
-    sym = lazy and args.storage in ("sym", "auto") and world == 1
+    sym = lazy and args.storage in ("sym", "auto") and (world == 1 or not args.no_p2p)
     solver.set_option("qn_storage", 1 if sym else 0)
 
     def run_steps(k):
@@ -251,7 +252,7 @@ def main():
     gemv_bytes = 1.0 * rows_local * n * 8.0
     iter_bytes = (2.0 if lazy else 3.0) * rows_local * n * 8.0
     if sym:
-        upd_bytes = iter_bytes = 1.0 * n * n * 8.0  # read + write of the lower triangle
+        upd_bytes = iter_bytes = 1.0 * n * n * 8.0 / world  # read + write of (this rank's share of) the lower triangle
     peak, peak_src = hbm_peak()
     sym_parts = None
     if sym:  # slot 0 = streaming pass, slot 1 = column fold + epilogue; the roofline is quoted on their sum
@@ -314,6 +315,7 @@ def main():
         barrier()
         t0 = time.perf_counter()
         s2 = osb.BFGS(TOL, x0, ctx=ctx).set_option("engine", 2).set_option("qn_schedule", 1 if lazy else 0)
+        s2.set_option("qn_storage", 1 if sym else 0)
         try:
             s2.minimize(osb.BackTracking(1e-4, 0.5), obj, args.steps, MAX_LS)
         except osb.MaxIterReached:
@@ -344,10 +346,13 @@ def main():
                            "lazy: 1 RMW pass of H per iteration (2 n^2 8 B)" if lazy else "eager: gemv + fused update (3 n^2 8 B)",
                            "storage": "packed lower triangle, 8-row tiles" if sym else "full n x n row-major",
                            "l2": "inputs larger than L2 (H = %.2f GiB per GPU, streamed every step)" % (
-                               (n * (n + 8) / 2 if sym else rows_local * n) * 8 / 2 ** 30),
-                           "parallelism": "row-block sharded H over %d GPU(s); exchange: %s" % (
-                               world, "none" if world == 1 else ("NCCL all-gather of the h / w slices" if (args.no_p2p or not lazy)
-                                                                 else "peer-memory all-gather fused into the lazy kernel (NVLink stores + flags)"))},
+                               (n * (n + 8) / 2 / world if sym else rows_local * n) * 8 / 2 ** 30),
+                           "parallelism": ("packed triangle sharded by tile pairs over %d GPU(s); exchange: %s" if sym else
+                                           "row-block sharded H over %d GPU(s); exchange: %s") % (
+                               world, "none" if world == 1 else (
+                                   "per-rank {h, w} contributions stored into every peer's slot by the fold kernel (NVLink stores + flags), summed in rank order by the head" if sym
+                                   else "NCCL all-gather of the h / w slices" if (args.no_p2p or not lazy)
+                                   else "peer-memory all-gather fused into the lazy kernel (NVLink stores + flags)"))},
                 "roofline": roofline, "cpu_baseline": cb_line, "e2e": e2e,
                 "gpu_launches": int(c1["launches"] - c0["launches"]),
                 "ls_trials_per_step": (c1["ls_trials"] - c0["ls_trials"]) / args.steps,

@@ -106,7 +106,8 @@ int osb_ctx_synchronize(osb_ctx* ctx);
 /* the CUDA stream (cudaStream_t) every kernel of this context is launched on */
 void* osb_ctx_stream(osb_ctx* ctx);
 /* counters since context creation: [0] kernel launches, [1] objective evaluations,
- * [2] line-search trials, [3] host<->device synchronisations, [4] collectives */
+ * [2] line-search trials, [3] host<->device synchronisations, [4] collectives,
+ * [5] passes over the sharded packed triangle (multi-GPU, qn_storage = 1) */
 int osb_ctx_counters(const osb_ctx* ctx, int64_t out[8]);
 
 /* ---- objectives: the device counterpart of `FnMut(&DVector<f64>) -> FuncEvalMultivariate` ---

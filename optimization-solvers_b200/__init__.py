@@ -334,7 +334,8 @@ class Context:
         out = (C.c_int64 * 8)()
         lib().osb_ctx_counters(self.handle, out)
         v = list(out)
-        return dict(launches=v[0], objective_evals=v[1], ls_trials=v[2], host_syncs=v[3], collectives=v[4])
+        return dict(launches=v[0], objective_evals=v[1], ls_trials=v[2], host_syncs=v[3], collectives=v[4],
+                    sharded_packed_passes=v[5])
 
     def close(self):
         if self.handle:

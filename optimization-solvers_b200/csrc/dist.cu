@@ -78,7 +78,10 @@ void Ctx::all_gather_inplace(double* buf, int64_t count) {
 }
 
 // ---- peer-memory exchange region (CUDA IPC) -----------------------------------------------------
-static size_t xchg_bytes(int world) { return sizeof(double) * 4 * (size_t)XCHG_LD + sizeof(unsigned long long) * (size_t)(world + 8); }
+static size_t xchg_bytes(int world) {
+  // 4 exchanged vectors | flags (64 words reserved) | sharded packed storage: 2 parities x world x {h, w} slots
+  return sizeof(double) * (size_t)(XSLOT_OFF + 2 * (int64_t)world * 2 * XSLOT_LD);
+}
 
 void ctx_ipc_export(Ctx* ctx, void* out64) {
   ctx->use();
@@ -97,6 +100,7 @@ void ctx_ipc_export(Ctx* ctx, void* out64) {
 void ctx_ipc_connect(Ctx* ctx, const void* handles) {
   ctx->use();
   OSB_REQUIRE(ctx->xchg != nullptr, OSB_ERROR_INPUT_PARAMS, "call osb_ctx_ipc_handle first");
+  OSB_REQUIRE(ctx->world + 8 <= 64, OSB_ERROR_INPUT_PARAMS, "peer-memory exchange supports at most 56 ranks");
   std::vector<double*> ptrs(ctx->world, nullptr);
   for (int r = 0; r < ctx->world; ++r) {
     if (r == ctx->rank) {

@@ -385,15 +385,36 @@ void Solver::ensure_full() {
   }
   H_virtual_identity = false;
 }
+void ctx_all_reduce_sum(Ctx* ctx, double* buf, int64_t count);  // dist.cu
 void Solver::sym_to_full() {
   if (!sym_current) return;
   ensure_full();
-  qn_sym_unpack(ctx, Hsym.p, ld, n, H.p);
+  if (ctx->world > 1) {
+    // tile pairs are spread over the ranks: every rank unpacks its tiles into a zeroed n x n scratch (both triangles),
+    // the scratches are summed over the ranks, and the local row block is copied out.  Only getters and engine /
+    // schedule switches come here.
+    DBuf full;
+    full.alloc(qn_rows_padded(n) * ld);
+    full.zero(ctx->stream);
+    qn_sym_unpack_sharded(ctx, Hsym.p, ld, n, full.p);
+    ctx_all_reduce_sum(ctx, full.p, n * ld);
+    OSB_CUDA(cudaMemcpyAsync(H.p, full.p + row0 * ld, sizeof(double) * (size_t)(nrows * ld), cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->sync();
+    Hsym.release();  // the local tile set is only meaningful together with H_virtual_identity / sym_current
+    colpart.release();
+  } else {
+    qn_sym_unpack(ctx, Hsym.p, ld, n, H.p);
+  }
   sym_current = false;
 }
 
 HeadEpi Solver::head_epi() const {
-  if (!defer_epi) return HeadEpi{-1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (!defer_epi) return HeadEpi{-1, nullptr, nullptr, nullptr, nullptr, 1, 0, nullptr, nullptr, nullptr};
+  if (sym_sharded) {  // per-rank slots of the exchange region: [parity][rank][h | w][XSLOT_LD]
+    const double* b0 = ctx->xchg + XSLOT_OFF;
+    const double* b1 = b0 + (int64_t)ctx->world * 2 * XSLOT_LD;
+    return HeadEpi{qn_kind, b0, b0 + XSLOT_LD, b1, b1 + XSLOT_LD, ctx->world, 2 * XSLOT_LD, u.p, ps.p, ph.p};
+  }
   const double* h2 = nullptr;
   const double* w2 = nullptr;
   const double* h1 = h.p;
@@ -404,7 +425,7 @@ HeadEpi Solver::head_epi() const {
     h2 = ctx->xchg + 2 * XCHG_LD;
     w2 = ctx->xchg + 3 * XCHG_LD;
   }
-  return HeadEpi{qn_kind, h1, w1, h2, w2, u.p, ps.p, ph.p};
+  return HeadEpi{qn_kind, h1, w1, h2, w2, 1, 0, u.p, ps.p, ph.p};
 }
 void Solver::finish_epilogue() {
   if (!defer_epi) return;
@@ -426,18 +447,20 @@ void Solver::qn_after_step() {
     u_valid = true;
     return;
   }
-  if (qn_schedule == 1 && qn_storage == 1 && h_symmetric && ctx->world == 1 && (qn_kind == QN_BFGS || qn_kind == QN_DFP)) {
+  if (qn_schedule == 1 && qn_storage == 1 && h_symmetric && (ctx->world == 1 || sym_sharded) && (qn_kind == QN_BFGS || qn_kind == QN_DFP)) {
     // packed symmetric storage: the pass moves n^2 * 8 B (read + write of the lower triangle).  A pending
     // update means "the stored matrix lags by one rank-2 term": packing the lagging matrix keeps that meaning.
     if (!sym_current) {
       if (Hsym.p == nullptr) {
-        Hsym.alloc_pooled(qn_sym_doubles(n));
+        Hsym.alloc_pooled(sym_sharded ? qn_sym_doubles_sharded(n, ctx->world, ctx->rank) : qn_sym_doubles(n));
         colpart.alloc_pooled((int64_t)qn_sym_grid(ctx, n) * 2 * ld);
       }
       if (H_virtual_identity) {
-        qn_sym_set_identity(ctx, n, Hsym.p);
+        if (sym_sharded) qn_sym_set_identity_sharded(ctx, n, Hsym.p);
+        else qn_sym_set_identity(ctx, n, Hsym.p);
         H_virtual_identity = false;
       } else {
+        OSB_REQUIRE(!sym_sharded, OSB_ERR_UNSUPPORTED, "sharded packed storage starts from H = I");  // (guarded by the caller)
         qn_sym_pack(ctx, H.p, ld, n, Hsym.p);
       }
       sym_current = true;
@@ -445,6 +468,12 @@ void Solver::qn_after_step() {
     QNLazyArgs a{nullptr, ld, nrows, row0, n, d_state, ps.p, ph.p, y.p, g.p, s.p, h.p, wv.p, u.p, ps.p, ph.p,
                  ctx->gemv_ticket, qn_kind, nullptr, ctx->d_seq, 1, 0};
     a.defer_epi = defer_epi ? 1 : 0;
+    if (sym_sharded) {  // rows this rank does not own contribute nothing to its slot
+      OSB_CUDA(cudaMemsetAsync(h.p, 0, sizeof(double) * (size_t)ld, ctx->stream));
+      OSB_CUDA(cudaMemsetAsync(wv.p, 0, sizeof(double) * (size_t)ld, ctx->stream));
+      ctx->counters[4]++;  // one fused exchange
+      ctx->counters[5]++;  // passes over the sharded packed triangle
+    }
     prof_mark();  // slot 0: the streaming pass, slot 1: the column fold + epilogue
     qn_launch_lazy_sym(ctx, a, Hsym.p, colpart.p, n, ld, 0);
     prof_mark();
@@ -717,6 +746,13 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
   const bool ls_bounded = ls->p.kind == LS_BACKTRACKING_B || ls->p.kind == LS_MORETHUENTE_B;
   // lazy schedule + cluster head: the O(n) epilogue of the pass runs at the top of the next head (8 SMs instead of 1)
   epi_p2p = ctx->world > 1 && ctx->p2p_ready && ld <= XCHG_LD && use_p2p;
+  // packed symmetric storage sharded by tile pairs: needs the fused peer-memory exchange, the cluster head (it sums the
+  // per-rank slots), an even tile count, and a matrix that never existed as row blocks on this rank (H = I so far, or
+  // already packed): row blocks -> tile pairs would be an all-to-all
+  sym_sharded = ctx->world > 1 && qn_storage == 1 && qn_schedule == 1 && epi_p2p && h_symmetric && (qn_kind == QN_BFGS || qn_kind == QN_DFP) &&
+                n % 16 == 0 && n <= XSLOT_LD && (n / 16) >= ctx->world && (H_virtual_identity || sym_current) &&
+                qn_device_head_is_cluster(obj->functor_kind(), n, head_variant);
+  if (!sym_sharded && sym_current && ctx->world > 1) sym_to_full();
   static const bool no_defer = getenv("OSB_NO_DEFER") != nullptr;  // experiment switch
   defer_epi = !no_defer && qn_schedule == 1 && (qn_kind == QN_BFGS || qn_kind == QN_DFP) && n > QN_SMALL_N &&
               (qn_storage == 1 || qn_variant == 0) &&
@@ -756,6 +792,10 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
     }
     return true;
   };
+  if (!defer_epi && sym_sharded) {  // (only with the OSB_NO_DEFER experiment switch)
+    sym_sharded = false;
+    sym_to_full();
+  }
   for (int64_t it = 0; it < max_iter && !stop; ++it) {
     qn_device_launch_head(ctx, obj->functor_kind(), obj->functor_ptr(0), obj->functor_ptr(1), bounded, d_ls, n, tol, max_ls,
                           d_state, x.p, g.p, d.p, xt.p, gt.p, s.p, y.p, u.p, bounded ? lb.p : nullptr, bounded ? ub.p : nullptr,
@@ -816,6 +856,7 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
   }
   finish_epilogue();
   defer_epi = false;
+  sym_sharded = false;
   fetch_state();
   OSB_CUDA(cudaMemcpyAsync(&ls->p, d_ls, sizeof(LSParams), cudaMemcpyDeviceToHost, stm));
   ctx->sync();

@@ -202,6 +202,10 @@ void qn_launch_update(Ctx* ctx, int kind, double* H, int64_t ld, int64_t nrows, 
 // lazy (2-pass-less) schedule: ONE read-modify-write per iteration — applies the pending update while
 // computing h = H y and w = H g with the updated rows; the epilogue forms the new pending update and u.
 constexpr int64_t XCHG_LD = 65536;  // capacity (doubles) of one exchanged vector
+// sharded packed-symmetric storage: after the flags, 2 parities x world ranks x {h, w} slots of XSLOT_LD doubles; every
+// rank's contribution (row sums of its tiles + its column sums) lands in slot `rank` of every rank's region
+constexpr int64_t XSLOT_LD = 16384;
+constexpr int64_t XSLOT_OFF = 4 * XCHG_LD + 64;  // (flags: world + 8 <= 64 64-bit words)
 // Deferred lazy-schedule epilogue, executed by the 8-CTA cluster head (a single CTA is bound by one SM's L2 port:
 // 1.3 MB of O(n) vectors took 16 us of a 450 us iteration at n = 16384).
 struct HeadEpi {
@@ -210,6 +214,8 @@ struct HeadEpi {
   const double* w;   // H g
   const double* h2;  // peer-memory exchange: h, w of the odd-parity exchange buffers (st->epi == 2), else null
   const double* w2;
+  int nslots;        // > 1: h and w are the rank-ordered sums of `nslots` vectors `slot_stride` doubles apart
+  int64_t slot_stride;  //      (sharded packed storage: one slot per rank in the exchange region)
   double* u_out;     // u = H+ g (also kept for getters)
   double* ps_out;    // pending p <- s
   double* ph_out;    // pending q <- h
@@ -244,6 +250,9 @@ int64_t qn_sym_doubles(int64_t n);
 int qn_sym_grid(Ctx* ctx, int64_t n);
 void qn_sym_pack(Ctx* ctx, const double* H, int64_t ld, int64_t n, double* P);
 void qn_sym_set_identity(Ctx* ctx, int64_t n, double* P);
+int64_t qn_sym_doubles_sharded(int64_t n, int world, int rank);
+void qn_sym_set_identity_sharded(Ctx* ctx, int64_t n, double* P);
+void qn_sym_unpack_sharded(Ctx* ctx, const double* P, int64_t ld, int64_t n, double* Hfull_zeroed);
 void qn_sym_unpack(Ctx* ctx, const double* P, int64_t ld, int64_t n, double* H);
 void qn_launch_lazy_sym(Ctx* ctx, const QNLazyArgs& a, double* P, double* colpart, int64_t n, int64_t ld, int phase);
 // apply a pending update to the stored matrix (getters, engine switches)
@@ -302,6 +311,7 @@ struct Solver {
   void ensure_full();               // materialise the full row-major H
   bool defer_epi = false;  // minimize_device with the cluster head: the lazy pass leaves its epilogue to the next head
   bool epi_p2p = false;    // ... and h, w live in the peer-memory exchange buffers
+  bool sym_sharded = false;  // packed symmetric storage sharded by tile pairs over the ranks (this minimize call)
   HeadEpi head_epi() const;
   void finish_epilogue();  // run an owed epilogue now (no head follows)
   int qn_storage = 0;     // 0 = full n x n, 1 = packed symmetric lower triangle (lazy schedule, BFGS/DFP, single GPU)

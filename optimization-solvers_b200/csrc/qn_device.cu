@@ -488,8 +488,16 @@ __device__ __noinline__ double cluster_min_rt(double v, double* smem_cta, double
 // y.h, s.g, h.g with element i = gt + k * NT (a mapping that does not depend on the functor's block size, so the
 // head and the stand-alone finisher add in the same order), then the coefficients of qn_kernels.cu's
 // lazy_epilogue_body.  Returns ca, cb of  u = w + (s ca + h cb); the leader publishes the coefficients.
+// h or w of the deferred epilogue: one vector, or (sharded packed storage) the sum of the per-rank slots in rank order —
+// every rank adds the same numbers in the same order, so all ranks hold the same bits
+__device__ __forceinline__ double epi_ld(const double* __restrict__ base, int nslots, int64_t stride, int64_t i) {
+  double v = __ldcg(base + i);
+  for (int r = 1; r < nslots; ++r) v = v + __ldcg(base + (int64_t)r * stride + i);
+  return v;
+}
+
 template <int EPT>
-__device__ __forceinline__ void cluster_epilogue_coefs(int kind, const double* __restrict__ hh, const double* s, const double* y,
+__device__ __forceinline__ void cluster_epilogue_coefs(int kind, int nslots, int64_t slot_stride, const double* __restrict__ hh, const double* s, const double* y,
                                                        const double* g, int64_t n, DevState* st, bool leader, int gt,
                                                        double* smem_cta, double* part, double* res, int& phase, double& ca,
                                                        double& cb) {
@@ -499,7 +507,7 @@ __device__ __forceinline__ void cluster_epilogue_coefs(int kind, const double* _
   for (int k = 0; k < EPT; ++k) {
     const int64_t i = gt + (int64_t)k * NT;
     const bool ok = i < n;
-    hv[k] = ok ? __ldcg(hh + i) : 0.0;
+    hv[k] = ok ? epi_ld(hh, nslots, slot_stride, i) : 0.0;
     gv[k] = ok ? g[i] : 0.0;
     yv[k] = ok ? y[i] : 0.0;
     sv[k] = ok ? s[i] : 0.0;
@@ -558,7 +566,7 @@ qn_epilogue_cluster_kernel(HeadEpi e, int64_t n, DevState* __restrict__ st, cons
   const bool skip = st->skip != 0;
   int phase = 0;
   double ca = 0.0, cb = 0.0;
-  if (!skip) cluster_epilogue_coefs<EPT>(e.kind, hh, s, y, g, n, st, leader, gt, smem_cta, part, res, phase, ca, cb);
+  if (!skip) cluster_epilogue_coefs<EPT>(e.kind, e.nslots, e.slot_stride, hh, s, y, g, n, st, leader, gt, smem_cta, part, res, phase, ca, cb);
   else if (leader) {  // bfgs.rs:106-112: no new update; the stored matrix is exact once the pending one is applied
     st->pending = 0;
     st->pc0 = st->pc1 = st->pc2 = 0.0;
@@ -568,11 +576,11 @@ qn_epilogue_cluster_kernel(HeadEpi e, int64_t n, DevState* __restrict__ st, cons
   for (int k = 0; k < EPT; ++k) {
     const int64_t i = gt + (int64_t)k * NT;
     if (i < n) {
-      const double wi = __ldcg(ww + i);
+      const double wi = epi_ld(ww, e.nslots, e.slot_stride, i);
       if (skip) {
         e.u_out[i] = wi;
       } else {
-        const double si = s[i], hi = __ldcg(hh + i);
+        const double si = s[i], hi = epi_ld(hh, e.nslots, e.slot_stride, i);
         e.u_out[i] = wi + (si * ca + hi * cb);
         e.ps_out[i] = si;
         e.ph_out[i] = hi;
@@ -622,7 +630,7 @@ qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol,
   const double* __restrict__ epi_w = epi_flag == 2 ? epi.w2 : epi.w;
   double epi_ca = 0.0, epi_cb = 0.0;
   if (epi_flag) {
-    if (!epi_skip) cluster_epilogue_coefs<EPT>(epi.kind, epi_h, s, y, g, n, st, leader, gt, smem_cta, part, res, phase, epi_ca, epi_cb);
+    if (!epi_skip) cluster_epilogue_coefs<EPT>(epi.kind, epi.nslots, epi.slot_stride, epi_h, s, y, g, n, st, leader, gt, smem_cta, part, res, phase, epi_ca, epi_cb);
     else if (leader) {
       st->pending = 0;
       st->pc0 = st->pc1 = st->pc2 = 0.0;
@@ -649,11 +657,11 @@ qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol,
         const double xi = x[i], gi = g[i];
         double ui;
         if (epi_flag) {  // u = H+ g = w + (s ca + h cb); the vectors of the now pending update are saved
-          const double wi = __ldcg(epi_w + i);
+          const double wi = epi_ld(epi_w, epi.nslots, epi.slot_stride, i);
           if (epi_skip) {
             ui = wi;
           } else {
-            const double si = s[i], hi = __ldcg(epi_h + i);
+            const double si = s[i], hi = epi_ld(epi_h, epi.nslots, epi.slot_stride, i);
             ui = wi + (si * epi_ca + hi * epi_cb);
             epi.ps_out[i] = si;
             epi.ph_out[i] = hi;

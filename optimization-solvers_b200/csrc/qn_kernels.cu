@@ -784,10 +784,31 @@ __host__ __device__ inline int64_t sym_tile_offset(int64_t tile) {              
 }
 int64_t qn_sym_doubles(int64_t n) { return sym_tile_offset((n + 7) / 8) + 8 * sym_lpad((n + 7) / 8); }
 
+// Sharded layout (world > 1, ntiles even): tile PAIRS (p, T-1-p) are dealt round-robin over the ranks (pair p belongs
+// to rank p % world) and stored pair by pair; lpad(p) + lpad(T-1-p) = 8 T + 16 for every p when T is even, so the
+// local offset is a closed form: local pair index * 8 (8 T + 16), the short tile p first.
+__host__ __device__ inline int64_t symsh_pair_doubles(int64_t T) { return 8 * (8 * T + 16); }
+__host__ __device__ inline int64_t symsh_tile_offset(int64_t tile, int64_t T, int world) {
+  const int64_t half = T / 2;
+  const int64_t pairi = tile < half ? tile : T - 1 - tile;
+  return (pairi / world) * symsh_pair_doubles(T) + (tile < half ? 0 : 8 * sym_lpad(pairi));
+}
+__host__ __device__ inline int64_t symsh_local_pairs(int64_t T, int world, int rank) {
+  const int64_t half = T / 2;
+  return half > rank ? (half - rank + world - 1) / world : 0;
+}
+int64_t qn_sym_doubles_sharded(int64_t n, int world, int rank) {
+  const int64_t T = (n + QN_R - 1) / QN_R;
+  return symsh_local_pairs(T, world, rank) * symsh_pair_doubles(T);
+}
+
 struct QNSymArgs {
-  double* P;         // packed matrix
+  double* P;         // packed matrix (this rank's tiles when sharded)
   double* colpart;   // gridDim x 2 x ld per-CTA column partials (h then w)
   int64_t n, ld;
+  int world, rank;   // sharded: pairs p = rank, rank + world, ...
+  double* const* peers;        // exchange regions (fold kernel, sharded)
+  unsigned long long* seq;     // exchange sequence number
 };
 
 // 16 per-thread values -> warp sums with 16 double shuffles (recursive halving) instead of 80; after the call
@@ -807,7 +828,9 @@ __device__ __forceinline__ double warp_sum16(double (&v)[16]) {
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
-template <int KIND>
+// SHARDED is a template parameter so that the single-GPU instantiation keeps exactly its own loop structure (the
+// 128-register streaming loop is sensitive to anything that stays live across it).
+template <int KIND, bool SHARDED>
 __global__ void __launch_bounds__(QN_T, 1) qn_lazy_sym_kernel(QNLazyArgs a, QNSymArgs sa) {
   DevState* st = a.st;
   if (st->done) return;
@@ -835,10 +858,27 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_sym_kernel(QNLazyArgs a, QNSy
   // one pair; plain round-robin leaves the CTA holding the longest tiles 7 % above the average.
   const int64_t ntiles = (n + QN_R - 1) / QN_R;
   const int64_t nhalf = (ntiles + 1) / 2;
-  for (int64_t pairi = blockIdx.x; pairi < nhalf; pairi += gridDim.x)
-  for (int side = 0; side < 2; ++side) {
-    const int64_t tile = side == 0 ? pairi : ntiles - 1 - pairi;
-    if (side == 1 && tile == pairi) continue;  // odd tile count: the middle tile only once
+  // Sharded: a rank owns nlp pairs = 2 nlp tiles; dealing whole pairs would quantise the work to ceil(nlp / grid) rounds
+  // (4 instead of 3.46 at 2 GPUs).  The local tiles are therefore dealt ONE BY ONE in decreasing length, in snake order
+  // (round k left-to-right for even k, right-to-left for odd k): position q < nlp is tile T-1-(rank + q world), position
+  // q >= nlp is tile rank + (2 nlp - 1 - q) world.  Static, hence deterministic.
+  constexpr bool sharded = SHARDED;
+  const int64_t nlp = SHARDED ? symsh_local_pairs(ntiles, sa.world, sa.rank) : nhalf;
+  const int64_t nunits = SHARDED ? 2 * nlp : nlp;
+  for (int64_t uq0 = blockIdx.x, kround = 0; SHARDED ? kround * (int64_t)gridDim.x < nunits : uq0 < nunits; uq0 += gridDim.x, ++kround)
+  for (int side = 0; side < (SHARDED ? 1 : 2); ++side) {
+    int64_t tile;
+    if (SHARDED) {
+      const int64_t pos = (kround & 1) ? (int64_t)gridDim.x - 1 - blockIdx.x : blockIdx.x;
+      const int64_t uq = kround * gridDim.x + pos;
+      if (uq >= nunits) continue;
+      const int64_t pairi = uq < nlp ? sa.rank + uq * sa.world : sa.rank + (2 * nlp - 1 - uq) * sa.world;
+      tile = uq < nlp ? ntiles - 1 - pairi : pairi;
+    } else {
+      const int64_t pairi = uq0;
+      tile = side == 0 ? pairi : ntiles - 1 - pairi;
+      if (side == 1 && tile == pairi) continue;  // odd tile count: the middle tile only once
+    }
     const int64_t r0 = tile * QN_R;
     const int rows_here = (int)((n - r0) < QN_R ? (n - r0) : QN_R);
     const int64_t lpad = sym_lpad(tile);
@@ -855,7 +895,7 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_sym_kernel(QNLazyArgs a, QNSy
       rowv[threadIdx.x] = ok ? make_double4(p[i], q[i], yv[i], gv[i]) : make_double4(0.0, 0.0, 0.0, 0.0);
     }
     __syncthreads();  // (A) rowv[tpar] visible; also orders the previous tile's red[tpar^1] readers before its next reuse
-    double* __restrict__ base = sa.P + sym_tile_offset(tile);
+    double* __restrict__ base = sa.P + (sharded ? symsh_tile_offset(tile, ntiles, sa.world) : sym_tile_offset(tile));
     for (int col = 2 * threadIdx.x; col < (int)lpad; col += QN_CHUNK) {
       // element validity: columns >= ncols are padding (never stored, never updated)
       const bool v0 = col < ncols, v1 = col + 1 < ncols;
@@ -946,6 +986,8 @@ __global__ void __launch_bounds__(FOLD_T) qn_sym_fold_kernel(const __grid_consta
   __shared__ double smem[3 * 32];
   __shared__ bool is_last;
   const int64_t ld = sa.ld;
+  const unsigned long long seq = sa.world > 1 ? *sa.seq + 1ULL : 0ULL;  // this exchange's sequence number
+  const int par = (int)(seq & 1ULL);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int vec = warp / FOLD_G, grp = warp % FOLD_G;
   const int per = (nparts + FOLD_G - 1) / FOLD_G;
@@ -985,9 +1027,46 @@ __global__ void __launch_bounds__(FOLD_T) qn_sym_fold_kernel(const __grid_consta
         tot.y = tot.y + part[vec][g][lane].y;
       }
       double* dst = vec == 0 ? a.h : a.w;
-      dst[j] = dst[j] + tot.x;
-      if (j + 1 < sa.n) dst[j + 1] = dst[j + 1] + tot.y;
+      const double vx = dst[j] + tot.x;
+      const double vy = (j + 1 < sa.n) ? dst[j + 1] + tot.y : 0.0;
+      if (sa.world > 1) {
+        // this rank's contribution (its tiles' row sums + its column sums) goes straight into slot `rank` of every
+        // rank's exchange region; the head adds the slots in rank order
+        const int64_t off = XSLOT_OFF + ((int64_t)(par * sa.world + sa.rank) * 2 + vec) * XSLOT_LD + j;
+        for (int pr = 0; pr < sa.world; ++pr) *reinterpret_cast<double2*>(sa.peers[pr] + off) = make_double2(vx, vy);
+      } else {
+        dst[j] = vx;
+        if (j + 1 < sa.n) dst[j + 1] = vy;
+      }
     }
+  }
+  if (sa.world > 1) {
+    // same protocol as qn_lazy_kernel<.., P2P>: fence this CTA's peer stores, the last CTA publishes the sequence
+    // number on every rank and waits for every rank's; the epilogue is always left to the head
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned int t = atomicAdd(ticket, 1u);
+      is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence_system();
+    unsigned long long* myflags = reinterpret_cast<unsigned long long*>(sa.peers[sa.rank] + 4 * XCHG_LD);
+    if (threadIdx.x < sa.world) {
+      unsigned long long* f = reinterpret_cast<unsigned long long*>(sa.peers[threadIdx.x] + 4 * XCHG_LD) + sa.rank;
+      st_release_sys(f, seq);
+      while (ld_acquire_sys(myflags + threadIdx.x) < seq) {
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      st->epi = 1 + par;
+      *sa.seq = seq;
+      *ticket = 0u;
+    }
+    return;
   }
   if (a.defer_epi) {  // the next cluster head forms the coefficients and u on 8 SMs; the kernel boundary orders h, w before it
     if (blockIdx.x == 0 && threadIdx.x == 0) st->epi = 1;
@@ -1042,6 +1121,45 @@ __global__ void qn_sym_identity_kernel(int64_t n, double* __restrict__ P) {
     P[sym_tile_offset(tile) + (i % QN_R) * sym_lpad(tile) + i] = 1.0;  // bfgs.rs:30-33: H_0 = I, straight into the packed layout
   }
 }
+__global__ void qn_symsh_identity_kernel(int64_t n, double* __restrict__ P, int world, int rank) {
+  const int64_t T = (n + QN_R - 1) / QN_R;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t tile = i / QN_R;
+    const int64_t pairi = tile < T / 2 ? tile : T - 1 - tile;
+    if (pairi % world == rank) P[symsh_tile_offset(tile, T, world) + (i % QN_R) * sym_lpad(tile) + i] = 1.0;
+  }
+}
+void qn_sym_set_identity_sharded(Ctx* ctx, int64_t n, double* P) {
+  OSB_CUDA(cudaMemsetAsync(P, 0, sizeof(double) * (size_t)qn_sym_doubles_sharded(n, ctx->world, ctx->rank), ctx->stream));
+  qn_symsh_identity_kernel<<<ctx->red_grid(n), RED_THREADS, 0, ctx->stream>>>(n, P, ctx->world, ctx->rank);
+  ctx->counters[0]++;
+}
+// this rank's tiles -> a FULL n x n matrix (both triangles of every owned element; everything else untouched, i.e.
+// zero in a zeroed buffer): the sum over ranks of these matrices is H
+__global__ void __launch_bounds__(256) qn_symsh_unpack_kernel(const double* __restrict__ P, int64_t ld, int64_t n, double* __restrict__ H,
+                                                             int world, int rank) {
+  const int64_t T = (n + QN_R - 1) / QN_R;
+  const int64_t nlp = symsh_local_pairs(T, world, rank);
+  for (int64_t q = blockIdx.x; q < 2 * nlp; q += gridDim.x) {
+    const int64_t pairi = (q >> 1) * world + rank;
+    const int64_t tile = (q & 1) == 0 ? pairi : T - 1 - pairi;
+    const int64_t r0 = tile * QN_R, lpad = sym_lpad(tile);
+    const int64_t ncols = r0 + QN_R < n ? r0 + QN_R : n;
+    const double* base = P + symsh_tile_offset(tile, T, world);
+    for (int64_t e = threadIdx.x; e < QN_R * lpad; e += blockDim.x) {
+      const int64_t r = e / lpad, c = e % lpad;
+      if (r0 + r < n && c < ncols) {
+        const double v = base[e];
+        H[(r0 + r) * ld + c] = v;
+        if (c < r0) H[c * ld + r0 + r] = v;
+      }
+    }
+  }
+}
+void qn_sym_unpack_sharded(Ctx* ctx, const double* P, int64_t ld, int64_t n, double* Hfull_zeroed) {
+  qn_symsh_unpack_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(P, ld, n, Hfull_zeroed, ctx->world, ctx->rank);
+  ctx->counters[0]++;
+}
 void qn_sym_set_identity(Ctx* ctx, int64_t n, double* P) {
   OSB_CUDA(cudaMemsetAsync(P, 0, sizeof(double) * (size_t)qn_sym_doubles(n), ctx->stream));
   qn_sym_identity_kernel<<<ctx->red_grid(n), RED_THREADS, 0, ctx->stream>>>(n, P);
@@ -1055,15 +1173,25 @@ void qn_sym_unpack(Ctx* ctx, const double* P, int64_t ld, int64_t n, double* H) 
   qn_sym_unpack_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(P, ld, n, H);
   ctx->counters[0]++;
 }
-int qn_sym_grid(Ctx* ctx, int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + QN_R - 1) / QN_R, (int64_t)ctx->num_sms)); }
+int qn_sym_grid(Ctx* ctx, int64_t n) {
+  const int64_t T = (n + QN_R - 1) / QN_R;
+  const int64_t units = ctx->world > 1 ? 2 * symsh_local_pairs(T, ctx->world, ctx->rank) : T;  // sharded: local tiles
+  return (int)std::max<int64_t>(1, std::min<int64_t>(units, (int64_t)ctx->num_sms));
+}
 
 void qn_launch_lazy_sym(Ctx* ctx, const QNLazyArgs& a, double* P, double* colpart, int64_t n, int64_t ld, int phase) {
-  QNSymArgs sa{P, colpart, n, ld};
+  const bool sharded = ctx->world > 1;
+  QNSymArgs sa{P, colpart, n, ld, sharded ? ctx->world : 1, sharded ? ctx->rank : 0, sharded ? ctx->d_peers : nullptr, ctx->d_seq};
   const int grid = qn_sym_grid(ctx, n);
   const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 63) / 64, (int64_t)ctx->num_sms * 2));
   if (phase == 0) {  // the streaming pass over the packed triangle
-    if (a.kind == QN_BFGS) qn_lazy_sym_kernel<QN_BFGS><<<grid, QN_T, 0, ctx->stream>>>(a, sa);
-    else qn_lazy_sym_kernel<QN_DFP><<<grid, QN_T, 0, ctx->stream>>>(a, sa);
+    if (sharded) {
+      if (a.kind == QN_BFGS) qn_lazy_sym_kernel<QN_BFGS, true><<<grid, QN_T, 0, ctx->stream>>>(a, sa);
+      else qn_lazy_sym_kernel<QN_DFP, true><<<grid, QN_T, 0, ctx->stream>>>(a, sa);
+    } else {
+      if (a.kind == QN_BFGS) qn_lazy_sym_kernel<QN_BFGS, false><<<grid, QN_T, 0, ctx->stream>>>(a, sa);
+      else qn_lazy_sym_kernel<QN_DFP, false><<<grid, QN_T, 0, ctx->stream>>>(a, sa);
+    }
   } else {  // fold of the per-CTA column partials + coefficient epilogue
     if (a.kind == QN_BFGS) qn_sym_fold_kernel<QN_BFGS><<<fgrid, FOLD_T, 0, ctx->stream>>>(a, sa, grid, a.ticket);
     else qn_sym_fold_kernel<QN_DFP><<<fgrid, FOLD_T, 0, ctx->stream>>>(a, sa, grid, a.ticket);

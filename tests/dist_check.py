@@ -57,6 +57,32 @@ def main():
         print("rank %d %s n=%d k=%d schedule=%d p2p=%d bit-identical to single GPU: %s"
               % (rank, kind, n, res[0][0], sched, p2p, same), flush=True)
         ok &= bool(same)
+    # ---- packed symmetric storage sharded by tile pairs (fused peer-memory exchange of per-rank slots, summed in rank
+    # order by the head): same trajectory as one GPU to rounding of the summation order, identical on all ranks
+    for kind, n, iters in (("BFGS", 2048, 40), ("DFP", 1024, 25), ("BFGS", 16384, 12)):
+        x0 = rosen_x0(n, 5)
+        res = []
+        for c in (ctx, solo):
+            s = getattr(osb, kind)(1e-8, x0, ctx=c).set_option("engine", 2).set_option("qn_schedule", 1).set_option("qn_storage", 1)
+            try:
+                s.minimize(osb.BackTracking(1e-4, 0.5), osb.ExtendedRosenbrock(n, ctx=c), iters, 20)
+            except osb.MaxIterReached:
+                pass
+            launches = c.counters()["sharded_packed_passes"]
+            H = s.approx_inv_hessian()  # (collective on the sharded context: all ranks call it)
+            res.append((s.k(), s.x(), s.s_norm(), H, launches))
+            s.close()
+        rows = slice(rank * n // world, (rank + 1) * n // world)
+        xs = [None] * world
+        dist.all_gather_object(xs, res[0][1].tobytes())
+        same_on_ranks = all(b == xs[0] for b in xs)
+        dx = float(np.max(np.abs(res[0][1] - res[1][1])))
+        dH = float(np.max(np.abs(res[0][3][rows] - res[1][3][rows])))
+        good = res[0][0] == res[1][0] and res[0][4] > 0 and res[1][4] == 0 and same_on_ranks and dx <= 1e-9 and dH <= 1e-8 * max(1.0, float(np.max(np.abs(res[1][3][rows]))))
+        print("rank %d %s n=%d k=%d/%d packed storage sharded by tile pairs: ranks identical %s, max|dx| vs one GPU %.2e, max|dH| %.2e -> %s"
+              % (rank, kind, n, res[0][0], res[1][0], same_on_ranks, dx, dH, good), flush=True)
+        ok &= bool(good)
+
     # ---- C2 shape: GradientDescent on a row-sharded dense quadratic (A row-block sharded, x / g replicated, all-gather
     # of (A x)_p): bit-identical to one GPU
     n = 4096
