@@ -1043,7 +1043,7 @@ __global__ void __launch_bounds__(FOLD_T) qn_sym_fold_kernel(const __grid_consta
   if (sa.world > 1) {
     // same protocol as qn_lazy_kernel<.., P2P>: fence this CTA's peer stores, the last CTA publishes the sequence
     // number on every rank and waits for every rank's; the epilogue is always left to the head
-    __threadfence_system();
+    if (grp == 0) __threadfence_system();  // only the two warps that stored to the peers
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();
