@@ -81,7 +81,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.01)
 
     def summary(self):
         if not self.samples:
@@ -192,7 +192,12 @@ def main():
         dist.broadcast_object_list(uid, src=0)
         ctx = osb.Context(local_rank, rank, world, uid[0])
         if not args.no_p2p:
-            ctx.connect_peers()  # CUDA IPC: fused NVLink all-gather inside the lazy kernel
+            # CUDA IPC: the exchange is fused into the kernels over NVLink peer memory; without it (no peer access,
+            # IPC disabled) every rank falls back to the NCCL path together
+            if not ctx.connect_peers(strict=False):
+                args.no_p2p = True
+                if rank == 0:
+                    print("bench: peer-memory exchange unavailable, using NCCL all-gathers and full storage", file=sys.stderr)
     else:
         ctx = osb.Context(local_rank)
     osb.set_default_context(ctx)
@@ -208,6 +213,7 @@ def main():
     ls = osb.BackTracking(1e-4, 0.5)
     lazy = args.schedule == "lazy"
     solver = osb.BFGS(TOL, x0, ctx=ctx).set_option("engine", 2).set_option("qn_schedule", 1 if lazy else 0)
+    solver.set_option("use_p2p", 0 if args.no_p2p else 1)
     solver.set_option("head_kernel", args.head)
     solver.set_option("qn_kernel", args.qn_kernel)
     sym = lazy and args.storage in ("sym", "auto") and (world == 1 or not args.no_p2p)
@@ -315,6 +321,7 @@ def main():
         barrier()
         t0 = time.perf_counter()
         s2 = osb.BFGS(TOL, x0, ctx=ctx).set_option("engine", 2).set_option("qn_schedule", 1 if lazy else 0)
+        s2.set_option("use_p2p", 0 if args.no_p2p else 1)
         s2.set_option("qn_storage", 1 if sym else 0)
         try:
             s2.minimize(osb.BackTracking(1e-4, 0.5), obj, args.steps, MAX_LS)

@@ -300,14 +300,32 @@ class Context:
         buf = C.create_string_buffer(blob, len(blob))
         _check(lib().osb_ctx_ipc_connect(self.handle, buf))
 
-    def connect_peers(self):
-        """All-gather the IPC handles over torch.distributed and connect (fused NVLink all-gather)."""
+    def connect_peers(self, strict=True):
+        """All-gather the IPC handles over torch.distributed and connect (fused NVLink exchange).  Returns True when
+        EVERY rank connected.  With strict=False a failure on any rank (no peer access between two GPUs, IPC disabled
+        in a container) is not an error: all ranks return False together and keep using the NCCL path."""
         import torch.distributed as dist
-        mine = self.ipc_handle()
+        ok, err = 1, None
+        try:
+            mine = self.ipc_handle()
+        except Exception as e:  # noqa: BLE001 - reported below, after the collective
+            mine, ok, err = b"\0" * 64, 0, e
         allh = [None] * dist.get_world_size()
         dist.all_gather_object(allh, mine)
-        self.ipc_connect(allh)
-        dist.barrier()
+        oks = [None] * dist.get_world_size()
+        dist.all_gather_object(oks, ok)
+        if all(oks):
+            try:
+                self.ipc_connect(allh)
+            except Exception as e:  # noqa: BLE001
+                ok, err = 0, e
+        else:
+            ok = 0
+        dist.all_gather_object(oks, ok)
+        self.p2p = bool(all(oks))
+        if not self.p2p and strict:
+            raise err if err is not None else DeviceError("peer-memory exchange unavailable on another rank")
+        return self.p2p
 
     def set_vector_sharding(self, on=True):
         """Index-range sharding of GD / PGD / SPG over the ranks of this context (see include/optsolv_b200.h)."""
