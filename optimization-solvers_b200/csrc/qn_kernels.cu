@@ -972,10 +972,11 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_sym_kernel(QNLazyArgs a, QNSy
   }
 }
 
-// h_j += sum over CTAs of the column partials (fixed shape: 4 groups of consecutive CTAs summed in order, then
-// ((g0 + g1) + (g2 + g3))); then the O(n) epilogue (y.h, coefficients, u) by the last CTA.
-// CTA = 8 warps = {h, w} x 4 groups, lane = column within a block of 32 columns: every load is a coalesced
-// 256-byte row of one partial vector, 512 CTAs keep all SMs busy (a one-thread-per-column version took 58 us).
+// h_j += sum over CTAs of the column partials; then, depending on the mode, the O(n) epilogue by the last CTA (host
+// engine), nothing (the next cluster head runs it), or — sharded — the push of this rank's contribution to every peer.
+// Fixed summation shape: FOLD_G groups of consecutive CTAs summed in order, then the groups in order.
+// CTA = 16 warps = {h, w} x FOLD_G groups, lane = 2 columns of a block of 64: every load is a coalesced 512-byte piece
+// of one partial vector, 8 loads in flight per thread (a one-thread-per-column version took 58 us, this one 6).
 constexpr int FOLD_T = 512;   // = QN_T: the fused epilogue then adds in the same order as the full-storage kernel's
 constexpr int FOLD_G = FOLD_T / 64;  // groups of partial rows per vector
 template <int KIND>
@@ -993,7 +994,7 @@ __global__ void __launch_bounds__(FOLD_T) qn_sym_fold_kernel(const __grid_consta
   const int per = (nparts + FOLD_G - 1) / FOLD_G;
   const int cb = grp * per, ce = (cb + per < nparts) ? cb + per : nparts;
   // a warp reads 512 contiguous bytes of one partial row per load and keeps 8 loads in flight; the order of the
-  // additions is fixed by (nparts, 4 groups), not by timing
+  // additions is fixed by (nparts, FOLD_G groups), not by timing
   for (int64_t j0 = (int64_t)blockIdx.x * 64; j0 < sa.n; j0 += (int64_t)gridDim.x * 64) {
     const int64_t j = j0 + 2 * lane;  // ld is a multiple of 8 and the pad columns of colpart are zero, so j + 1 < ld is readable
     double2 acc = make_double2(0.0, 0.0);

@@ -43,11 +43,18 @@ extern "C" {
     pub fn osb_ctx_create_dist(device: c_int, rank: c_int, world: c_int, nccl_unique_id: *const c_void,
                                out: *mut *mut osb_ctx) -> c_int;
     pub fn osb_nccl_unique_id(out128: *mut c_void) -> c_int;
+    pub fn osb_ctx_ipc_handle(ctx: *mut osb_ctx, out64: *mut c_void) -> c_int;
+    pub fn osb_ctx_ipc_connect(ctx: *mut osb_ctx, handles_world_x_64: *const c_void) -> c_int;
+    pub fn osb_ctx_set_vector_sharding(ctx: *mut osb_ctx, on: c_int) -> c_int;
+    pub fn osb_ctx_trim_memory(ctx: *mut osb_ctx) -> c_int;
     pub fn osb_ctx_destroy(ctx: *mut osb_ctx);
 
     pub fn osb_objective_create_dense_quadratic(ctx: *mut osb_ctx, n: i64, a: *const c_double, b: *const c_double,
                                                 out: *mut *mut osb_objective) -> c_int;
     pub fn osb_objective_create_rosenbrock(ctx: *mut osb_ctx, n: i64, out: *mut *mut osb_objective) -> c_int;
+    pub fn osb_objective_create_separable_quadratic_generated(ctx: *mut osb_ctx, n: i64, out: *mut *mut osb_objective) -> c_int;
+    pub fn osb_objective_create_separable_quadratic_generated_shard(ctx: *mut osb_ctx, n_local: i64, index0: i64,
+                                                                    out: *mut *mut osb_objective) -> c_int;
     pub fn osb_objective_create_logistic_generated(ctx: *mut osb_ctx, m: i64, n: i64, lambda: c_double,
                                                    out: *mut *mut osb_objective) -> c_int;
     pub fn osb_objective_create_host(ctx: *mut osb_ctx, n: i64, f: osb_host_eval_fn, user: *mut c_void,
