@@ -96,6 +96,12 @@ int osb_ctx_ipc_connect(osb_ctx* ctx, const void* handles_world_x_64);
  * the path (f, g.d, s.y, s.s, the inf-norms of number.rs:27-31 and projected_gradient_descent.rs:76-83) is
  * combined across ranks in rank order.  Replaces nothing in the reference (single-threaded); SURVEY 8e. */
 int osb_ctx_set_vector_sharding(osb_ctx* ctx, int on);
+/* Host-only description of the packed symmetric layouts (qn_storage = 1; no GPU needed): the 8-row tile `tile` of an
+ * n x n matrix is owned by rank *owner and starts *offset_doubles into that rank's packed array, rows *row_stride_doubles
+ * apart; *rank_total_doubles is the size of rank `rank`'s array.  world = 1: all tiles consecutive.  world > 1: tile
+ * pairs (p, T-1-p) dealt round-robin over the ranks, see DESIGN.md section 6. */
+int osb_sym_layout(int64_t n, int world, int rank, int64_t tile, int* owner, int64_t* offset_doubles, int64_t* row_stride_doubles,
+                   int64_t* rank_total_doubles);
 /* The n x n matrices of destroyed solvers are kept in a small per-device pool (at most 6 buffers / 6 GiB) and reused by
  * the next solver of the same size; this returns them to the driver (context destruction does it too). */
 int osb_ctx_trim_memory(osb_ctx* ctx);

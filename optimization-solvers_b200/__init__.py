@@ -62,6 +62,7 @@ def lib():
             "osb_objective_create_separable_quadratic_generated": (ci, [_vp, i64, pp]),
             "osb_objective_create_separable_quadratic_generated_shard": (ci, [_vp, i64, i64, pp]),
             "osb_ctx_set_vector_sharding": (ci, [_vp, ci]), "osb_ctx_trim_memory": (ci, [_vp]),
+            "osb_sym_layout": (ci, [i64, ci, ci, i64, C.POINTER(ci), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
             "osb_objective_create_logistic_generated": (ci, [_vp, i64, i64, dbl, pp]),
             "osb_objective_create_host": (ci, [_vp, i64, HOST_EVAL, _vp, ci, pp]),
             "osb_objective_create_user": (ci, [_vp, i64, DEVICE_EVAL, _vp, ci, pp]),
@@ -918,6 +919,13 @@ class PnormDescent(_Solver):
 
     def inverse_p(self):
         return self.approx_inv_hessian()
+
+
+def sym_layout(n, world, rank, tile):
+    """(owner, offset, row_stride, rank_total) of an 8-row tile in the packed symmetric layout (host-only query)."""
+    owner, off, ldp, tot = C.c_int(), C.c_int64(), C.c_int64(), C.c_int64()
+    _check(lib().osb_sym_layout(n, world, rank, tile, C.byref(owner), C.byref(off), C.byref(ldp), C.byref(tot)))
+    return owner.value, off.value, ldp.value, tot.value
 
 
 # ---- batched mode -----------------------------------------------------------------------------

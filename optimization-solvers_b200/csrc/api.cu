@@ -111,6 +111,18 @@ int osb_ctx_set_vector_sharding(osb_ctx* ctx, int on) {
   return OSB_OK;
   OSB_CATCH
 }
+int osb_sym_layout(int64_t n, int world, int rank, int64_t tile, int* owner, int64_t* offset_doubles, int64_t* row_stride_doubles,
+                   int64_t* rank_total_doubles) {
+  OSB_TRY
+  const int64_t T = (n + 7) / 8;
+  OSB_REQUIRE(n >= 1 && world >= 1 && rank >= 0 && rank < world && tile >= 0 && tile < T, OSB_ERROR_INPUT_PARAMS, "bad layout query");
+  OSB_REQUIRE(world == 1 || (n % 16 == 0 && n / 16 >= world), OSB_ERROR_INPUT_PARAMS,
+              "the sharded packed layout needs n divisible by 16 and at least one tile pair per rank");
+  qn_sym_layout(n, world, tile, owner, offset_doubles, row_stride_doubles);
+  *rank_total_doubles = world == 1 ? qn_sym_doubles(n) : qn_sym_doubles_sharded(n, world, rank);
+  return OSB_OK;
+  OSB_CATCH
+}
 int osb_ctx_trim_memory(osb_ctx* ctx) {
   OSB_TRY
   C(ctx)->use();

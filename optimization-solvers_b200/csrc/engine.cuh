@@ -251,6 +251,7 @@ int qn_sym_grid(Ctx* ctx, int64_t n);
 void qn_sym_pack(Ctx* ctx, const double* H, int64_t ld, int64_t n, double* P);
 void qn_sym_set_identity(Ctx* ctx, int64_t n, double* P);
 int64_t qn_sym_doubles_sharded(int64_t n, int world, int rank);
+void qn_sym_layout(int64_t n, int world, int64_t tile, int* owner, int64_t* offset, int64_t* lpad);
 void qn_sym_set_identity_sharded(Ctx* ctx, int64_t n, double* P);
 void qn_sym_unpack_sharded(Ctx* ctx, const double* P, int64_t ld, int64_t n, double* Hfull_zeroed);
 void qn_sym_unpack(Ctx* ctx, const double* P, int64_t ld, int64_t n, double* H);

@@ -802,6 +802,20 @@ int64_t qn_sym_doubles_sharded(int64_t n, int world, int rank) {
   return symsh_local_pairs(T, world, rank) * symsh_pair_doubles(T);
 }
 
+// host-side description of the packed layouts (tests, tools): where tile `tile` of an n x n matrix lives
+void qn_sym_layout(int64_t n, int world, int64_t tile, int* owner, int64_t* offset, int64_t* lpad) {
+  const int64_t T = (n + QN_R - 1) / QN_R;
+  *lpad = sym_lpad(tile);
+  if (world <= 1) {
+    *owner = 0;
+    *offset = sym_tile_offset(tile);
+  } else {
+    const int64_t pairi = tile < T / 2 ? tile : T - 1 - tile;
+    *owner = (int)(pairi % world);
+    *offset = symsh_tile_offset(tile, T, world);
+  }
+}
+
 struct QNSymArgs {
   double* P;         // packed matrix (this rank's tiles when sharded)
   double* colpart;   // gridDim x 2 x ld per-CTA column partials (h then w)

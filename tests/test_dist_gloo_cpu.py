@@ -124,3 +124,33 @@ dist.destroy_process_group()
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_packed_symmetric_layouts_tile_the_storage_exactly():
+    """Host logic of the packed storage, single GPU and sharded by tile pairs: every tile has
+    exactly one owner, the tiles of a rank are disjoint, in bounds and leave no gap, and the ranks' loads are equal."""
+    import importlib
+    sys.path.insert(0, ROOT)
+    osb = importlib.import_module("optimization-solvers_b200")
+    for n in (16, 128, 2048, 16384):
+        T = (n + 7) // 8
+        for world in (1, 2, 4, 8):
+            if world > 1 and n // 16 < world:
+                continue
+            spans = {r: [] for r in range(world)}
+            totals = {}
+            for tile in range(T):
+                for r in range(world):
+                    owner, off, ldp, tot = osb.sym_layout(n, world, r, tile)
+                    totals[r] = tot
+                assert 0 <= owner < world and ldp >= 8 * (tile + 1) and ldp % 16 == 0
+                spans[owner].append((off, off + 8 * ldp))
+            for r in range(world):
+                sp = sorted(spans[r])
+                # (the single-GPU array carries one spare zero tile after the last one; the sharded arrays are exact)
+                assert sp[0][0] == 0 and (sp[-1][1] == totals[r] if world > 1 else sp[-1][1] <= totals[r])
+                assert all(sp[i][1] == sp[i + 1][0] for i in range(len(sp) - 1))  # no overlap, no gap
+            if world > 1:
+                assert len(set(totals.values())) == 1 or max(totals.values()) - min(totals.values()) <= 8 * (8 * T + 16)
+    with pytest.raises(osb.ErrorInputParams):
+        osb.sym_layout(24, 2, 0, 0)  # odd tile count cannot be sharded by pairs
