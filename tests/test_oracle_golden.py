@@ -164,3 +164,29 @@ def test_small_inverses(orc):
         except orc.MaxIterReached:
             pass
         assert np.allclose(s.x(), np.linalg.solve(H, g), rtol=1e-10, atol=1e-12)
+
+
+def _load_golden():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_trajectories.json")) as f:
+        return json.load(f)
+
+
+def test_oracle_reproduces_the_committed_vectors(orc):
+    """tests/golden/oracle_trajectories.json (tools/make_golden.py): the oracle of today gives the committed outcomes —
+    bit for bit where only n <= 5 vector arithmetic is involved, to 1e-12 where the host's dot / GEMV code runs."""
+    import numpy as np
+    from golden_cases import BIT_EXACT, CASES
+    gold = _load_golden()
+    assert set(gold) == set(CASES)
+    for name, script in CASES.items():
+        r, g = script(orc), gold[name]
+        assert (r["status"], int(r["k"]), r["reason"]) == (g["status"], g["k"], g["reason"]), name
+        x, gx = np.asarray(r["x"]), np.asarray(g["x"])
+        if name in BIT_EXACT:
+            assert np.array_equal(x, gx), name
+        else:
+            assert np.all(np.abs(x - gx) <= 1e-12 * max(1.0, float(np.max(np.abs(gx))))), name
+        if g["active_set"] is not None:
+            assert np.array_equal(np.asarray(r["active_set"]), np.asarray(g["active_set"])), name
