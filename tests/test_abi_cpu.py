@@ -89,3 +89,56 @@ def test_host_automaton_quirks(osb):
     t, _ = ls.step_len_scalar(lambda t, p: (t * t - t, 2 * t - 1, 0.0), 0.0, -1.0, 10, tmax_candidate=0.25)
     assert t <= 0.25
     assert osb.lib().osb_linesearch_t_max(ls._host_handle) == 0.25
+
+
+def _rosen2(x):
+    a, b = x[0], x[1]
+    t1 = b - a * a
+    t2 = 1.0 - a
+    return 100.0 * (t1 * t1) + t2 * t2, np.array([-400.0 * (a * t1) - 2.0 * t2, 200.0 * t1])
+
+
+def _quartic(x):
+    a, b = x[0], x[1]
+    return (a * a) * (a * a) + 3.0 * (b * b) + a * b, np.array([4.0 * (a * a * a) + b, 6.0 * b + a])
+
+
+def _logbarrier(x):
+    # finite only for x0 < 1: trials that leave the domain return NaN (backtracking.rs:37-41, morethuente NaN clamps)
+    a, b = x[0], x[1]
+    if a >= 1.0:
+        return float("nan"), np.array([float("nan"), float("nan")])
+    return -math.log(1.0 - a) + 0.5 * (b * b) + 0.5 * (a * a), np.array([1.0 / (1.0 - a) + a, b])
+
+
+@pytest.mark.parametrize("fname", ["rosen2", "quartic", "logbarrier"])
+def test_host_automaton_matches_oracle_on_nonquadratic_models(osb, orc, fname):
+    """The same comparison on non-quadratic 2-D models — curved valleys, quartic growth, a domain boundary that makes
+    trials return NaN — over random points, descent and non-descent directions, large and tiny scalings, and
+    non-default parameters: the automaton (the code both GPU engines run) and the oracle's restatement of
+    backtracking.rs / morethuente.rs / gll_quadratic.rs must return bit-identical steps."""
+    f = {"rosen2": _rosen2, "quartic": _quartic, "logbarrier": _logbarrier}[fname]
+    rng = np.random.default_rng(11)
+    makers = [
+        lambda m: m.BackTracking(1e-4, 0.5),
+        lambda m: m.BackTracking(0.3, 0.8),
+        lambda m: m.MoreThuente.default(),
+        lambda m: m.MoreThuente.default().with_c2(0.9).with_c1(1e-3).with_t_max(10.0),
+        lambda m: m.MoreThuente.default().with_t_min(1e-6).with_deltas(0.5, 0.66, 4.0),
+        lambda m: m.GLLQuadratic(1e-4, 5),
+    ]
+    checked = 0
+    for trial in range(60):
+        x = rng.uniform(-2.0, 0.9, 2) if fname == "logbarrier" else rng.uniform(-2.5, 2.5, 2)
+        val, g = f(x)
+        scale = [1.0, 1e-3, 37.0, 1e3][trial % 4]
+        d = -g * scale
+        if trial % 7 == 6:
+            d = rng.uniform(-1, 1, 2) * scale  # arbitrary (possibly ascent) direction
+        gd0 = float(g[0] * d[0] + g[1] * d[1])
+        for mk in makers:
+            t_ref = mk(orc).compute_step_len(x, d, f, 25)
+            t_dev, _ = mk(osb).step_len_scalar(_phi_of(f, x, d), val, gd0, 25)
+            assert (t_dev == t_ref) or (math.isnan(t_dev) and math.isnan(t_ref)), (fname, trial, t_dev, t_ref)
+            checked += 1
+    assert checked == 360
