@@ -142,3 +142,49 @@ def test_host_automaton_matches_oracle_on_nonquadratic_models(osb, orc, fname):
             assert (t_dev == t_ref) or (math.isnan(t_dev) and math.isnan(t_ref)), (fname, trial, t_dev, t_ref)
             checked += 1
     assert checked == 360
+
+
+@pytest.mark.parametrize("fname", ["quad2", "rosen2", "quartic"])
+def test_host_automaton_bounded_searches_match_oracle(osb, orc, fname):
+    """BackTrackingB (objective at the PROJECTED trial, decrease measured with ||x_t - x||^2, backtracking_b.rs:24-34,
+    52-90) and MoreThuenteB (feasible-step cap from the bounds, morethuente_b.rs:185-201) against the oracle's
+    restatement, over random boxes, interior and boundary points: bit-identical steps."""
+    f = {"quad2": quad2(9.0, True), "rosen2": _rosen2, "quartic": _quartic}[fname]
+    rng = np.random.default_rng(5)
+    n_bt = n_mt = 0
+    for trial in range(50):
+        lb = rng.uniform(-3.0, -0.5, 2)
+        ub = rng.uniform(0.5, 3.0, 2)
+        x = rng.uniform(lb, ub)
+        if trial % 5 == 0:
+            x[0] = ub[0]  # on a face
+        val, g = f(x)
+        d = -g * [1.0, 0.05, 20.0][trial % 3]
+        gd0 = float(g[0] * d[0] + g[1] * d[1])
+
+        def phi(t, projected):
+            xt = x + t * d
+            if projected:
+                xt = np.minimum(np.maximum(xt, lb), ub)
+            v, gg = f(xt)
+            dx = xt - x
+            return (v, float(gg[0] * d[0] + gg[1] * d[1]), float(dx[0] * dx[0] + dx[1] * dx[1]))
+
+        t_ref = orc.BackTrackingB(1e-4, 0.5, lb, ub).compute_step_len(x, d, f, 30)
+        t_dev, _ = osb.BackTrackingB(1e-4, 0.5, lb, ub).step_len_scalar(phi, val, gd0, 30)
+        assert t_dev == t_ref, ("BackTrackingB", fname, trial, t_dev, t_ref)
+        n_bt += 1
+        # morethuente_b.rs:185-197: largest step that keeps x + t d inside the box
+        cand = float("inf")
+        for i in range(2):
+            if d[i] > 0.0:
+                cand = min(cand, (ub[i] - x[i]) / d[i])
+            elif d[i] < 0.0:
+                cand = min(cand, (lb[i] - x[i]) / d[i])
+        mref = orc.MoreThuenteB(2).with_lower_bound(lb).with_upper_bound(ub)
+        mdev = osb.MoreThuenteB(2).with_lower_bound(lb).with_upper_bound(ub)
+        t_ref = mref.compute_step_len(x, d, f, 30)
+        t_dev, _ = mdev.step_len_scalar(phi, val, gd0, 30, tmax_candidate=cand)
+        assert (t_dev == t_ref) or (math.isnan(t_dev) and math.isnan(t_ref)), ("MoreThuenteB", fname, trial, t_dev, t_ref)
+        n_mt += 1
+    assert n_bt == n_mt == 50
