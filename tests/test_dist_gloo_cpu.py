@@ -154,3 +154,39 @@ def test_packed_symmetric_layouts_tile_the_storage_exactly():
                 assert len(set(totals.values())) == 1 or max(totals.values()) - min(totals.values()) <= 8 * (8 * T + 16)
     with pytest.raises(osb.ErrorInputParams):
         osb.sym_layout(24, 2, 0, 0)  # odd tile count cannot be sharded by pairs
+
+
+def test_snake_dealing_of_local_tiles_covers_and_balances():
+    """Restatement of the tile schedule of qn_lazy_sym_kernel<.., SHARDED> (csrc/qn_kernels.cu): a rank's tiles, in
+    decreasing length, are dealt to its CTAs in snake order.  Every local tile is visited exactly once, and the
+    heaviest CTA carries at most max(longest tile, mean + one tile) columns — the quantisation figures quoted in
+    DESIGN.md section 6 (0.865 at 8 GPUs, near 1 at 2 GPUs) follow from it."""
+    n, G = 16384, 148
+    T = n // 8
+    for world in (2, 4, 8):
+        for rank in range(world):
+            half = T // 2
+            nlp = (half - rank + world - 1) // world
+            nunits = 2 * nlp
+            grid = min(nunits, G)
+            seen, load = [], [0] * grid
+            for b in range(grid):
+                k = 0
+                while k * grid < nunits:
+                    pos = grid - 1 - b if (k & 1) else b
+                    uq = k * grid + pos
+                    k += 1
+                    if uq >= nunits:
+                        continue
+                    pairi = rank + uq * world if uq < nlp else rank + (2 * nlp - 1 - uq) * world
+                    tile = T - 1 - pairi if uq < nlp else pairi
+                    seen.append(tile)
+                    load[b] += 8 * (tile + 1)
+            owned = sorted(t for t in range(T) if min(t, T - 1 - t) % world == rank)
+            assert sorted(seen) == owned
+            mean = sum(load) / grid
+            assert max(load) <= max(n, mean + n / 2), (world, rank, max(load), mean)
+            if world == 2:
+                assert max(load) / mean < 1.03
+            if world == 8:
+                assert abs(mean / max(load) - 0.865) < 0.01
