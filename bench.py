@@ -130,7 +130,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; libgomp reads the variable when the oracle library is loaded
+    # (measured: with the variable at 1, asking for 8 threads afterwards runs 10x slower than 8 threads should)
+    os.environ["OMP_NUM_THREADS"] = str(threads)
     from oracle import oracle as O
     O.build()
     threads = min(threads, max(1, O.lib().orc_max_threads()))

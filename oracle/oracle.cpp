@@ -1143,7 +1143,9 @@ void orc_set_threads(int t) {
 }
 int orc_max_threads() {
 #ifdef _OPENMP
-  return omp_get_max_threads();
+  // processors available to the process — NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1, and the
+  // reference arm of bench.py is asked to use every host thread it can; orc_set_threads() overrides the environment
+  return omp_get_num_procs();
 #else
   return 1;
 #endif
