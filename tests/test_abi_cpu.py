@@ -188,3 +188,22 @@ def test_host_automaton_bounded_searches_match_oracle(osb, orc, fname):
         assert (t_dev == t_ref) or (math.isnan(t_dev) and math.isnan(t_ref)), ("MoreThuenteB", fname, trial, t_dev, t_ref)
         n_mt += 1
     assert n_bt == n_mt == 50
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the CUDA arm) needs no GPU: one JSON line with the
+    metric, unit, config and the cpu_baseline / e2e objects of the measurement contract."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "bfgs_iterations_per_second_n16384_f64"
+    assert line["unit"] == "iterations/s" and line["higher_is_better"] is True and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "sample" in line["cpu_baseline"]
+    assert line["e2e"] == {"value": line["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["n"] == 16384 and "workload" in line["config"]
