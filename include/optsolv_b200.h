@@ -90,6 +90,11 @@ int osb_ctx_create_dist(int device, int rank, int world, const void* nccl_unique
  * instead of NCCL calls. */
 int osb_ctx_ipc_handle(osb_ctx* ctx, void* out64);
 int osb_ctx_ipc_connect(osb_ctx* ctx, const void* handles_world_x_64);
+/* Drops the peer mappings and the exchange region again (p2p off): EVERY rank must call it when the connect did not
+ * succeed on every rank, otherwise the connected ranks would wait in the fused exchange for a rank that sits in
+ * NCCL.  (The in-kernel waits are bounded all the same: ~5 s without progress end the solve with
+ * OSB_ABNORMAL_TERMINATION.) */
+int osb_ctx_ipc_close(osb_ctx* ctx);
 /* Index-range sharding of the O(n) solvers (world > 1): when on, GradientDescent / ProjectedGradientDescent /
  * SpectralProjectedGradient created on this context own a contiguous SLICE of the variables (their n, x0, lb, ub are
  * the local ones; objectives must be block-functor objectives created for the same slice), and every scalar of
@@ -204,16 +209,26 @@ typedef void (*osb_callback_fn)(void* user, osb_solver* s);
 int osb_minimize(osb_solver* s, osb_linesearch* ls, osb_objective* obj, int64_t max_iter_solver,
                  int64_t max_iter_line_search, osb_callback_fn callback, void* user);
 
-/* options (before minimize):
- *   "engine"        0 = auto (device-resident control when solver/line search/objective allow it),
- *                   1 = host-driven control only, 2 = device-resident only (error if unsupported)
- *   "record_trace"  1 = keep per-iteration (f, t, s_norm, y_norm) for osb_solver_trace
- *   "qn_schedule"   0 = eager (h = H y, then fused update: 3 n^2 8 B per iteration),
- *                   1 = lazy (one read-modify-write per iteration: 2 n^2 8 B; BFGS/DFP, device engine)
- *   "use_p2p"       lazy schedule on an IPC-connected multi-GPU context: 1 = fused peer-memory all-gather (default), 0 = NCCL
- *   "head_kernel"   device engine head: 0 = 8-CTA cluster (default), 1 = single CTA + shared memory, 2 = generic
- *   "qn_kernel"     dense quasi-Newton kernel variant: 0 = default, see DESIGN.md
- *   "profile_kernels" 1 = bracket the two H passes with CUDA events (osb_solver_kernel_timing) */
+/* options (set before minimize; every one has a default that needs no call):
+ *   "engine"             0 = auto (default: device-resident control whenever solver, line search and objective allow it),
+ *                        1 = host-driven control only, 2 = device-resident only (OSB_ERR_UNSUPPORTED if it does not apply)
+ *   "qn_schedule"       -1 = auto (default: lazy for BFGS / DFP with n > 5, eager otherwise),
+ *                        0 = eager (h = H y, then fused update: 3 n^2 8 B per iteration),
+ *                        1 = lazy (one read-modify-write per iteration, the update of iteration k is applied by the pass of
+ *                            iteration k + 1: 2 n^2 8 B; BFGS / DFP)
+ *   "qn_storage"        -1 = auto (default: packed whenever the lazy schedule runs), 0 = full n x n row-major,
+ *                        1 = packed lower triangle in 8-row tiles (n^2 8 B per iteration; on several GPUs sharded by tile
+ *                            pairs, which needs the peer-memory exchange)
+ *   "callback_run_ahead" -1 / 1 = (default) the callback of iteration k is delivered from pinned snapshots of x, g, f, k,
+ *                        s_norm, y_norm while the device already runs iteration k + 1; any other getter inside such a
+ *                        callback returns OSB_ERR_UNSUPPORTED.  0 = the device waits for the callback (every getter works)
+ *   "record_trace"       1 = keep per-iteration (f, t, s_norm, y_norm) for osb_solver_trace
+ *   "use_p2p"            multi-GPU: 1 = (default) fused peer-memory exchange when the context is IPC-connected, 0 = NCCL
+ *   "head_kernel"        device engine head: 0 = 8-CTA cluster (default), 1 = single CTA + shared memory, 2 = generic
+ *   "qn_kernel"          kernel variant of the H pass (diagnostics, default 0).  Full storage: 1 = TMA-staged ring.  Packed
+ *                        storage: bit 0 = two 256-thread CTAs per SM, bit 1 = ping-pong (out-of-place) storage,
+ *                        bit 2 = zero-first column partials (round-1 behaviour)
+ *   "profile_kernels"    1 = bracket the H pass(es) with CUDA events (osb_solver_kernel_timing) */
 int osb_solver_set_option(osb_solver* s, const char* name, int64_t value);
 int osb_solver_set_lambdas(osb_solver* s, double lambda_min, double lambda_max); /* spg.rs:23-27 */
 
@@ -241,6 +256,10 @@ int osb_solver_trace(const osb_solver* s, double* f, double* t, double* s_norm, 
 /* with option "profile_kernels" = 1: mean device ms (CUDA-event pairs on the launching stream) of
  * out[0] pass 1 (h = H y), out[1] pass 2 (fused update) over the last minimize; out[2] = #iterations timed */
 int osb_solver_kernel_timing(const osb_solver* s, double out[3]);
+/* which path the last minimize() took (the defaults are "auto"): out[0] engine (1 host-driven, 2 device-resident control),
+ * out[1] schedule in force (0 eager, 1 lazy), out[2] storage in force (0 full n x n, 1 packed lower triangle), out[3] packed
+ * triangle sharded over the ranks, out[4] fused peer-memory exchange used, out[5] ranks, out[6] kernel variant, out[7] 0 */
+int osb_solver_path_info(const osb_solver* s, int64_t out[8]);
 /* device time (ms, CUDA events on the context stream) and outer iterations of the last minimize */
 int osb_solver_last_timing(const osb_solver* s, double* ms, int64_t* iterations);
 

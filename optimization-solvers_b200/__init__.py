@@ -53,7 +53,7 @@ def lib():
             "osb_last_error_string": (C.c_char_p, []), "osb_version": (C.c_char_p, []),
             "osb_ctx_create": (ci, [ci, pp]), "osb_nccl_unique_id": (ci, [_vp]),
             "osb_ctx_create_dist": (ci, [ci, ci, ci, _vp, pp]), "osb_ctx_destroy": (None, [_vp]),
-            "osb_ctx_ipc_handle": (ci, [_vp, _vp]), "osb_ctx_ipc_connect": (ci, [_vp, _vp]),
+            "osb_ctx_ipc_handle": (ci, [_vp, _vp]), "osb_ctx_ipc_connect": (ci, [_vp, _vp]), "osb_ctx_ipc_close": (ci, [_vp]),
             "osb_ctx_rank": (ci, [_vp]), "osb_ctx_world": (ci, [_vp]), "osb_ctx_synchronize": (ci, [_vp]),
             "osb_ctx_stream": (_vp, [_vp]), "osb_ctx_counters": (ci, [_vp, C.POINTER(i64)]),
             "osb_objective_create_dense_quadratic": (ci, [_vp, i64, _dp, _dp, pp]),
@@ -95,6 +95,7 @@ def lib():
             "osb_solver_trace_len": (i64, [_vp]), "osb_solver_trace": (ci, [_vp, _dp, _dp, _dp, _dp]),
             "osb_solver_last_timing": (ci, [_vp, _dp, C.POINTER(i64)]),
             "osb_solver_kernel_timing": (ci, [_vp, _dp]),
+            "osb_solver_path_info": (ci, [_vp, C.POINTER(i64)]),
             "osb_batched_bfgs_rosenbrock": (ci, [_vp, i64, i64, _dp, dbl, i64, i64, dbl, dbl, _dp, _dp, i32p, i32p,
                                                  i32p, _dp]),
             "osb_batched_bfgs_rosenbrock_generated": (ci, [_vp, i64, i64, i64, dbl, i64, i64, dbl, dbl, _dp, _dp,
@@ -324,6 +325,10 @@ class Context:
             ok = 0
         dist.all_gather_object(oks, ok)
         self.p2p = bool(all(oks))
+        if not self.p2p:
+            # not unanimous: the ranks that did connect must drop their mappings too, or they would take the fused
+            # peer-memory path and wait for a rank that sits in an NCCL call
+            lib().osb_ctx_ipc_close(self.handle)
         if not self.p2p and strict:
             raise err if err is not None else DeviceError("peer-memory exchange unavailable on another rank")
         return self.p2p
@@ -858,6 +863,21 @@ class _Solver:
         ms, it = C.c_double(), C.c_int64()
         lib().osb_solver_last_timing(self.handle, C.byref(ms), C.byref(it))
         return ms.value, it.value
+
+    def path_info(self):
+        """Which path the last minimize() took (the options default to auto): see osb_solver_path_info."""
+        out = (C.c_int64 * 8)()
+        lib().osb_solver_path_info(self.handle, out)
+        eng, sched, stor, shard, p2p, world, variant = (int(out[i]) for i in range(7))
+        return dict(engine={1: "host-driven control", 2: "device-resident control"}.get(eng, "none"), schedule=sched, storage=stor,
+                    schedule_name=("lazy: 1 RMW pass of the stored matrix per iteration" if sched == 1 else "eager: gemv + fused update (3 n^2 8 B)"),
+                    storage_name=("packed lower triangle, 8-row tiles (n^2 8 B per pass)" if stor == 1 else "full n x n row-major"),
+                    sharded_packed=bool(shard), p2p=bool(p2p), world=world, variant=variant,
+                    parallelism=("1 GPU" if world == 1 else
+                                 "packed triangle sharded by tile pairs over %d GPUs; per-rank {h, w} contributions stored into every "
+                                 "peer's slot (NVLink stores + flags), summed in rank order" % world if shard else
+                                 "row-block sharded H over %d GPUs; %s" % (world, "peer-memory all-gather fused into the pass kernel"
+                                                                           if p2p else "NCCL all-gather of the h / w slices")))
 
     def kernel_timing(self):
         out = (C.c_double * 3)()

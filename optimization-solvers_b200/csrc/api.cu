@@ -14,7 +14,7 @@ void ctx_ipc_close(Ctx* ctx);
 }  // namespace osb
 
 using namespace osb;
-namespace osb { double bench_syrk_dmma(Ctx* ctx, Objective* obj, int reps); extern long long* g_head_tdbg; void exp_launch(Ctx* ctx, int which, double* M, double* N, int64_t total_doubles); }
+namespace osb { double bench_syrk_dmma(Ctx* ctx, Objective* obj, int reps); }
 
 #define OSB_TRY try {
 #define OSB_CATCH                                  \
@@ -77,6 +77,14 @@ int osb_ctx_ipc_handle(osb_ctx* ctx, void* out64) {
 int osb_ctx_ipc_connect(osb_ctx* ctx, const void* handles) {
   OSB_TRY
   ctx_ipc_connect(C(ctx), handles);
+  return OSB_OK;
+  OSB_CATCH
+}
+int osb_ctx_ipc_close(osb_ctx* ctx) {
+  OSB_TRY
+  C(ctx)->use();
+  C(ctx)->sync();
+  ctx_ipc_close(C(ctx));
   return OSB_OK;
   OSB_CATCH
 }
@@ -398,16 +406,10 @@ int osb_solver_set_option(osb_solver* s, const char* name, int64_t value) {
   else if (nm == "record_trace") S(s)->record_trace = (int)value;
   else if (nm == "callback_run_ahead") S(s)->callback_run_ahead = (int)value;
   else if (nm == "qn_kernel") S(s)->qn_variant = (int)value;
-  else if (nm == "qn_schedule") S(s)->qn_schedule = (int)value;
-  else if (nm == "qn_storage") S(s)->qn_storage = (int)value;
+  else if (nm == "qn_schedule") S(s)->opt_schedule = (int)value;
+  else if (nm == "qn_storage") S(s)->opt_storage = (int)value;
   else if (nm == "use_p2p") S(s)->use_p2p = (int)value;
-  else if (nm == "head_debug") {
-    if (value && !g_head_tdbg) {
-      OSB_CUDA(cudaMalloc(&g_head_tdbg, 32 * sizeof(long long)));
-      OSB_CUDA(cudaMemset(g_head_tdbg, 0, 32 * sizeof(long long)));
-    }
-    if (!value) g_head_tdbg = nullptr;
-  } else if (nm == "head_kernel") S(s)->head_variant = (int)value;
+  else if (nm == "head_kernel") S(s)->head_variant = (int)value;
   else if (nm == "profile_kernels") S(s)->profile_kernels = (int)value;
   else throw Error(OSB_ERROR_INPUT_PARAMS, "unknown option " + nm);
   return OSB_OK;
@@ -437,6 +439,9 @@ int osb_solver_x(osb_solver* s, double* out) {
 int osb_solver_set_x(osb_solver* s, const double* in) {
   OSB_TRY
   Solver* p = S(s);
+  OSB_REQUIRE(p->cb_x_mirror == nullptr, OSB_ERR_UNSUPPORTED,
+              "inside a run-ahead callback only x, f, grad, k, s_norm, y_norm are available (the device is already one "
+              "iteration ahead): set option callback_run_ahead = 0 for callbacks that need anything else");
   p->ctx->use();
   p->x.upload(in, p->n, p->ctx->stream);
   p->ctx->sync();
@@ -461,6 +466,10 @@ int osb_solver_f(osb_solver* s, double* f_out) {
 int osb_solver_grad(osb_solver* s, double* out) {
   OSB_TRY
   Solver* p = S(s);
+  if (p->cb_g_mirror) {
+    std::memcpy(out, p->cb_g_mirror, sizeof(double) * (size_t)p->n);
+    return OSB_OK;
+  }
   p->ctx->use();
   p->g.download(out, p->n, p->ctx->stream);
   p->ctx->sync();
@@ -472,6 +481,9 @@ double osb_solver_y_norm(const osb_solver* s) { return S(s)->has_y ? S(s)->y_nor
 int osb_solver_clear_norms(osb_solver* s) {
   OSB_TRY
   Solver* p = S(s);
+  OSB_REQUIRE(p->cb_x_mirror == nullptr, OSB_ERR_UNSUPPORTED,
+              "inside a run-ahead callback only x, f, grad, k, s_norm, y_norm are available (the device is already one "
+              "iteration ahead): set option callback_run_ahead = 0 for callbacks that need anything else");
   p->ctx->use();
   p->fetch_state();
   p->h_state->has_s = p->h_state->has_y = 0;
@@ -485,6 +497,9 @@ double osb_solver_decrement_squared(const osb_solver* s) { return S(s)->has_dec 
 int osb_solver_inv_hessian(osb_solver* s, double* out) {
   OSB_TRY
   Solver* p = S(s);
+  OSB_REQUIRE(p->cb_x_mirror == nullptr, OSB_ERR_UNSUPPORTED,
+              "inside a run-ahead callback only x, f, grad, k, s_norm, y_norm are available (the device is already one "
+              "iteration ahead): set option callback_run_ahead = 0 for callbacks that need anything else");
   OSB_REQUIRE(p->is_qn || p->kind == OSB_PNORM, OSB_ERROR_INPUT_PARAMS, "solver holds no n x n matrix");
   p->ctx->use();
   p->flush_pending();
@@ -499,6 +514,9 @@ int osb_solver_inv_hessian(osb_solver* s, double* out) {
 int osb_solver_set_inv_hessian(osb_solver* s, const double* in) {
   OSB_TRY
   Solver* p = S(s);
+  OSB_REQUIRE(p->cb_x_mirror == nullptr, OSB_ERR_UNSUPPORTED,
+              "inside a run-ahead callback only x, f, grad, k, s_norm, y_norm are available (the device is already one "
+              "iteration ahead): set option callback_run_ahead = 0 for callbacks that need anything else");
   OSB_REQUIRE(p->is_qn || p->kind == OSB_PNORM, OSB_ERROR_INPUT_PARAMS, "solver holds no n x n matrix");
   p->ctx->use();
   p->flush_pending();
@@ -511,6 +529,11 @@ int osb_solver_set_inv_hessian(osb_solver* s, const double* in) {
           sym = false;
           break;
         }
+    // BFGS / DFP / SR1 are implemented in their symmetric rank-2 / rank-1 forms (H y serves as row AND column factor):
+    // with a non-symmetric H the reference's products (bfgs.rs:121-124, dfp.rs:120) would need H^T y as well.  The
+    // crate has no setter for approx_inv_hessian (it starts from I and stays symmetric), so this is an input error.
+    OSB_REQUIRE(sym || !p->is_qn || p->qn_kind == QN_BROYDEN, OSB_ERROR_INPUT_PARAMS,
+                "BFGS / DFP / SR1 need a symmetric inverse-Hessian approximation (Broyden and PnormDescent accept any matrix)");
     p->h_symmetric = sym;
   }
   OSB_CUDA(cudaMemcpy2DAsync(p->H.p, p->ld * sizeof(double), in + p->row0 * p->n, p->n * sizeof(double), p->n * sizeof(double),
@@ -523,6 +546,9 @@ int osb_solver_set_inv_hessian(osb_solver* s, const double* in) {
 int osb_solver_active_set(osb_solver* s, uint8_t* out) {
   OSB_TRY
   Solver* p = S(s);
+  OSB_REQUIRE(p->cb_x_mirror == nullptr, OSB_ERR_UNSUPPORTED,
+              "inside a run-ahead callback only x, f, grad, k, s_norm, y_norm are available (the device is already one "
+              "iteration ahead): set option callback_run_ahead = 0 for callbacks that need anything else");
   OSB_REQUIRE(p->bounded, OSB_ERROR_INPUT_PARAMS, "solver has no bounds");
   p->ctx->use();
   uint8_t* d_out = nullptr;
@@ -551,10 +577,16 @@ int osb_solver_kernel_timing(const osb_solver* s, double out[3]) {
   out[2] = S(s)->prof_ms[2];
   return OSB_OK;
 }
-int osb_debug_head_stamps(long long out[32]) {
-  if (!g_head_tdbg) return OSB_ERROR_INPUT_PARAMS;
-  cudaDeviceSynchronize();
-  cudaMemcpy(out, g_head_tdbg, 32 * sizeof(long long), cudaMemcpyDeviceToHost);
+int osb_solver_path_info(const osb_solver* s, int64_t out[8]) {
+  const Solver* p = S(s);
+  out[0] = p->last_engine;
+  out[1] = p->qn_schedule;
+  out[2] = p->qn_storage;
+  out[3] = p->last_sym_sharded ? 1 : 0;
+  out[4] = p->last_p2p ? 1 : 0;
+  out[5] = p->ctx->world;
+  out[6] = p->qn_variant;
+  out[7] = 0;
   return OSB_OK;
 }
 int osb_solver_last_timing(const osb_solver* s, double* ms, int64_t* iters) {
@@ -619,7 +651,7 @@ int osb_bench_qn_kernel(osb_ctx* ctxh, int which, int64_t n, int reps, int varia
     ctx->sync();
   }
   if (which == 2) scratch.alloc(((n + 63) / 64) * ld);
-  if (which == 3 || which >= 10) H2.alloc(qn_rows_padded(n) * ld);
+  if (which == 3) H2.alloc(qn_rows_padded(n) * ld);
   cudaEvent_t e0, e1;
   OSB_CUDA(cudaEventCreate(&e0));
   OSB_CUDA(cudaEventCreate(&e1));
@@ -627,7 +659,6 @@ int osb_bench_qn_kernel(osb_ctx* ctxh, int which, int64_t n, int reps, int varia
     if (which == 0) qn_launch_gemv(ctx, H.p, ld, n, 0, st, a.p, out.p, b.p, out.p, variant);
     else if (which == 1) qn_launch_update(ctx, QN_BFGS, H.p, ld, n, 0, st, a.p, b.p, c.p, c.p, out.p, variant);
     else if (which == 2) qn_launch_gemvT(ctx, H.p, ld, n, 0, st, a.p, out.p, scratch.p);
-    else if (which >= 10) exp_launch(ctx, which, H.p, H2.p, n * ld);
     else OSB_CUDA(cudaMemcpyAsync(H2.p, H.p, sizeof(double) * (size_t)(n * ld), cudaMemcpyDeviceToDevice, ctx->stream));
   };
   for (int i = 0; i < 3; ++i) run();

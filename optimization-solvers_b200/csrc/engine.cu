@@ -264,6 +264,7 @@ Solver::~Solver() {
   pool_put(1, sizeof(DevState), h_state);
   pool_put(1, 2 * sizeof(DevState), cb_snap);
   pool_put(1, 2 * sizeof(double) * (size_t)ld, cb_xsnap);
+  pool_put(1, 2 * sizeof(double) * (size_t)ld, cb_gsnap);
   pool_put(0, sizeof(LSParams), d_ls_buf);
   pool_put(1, 2 * sizeof(DevState), poll_snap);
   if (ev0) cudaEventDestroy(ev0);
@@ -289,6 +290,7 @@ void Solver::compute_conv_scalar(Objective*) {
 
 // dense SPD solve for the Newton family (newton.cu)
 int newton_solve(Ctx* ctx, int64_t n, int64_t ld, const double* hess, double* chol, const double* g, double* w_out);
+int newton_solve_lu(Ctx* ctx, int64_t n, int64_t ld, const double* hess, double* lu, int* perm, double* tmp, const double* rhs, double* w_out);
 
 int Solver::compute_direction(Objective*, LineSearch* ls) {
   double* out3 = &d_state->gd0;  // {gd0, tmaxc, dinf}
@@ -320,13 +322,29 @@ int Solver::compute_direction(Objective*, LineSearch* ls) {
       vec_projected_direction(ctx, n, x.p, u.p, 1.0, false, lb.p, ub.p, g.p, d.p, out3);  // bfgs_b.rs:72-75
       break;
     case OSB_NEWTON: {
-      // newton/mod.rs:31-47.  The reference inverts with LU; for the SPD Hessians of the configs a
-      // Cholesky solve gives the same direction to O(cond * eps); a non-SPD Hessian is reported.
+      // newton/mod.rs:31-47.  The reference inverts with LU (try_inverse); for the SPD Hessians of the configs a
+      // Cholesky solve gives the same direction to O(cond * eps).  A Hessian that is not SPD goes through LU with
+      // partial pivoting like the reference's; a singular one (exact zero pivot) takes d = -g and leaves the
+      // decrement untouched (newton/mod.rs:43-46).  cholesky().unwrap() panics belong to ProjectedNewton / SPN only.
+      newton_singular = false;
+      bool use_lu = false;
       int rc = newton_solve(ctx, n, ld, hess.p, chol.p, g.p, w.p);
+      if (rc == OSB_PANIC_NOT_SPD) {
+        use_lu = true;
+        if (!lu_perm.p) lu_perm.alloc(ld);  // n ints + n doubles of scratch
+        int* perm = reinterpret_cast<int*>(lu_perm.p);
+        rc = newton_solve_lu(ctx, n, ld, hess.p, chol.p, perm, xt.p, g.p, w.p);
+        if (rc == OSB_PANIC_NOT_SPD) {  // singular
+          newton_singular = true;
+          vec_neg(ctx, n, g.p, d.p, g.p, out3);
+          break;
+        }
+      }
       if (rc != OSB_OK) return rc;
       vec_neg(ctx, n, w.p, d.p, g.p, out3);  // d = -(H^-1 g)
       // decrement^2 = (H^-1 d) . d
-      rc = newton_solve(ctx, n, ld, nullptr, chol.p, d.p, w.p);
+      if (use_lu) rc = newton_solve_lu(ctx, n, ld, nullptr, chol.p, reinterpret_cast<int*>(lu_perm.p), xt.p, d.p, w.p);
+      else rc = newton_solve(ctx, n, ld, nullptr, chol.p, d.p, w.p);
       if (rc != OSB_OK) return rc;
       vec_dot(ctx, n, w.p, d.p, &d_state->dinf);
       break;
@@ -386,8 +404,20 @@ void Solver::ensure_full() {
   H_virtual_identity = false;
 }
 void ctx_all_reduce_sum(Ctx* ctx, double* buf, int64_t count);  // dist.cu
+void Solver::sym_settle_pingpong() {
+  if (!sym_pingpong_dirty) return;
+  fetch_state();
+  if (h_state->pp) {
+    std::swap(Hsym.p, Hsym2.p);
+    h_state->pp = 0;
+    OSB_CUDA(cudaMemcpyAsync(&d_state->pp, &h_state->pp, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->sync();
+  }
+  sym_pingpong_dirty = false;
+}
 void Solver::sym_to_full() {
   if (!sym_current) return;
+  sym_settle_pingpong();
   ensure_full();
   if (ctx->world > 1) {
     // tile pairs are spread over the ranks: every rank unpacks its tiles into a zeroed n x n scratch (both triangles),
@@ -451,10 +481,7 @@ void Solver::qn_after_step() {
     // packed symmetric storage: the pass moves n^2 * 8 B (read + write of the lower triangle).  A pending
     // update means "the stored matrix lags by one rank-2 term": packing the lagging matrix keeps that meaning.
     if (!sym_current) {
-      if (Hsym.p == nullptr) {
-        Hsym.alloc_pooled(sym_sharded ? qn_sym_doubles_sharded(n, ctx->world, ctx->rank) : qn_sym_doubles(n));
-        colpart.alloc_pooled((int64_t)qn_sym_grid(ctx, n) * 2 * ld);
-      }
+      if (Hsym.p == nullptr) Hsym.alloc_pooled(sym_sharded ? qn_sym_doubles_sharded(n, ctx->world, ctx->rank) : qn_sym_doubles(n));
       if (H_virtual_identity) {
         if (sym_sharded) qn_sym_set_identity_sharded(ctx, n, Hsym.p);
         else qn_sym_set_identity(ctx, n, Hsym.p);
@@ -474,12 +501,20 @@ void Solver::qn_after_step() {
       ctx->counters[4]++;  // one fused exchange
       ctx->counters[5]++;  // passes over the sharded packed triangle
     }
+    const int pgrid = qn_sym_grid(ctx, n, qn_variant);
+    if (colpart.p == nullptr || colpart_grid != pgrid) {
+      colpart.alloc_pooled((int64_t)pgrid * 2 * ld);
+      colpart_grid = pgrid;
+    }
+    const bool pingpong = (qn_variant & 2) != 0;
+    if (pingpong && Hsym2.n != Hsym.n) Hsym2.alloc_pooled(Hsym.n);
     prof_mark();  // slot 0: the streaming pass, slot 1: the column fold + epilogue
-    qn_launch_lazy_sym(ctx, a, Hsym.p, colpart.p, n, ld, 0);
+    qn_launch_lazy_sym(ctx, a, Hsym.p, pingpong ? Hsym2.p : Hsym.p, colpart.p, n, ld, 0, qn_variant);
     prof_mark();
     prof_mark();
-    qn_launch_lazy_sym(ctx, a, Hsym.p, colpart.p, n, ld, 1);
+    qn_launch_lazy_sym(ctx, a, Hsym.p, pingpong ? Hsym2.p : Hsym.p, colpart.p, n, ld, 1, qn_variant);
     prof_mark();
+    sym_pingpong_dirty = pingpong;  // which buffer is current is DevState.pp until sym_settle_pingpong()
     lazy_used = true;
     u_valid = true;
     return;
@@ -538,8 +573,32 @@ bool Solver::device_engine_supported(const LineSearch* ls, const Objective* obj)
   return true;
 }
 
+// Options in force for this minimize() call.  Auto (-1) = the fast path wherever it applies: the lazy schedule on the
+// packed lower triangle for BFGS / DFP (their H stays exactly symmetric), the eager schedule for Broyden / SR1.
+void Solver::resolve_options() {
+  if (!is_qn) return;
+  const bool sym_kind = (qn_kind == QN_BFGS || qn_kind == QN_DFP) && h_symmetric && n > QN_SMALL_N;
+  qn_schedule = opt_schedule < 0 ? (sym_kind ? 1 : 0) : opt_schedule;
+  qn_storage = opt_storage < 0 ? ((qn_schedule == 1 && sym_kind) ? 1 : 0) : opt_storage;
+}
+
+// u = H g from scratch: only when no H pass has produced it (first iteration, after set_x / set_inv_hessian)
+void Solver::recompute_u() {
+  flush_pending();  // needs the exact H
+  if (H_virtual_identity) {  // H = I: u = g
+    OSB_CUDA(cudaMemcpyAsync(u.p, g.p, sizeof(double) * (size_t)ld, cudaMemcpyDeviceToDevice, ctx->stream));
+  } else {
+    ensure_full();
+    if (n <= QN_SMALL_N && ctx->world == 1) qn_small_gemv(ctx, n, ld, H.p, g.p, u.p);
+    else qn_launch_gemv(ctx, H.p, ld, nrows, row0, nullptr, g.p, u.p, nullptr, nullptr, qn_variant);
+    if (ctx->world > 1) ctx->all_gather_inplace(u.p, nrows);
+  }
+  u_valid = true;
+}
+
 int Solver::minimize(LineSearch* ls, Objective* obj, int64_t max_iter, int64_t max_ls, osb_callback_fn cb, void* user) {
   ctx->use();
+  resolve_options();
   OSB_REQUIRE(obj->n == n, OSB_ERROR_INPUT_PARAMS, "objective dimension does not match the solver");
   OSB_REQUIRE(!kind_needs_hessian(kind) || obj->provides_hessian(), OSB_PANIC_NO_HESSIAN, "Hessian not available in the oracle");
   if ((ls->p.kind == LS_BACKTRACKING_B || ls->p.kind == LS_MORETHUENTE_B))
@@ -549,10 +608,17 @@ int Solver::minimize(LineSearch* ls, Objective* obj, int64_t max_iter, int64_t m
               "device-resident engine needs a quasi-Newton solver and a block-functor objective");
   OSB_CUDA(cudaEventRecord(ev0, ctx->stream));
   int rc;
-  if (dev_ok && engine != 1) rc = minimize_device(ls, obj, max_iter, max_ls, cb, user);
-  else rc = minimize_host(ls, obj, max_iter, max_ls, cb, user);
+  last_sym_sharded = last_p2p = false;
+  if (dev_ok && engine != 1) {
+    last_engine = 2;
+    rc = minimize_device(ls, obj, max_iter, max_ls, cb, user);
+  } else {
+    last_engine = 1;
+    rc = minimize_host(ls, obj, max_iter, max_ls, cb, user);
+  }
   OSB_CUDA(cudaEventRecord(ev1, ctx->stream));
   OSB_CUDA(cudaEventSynchronize(ev1));
+  sym_settle_pingpong();
   float ms = 0.f;
   OSB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
   last_ms = ms;
@@ -562,7 +628,7 @@ int Solver::minimize(LineSearch* ls, Objective* obj, int64_t max_iter, int64_t m
 }
 
 int Solver::minimize_host(LineSearch* ls, Objective* obj, int64_t max_iter, int64_t max_ls, osb_callback_fn cb, void* user) {
-  if (is_qn) {
+  if (is_qn && qn_schedule != 1) {  // eager: works on the exact, full matrix (lazy: the stored matrix may lag / be packed)
     flush_pending();
     ensure_full();
   }
@@ -582,12 +648,7 @@ int Solver::minimize_host(LineSearch* ls, Objective* obj, int64_t max_iter, int6
       have_hess = needs_h;
       u_valid = false;
     }
-    if (is_qn && !u_valid) {
-      if (n <= QN_SMALL_N && ctx->world == 1) qn_small_gemv(ctx, n, ld, H.p, g.p, u.p);
-      else qn_launch_gemv(ctx, H.p, ld, nrows, row0, nullptr, g.p, u.p, nullptr, nullptr, qn_variant);
-      if (ctx->world > 1) ctx->all_gather_inplace(u.p, nrows);
-      u_valid = true;
-    }
+    if (is_qn && !u_valid) recompute_u();
     compute_conv_scalar(obj);
     bool dir_done = false;
     if (!needs_h) {  // cheap directions are issued speculatively so that one fetch serves both decisions
@@ -623,7 +684,7 @@ int Solver::minimize_host(LineSearch* ls, Objective* obj, int64_t max_iter, int6
       int rc = compute_direction(obj, ls);
       if (rc != OSB_OK) return rc;
       fetch_state();
-      if (kind == OSB_NEWTON) {
+      if (kind == OSB_NEWTON && !newton_singular) {
         decrement_squared = h_state->dinf;
         has_dec = true;
       }
@@ -708,18 +769,7 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
     have_eval = true;
     u_valid = false;
   }
-  if (!u_valid) {
-    flush_pending();  // u = H g needs the exact H
-    if (H_virtual_identity) {  // H = I: u = g
-      OSB_CUDA(cudaMemcpyAsync(u.p, g.p, sizeof(double) * (size_t)ld, cudaMemcpyDeviceToDevice, stm));
-    } else {
-      ensure_full();
-      if (n <= QN_SMALL_N && ctx->world == 1) qn_small_gemv(ctx, n, ld, H.p, g.p, u.p);
-      else qn_launch_gemv(ctx, H.p, ld, nrows, row0, nullptr, g.p, u.p, nullptr, nullptr, qn_variant);
-      if (ctx->world > 1) ctx->all_gather_inplace(u.p, nrows);
-    }
-    u_valid = true;
-  }
+  if (!u_valid) recompute_u();
   // control block: keep f / norms, reset the run flags
   fetch_state();
   h_state->k = 0;
@@ -753,8 +803,9 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
                 n % 16 == 0 && n <= XSLOT_LD && (n / 16) >= ctx->world && (H_virtual_identity || sym_current) &&
                 qn_device_head_is_cluster(obj->functor_kind(), n, head_variant);
   if (!sym_sharded && sym_current && ctx->world > 1) sym_to_full();
-  static const bool no_defer = getenv("OSB_NO_DEFER") != nullptr;  // experiment switch
-  defer_epi = !no_defer && qn_schedule == 1 && (qn_kind == QN_BFGS || qn_kind == QN_DFP) && n > QN_SMALL_N &&
+  last_sym_sharded = sym_sharded;
+  last_p2p = epi_p2p;
+  defer_epi = qn_schedule == 1 && (qn_kind == QN_BFGS || qn_kind == QN_DFP) && n > QN_SMALL_N &&
               (qn_storage == 1 || qn_variant == 0) &&
               qn_device_head_is_cluster(obj->functor_kind(), n, head_variant);
   // ---- run-ahead delivery of callbacks / trace records (see engine.cuh: callback_run_ahead)
@@ -766,6 +817,7 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
     if (!cb_snap) {
       cb_snap = (DevState*)pool_get(1, 2 * sizeof(DevState));
       cb_xsnap = (double*)pool_get(1, 2 * sizeof(double) * (size_t)ld);
+      cb_gsnap = (double*)pool_get(1, 2 * sizeof(double) * (size_t)ld);
     }
     OSB_CUDA(cudaEventCreateWithFlags(&cbev[0], cudaEventDisableTiming));
     OSB_CUDA(cudaEventCreateWithFlags(&cbev[1], cudaEventDisableTiming));
@@ -785,17 +837,15 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
     cb_f_before = sn.f;
     if (cb) {
       cb_x_mirror = cb_xsnap + (size_t)sl * ld;
+      cb_g_mirror = cb_gsnap + (size_t)sl * ld;
       cb_state_mirror = &cb_snap[sl];
       cb(user, reinterpret_cast<osb_solver*>(this));
       cb_x_mirror = nullptr;
+      cb_g_mirror = nullptr;
       cb_state_mirror = nullptr;
     }
     return true;
   };
-  if (!defer_epi && sym_sharded) {  // (only with the OSB_NO_DEFER experiment switch)
-    sym_sharded = false;
-    sym_to_full();
-  }
   for (int64_t it = 0; it < max_iter && !stop; ++it) {
     qn_device_launch_head(ctx, obj->functor_kind(), obj->functor_ptr(0), obj->functor_ptr(1), bounded, d_ls, n, tol, max_ls,
                           d_state, x.p, g.p, d.p, xt.p, gt.p, s.p, y.p, u.p, bounded ? lb.p : nullptr, bounded ? ub.p : nullptr,
@@ -805,6 +855,7 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
       // snapshot of this iteration, then keep going: the previous iteration's callback runs while the device works
       OSB_CUDA(cudaMemcpyAsync(&cb_snap[cb_slot], d_state, sizeof(DevState), cudaMemcpyDeviceToHost, stm));
       OSB_CUDA(cudaMemcpyAsync(cb_xsnap + (size_t)cb_slot * ld, x.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, stm));
+      if (cb) OSB_CUDA(cudaMemcpyAsync(cb_gsnap + (size_t)cb_slot * ld, g.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, stm));
       OSB_CUDA(cudaEventRecord(cbev[cb_slot], stm));
       if (cb_prev >= 0 && !deliver(cb_prev)) {
         cb_prev = -1;

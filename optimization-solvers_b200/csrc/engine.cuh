@@ -37,6 +37,8 @@ struct DevState {
   int reason;  // OSB_REASON_*
   int ls_evals;
   int pending;  // lazy schedule: stored matrix = H - rank2(ps, ph; pc0..pc2) still to be applied
+  int pp;       // ping-pong packed storage (pass variant bit 1): 0 = the current matrix is in Hsym, 1 = in Hsym2; toggled on
+                // the device by the fold kernel, so that predicated (no-op) launches after `done` do not flip it
   int epi;      // lazy schedule: h = H y and w = H g are fresh and their O(n) epilogue is still owed (deferred to the next
                 // cluster head, or to qn_launch_epilogue_cluster when no head follows)
 };
@@ -247,7 +249,7 @@ void qn_launch_lazy(Ctx* ctx, const QNLazyArgs& a, int variant = 0);
 void qn_launch_lazy_epilogue(Ctx* ctx, const QNLazyArgs& a);
 // packed symmetric storage (lower triangle in 8-row tiles): one pass moves n^2 * 8 B
 int64_t qn_sym_doubles(int64_t n);
-int qn_sym_grid(Ctx* ctx, int64_t n);
+int qn_sym_grid(Ctx* ctx, int64_t n, int variant);
 void qn_sym_pack(Ctx* ctx, const double* H, int64_t ld, int64_t n, double* P);
 void qn_sym_set_identity(Ctx* ctx, int64_t n, double* P);
 int64_t qn_sym_doubles_sharded(int64_t n, int world, int rank);
@@ -255,7 +257,7 @@ void qn_sym_layout(int64_t n, int world, int64_t tile, int* owner, int64_t* offs
 void qn_sym_set_identity_sharded(Ctx* ctx, int64_t n, double* P);
 void qn_sym_unpack_sharded(Ctx* ctx, const double* P, int64_t ld, int64_t n, double* Hfull_zeroed);
 void qn_sym_unpack(Ctx* ctx, const double* P, int64_t ld, int64_t n, double* H);
-void qn_launch_lazy_sym(Ctx* ctx, const QNLazyArgs& a, double* P, double* colpart, int64_t n, int64_t ld, int phase);
+void qn_launch_lazy_sym(Ctx* ctx, const QNLazyArgs& a, double* P, double* Pout, double* colpart, int64_t n, int64_t ld, int phase, int variant);
 // apply a pending update to the stored matrix (getters, engine switches)
 void qn_launch_flush(Ctx* ctx, int kind, double* M, int64_t ld, int64_t nrows, int64_t row0, DevState* st, const double* ps,
                      const double* ph);
@@ -287,12 +289,14 @@ struct Solver {
   // only then is the callback for iteration k delivered; inside it x(), f(), k(), s_norm(), y_norm() read the
   // snapshot.  Any other getter (or a mutation) inside the callback would see the solver one iteration ahead:
   // hence an option and not the default.
-  int callback_run_ahead = 0;
+  int callback_run_ahead = -1;  // -1 = auto (on), 0 = stalling delivery, 1 = on
   LSParams* d_ls_buf = nullptr;      // device copy of the line-search parameters (minimize_device)
   DevState* poll_snap = nullptr;     // 2 pinned slots of the polling snapshots
   DevState* cb_snap = nullptr;       // 2 pinned slots
   double* cb_xsnap = nullptr;        // 2 x ld doubles, pinned
   const double* cb_x_mirror = nullptr;  // non-null while a run-ahead callback is being delivered
+  const double* cb_g_mirror = nullptr;
+  double* cb_gsnap = nullptr;           // 2 x ld doubles, pinned
   const DevState* cb_state_mirror = nullptr;
   int qn_variant = 0;
   int head_variant = 0;  // 0 = cluster head, 1 = single-CTA smem head, 2 = generic single-CTA head
@@ -305,6 +309,14 @@ struct Solver {
   int64_t ld = 0, row0 = 0, nrows = 0;  // local row block of H
   DBuf H, u, h, pvec, vvec, scratch;
   DBuf wv, ps, ph;        // lazy schedule: w = H g, pending p and q
+  // Options as the caller set them (-1 = auto) and the values in force for the current minimize() call.  Auto picks the
+  // lazy schedule and the packed symmetric storage whenever they apply (BFGS / DFP, symmetric H, n > QN_SMALL_N): a caller
+  // that writes `BFGS::new(tol, x0)` + `minimize(...)` like examples/bfgs_example.rs:46-52 gets the n^2 8 B path.
+  int opt_schedule = -1, opt_storage = -1;
+  int last_engine = 0;         // what the last minimize() ran: 1 = host-driven, 2 = device-resident control
+  bool last_sym_sharded = false, last_p2p = false;
+  void resolve_options();
+  void recompute_u();     // u = H g from the exact matrix (first iteration, after set_x / set_inv_hessian)
   int qn_schedule = 0;    // 0 = eager (h = H y, then fused update: 3 n^2 8 B), 1 = lazy (one RMW: 2 n^2 8 B)
   bool lazy_used = false;
   bool H_virtual_identity = false;  // H = I and not materialised yet (large n: the 2 GiB buffer is allocated on first need;
@@ -316,14 +328,18 @@ struct Solver {
   HeadEpi head_epi() const;
   void finish_epilogue();  // run an owed epilogue now (no head follows)
   int qn_storage = 0;     // 0 = full n x n, 1 = packed symmetric lower triangle (lazy schedule, BFGS/DFP, single GPU)
-  DBuf Hsym, colpart;     // packed matrix and per-CTA column partials
+  DBuf Hsym, Hsym2, colpart;  // packed matrix (+ its ping-pong twin, pass variant bit 1) and per-CTA column partials
+  int colpart_grid = 0;
+  bool sym_pingpong_dirty = false;
   bool sym_current = false;  // the packed copy (not H) holds the current matrix
   bool h_symmetric = true;   // false after set_inv_hessian with a non-symmetric matrix (then full storage is used)
   void sym_to_full();
+  void sym_settle_pingpong();  // make Hsym the buffer that holds the current matrix (host pointers swap, DevState.pp = 0)
   int use_p2p = 1;        // lazy schedule, world > 1: fused peer-memory all-gather when the context is IPC-connected
   void flush_pending();
   // Newton family
-  DBuf hess, chol;
+  DBuf hess, chol, lu_perm;
+  bool newton_singular = false;  // this iteration's Hessian had an exactly zero pivot: d = -g (newton/mod.rs:43-46)
   bool has_dec = false;
   double decrement_squared = NAN;
   // spectral

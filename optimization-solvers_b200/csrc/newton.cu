@@ -6,6 +6,8 @@
 // k = 0..j-1 in order, `a + (-L_jk) * L_ik`), so the factor is bit-identical to the reference's;
 // the forward solve is the same column-oriented axpy sweep.  Larger systems go through the blocked
 // path (chol_blocked.cu).
+#include <algorithm>
+
 #include "engine.cuh"
 
 namespace osb {
@@ -110,6 +112,144 @@ int newton_solve(Ctx* ctx, int64_t n, int64_t ld, const double* hess, double* ch
     ctx->sync();
     if (fail) return OSB_PANIC_NOT_SPD;
   }
+  return OSB_OK;
+}
+
+// ---- LU with partial pivoting: plain Newton on a Hessian that is not SPD ---------------------
+// newton/mod.rs:31-47 inverts with `try_inverse` (nalgebra: Gauss elimination with partial pivoting for n >= 5), so an
+// indefinite but invertible Hessian is a normal iteration there, and a singular one (an exactly zero pivot) falls back
+// to d = -g.  The Cholesky above is the fast path for the SPD Hessians of the configs; when it reports a non-positive
+// pivot, OSB_NEWTON comes here.  Right-looking elimination, two launches per column (pivot search + row swap on one CTA,
+// rank-1 update of the trailing block on the grid): a fallback, not a tuned path.  Pivot rule = nalgebra's icamax
+// (first row of maximal |a|).  `lu` holds L (unit lower, multipliers) and U; perm[i] = source row of row i.
+constexpr int LU_T = 1024;
+__global__ void __launch_bounds__(256) lu_copy_kernel(int64_t n, int64_t ld, const double* __restrict__ A, double* __restrict__ LU, int* __restrict__ perm,
+                                                      int* __restrict__ fail) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n * ld; e += (int64_t)gridDim.x * blockDim.x) LU[e] = A[e];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) perm[i] = (int)i;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *fail = 0;
+}
+__global__ void __launch_bounds__(LU_T) lu_pivot_kernel(int64_t n, int64_t ld, double* __restrict__ LU, int* __restrict__ perm, int64_t k,
+                                                        int* __restrict__ fail) {
+  if (*fail) return;
+  __shared__ double sv[LU_T / 32];
+  __shared__ int64_t si[LU_T / 32];
+  __shared__ int64_t s_piv;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double best = -1.0;
+  int64_t bi = n;
+  for (int64_t r = k + tid; r < n; r += LU_T) {
+    const double v = fabs(LU[r * ld + k]);
+    if (v > best) {  // ascending r per thread: ties keep the smaller row
+      best = v;
+      bi = r;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) {
+      best = ov;
+      bi = oi;
+    }
+  }
+  if (lane == 0) {
+    sv[warp] = best;
+    si[warp] = bi;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < LU_T / 32; ++w)
+      if (sv[w] > best || (sv[w] == best && si[w] < bi)) {
+        best = sv[w];
+        bi = si[w];
+      }
+    // NaN columns: every compare is false, bi stays n -> treated like the reference's `diag == 0` failure is NOT right
+    // (NaN != 0 there and the inverse is full of NaN); keep row k as the pivot in that case
+    if (bi >= n) bi = k;
+    s_piv = bi;
+    if (LU[bi * ld + k] == 0.0) *fail = 1;  // lu.rs: `if diag.is_zero() { return false }`
+    else if (bi != k) {
+      const int t = perm[k];
+      perm[k] = perm[bi];
+      perm[bi] = t;
+    }
+  }
+  __syncthreads();
+  const int64_t piv = s_piv;
+  if (piv == k || LU[piv * ld + k] == 0.0) return;
+  for (int64_t c = tid; c < n; c += LU_T) {
+    const double a = LU[k * ld + c];
+    LU[k * ld + c] = LU[piv * ld + c];
+    LU[piv * ld + c] = a;
+  }
+}
+__global__ void __launch_bounds__(256) lu_update_kernel(int64_t n, int64_t ld, double* __restrict__ LU, int64_t k, const int* __restrict__ fail) {
+  if (*fail) return;
+  const double inv_diag = 1.0 / LU[k * ld + k];  // lu.rs gauss_step: multipliers = column * (1 / pivot)
+  for (int64_t r = k + 1 + blockIdx.x; r < n; r += gridDim.x) {
+    const double m = LU[r * ld + k] * inv_diag;
+    const double nm = -m;
+    for (int64_t c = k + 1 + threadIdx.x; c < n; c += blockDim.x) LU[r * ld + c] = nm * LU[k * ld + c] + LU[r * ld + c];
+    __syncthreads();
+    if (threadIdx.x == 0) LU[r * ld + k] = m;
+    __syncthreads();
+  }
+}
+// out = U^-1 L^-1 P rhs (column-oriented substitutions, like solve_lower/upper_triangular_mut)
+__global__ void __launch_bounds__(LU_T) lu_solve_kernel(int64_t n, int64_t ld, const double* __restrict__ LU, const int* __restrict__ perm,
+                                                        const double* __restrict__ rhs, double* __restrict__ b, double* __restrict__ tmp,
+                                                        const int* __restrict__ fail) {
+  if (*fail) return;
+  const int tid = threadIdx.x;
+  __shared__ double s_coeff;
+  for (int64_t i = tid; i < n; i += LU_T) tmp[i] = rhs[perm[i]];
+  __syncthreads();
+  for (int64_t i = tid; i < n; i += LU_T) b[i] = tmp[i];
+  __syncthreads();
+  for (int64_t i = 0; i + 1 < n; ++i) {
+    const double nc = -b[i];
+    __syncthreads();
+    for (int64_t r = i + 1 + tid; r < n; r += LU_T) b[r] = nc * LU[r * ld + i] + b[r];
+    __syncthreads();
+  }
+  for (int64_t i = n; i-- > 0;) {
+    if (tid == 0) {
+      s_coeff = b[i] / LU[i * ld + i];
+      b[i] = s_coeff;
+    }
+    __syncthreads();
+    const double nc = -s_coeff;
+    for (int64_t r = tid; r < i; r += LU_T) b[r] = nc * LU[r * ld + i] + b[r];
+    __syncthreads();
+  }
+}
+
+// factor (hess != nullptr) and/or solve with the LU in `lu`; returns OSB_OK, or OSB_PANIC_NOT_SPD standing for
+// "singular" (the caller maps it to the reference's d = -g fallback)
+int newton_solve_lu(Ctx* ctx, int64_t n, int64_t ld, const double* hess, double* lu, int* perm, double* tmp, const double* rhs, double* w_out) {
+  static thread_local int* d_fail = nullptr;
+  if (!d_fail) OSB_CUDA(cudaMalloc(&d_fail, sizeof(int)));
+  cudaStream_t st = ctx->stream;
+  if (hess) {
+    lu_copy_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(n, ld, hess, lu, perm, d_fail);
+    ctx->counters[0]++;
+    for (int64_t k = 0; k < n; ++k) {
+      lu_pivot_kernel<<<1, LU_T, 0, st>>>(n, ld, lu, perm, k, d_fail);
+      ctx->counters[0]++;
+      if (k + 1 < n) {
+        const int grid = (int)std::min<int64_t>(n - k - 1, (int64_t)ctx->num_sms * 4);
+        lu_update_kernel<<<grid, 256, 0, st>>>(n, ld, lu, k, d_fail);
+        ctx->counters[0]++;
+      }
+    }
+    int fail = 0;
+    OSB_CUDA(cudaMemcpyAsync(&fail, d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ctx->sync();
+    if (fail) return OSB_PANIC_NOT_SPD;
+  }
+  lu_solve_kernel<<<1, LU_T, 0, st>>>(n, ld, lu, perm, rhs, w_out, tmp, d_fail);
+  ctx->counters[0]++;
   return OSB_OK;
 }
 

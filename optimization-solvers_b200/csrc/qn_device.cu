@@ -595,13 +595,10 @@ __global__ void __cluster_dims__(HC_CTAS, 1, 1) __launch_bounds__(HC_T, 1)
 qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol, int64_t max_ls, DevState* __restrict__ st,
                        double* __restrict__ x, double* __restrict__ g, double* __restrict__ s, double* __restrict__ y,
                        const double* __restrict__ u, const double* __restrict__ lb, const double* __restrict__ ub,
-                       const double* __restrict__ ls_lb, const double* __restrict__ ls_ub, int spec_on, long long* tdbg, HeadEpi epi) {
+                       const double* __restrict__ ls_lb, const double* __restrict__ ls_ub, int spec_on, HeadEpi epi) {
   constexpr int BS = Fn::BS;
   constexpr int KPT = EPT / BS;
   constexpr int NT = HC_CTAS * HC_T;
-  int tslot = 0;
-#define OSB_TS() do { if (tdbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && tslot < 30) tdbg[tslot++] = clock64(); } while (0)
-  OSB_TS();
   constexpr int SPEC = 4;  // backtracking trials evaluated per reduction round (speculatively)
   constexpr bool IS_BT = LSK == LS_BACKTRACKING || LSK == LS_BACKTRACKING_B;
   cg::cluster_group cluster = cg::this_cluster();
@@ -630,14 +627,10 @@ qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol,
   const double* __restrict__ epi_w = epi_flag == 2 ? epi.w2 : epi.w;
   double epi_ca = 0.0, epi_cb = 0.0;
   if (epi_flag) {
+    // (skip: the leader clears st->epi / pending only AFTER a cluster barrier below — every CTA reads st->epi above, and
+    //  a CTA arriving late must not see the flag already cleared)
     if (!epi_skip) cluster_epilogue_coefs<EPT>(epi.kind, epi.nslots, epi.slot_stride, epi_h, s, y, g, n, st, leader, gt, smem_cta, part, res, phase, epi_ca, epi_cb);
-    else if (leader) {
-      st->pending = 0;
-      st->pc0 = st->pc1 = st->pc2 = 0.0;
-      st->epi = 0;
-    }
   }
-  OSB_TS();
   int why = OSB_REASON_NONE;
   if (st->has_s && st->s_norm < tol) why = OSB_REASON_S_NORM;        // bfgs.rs:67-69
   else if (st->has_y && st->y_norm < tol) why = OSB_REASON_Y_NORM;   // bfgs.rs:70-72
@@ -695,16 +688,24 @@ qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol,
       st->reason = why;
     }
     cluster.sync();  // peers may still be reading this CTA's partials of the epilogue reduction
+    if (leader && epi_flag && epi_skip) {  // bfgs.rs:106-112: no new update; the stored matrix is exact once the pending one is applied
+      st->pending = 0;
+      st->pc0 = st->pc1 = st->pc2 = 0.0;
+      st->epi = 0;
+    }
     return;
   }
-  OSB_TS();
   {
     double a2[2] = {acc[0], acc[1]};
     cluster_sum<2>(a2, smem_cta, part, res, phase);
     acc[0] = a2[0];
     acc[1] = a2[1];
   }
-  OSB_TS();
+  if (leader && epi_flag && epi_skip) {  // (unreachable today: skip implies a norm below tol, i.e. termination above)
+    st->pending = 0;
+    st->pc0 = st->pc1 = st->pc2 = 0.0;
+    st->epi = 0;
+  }
   if (sqrt(acc[0]) < tol) {  // bfgs.rs:74
     if (leader) {
       st->done = 1;
@@ -720,7 +721,6 @@ qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol,
   LSParams p = *lsp;
   LSMachine m;
   m.template begin<LSK>(p, f0, gd0, max_ls, tmaxc);
-  OSB_TS();
   int evals = 0;
   // Backtracking visits t, t*beta, t*beta^2, ... whatever the outcome of a trial (backtracking.rs:37-55
   // multiplies by beta on both the NaN and the rejection branch), so up to SPEC consecutive trials are
@@ -760,9 +760,7 @@ qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol,
         }
       }
     }
-    OSB_TS();
     cluster_sum<3 * NSPEC>(aS, smem_cta, part, res, phase);
-    OSB_TS();
 #pragma unroll
     for (int q = 0; q < NSPEC; ++q) {
       if (!m.done && m.request(p) == ts[q]) {
@@ -801,9 +799,7 @@ qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol,
       }
     }
   }
-  OSB_TS();
   cluster_sum<4>(acc, smem_cta, part, res, phase);
-  OSB_TS();
   if (leader) {
     st->f = acc[3];
     st->ft = acc[3];
@@ -823,23 +819,17 @@ qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol,
     // only GLLQuadratic.f_previous and MoreThuenteB.t_max persist across outer iterations
     if (LSK == LS_GLL || LSK == LS_MORETHUENTE_B) *lsp = p;
   }
-  OSB_TS();
   cluster.sync();  // keep every CTA's shared memory alive until all peers have read it
-  OSB_TS();
-  if (tdbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) tdbg[31] = tslot;
-#undef OSB_TS
 }
-
-long long* g_head_tdbg = nullptr;  // debug: device buffer of 32 clock64 stamps (option "head_debug")
 
 template <class Fn, int LSK>
 static void launch_head_cluster_k(Ctx* ctx, Fn fn, bool bounded, LSParams* d_ls, int64_t n, double tol, int64_t max_ls, DevState* st,
                                   double* x, double* g, double* s, double* y, const double* u, const double* lb, const double* ub,
                                   const double* ls_lb, const double* ls_ub, int spec_on, const HeadEpi& epi) {
   if (bounded)
-    qn_head_cluster_kernel<Fn, true, 4, LSK><<<HC_CTAS, HC_T, 0, ctx->stream>>>(fn, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub, spec_on, g_head_tdbg, epi);
+    qn_head_cluster_kernel<Fn, true, 4, LSK><<<HC_CTAS, HC_T, 0, ctx->stream>>>(fn, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub, spec_on, epi);
   else
-    qn_head_cluster_kernel<Fn, false, 4, LSK><<<HC_CTAS, HC_T, 0, ctx->stream>>>(fn, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub, spec_on, g_head_tdbg, epi);
+    qn_head_cluster_kernel<Fn, false, 4, LSK><<<HC_CTAS, HC_T, 0, ctx->stream>>>(fn, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub, spec_on, epi);
 }
 
 template <class Fn>

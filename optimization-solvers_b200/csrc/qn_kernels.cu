@@ -305,6 +305,26 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 
+// Bounded wait for a peer's flag: a dead or diverged peer must not wedge this GPU.  After ~5 s without progress the
+// run is terminated (DevState.done, status AbnormalTermination); every later launch of the solve is then a no-op.
+__device__ __forceinline__ bool wait_flag_sys(const unsigned long long* p, unsigned long long seq) {
+  unsigned long long t0 = 0;
+  unsigned int spins = 0;
+  while (ld_acquire_sys(p) < seq) {
+    if ((++spins & 1023u) == 0u) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 5000000000ULL) return false;
+    }
+  }
+  return true;
+}
+__device__ __forceinline__ void peer_timeout(DevState* st) {
+  st->done = 1;
+  st->status = OSB_ABNORMAL_TERMINATION;
+}
+
 // ---- lazy schedule -------------------------------------------------------------------------
 // Stored matrix M = H_k minus the update of iteration k-1 (pending).  One read-modify-write:
 //     M_ij <- M_ij + pc0 p_i p_j + pc1 (p_i q_j + q_i p_j) + pc2 q_i q_j      (now M = H_k exactly)
@@ -513,8 +533,7 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_kernel(const __grid_constant_
     if (threadIdx.x < a.world) {
       unsigned long long* f = reinterpret_cast<unsigned long long*>(a.peers[threadIdx.x] + 4 * XCHG_LD) + a.rank;
       st_release_sys(f, seq);
-      while (ld_acquire_sys(myflags + threadIdx.x) < seq) {
-      }
+      if (!wait_flag_sys(myflags + threadIdx.x, seq)) peer_timeout(st);
     }
     __syncthreads();
     if (DEFER) {  // all ranks' rows have arrived in this rank's exchange buffers of parity `par`
@@ -748,8 +767,7 @@ __global__ void __launch_bounds__(TM_T, 1) qn_lazy_tma_kernel(const __grid_const
     if (tid < a.world) {
       unsigned long long* f = reinterpret_cast<unsigned long long*>(a.peers[tid] + 4 * XCHG_LD) + a.rank;
       st_release_sys(f, seq);
-      while (ld_acquire_sys(myflags + tid) < seq) {
-      }
+      if (!wait_flag_sys(myflags + tid, seq)) peer_timeout(st);
     }
     __syncthreads();
     lazy_epilogue_body<KIND>(a, a.peers[a.rank] + (int64_t)(par * 2 + 0) * XCHG_LD,
@@ -818,11 +836,15 @@ void qn_sym_layout(int64_t n, int world, int64_t tile, int* owner, int64_t* offs
 
 struct QNSymArgs {
   double* P;         // packed matrix (this rank's tiles when sharded)
+  double* Pout;      // ping-pong variant: the pass reads P and writes Pout (== P in place)
   double* colpart;   // gridDim x 2 x ld per-CTA column partials (h then w)
   int64_t n, ld;
   int world, rank;   // sharded: pairs p = rank, rank + world, ...
   double* const* peers;        // exchange regions (fold kernel, sharded)
   unsigned long long* seq;     // exchange sequence number
+  int pass_grid;     // grid of the streaming pass (= number of column-partial vectors)
+  int zeroed;        // 1: the pass zeroes its partial vector first (legacy variant); 0: the first (longest) tile of a CTA
+                     //    WRITES the partial, columns at or beyond that tile's first row are never read (sym_first_row)
 };
 
 // 16 per-thread values -> warp sums with 16 double shuffles (recursive halving) instead of 80; after the call
@@ -842,16 +864,54 @@ __device__ __forceinline__ double warp_sum16(double (&v)[16]) {
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
+// Static assignment of tiles to the CTAs of the pass (deterministic: a row's sums are formed inside one CTA, the column
+// partials are folded in CTA order).
+//   one GPU: tile t has 8 (t + 1) stored columns; tiles are dealt in PAIRS (T-1-p, p) of equal total length, pair p to
+//            CTA p % grid, the LONG tile of a pair first (plain round-robin leaves the CTA with the longest tiles 7 % above
+//            the average);
+//   sharded: the rank owns the pairs p = rank, rank + world, ... = 2 nlp tiles; they are dealt ONE BY ONE in decreasing
+//            length in snake order (round k left-to-right for even k, right-to-left for odd k): position q < nlp is tile
+//            T-1-(rank + q world), position q >= nlp is tile rank + (2 nlp - 1 - q) world (whole pairs would quantise
+//            the work to ceil(nlp / grid) rounds: 4 instead of 3.46 at 2 GPUs).
+// Either way the FIRST tile a CTA processes is its longest one: its column contributions initialise the CTA's partial
+// vector (no zeroing pass, no 39 MB of zeros through L2), and every later tile adds into a prefix of it.
+template <bool SHARDED>
+__host__ __device__ inline int64_t sym_cta_tile(int64_t ntiles, int world, int rank, int grid, int cta, int64_t step) {
+  if (SHARDED) {
+    const int64_t nlp = symsh_local_pairs(ntiles, world, rank);
+    const int64_t pos = (step & 1) ? (int64_t)grid - 1 - cta : cta;
+    const int64_t uq = step * grid + pos;
+    if (uq >= 2 * nlp) return -1;
+    const int64_t pairi = uq < nlp ? rank + uq * world : rank + (2 * nlp - 1 - uq) * world;
+    return uq < nlp ? ntiles - 1 - pairi : pairi;
+  } else {
+    const int64_t nhalf = (ntiles + 1) / 2;
+    const int64_t pairi = (step >> 1) * grid + cta;
+    if (pairi >= nhalf) return -1;
+    const int64_t longt = ntiles - 1 - pairi;
+    if ((step & 1) == 0) return longt;
+    return longt == pairi ? -1 : pairi;  // odd tile count: the middle tile only once
+  }
+}
+// first row of the first tile of CTA `cta`: the columns [0, that) of its partial vector are valid after the pass
+template <bool SHARDED>
+__host__ __device__ inline int64_t sym_first_row(int64_t ntiles, int world, int rank, int grid, int cta) {
+  const int64_t t = sym_cta_tile<SHARDED>(ntiles, world, rank, grid, cta, 0);
+  return t < 0 ? 0 : t * QN_R;
+}
+
 // SHARDED is a template parameter so that the single-GPU instantiation keeps exactly its own loop structure (the
-// 128-register streaming loop is sensitive to anything that stays live across it).
-template <int KIND, bool SHARDED>
-__global__ void __launch_bounds__(QN_T, 1) qn_lazy_sym_kernel(QNLazyArgs a, QNSymArgs sa) {
+// 128-register streaming loop is sensitive to anything that stays live across it).  NT = threads per CTA: 512 (one
+// CTA per SM) or 256 (two independent CTAs per SM: one streams while the other drains into its tile-end reduction).
+// OOP: ping-pong storage, the pass reads sa.P and writes sa.Pout.  ZERO: legacy zero-first partials.
+template <int KIND, bool SHARDED, int NT, bool OOP, bool ZERO>
+__global__ void __launch_bounds__(NT, 512 / NT) qn_lazy_sym_kernel(QNLazyArgs a, QNSymArgs sa) {
   DevState* st = a.st;
   if (st->done) return;
   const double c0 = st->pc0, c1 = st->pc1, c2 = st->pc2;
   const unsigned long long pol = l2_evict_first_policy();
-  __shared__ double red2[2][QN_T / 32][16];  // double-buffered by tile parity: two barriers per tile instead of four
-  __shared__ double4 rowv2[2][QN_R];         // p_i, q_i, y_i, g_i of the tile's rows
+  __shared__ double red2[2][NT / 32][16];  // double-buffered by tile parity: two barriers per tile instead of four
+  __shared__ double4 rowv2[2][QN_R];       // p_i, q_i, y_i, g_i of the tile's rows
   int tpar = 0;
   const int64_t n = sa.n, ld = sa.ld;
   const double* __restrict__ p = a.ps;
@@ -861,37 +921,21 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_sym_kernel(QNLazyArgs a, QNSy
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* __restrict__ cph = sa.colpart + (int64_t)blockIdx.x * 2 * ld;
   double* __restrict__ cpw = cph + ld;
-  // zero this CTA's column partials (columns it will touch are a subset of [0, n))
-  for (int64_t j = 2 * threadIdx.x; j < ld; j += 2 * QN_T) {
-    *reinterpret_cast<double2*>(cph + j) = make_double2(0.0, 0.0);
-    *reinterpret_cast<double2*>(cpw + j) = make_double2(0.0, 0.0);
+  if (ZERO) {
+    for (int64_t j = 2 * threadIdx.x; j < ld; j += 2 * NT) {
+      *reinterpret_cast<double2*>(cph + j) = make_double2(0.0, 0.0);
+      *reinterpret_cast<double2*>(cpw + j) = make_double2(0.0, 0.0);
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  // Tile t has 8 (t + 1) stored columns: tiles are processed in PAIRS (t, ntiles - 1 - t) of equal total length,
-  // pairs dealt round-robin — a static (hence deterministic) assignment that balances the triangle to within
-  // one pair; plain round-robin leaves the CTA holding the longest tiles 7 % above the average.
   const int64_t ntiles = (n + QN_R - 1) / QN_R;
-  const int64_t nhalf = (ntiles + 1) / 2;
-  // Sharded: a rank owns nlp pairs = 2 nlp tiles; dealing whole pairs would quantise the work to ceil(nlp / grid) rounds
-  // (4 instead of 3.46 at 2 GPUs).  The local tiles are therefore dealt ONE BY ONE in decreasing length, in snake order
-  // (round k left-to-right for even k, right-to-left for odd k): position q < nlp is tile T-1-(rank + q world), position
-  // q >= nlp is tile rank + (2 nlp - 1 - q) world.  Static, hence deterministic.
-  constexpr bool sharded = SHARDED;
-  const int64_t nlp = SHARDED ? symsh_local_pairs(ntiles, sa.world, sa.rank) : nhalf;
-  const int64_t nunits = SHARDED ? 2 * nlp : nlp;
-  for (int64_t uq0 = blockIdx.x, kround = 0; SHARDED ? kround * (int64_t)gridDim.x < nunits : uq0 < nunits; uq0 += gridDim.x, ++kround)
-  for (int side = 0; side < (SHARDED ? 1 : 2); ++side) {
-    int64_t tile;
-    if (SHARDED) {
-      const int64_t pos = (kround & 1) ? (int64_t)gridDim.x - 1 - blockIdx.x : blockIdx.x;
-      const int64_t uq = kround * gridDim.x + pos;
-      if (uq >= nunits) continue;
-      const int64_t pairi = uq < nlp ? sa.rank + uq * sa.world : sa.rank + (2 * nlp - 1 - uq) * sa.world;
-      tile = uq < nlp ? ntiles - 1 - pairi : pairi;
-    } else {
-      const int64_t pairi = uq0;
-      tile = side == 0 ? pairi : ntiles - 1 - pairi;
-      if (side == 1 && tile == pairi) continue;  // odd tile count: the middle tile only once
+  const int pp = OOP ? st->pp : 0;  // which buffer holds the current matrix (toggled by the fold kernel)
+  bool first = !ZERO;
+  for (int64_t step = 0;; ++step) {
+    const int64_t tile = sym_cta_tile<SHARDED>(ntiles, sa.world, sa.rank, (int)gridDim.x, (int)blockIdx.x, step);
+    if (tile < 0) {
+      if (SHARDED || (step & 1) == 0) break;  // (one GPU, odd step: only the middle tile of an odd count is skipped)
+      continue;
     }
     const int64_t r0 = tile * QN_R;
     const int rows_here = (int)((n - r0) < QN_R ? (n - r0) : QN_R);
@@ -909,8 +953,10 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_sym_kernel(QNLazyArgs a, QNSy
       rowv[threadIdx.x] = ok ? make_double4(p[i], q[i], yv[i], gv[i]) : make_double4(0.0, 0.0, 0.0, 0.0);
     }
     __syncthreads();  // (A) rowv[tpar] visible; also orders the previous tile's red[tpar^1] readers before its next reuse
-    double* __restrict__ base = sa.P + (sharded ? symsh_tile_offset(tile, ntiles, sa.world) : sym_tile_offset(tile));
-    for (int col = 2 * threadIdx.x; col < (int)lpad; col += QN_CHUNK) {
+    const int64_t toff = SHARDED ? symsh_tile_offset(tile, ntiles, sa.world) : sym_tile_offset(tile);
+    const double* __restrict__ base = (OOP && pp ? sa.Pout : sa.P) + toff;
+    double* __restrict__ obase = (OOP && !pp ? sa.Pout : sa.P) + toff;
+    for (int col = 2 * threadIdx.x; col < (int)lpad; col += 2 * NT) {
       // element validity: columns >= ncols are padding (never stored, never updated)
       const bool v0 = col < ncols, v1 = col + 1 < ncols;
       if (!v0) continue;
@@ -921,8 +967,9 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_sym_kernel(QNLazyArgs a, QNSy
       double2 hv[QN_R];
 #pragma unroll
       for (int r = 0; r < QN_R; ++r) hv[r] = r < rows_here ? ld_stream_ef(base + r * lpad + col, pol) : make_double2(0.0, 0.0);
-      // column contributions only strictly left of the diagonal block
-      const bool c0ok = col < (int)r0, c1ok = col + 1 < (int)r0;
+      // column contributions only strictly left of the diagonal block (r0 is a multiple of 8 and col is even: the pair
+      // (col, col + 1) is on the same side)
+      const bool cok = col < (int)r0;
       double ch0 = 0.0, ch1 = 0.0, cw0 = 0.0, cw1 = 0.0;
 #pragma unroll
       for (int r = 0; r < QN_R; ++r) {
@@ -947,21 +994,24 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_sym_kernel(QNLazyArgs a, QNSy
           ch1 = fma(hn.y, rv.z, ch1);
           cw0 = fma(hn.x, rv.w, cw0);
           cw1 = fma(hn.y, rv.w, cw1);
-          st_stream_ef(base + r * lpad + col, hn, pol);
+          st_stream_ef(obase + r * lpad + col, hn, pol);
         }
       }
-      if (c0ok) {
-        double2 oh = *reinterpret_cast<double2*>(cph + col), ow = *reinterpret_cast<double2*>(cpw + col);
+      if (cok) {
+        double2 oh = make_double2(0.0, 0.0), ow = make_double2(0.0, 0.0);
+        if (!first) {
+          oh = *reinterpret_cast<double2*>(cph + col);
+          ow = *reinterpret_cast<double2*>(cpw + col);
+        }
         oh.x += ch0;
         ow.x += cw0;
-        if (c1ok) {
-          oh.y += ch1;
-          ow.y += cw1;
-        }
+        oh.y += ch1;
+        ow.y += cw1;
         *reinterpret_cast<double2*>(cph + col) = oh;
         *reinterpret_cast<double2*>(cpw + col) = ow;
       }
     }
+    first = false;
     {
       double v16[16];
 #pragma unroll
@@ -976,7 +1026,7 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_sym_kernel(QNLazyArgs a, QNSy
     if (threadIdx.x < 2 * QN_R) {
       double v = 0.0;
 #pragma unroll
-      for (int w = 0; w < QN_T / 32; ++w) v = v + red[w][threadIdx.x];
+      for (int w = 0; w < NT / 32; ++w) v = v + red[w][threadIdx.x];
       const int r = threadIdx.x % QN_R;
       if (r < rows_here) {
         if (threadIdx.x < QN_R) a.h[r0 + r] = v;
@@ -993,10 +1043,12 @@ __global__ void __launch_bounds__(QN_T, 1) qn_lazy_sym_kernel(QNLazyArgs a, QNSy
 // of one partial vector, 8 loads in flight per thread (a one-thread-per-column version took 58 us, this one 6).
 constexpr int FOLD_T = 512;   // = QN_T: the fused epilogue then adds in the same order as the full-storage kernel's
 constexpr int FOLD_G = FOLD_T / 64;  // groups of partial rows per vector
+constexpr int FOLD_MAXPARTS = 1024;  // >= the largest pass grid (2 CTAs per SM)
 template <int KIND>
 __global__ void __launch_bounds__(FOLD_T) qn_sym_fold_kernel(const __grid_constant__ QNLazyArgs a, QNSymArgs sa, int nparts, unsigned int* ticket) {
   DevState* st = a.st;
   if (st->done) return;
+  if (sa.Pout != sa.P && blockIdx.x == 0 && threadIdx.x == 0) st->pp ^= 1;  // ping-pong: the pass wrote the other buffer
   __shared__ double2 part[2][FOLD_G][32];
   __shared__ double smem[3 * 32];
   __shared__ bool is_last;
@@ -1007,6 +1059,15 @@ __global__ void __launch_bounds__(FOLD_T) qn_sym_fold_kernel(const __grid_consta
   const int vec = warp / FOLD_G, grp = warp % FOLD_G;
   const int per = (nparts + FOLD_G - 1) / FOLD_G;
   const int cb = grp * per, ce = (cb + per < nparts) ? cb + per : nparts;
+  // partial vector c is valid on the columns [0, ext_s[c]) only (the pass never wrote the rest)
+  __shared__ int ext_s[FOLD_MAXPARTS];
+  {
+    const int64_t T = (sa.n + QN_R - 1) / QN_R;
+    for (int c = threadIdx.x; c < nparts; c += FOLD_T)
+      ext_s[c] = sa.zeroed ? (int)ld
+                           : (int)(sa.world > 1 ? sym_first_row<true>(T, sa.world, sa.rank, nparts, c) : sym_first_row<false>(T, 1, 0, nparts, c));
+    __syncthreads();
+  }
   // a warp reads 512 contiguous bytes of one partial row per load and keeps 8 loads in flight; the order of the
   // additions is fixed by (nparts, FOLD_G groups), not by timing
   for (int64_t j0 = (int64_t)blockIdx.x * 64; j0 < sa.n; j0 += (int64_t)gridDim.x * 64) {
@@ -1018,7 +1079,8 @@ __global__ void __launch_bounds__(FOLD_T) qn_sym_fold_kernel(const __grid_consta
       for (; c + 8 <= ce; c += 8) {
         double2 v[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = __ldcg(reinterpret_cast<const double2*>(src + (int64_t)(c + k) * 2 * ld));
+        for (int k = 0; k < 8; ++k)
+          v[k] = j < ext_s[c + k] ? __ldcg(reinterpret_cast<const double2*>(src + (int64_t)(c + k) * 2 * ld)) : make_double2(0.0, 0.0);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           acc.x = acc.x + v[k].x;
@@ -1026,7 +1088,7 @@ __global__ void __launch_bounds__(FOLD_T) qn_sym_fold_kernel(const __grid_consta
         }
       }
       for (; c < ce; ++c) {
-        const double2 v = __ldcg(reinterpret_cast<const double2*>(src + (int64_t)c * 2 * ld));
+        const double2 v = j < ext_s[c] ? __ldcg(reinterpret_cast<const double2*>(src + (int64_t)c * 2 * ld)) : make_double2(0.0, 0.0);
         acc.x = acc.x + v.x;
         acc.y = acc.y + v.y;
       }
@@ -1072,8 +1134,7 @@ __global__ void __launch_bounds__(FOLD_T) qn_sym_fold_kernel(const __grid_consta
     if (threadIdx.x < sa.world) {
       unsigned long long* f = reinterpret_cast<unsigned long long*>(sa.peers[threadIdx.x] + 4 * XCHG_LD) + sa.rank;
       st_release_sys(f, seq);
-      while (ld_acquire_sys(myflags + threadIdx.x) < seq) {
-      }
+      if (!wait_flag_sys(myflags + threadIdx.x, seq)) peer_timeout(st);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1188,24 +1249,40 @@ void qn_sym_unpack(Ctx* ctx, const double* P, int64_t ld, int64_t n, double* H) 
   qn_sym_unpack_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(P, ld, n, H);
   ctx->counters[0]++;
 }
-int qn_sym_grid(Ctx* ctx, int64_t n) {
+// pass variants (option "qn_kernel" with packed storage): bit 0 = two 256-thread CTAs per SM instead of one of 512,
+// bit 1 = ping-pong storage (read P, write Pout), bit 2 = legacy zero-first column partials
+int qn_sym_grid(Ctx* ctx, int64_t n, int variant) {
   const int64_t T = (n + QN_R - 1) / QN_R;
   const int64_t units = ctx->world > 1 ? 2 * symsh_local_pairs(T, ctx->world, ctx->rank) : T;  // sharded: local tiles
-  return (int)std::max<int64_t>(1, std::min<int64_t>(units, (int64_t)ctx->num_sms));
+  const int per_sm = (variant & 1) ? 2 : 1;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(units, (int64_t)ctx->num_sms * per_sm));
 }
 
-void qn_launch_lazy_sym(Ctx* ctx, const QNLazyArgs& a, double* P, double* colpart, int64_t n, int64_t ld, int phase) {
+template <int KIND, bool SHARDED>
+static void launch_sym_pass(int grid, cudaStream_t stream, const QNLazyArgs& a, const QNSymArgs& sa, int variant) {
+  switch (variant & 7) {
+    case 0: qn_lazy_sym_kernel<KIND, SHARDED, 512, false, false><<<grid, 512, 0, stream>>>(a, sa); break;
+    case 1: qn_lazy_sym_kernel<KIND, SHARDED, 256, false, false><<<grid, 256, 0, stream>>>(a, sa); break;
+    case 2: qn_lazy_sym_kernel<KIND, SHARDED, 512, true, false><<<grid, 512, 0, stream>>>(a, sa); break;
+    case 3: qn_lazy_sym_kernel<KIND, SHARDED, 256, true, false><<<grid, 256, 0, stream>>>(a, sa); break;
+    default: qn_lazy_sym_kernel<KIND, SHARDED, 512, false, true><<<grid, 512, 0, stream>>>(a, sa); break;
+  }
+}
+
+void qn_launch_lazy_sym(Ctx* ctx, const QNLazyArgs& a, double* P, double* Pout, double* colpart, int64_t n, int64_t ld, int phase, int variant) {
   const bool sharded = ctx->world > 1;
-  QNSymArgs sa{P, colpart, n, ld, sharded ? ctx->world : 1, sharded ? ctx->rank : 0, sharded ? ctx->d_peers : nullptr, ctx->d_seq};
-  const int grid = qn_sym_grid(ctx, n);
+  const int grid = qn_sym_grid(ctx, n, variant);
+  OSB_REQUIRE(grid <= FOLD_MAXPARTS, OSB_ERR_UNSUPPORTED, "pass grid exceeds the fold's partial table");
+  QNSymArgs sa{P, Pout, colpart, n, ld, sharded ? ctx->world : 1, sharded ? ctx->rank : 0, sharded ? ctx->d_peers : nullptr, ctx->d_seq,
+               grid, (variant & 4) ? 1 : 0};
   const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 63) / 64, (int64_t)ctx->num_sms * 2));
   if (phase == 0) {  // the streaming pass over the packed triangle
     if (sharded) {
-      if (a.kind == QN_BFGS) qn_lazy_sym_kernel<QN_BFGS, true><<<grid, QN_T, 0, ctx->stream>>>(a, sa);
-      else qn_lazy_sym_kernel<QN_DFP, true><<<grid, QN_T, 0, ctx->stream>>>(a, sa);
+      if (a.kind == QN_BFGS) launch_sym_pass<QN_BFGS, true>(grid, ctx->stream, a, sa, variant);
+      else launch_sym_pass<QN_DFP, true>(grid, ctx->stream, a, sa, variant);
     } else {
-      if (a.kind == QN_BFGS) qn_lazy_sym_kernel<QN_BFGS, false><<<grid, QN_T, 0, ctx->stream>>>(a, sa);
-      else qn_lazy_sym_kernel<QN_DFP, false><<<grid, QN_T, 0, ctx->stream>>>(a, sa);
+      if (a.kind == QN_BFGS) launch_sym_pass<QN_BFGS, false>(grid, ctx->stream, a, sa, variant);
+      else launch_sym_pass<QN_DFP, false>(grid, ctx->stream, a, sa, variant);
     }
   } else {  // fold of the per-CTA column partials + coefficient epilogue
     if (a.kind == QN_BFGS) qn_sym_fold_kernel<QN_BFGS><<<fgrid, FOLD_T, 0, ctx->stream>>>(a, sa, grid, a.ticket);

@@ -1027,7 +1027,9 @@ struct QuasiNewton : SYNorms, Bounded {
   bool bounded = false;
   int form = FORM_FAITHFUL;
   Mat H, I;  // approx_inv_hessian (column-major), stored identity (bfgs.rs:5,11)
-  void init(size_t n) { I = Mat::identity(n); H = I; }
+  // (the stored identity is only read by the faithful BFGS form: allocated on first use, so that the rank-2 form at
+  //  n = 16384 holds one 2 GiB matrix instead of two)
+  void init(size_t n) { H = Mat::identity(n); }
   bool has_converged(const Eval& e) override {  // bfgs.rs:64-76 (unprojected ||g||_2 also for *B: bfgs_b.rs:92-104)
     if (too_close_s()) { reason = R_SNORM; return true; }
     if (too_close_y()) { reason = R_YNORM; return true; }
@@ -1058,6 +1060,7 @@ struct QuasiNewton : SYNorms, Bounded {
         Mat w_a = outer(s, y);
         Mat w_b = bounded ? outer(y, s) : transpose(w_a);
         Mat innovation = outer(s, s);
+        if (I.r != H.r) I = Mat::identity(H.r);
         Mat left = msub(I, mscale(w_a, rho));
         Mat right = msub(I, mscale(w_b, rho));
         H = madd(matmul(matmul(left, H), right), mscale(innovation, rho));
@@ -1097,7 +1100,9 @@ struct QuasiNewton : SYNorms, Bounded {
     if (kind == QN_BFGS) {
       double ys = dot(y, s), rho = 1.0 / ys, yh = dot(y, h);
       double c = rho * rho * yh + rho;
-      for (size_t j = 0; j < n; ++j)
+      // (elementwise: threads over columns change no element's arithmetic)
+#pragma omp parallel for schedule(static)
+      for (long j = 0; j < (long)n; ++j)
         for (size_t i = 0; i < n; ++i) {
           double cross = s[i] * h[j] + h[i] * s[j];
           double ssq = s[i] * s[j];
@@ -1105,7 +1110,8 @@ struct QuasiNewton : SYNorms, Bounded {
         }
     } else if (kind == QN_DFP) {
       double sy = dot(s, y), yhy = dot(y, h);
-      for (size_t j = 0; j < n; ++j)
+#pragma omp parallel for schedule(static)
+      for (long j = 0; j < (long)n; ++j)
         for (size_t i = 0; i < n; ++i) H(i, j) = (H(i, j) + (s[i] * s[j]) / sy) - (h[i] * h[j]) / yhy;
     } else if (kind == QN_BROYDEN) {
       // H += (s - Hy) (s^T H) / (s.y) ; v = H^T s

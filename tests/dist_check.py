@@ -132,6 +132,41 @@ def main():
               % (rank, name, k1, k0, r1, r0, abs(f1 - f0) / abs(f0), np.max(np.abs(x1 - x0_[sl])), np.array_equal(a1, a0[sl]), good), flush=True)
         ok &= bool(good)
 
+    # ---- C5a shape: Newton on the logistic regression with the SAMPLES sharded over the ranks (all-reduce of f, g and the
+    # n x n Hessian, newton/mod.rs:26-49 replicated): same iteration count and reason, x within 1e-9, identical on all ranks
+    m_, n = 4096, 96
+    out = []
+    for c in (ctx, solo):
+        obj = osb.LogisticRegression.generated(m_, n, 1.0, ctx=c)
+        s = osb.Newton(1e-8, np.zeros(n), ctx=c)
+        st = "Ok"
+        try:
+            s.minimize(osb.BackTracking(1e-4, 0.5), obj, 50, 20)
+        except osb.SolverError as e:
+            st = type(e).__name__
+        out.append((st, s.k(), s.termination_reason(), s.x(), s.decrement_squared()))
+        s.close()
+    xs = [None] * world
+    dist.all_gather_object(xs, out[0][3].tobytes())
+    same_on_ranks = all(b == xs[0] for b in xs)
+    dx = float(np.max(np.abs(out[0][3] - out[1][3])) / max(1.0, float(np.max(np.abs(out[1][3])))))
+    good = out[0][:3] == out[1][:3] and out[0][0] == "Ok" and same_on_ranks and dx <= 1e-9
+    print("rank %d Newton logistic m=%d n=%d sample-sharded: %s k=%d/%d reason=%s ranks identical %s max rel|dx| %.2e -> %s"
+          % (rank, m_, n, out[0][0], out[0][1], out[1][1], out[0][2], same_on_ranks, dx, good), flush=True)
+    ok &= bool(good)
+
+    # ---- C4 shape: the batched mode split over the ranks (problem0 offsets, no collective): every rank's slice is
+    # bit-identical to the same problems solved in one single-GPU batch
+    np_, nb = 1024, 32
+    per = np_ // world
+    mine = osb.batched_bfgs_rosenbrock(nb, per, problem0=rank * per, ctx=ctx)
+    full = osb.batched_bfgs_rosenbrock(nb, np_, problem0=0, ctx=solo)
+    sl = slice(rank * per, (rank + 1) * per)
+    good = (np.array_equal(mine["x"], full["x"][sl]) and np.array_equal(mine["k"], full["k"][sl]) and
+            np.array_equal(mine["status"], full["status"][sl]) and np.array_equal(mine["reason"], full["reason"][sl]))
+    print("rank %d batched BFGS %d problems split over %d ranks: slice bit-identical to the single-GPU batch: %s" % (rank, np_, world, good), flush=True)
+    ok &= bool(good)
+
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.barrier()

@@ -101,3 +101,56 @@ def test_not_spd_is_reported_like_the_reference_panic(osb):
     s = osb.Newton(1e-8, [1.0, 1.0])
     with pytest.raises(osb.ReferencePanic):
         s.minimize(osb.NoSearch(), osb.ExtendedRosenbrock(2), 5, 5)
+
+
+def _nonconvex_oracle(m, n, singular):
+    """f = 1/2 x^T H x + 1/4 sum x_i^4 with an indefinite (or exactly singular) constant part H."""
+    rng = np.random.default_rng(7)
+    Q = np.round(rng.standard_normal((n, n)) * 4) / 8      # small dyadic entries: identical bits on both sides
+    H = Q + Q.T
+    H[np.diag_indices(n)] = np.where(np.arange(n) % 2 == 0, 3.0, -2.0)
+
+    def fn(x):
+        if singular:
+            # Hessian with an exactly zero first row / column: every pivot candidate of column 0 is 0.0
+            Hs = H.copy()
+            Hs[0, :] = 0.0
+            Hs[:, 0] = 0.0
+            return m.FuncEvalMultivariate(0.5 * x @ Hs @ x + x[0], Hs @ x + np.eye(n)[0]).with_hessian(Hs)
+        hess = H + np.diag(3.0 * x * x)
+        return m.FuncEvalMultivariate(0.5 * x @ H @ x + 0.25 * np.sum(x ** 4), H @ x + x ** 3).with_hessian(hess)
+    return fn
+
+
+@pytest.mark.parametrize("n", [3, 6, 40])
+def test_newton_indefinite_hessian_goes_through_lu_like_try_inverse(osb, orc, n):
+    # newton/mod.rs:36: try_inverse (LU with partial pivoting) accepts an indefinite Hessian; only ProjectedNewton / SPN
+    # panic on a failed Cholesky
+    def script(m, host):
+        fn = _nonconvex_oracle(m, n, False)
+        o = m.HostOracle(fn, n, True) if host else m.HostOracle(fn, True)
+        s = m.Newton(1e-10, np.linspace(-1.0, 1.0, n) * 0.5 + 0.25)
+        st = run(m, s, m.NoSearch(), o, 4, 5)
+        return st, s.k(), s.termination_reason(), s.x(), s.decrement_squared()
+
+    ref, got = script(orc, False), script(osb, True)
+    assert got[:3] == ref[:3], (got[:3], ref[:3])
+    assert close(got[3], ref[3], rtol=1e-9)
+    assert close(got[4], ref[4], rtol=1e-8)
+
+
+def test_newton_singular_hessian_falls_back_to_the_gradient(osb, orc):
+    # newton/mod.rs:43-46: try_inverse fails -> direction = -g, decrement_squared untouched (stays None here)
+    n = 6
+
+    def script(m, host):
+        fn = _nonconvex_oracle(m, n, True)
+        o = m.HostOracle(fn, n, True) if host else m.HostOracle(fn, True)
+        s = m.Newton(1e-10, np.full(n, 0.5))
+        st = run(m, s, m.BackTracking(1e-4, 0.5), o, 2, 30)
+        return st, s.k(), s.x(), s.decrement_squared()
+
+    ref, got = script(orc, False), script(osb, True)
+    assert got[:2] == ref[:2], (got[:2], ref[:2])
+    assert close(got[2], ref[2])
+    assert got[3] is None and ref[3] is None
