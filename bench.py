@@ -405,6 +405,8 @@ def apply_debug_options(solver, args):
         solver.set_option("engine", args.engine)
     if args.no_p2p:
         solver.set_option("use_p2p", 0)
+    if args.no_fused:
+        solver.set_option("fused_iteration", 0)
     return solver
 
 
@@ -480,13 +482,20 @@ def run_c3(args, env):
     ms = float(np.median(windows))
     value = K / (ms / 1000.0)
 
-    # ---- roofline of the dominant kernel: per-launch CUDA-event pairs over one more K-step window
+    # ---- roofline of the dominant kernel
+    info = solver.path_info()  # the path the timed windows took (library defaults unless a debug flag was given)
+    sym, lazy, fused = info["storage"] == 1, info["schedule"] == 1, info["fused"]
+    iterp = None
+    if fused:  # where the fused kernel's time goes: globaltimer stamps inside the kernel, one more K-step window
+        solver.set_option("profile_iter", 1)
+        run_steps(solver, K)
+        iterp = solver.iter_profile()
+        solver.set_option("profile_iter", 0)
+    # the H pass as its own launch (one launch per phase), CUDA-event pairs around every launch, one more K-step window
     solver.set_option("profile_kernels", 1)
     run_steps(solver, K)
     kt = solver.kernel_timing()
     solver.set_option("profile_kernels", 0)
-    info = solver.path_info()
-    sym, lazy = info["storage"] == 1, info["schedule"] == 1
     rows_local = n // world
     if sym:
         upd_bytes = iter_bytes = 1.0 * n * n * 8.0 / world  # read + write of (this rank's share of) the lower triangle
@@ -495,16 +504,25 @@ def run_c3(args, env):
         iter_bytes = (2.0 if lazy else 3.0) * rows_local * n * 8.0
     peak, peak_src = hbm_peak()
     pass_ms, tail_ms = kt["gemv_ms"], kt["update_ms"]
-    k_ms = (pass_ms + tail_ms) if sym else tail_ms
-    ach = upd_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
-    kname = ("qn_lazy_sym_kernel<BFGS> + qn_sym_fold_kernel (packed lower triangle: pending rank-2 RMW + row and column sums)" if sym else
-             "qn_lazy_kernel<BFGS> (pending rank-2 RMW + h = H y + w = H g in one pass)" if lazy
-             else "qn_update_kernel<BFGS> (fused rank-2 RMW + u = H' g)")
     step_bw = iter_bytes / (ms / K * 1e-3) / 1e9
+    if fused:
+        # the dominant kernel IS the iteration: algorithmic bytes of one iteration / (CUDA-event time of the timed window / K)
+        k_ms, ach = ms / K, step_bw
+        kname = ("qn_iter_kernel<Rosenbrock, BackTracking> (one cooperative launch per %d iterations: epilogue, line search on every SM, "
+                 "pending rank-2 RMW + row and column sums over the packed lower triangle, fold%s)" % (4, ", peer-memory exchange" if world > 1 else ""))
+    else:
+        k_ms = (pass_ms + tail_ms) if sym else tail_ms
+        ach = upd_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
+        kname = ("qn_lazy_sym_kernel<BFGS> + qn_sym_fold_kernel (packed lower triangle: pending rank-2 RMW + row and column sums)" if sym else
+                 "qn_lazy_kernel<BFGS> (pending rank-2 RMW + h = H y + w = H g in one pass)" if lazy
+                 else "qn_update_kernel<BFGS> (fused rank-2 RMW + u = H' g)")
     roofline = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": (ach / peak) if ach else None, "traffic": ncu_traffic() if (world == 1 and sym) else None,
-                "algorithmic_bytes_per_launch": upd_bytes, "ms_per_launch": k_ms,
-                "parts_ms": {"pass": pass_ms, "fold_or_update": tail_ms},
+                "algorithmic_bytes_per_launch": upd_bytes * (1 if not fused else 1), "ms_per_launch": k_ms,
+                "per": "iteration" if fused else "launch",
+                "inside_the_fused_kernel_ms": iterp,
+                "pass_inside_fused_frac": (upd_bytes / (iterp["pass_ms"] * 1e-3) / 1e9 / peak) if (iterp and iterp["pass_ms"] > 0) else None,
+                "one_launch_per_phase_ms": {"pass": pass_ms, "fold_or_update": tail_ms},
                 "pass_alone_frac": (upd_bytes / (pass_ms * 1e-3) / 1e9 / peak) if (sym and pass_ms > 0) else None,
                 "iteration_bytes": iter_bytes, "iteration_frac_of_peak": step_bw / peak,
                 # SURVEY 8d counts the 3-pass form, 3 n^2 8 B per iteration: the same step time on that byte count
@@ -604,7 +622,8 @@ def run_c3(args, env):
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload, "n": n, "line_search": "BackTracking(1e-4,0.5)", "tol": TOL,
                            "max_iter_line_search": MAX_LS, "options_set": "none (library defaults)" if not any(
-                               v is not None for v in (args.schedule, args.storage, args.qn_kernel, args.head, args.engine)) else "debug flags",
+                               v is not None for v in (args.schedule, args.storage, args.qn_kernel, args.head, args.engine)) and not args.no_fused else "debug flags",
+                           "kernel": info["kernel"],
                            "engine": info["engine"], "schedule": info["schedule_name"], "storage": info["storage_name"],
                            "l2": "inputs larger than L2 (H = %.2f GiB per GPU, streamed every step)" % (
                                (n * (n + 8) / 2 / world if sym else rows_local * n) * 8 / 2 ** 30),
@@ -775,6 +794,7 @@ def main():
     ap.add_argument("--qn-kernel", type=int, default=None)
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL all-gathers instead of the fused peer-memory exchange")
     ap.add_argument("--schedule", default=None, choices=["lazy", "eager"])
+    ap.add_argument("--no-fused", action="store_true", help="one launch per phase instead of the fused iteration kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

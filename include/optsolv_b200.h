@@ -228,7 +228,11 @@ int osb_minimize(osb_solver* s, osb_linesearch* ls, osb_objective* obj, int64_t 
  *   "qn_kernel"          kernel variant of the H pass (diagnostics, default 0).  Full storage: 1 = TMA-staged ring.  Packed
  *                        storage: bit 0 = two 256-thread CTAs per SM, bit 1 = ping-pong (out-of-place) storage,
  *                        bit 2 = zero-first column partials (round-1 behaviour)
- *   "profile_kernels"    1 = bracket the H pass(es) with CUDA events (osb_solver_kernel_timing) */
+ *   "fused_iteration"   -1 / 1 = (default) whole outer iterations in ONE cooperative kernel whenever the lazy schedule on
+ *                        packed storage runs under device-resident control (line search on every SM, H pass, fold and
+ *                        multi-GPU exchange separated by grid barriers only); 0 = one launch per phase
+ *   "profile_kernels"    1 = one launch per phase, the H pass(es) bracketed with CUDA events (osb_solver_kernel_timing)
+ *   "profile_iter"       1 = the fused kernel records where its time goes (osb_solver_iter_profile) */
 int osb_solver_set_option(osb_solver* s, const char* name, int64_t value);
 int osb_solver_set_lambdas(osb_solver* s, double lambda_min, double lambda_max); /* spg.rs:23-27 */
 
@@ -258,8 +262,12 @@ int osb_solver_trace(const osb_solver* s, double* f, double* t, double* s_norm, 
 int osb_solver_kernel_timing(const osb_solver* s, double out[3]);
 /* which path the last minimize() took (the defaults are "auto"): out[0] engine (1 host-driven, 2 device-resident control),
  * out[1] schedule in force (0 eager, 1 lazy), out[2] storage in force (0 full n x n, 1 packed lower triangle), out[3] packed
- * triangle sharded over the ranks, out[4] fused peer-memory exchange used, out[5] ranks, out[6] kernel variant, out[7] 0 */
+ * triangle sharded over the ranks, out[4] fused peer-memory exchange used, out[5] ranks, out[6] kernel variant,
+ * out[7] whole iterations ran in the fused cooperative kernel */
 int osb_solver_path_info(const osb_solver* s, int64_t out[8]);
+/* option "profile_iter": mean ms per iteration in out[0] head (epilogue, line search, next iterate), out[1] H pass,
+ * out[2] fold + exchange of the fused iteration kernel (globaltimer stamps of CTA 0); out[3] = iterations covered */
+int osb_solver_iter_profile(osb_solver* s, double out[4]);
 /* device time (ms, CUDA events on the context stream) and outer iterations of the last minimize */
 int osb_solver_last_timing(const osb_solver* s, double* ms, int64_t* iterations);
 

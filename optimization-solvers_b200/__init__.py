@@ -96,6 +96,7 @@ def lib():
             "osb_solver_last_timing": (ci, [_vp, _dp, C.POINTER(i64)]),
             "osb_solver_kernel_timing": (ci, [_vp, _dp]),
             "osb_solver_path_info": (ci, [_vp, C.POINTER(i64)]),
+            "osb_solver_iter_profile": (ci, [_vp, _dp]),
             "osb_batched_bfgs_rosenbrock": (ci, [_vp, i64, i64, _dp, dbl, i64, i64, dbl, dbl, _dp, _dp, i32p, i32p,
                                                  i32p, _dp]),
             "osb_batched_bfgs_rosenbrock_generated": (ci, [_vp, i64, i64, i64, dbl, i64, i64, dbl, dbl, _dp, _dp,
@@ -868,16 +869,25 @@ class _Solver:
         """Which path the last minimize() took (the options default to auto): see osb_solver_path_info."""
         out = (C.c_int64 * 8)()
         lib().osb_solver_path_info(self.handle, out)
-        eng, sched, stor, shard, p2p, world, variant = (int(out[i]) for i in range(7))
+        eng, sched, stor, shard, p2p, world, variant, fused = (int(out[i]) for i in range(8))
         return dict(engine={1: "host-driven control", 2: "device-resident control"}.get(eng, "none"), schedule=sched, storage=stor,
                     schedule_name=("lazy: 1 RMW pass of the stored matrix per iteration" if sched == 1 else "eager: gemv + fused update (3 n^2 8 B)"),
                     storage_name=("packed lower triangle, 8-row tiles (n^2 8 B per pass)" if stor == 1 else "full n x n row-major"),
-                    sharded_packed=bool(shard), p2p=bool(p2p), world=world, variant=variant,
+                    sharded_packed=bool(shard), p2p=bool(p2p), world=world, variant=variant, fused=bool(fused),
+                    kernel=("qn_iter_kernel: whole iterations (line search, H pass, fold, exchange) in one cooperative launch"
+                            if fused else "one launch per phase (head, pass, fold)"),
                     parallelism=("1 GPU" if world == 1 else
                                  "packed triangle sharded by tile pairs over %d GPUs; per-rank {h, w} contributions stored into every "
                                  "peer's slot (NVLink stores + flags), summed in rank order" % world if shard else
                                  "row-block sharded H over %d GPUs; %s" % (world, "peer-memory all-gather fused into the pass kernel"
                                                                            if p2p else "NCCL all-gather of the h / w slices")))
+
+    def iter_profile(self):
+        """Option "profile_iter" = 1: mean ms per iteration spent in the head (epilogue, line search, step), the H pass and
+        the fold + exchange of the fused iteration kernel (globaltimer stamps of CTA 0), and the iterations covered."""
+        out = (C.c_double * 4)()
+        _check(lib().osb_solver_iter_profile(self.handle, out))
+        return dict(head_ms=out[0], pass_ms=out[1], fold_ms=out[2], iterations=int(out[3]))
 
     def kernel_timing(self):
         out = (C.c_double * 3)()

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libosb_b200.so")
 OBJDIR = os.path.join(HERE, "build")
 SOURCES = ["api.cu", "engine.cu", "objectives.cu", "vec_kernels.cu", "qn_kernels.cu", "qn_small.cu", "qn_device.cu", "newton.cu", "logistic.cu",
-           "batched.cu", "dist.cu"]
+           "batched.cu", "dist.cu", "qn_iter.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
          "--extended-lambda", "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "-ccbin", "/usr/bin/g++"]

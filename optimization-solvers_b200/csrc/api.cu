@@ -411,6 +411,8 @@ int osb_solver_set_option(osb_solver* s, const char* name, int64_t value) {
   else if (nm == "use_p2p") S(s)->use_p2p = (int)value;
   else if (nm == "head_kernel") S(s)->head_variant = (int)value;
   else if (nm == "profile_kernels") S(s)->profile_kernels = (int)value;
+  else if (nm == "fused_iteration") S(s)->opt_fused = (int)value;
+  else if (nm == "profile_iter") S(s)->profile_iter = (int)value;
   else throw Error(OSB_ERROR_INPUT_PARAMS, "unknown option " + nm);
   return OSB_OK;
   OSB_CATCH
@@ -577,6 +579,23 @@ int osb_solver_kernel_timing(const osb_solver* s, double out[3]) {
   out[2] = S(s)->prof_ms[2];
   return OSB_OK;
 }
+int osb_solver_iter_profile(osb_solver* s, double out[4]) {
+  OSB_TRY
+  Solver* p = S(s);
+  out[0] = out[1] = out[2] = out[3] = 0.0;
+  if (!p->d_iter_prof) return OSB_OK;
+  p->ctx->use();
+  p->ctx->sync();
+  long long v[4];
+  OSB_CUDA(cudaMemcpy(v, p->d_iter_prof, sizeof(v), cudaMemcpyDeviceToHost));
+  const double its = v[3] > 0 ? (double)v[3] : 1.0;
+  out[0] = (double)v[0] * 1e-6 / its;
+  out[1] = (double)v[1] * 1e-6 / its;
+  out[2] = (double)v[2] * 1e-6 / its;
+  out[3] = (double)v[3];
+  return OSB_OK;
+  OSB_CATCH
+}
 int osb_solver_path_info(const osb_solver* s, int64_t out[8]) {
   const Solver* p = S(s);
   out[0] = p->last_engine;
@@ -586,7 +605,7 @@ int osb_solver_path_info(const osb_solver* s, int64_t out[8]) {
   out[4] = p->last_p2p ? 1 : 0;
   out[5] = p->ctx->world;
   out[6] = p->qn_variant;
-  out[7] = 0;
+  out[7] = p->last_fused ? 1 : 0;
   return OSB_OK;
 }
 int osb_solver_last_timing(const osb_solver* s, double* ms, int64_t* iters) {

@@ -80,7 +80,8 @@ void Ctx::all_gather_inplace(double* buf, int64_t count) {
 // ---- peer-memory exchange region (CUDA IPC) -----------------------------------------------------
 static size_t xchg_bytes(int world) {
   // 4 exchanged vectors | flags (64 words reserved) | sharded packed storage: 2 parities x world x {h, w} slots
-  return sizeof(double) * (size_t)(XSLOT_OFF + 2 * (int64_t)world * 2 * XSLOT_LD);
+  // | per-source-rank chunk flags of the fused iteration kernel (world x XFLAG2_LD 64-bit words)
+  return sizeof(double) * (size_t)(xflag2_off(world) + (int64_t)world * XFLAG2_LD);
 }
 
 void ctx_ipc_export(Ctx* ctx, void* out64) {

@@ -267,6 +267,7 @@ Solver::~Solver() {
   pool_put(1, 2 * sizeof(double) * (size_t)ld, cb_gsnap);
   pool_put(0, sizeof(LSParams), d_ls_buf);
   pool_put(1, 2 * sizeof(DevState), poll_snap);
+  if (d_iter_prof) cudaFree(d_iter_prof);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
 }
@@ -458,6 +459,13 @@ HeadEpi Solver::head_epi() const {
   return HeadEpi{qn_kind, h1, w1, h2, w2, 1, 0, u.p, ps.p, ph.p};
 }
 void Solver::finish_epilogue() {
+  if (iter_path) {  // the same kernel, epilogue only: the bits do not depend on who ran the epilogue
+    QNIterArgs a = iter_args;
+    a.iters = 0;
+    a.epi_only = 1;
+    qn_launch_iter(ctx, iter_fn_kind, iter_fn_a, iter_fn_b, bounded, iter_ls_kind, a);
+    return;
+  }
   if (!defer_epi) return;
   qn_launch_epilogue_cluster(ctx, head_epi(), n, d_state, s.p, y.p, g.p);
 }
@@ -470,6 +478,21 @@ void Solver::flush_pending() {
   lazy_used = false;
 }
 
+// A pending update means "the stored matrix lags by one rank-2 term": packing the lagging matrix keeps that meaning.
+void Solver::ensure_packed() {
+  if (sym_current) return;
+  if (Hsym.p == nullptr) Hsym.alloc_pooled(sym_sharded ? qn_sym_doubles_sharded(n, ctx->world, ctx->rank) : qn_sym_doubles(n));
+  if (H_virtual_identity) {
+    if (sym_sharded) qn_sym_set_identity_sharded(ctx, n, Hsym.p);
+    else qn_sym_set_identity(ctx, n, Hsym.p);
+    H_virtual_identity = false;
+  } else {
+    OSB_REQUIRE(!sym_sharded, OSB_ERR_UNSUPPORTED, "sharded packed storage starts from H = I");  // (guarded by the caller)
+    qn_sym_pack(ctx, H.p, ld, n, Hsym.p);
+  }
+  sym_current = true;
+}
+
 void Solver::qn_after_step() {
   const DevState* st = d_state;
   if (n <= QN_SMALL_N && ctx->world == 1) {  // reference operation order, bit-for-bit (qn_small.cu)
@@ -480,18 +503,7 @@ void Solver::qn_after_step() {
   if (qn_schedule == 1 && qn_storage == 1 && h_symmetric && (ctx->world == 1 || sym_sharded) && (qn_kind == QN_BFGS || qn_kind == QN_DFP)) {
     // packed symmetric storage: the pass moves n^2 * 8 B (read + write of the lower triangle).  A pending
     // update means "the stored matrix lags by one rank-2 term": packing the lagging matrix keeps that meaning.
-    if (!sym_current) {
-      if (Hsym.p == nullptr) Hsym.alloc_pooled(sym_sharded ? qn_sym_doubles_sharded(n, ctx->world, ctx->rank) : qn_sym_doubles(n));
-      if (H_virtual_identity) {
-        if (sym_sharded) qn_sym_set_identity_sharded(ctx, n, Hsym.p);
-        else qn_sym_set_identity(ctx, n, Hsym.p);
-        H_virtual_identity = false;
-      } else {
-        OSB_REQUIRE(!sym_sharded, OSB_ERR_UNSUPPORTED, "sharded packed storage starts from H = I");  // (guarded by the caller)
-        qn_sym_pack(ctx, H.p, ld, n, Hsym.p);
-      }
-      sym_current = true;
-    }
+    ensure_packed();
     QNLazyArgs a{nullptr, ld, nrows, row0, n, d_state, ps.p, ph.p, y.p, g.p, s.p, h.p, wv.p, u.p, ps.p, ph.p,
                  ctx->gemv_ticket, qn_kind, nullptr, ctx->d_seq, 1, 0};
     a.defer_epi = defer_epi ? 1 : 0;
@@ -502,7 +514,7 @@ void Solver::qn_after_step() {
       ctx->counters[5]++;  // passes over the sharded packed triangle
     }
     const int pgrid = qn_sym_grid(ctx, n, qn_variant);
-    if (colpart.p == nullptr || colpart_grid != pgrid) {
+    if (colpart.p == nullptr || colpart_grid < pgrid) {
       colpart.alloc_pooled((int64_t)pgrid * 2 * ld);
       colpart_grid = pgrid;
     }
@@ -608,7 +620,7 @@ int Solver::minimize(LineSearch* ls, Objective* obj, int64_t max_iter, int64_t m
               "device-resident engine needs a quasi-Newton solver and a block-functor objective");
   OSB_CUDA(cudaEventRecord(ev0, ctx->stream));
   int rc;
-  last_sym_sharded = last_p2p = false;
+  last_sym_sharded = last_p2p = last_fused = false;
   if (dev_ok && engine != 1) {
     last_engine = 2;
     rc = minimize_device(ls, obj, max_iter, max_ls, cb, user);
@@ -805,7 +817,63 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
   if (!sym_sharded && sym_current && ctx->world > 1) sym_to_full();
   last_sym_sharded = sym_sharded;
   last_p2p = epi_p2p;
-  defer_epi = qn_schedule == 1 && (qn_kind == QN_BFGS || qn_kind == QN_DFP) && n > QN_SMALL_N &&
+  // whole iterations in one cooperative kernel (qn_iter.cu): packed lazy schedule on one GPU or sharded by tile pairs
+  iter_path = opt_fused != 0 && !profile_kernels && qn_schedule == 1 && qn_storage == 1 && h_symmetric &&
+              (qn_kind == QN_BFGS || qn_kind == QN_DFP) && (ctx->world == 1 || sym_sharded) && head_variant == 0 &&
+              (qn_variant & 7) == 0 && qn_iter_supported(ctx, obj->functor_kind(), n, ctx->world);
+  if (iter_path) {
+    if (sym_current) sym_settle_pingpong();
+    ensure_packed();
+    const int g_it = qn_iter_grid(ctx);
+    if (colpart.p == nullptr || colpart_grid < g_it) {
+      colpart.alloc_pooled((int64_t)g_it * 2 * ld);
+      colpart_grid = g_it;
+    }
+    if (gpart.p == nullptr) gpart.alloc_pooled(qn_iter_gpart_doubles(ctx));
+    if (profile_iter && !d_iter_prof) {
+      OSB_CUDA(cudaMalloc(&d_iter_prof, 4 * sizeof(long long)));
+    }
+    if (profile_iter) OSB_CUDA(cudaMemsetAsync(d_iter_prof, 0, 4 * sizeof(long long), stm));
+    QNIterArgs a{};
+    a.n = n;
+    a.ld = ld;
+    a.tol = tol;
+    a.max_ls = max_ls;
+    a.kind = qn_kind;
+    a.iters = 0;
+    a.epi_only = 0;
+    a.st = d_state;
+    a.lsp = d_ls;
+    a.x = x.p;
+    a.g = g.p;
+    a.s = s.p;
+    a.y = y.p;
+    a.u = u.p;
+    a.ps = ps.p;
+    a.ph = ph.p;
+    a.h = h.p;
+    a.w = wv.p;
+    a.lb = bounded ? lb.p : nullptr;
+    a.ub = bounded ? ub.p : nullptr;
+    a.ls_lb = ls_bounded ? ls->lb.p : nullptr;
+    a.ls_ub = ls_bounded ? ls->ub.p : nullptr;
+    a.P = Hsym.p;
+    a.colpart = colpart.p;
+    a.gpart = gpart.p;
+    a.world = sym_sharded ? ctx->world : 1;
+    a.rank = sym_sharded ? ctx->rank : 0;
+    a.peers = sym_sharded ? ctx->d_peers : nullptr;
+    a.seq = ctx->d_seq;
+    a.prof = profile_iter ? d_iter_prof : nullptr;
+    iter_args = a;
+    iter_fn_kind = obj->functor_kind();
+    iter_fn_a = obj->functor_ptr(0);
+    iter_fn_b = obj->functor_ptr(1);
+    iter_ls_kind = ls->p.kind;
+    defer_epi = false;  // the epilogue is the fused kernel's own business
+  }
+  last_fused = iter_path;
+  defer_epi = !iter_path && qn_schedule == 1 && (qn_kind == QN_BFGS || qn_kind == QN_DFP) && n > QN_SMALL_N &&
               (qn_storage == 1 || qn_variant == 0) &&
               qn_device_head_is_cluster(obj->functor_kind(), n, head_variant);
   // ---- run-ahead delivery of callbacks / trace records (see engine.cuh: callback_run_ahead)
@@ -846,11 +914,26 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
     }
     return true;
   };
-  for (int64_t it = 0; it < max_iter && !stop; ++it) {
-    qn_device_launch_head(ctx, obj->functor_kind(), obj->functor_ptr(0), obj->functor_ptr(1), bounded, d_ls, n, tol, max_ls,
-                          d_state, x.p, g.p, d.p, xt.p, gt.p, s.p, y.p, u.p, bounded ? lb.p : nullptr, bounded ? ub.p : nullptr,
-                          ls_bounded ? ls->lb.p : nullptr, ls_bounded ? ls->ub.p : nullptr, head_variant, ls->p.kind, head_epi());
-    qn_after_step();
+  int64_t chunk = 1;
+  for (int64_t it = 0; it < max_iter && !stop; it += chunk) {
+    if (iter_path) {
+      // up to POLL iterations per launch; one per launch when a callback / trace wants every iteration's state
+      chunk = (cb != nullptr || record_trace) ? 1 : std::min<int64_t>(POLL, max_iter - it);
+      QNIterArgs a = iter_args;
+      a.iters = (int)chunk;
+      qn_launch_iter(ctx, iter_fn_kind, iter_fn_a, iter_fn_b, bounded, iter_ls_kind, a);
+      if (sym_sharded) {
+        ctx->counters[4] += chunk;  // fused exchanges
+        ctx->counters[5] += chunk;  // passes over the sharded packed triangle
+      }
+      lazy_used = true;
+      u_valid = true;
+    } else {
+      qn_device_launch_head(ctx, obj->functor_kind(), obj->functor_ptr(0), obj->functor_ptr(1), bounded, d_ls, n, tol, max_ls,
+                            d_state, x.p, g.p, d.p, xt.p, gt.p, s.p, y.p, u.p, bounded ? lb.p : nullptr, bounded ? ub.p : nullptr,
+                            ls_bounded ? ls->lb.p : nullptr, ls_bounded ? ls->ub.p : nullptr, head_variant, ls->p.kind, head_epi());
+      qn_after_step();
+    }
     if (run_ahead) {
       // snapshot of this iteration, then keep going: the previous iteration's callback runs while the device works
       OSB_CUDA(cudaMemcpyAsync(&cb_snap[cb_slot], d_state, sizeof(DevState), cudaMemcpyDeviceToHost, stm));
@@ -880,7 +963,7 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
       if (cb) cb(user, reinterpret_cast<osb_solver*>(this));
       continue;
     }
-    if ((it + 1) % POLL == 0) {
+    if (iter_path || (it + 1) % POLL == 0) {
       if (pending[slot]) {  // bound the run-ahead: wait for the older snapshot of this slot
         OSB_CUDA(cudaEventSynchronize(sev[slot]));
         ctx->counters[3]++;
@@ -908,6 +991,7 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
   finish_epilogue();
   defer_epi = false;
   sym_sharded = false;
+  iter_path = false;
   fetch_state();
   OSB_CUDA(cudaMemcpyAsync(&ls->p, d_ls, sizeof(LSParams), cudaMemcpyDeviceToHost, stm));
   ctx->sync();

@@ -258,6 +258,34 @@ void qn_sym_set_identity_sharded(Ctx* ctx, int64_t n, double* P);
 void qn_sym_unpack_sharded(Ctx* ctx, const double* P, int64_t ld, int64_t n, double* Hfull_zeroed);
 void qn_sym_unpack(Ctx* ctx, const double* P, int64_t ld, int64_t n, double* H);
 void qn_launch_lazy_sym(Ctx* ctx, const QNLazyArgs& a, double* P, double* Pout, double* colpart, int64_t n, int64_t ld, int phase, int variant);
+// whole outer iterations in one cooperative kernel (qn_iter.cu): head + line search + H pass + fold + exchange
+constexpr int64_t XFLAG2_LD = 256;  // per-source-rank chunk flags of the fused iteration kernel (one per CTA)
+HD int64_t xflag2_off(int world) { return XSLOT_OFF + 4 * (int64_t)world * XSLOT_LD; }  // doubles; after the {h, w} slots
+struct QNIterArgs {
+  int64_t n, ld;
+  double tol;
+  int64_t max_ls;
+  int kind;      // QN_BFGS / QN_DFP
+  int iters;     // outer iterations to run in this launch
+  int epi_only;  // 1: only run the epilogue an earlier pass left owed (end of minimize, before a stalling callback)
+  DevState* st;
+  LSParams* lsp;
+  double *x, *g, *s, *y, *u, *ps, *ph;
+  double *h, *w;  // row sums of the pass; after the fold (one GPU) h = H y and w = H g
+  const double *lb, *ub, *ls_lb, *ls_ub;
+  double* P;        // packed matrix (this rank's tiles)
+  double* colpart;  // grid x 2 x ld
+  double* gpart;    // 2 x grid x IT_GPK
+  int world, rank;
+  double* const* peers;
+  unsigned long long* seq;
+  long long* prof;  // optional [4]: ns in head / pass / fold+exchange (CTA 0), iterations
+};
+
+bool qn_iter_supported(Ctx* ctx, int functor_kind, int64_t n, int world);
+int qn_iter_grid(Ctx* ctx);
+int64_t qn_iter_gpart_doubles(Ctx* ctx);
+void qn_launch_iter(Ctx* ctx, int functor_kind, const double* fn_a, const double* fn_b, bool bounded, int ls_kind, const QNIterArgs& a);
 // apply a pending update to the stored matrix (getters, engine switches)
 void qn_launch_flush(Ctx* ctx, int kind, double* M, int64_t ld, int64_t nrows, int64_t row0, DevState* st, const double* ps,
                      const double* ph);
@@ -314,7 +342,7 @@ struct Solver {
   // that writes `BFGS::new(tol, x0)` + `minimize(...)` like examples/bfgs_example.rs:46-52 gets the n^2 8 B path.
   int opt_schedule = -1, opt_storage = -1;
   int last_engine = 0;         // what the last minimize() ran: 1 = host-driven, 2 = device-resident control
-  bool last_sym_sharded = false, last_p2p = false;
+  bool last_sym_sharded = false, last_p2p = false, last_fused = false;
   void resolve_options();
   void recompute_u();     // u = H g from the exact matrix (first iteration, after set_x / set_inv_hessian)
   int qn_schedule = 0;    // 0 = eager (h = H y, then fused update: 3 n^2 8 B), 1 = lazy (one RMW: 2 n^2 8 B)
@@ -331,6 +359,17 @@ struct Solver {
   DBuf Hsym, Hsym2, colpart;  // packed matrix (+ its ping-pong twin, pass variant bit 1) and per-CTA column partials
   int colpart_grid = 0;
   bool sym_pingpong_dirty = false;
+  // fused iteration kernel (qn_iter.cu): -1 = auto (on whenever it applies), 0 = off (one launch per phase)
+  int opt_fused = -1;
+  bool iter_path = false;        // this minimize() runs whole iterations in one cooperative kernel
+  QNIterArgs iter_args{};        // last launch parameters (the epilogue-only launch re-uses them)
+  int iter_fn_kind = 0, iter_ls_kind = 0;
+  const double* iter_fn_a = nullptr;
+  const double* iter_fn_b = nullptr;
+  DBuf gpart;                    // grid-reduction partials
+  long long* d_iter_prof = nullptr;  // option "profile_iter": ns in head / pass / fold (CTA 0) and iterations
+  int profile_iter = 0;
+  void ensure_packed();          // the packed copy holds the current matrix (identity / pack on first use)
   bool sym_current = false;  // the packed copy (not H) holds the current matrix
   bool h_symmetric = true;   // false after set_inv_hessian with a non-symmetric matrix (then full storage is used)
   void sym_to_full();

@@ -659,13 +659,66 @@ def test_packed_symmetric_storage_matches_full_storage(osb, orc, kind):
         run(osb, s, osb.BackTracking(1e-4, 0.5), osb.ExtendedRosenbrock(n), 8, 20)
         res.append((s.x(), s.approx_inv_hessian()))
     assert close(res[0][0], res[1][0], rtol=1e-9) and close(res[0][1], res[1][1], rtol=1e-8)
-    # a non-symmetric user matrix disables the packed path (results must equal full storage exactly)
+    # BFGS / DFP are implemented in their symmetric forms (H y is row AND column factor); the crate has no setter for
+    # approx_inv_hessian and its H stays symmetric, so a non-symmetric user matrix is an input error here, while a
+    # symmetric one is accepted and then packed (results equal full storage to rounding of the summation order)
     rng = np.random.default_rng(0)
     Hn = np.eye(64) + 0.01 * rng.standard_normal((64, 64))
+    s = getattr(osb, kind)(1e-8, rosen_x0(64, 3))
+    with pytest.raises(osb.ErrorInputParams):
+        s.set_approx_inv_hessian(Hn)
+    osb.Broyden(1e-8, rosen_x0(64, 3)).set_approx_inv_hessian(Hn)  # Broyden's H is not symmetric: accepted
+    Hs = 0.5 * (Hn + Hn.T)
     res = []
     for storage in (0, 1):
         s = getattr(osb, kind)(1e-8, rosen_x0(64, 3)).set_option("engine", 2).set_option("qn_schedule", 1).set_option("qn_storage", storage)
-        s.set_approx_inv_hessian(Hn)
+        s.set_approx_inv_hessian(Hs)
         run(osb, s, osb.BackTracking(1e-4, 0.5), osb.ExtendedRosenbrock(64), 5, 20)
         res.append(s.x())
-    assert np.array_equal(res[0], res[1])
+    assert close(res[0], res[1], rtol=1e-11)
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,n,iters", [("BFGS", 64, 30), ("DFP", 96, 20), ("BFGS", 2048, 25), ("BFGS", 16384, 10)])
+def test_fused_iteration_kernel_matches_one_launch_per_phase(osb, kind, n, iters):
+    """The default path runs whole iterations in one cooperative kernel (qn_iter.cu: line search on every SM, grid-wide
+    reductions in CTA order).  Same algebra as the head / pass / fold launches, different summation trees: identical
+    iteration counts and step norms / iterates to rounding of the summation order."""
+    x0 = rosen_x0(n, 61)
+    res = []
+    for fused in (1, 0):
+        s = getattr(osb, kind)(1e-8, x0).set_option("fused_iteration", fused)
+        st = run(osb, s, osb.BackTracking(1e-4, 0.5), osb.ExtendedRosenbrock(n), iters, 20)
+        info = s.path_info()
+        assert info["fused"] == bool(fused) and info["schedule"] == 1 and info["storage"] == 1, info
+        res.append((st, s.k(), s.x(), s.s_norm(), s.y_norm(), s.f()))
+    a, b = res
+    assert a[:2] == b[:2]
+    assert close(a[2], b[2], rtol=1e-10)
+    assert abs(a[3] - b[3]) <= 1e-9 * b[3] and abs(a[4] - b[4]) <= 1e-9 * b[4] and abs(a[5] - b[5]) <= 1e-10 * abs(b[5])
+
+
+def test_fused_iteration_kernel_other_searches_and_bounds(osb, orc):
+    """Fused kernel with the run-time line-search automaton (More-Thuente, GLL, bounded kinds), the bounded direction, the
+    separable functor, convergence inside a launch and repeated minimize() calls — against the oracle, free running."""
+    n = 256
+    lbv, ubv = np.full(n, -1.0), np.full(n, 1.0)
+
+    def script(m, cls, lsname):
+        obj = m.SeparableQuadratic.generated(n)
+        bounded = cls.endswith("B")
+        s = getattr(m, cls)(1e-7, np.zeros(n), lbv, ubv) if bounded else getattr(m, cls)(1e-7, np.zeros(n))
+        ls = {"mt": lambda: m.MoreThuente.default(), "gll": lambda: m.GLLQuadratic(1e-4, 5), "bt": lambda: m.BackTracking(1e-4, 0.5),
+              "btb": lambda: m.BackTrackingB(1e-4, 0.5, lbv, ubv),
+              "mtb": lambda: m.MoreThuenteB(n).with_lower_bound(lbv).with_upper_bound(ubv)}[lsname]()
+        st = run(m, s, ls, obj, 5, 30)
+        st2 = run(m, s, ls, obj, 200, 30)  # second call: continues from the state the first one left
+        return st, st2, s.k(), s.termination_reason(), s.x()
+
+    for cls, lsname in (("BFGS", "mt"), ("BFGS", "gll"), ("DFP", "bt"), ("BFGSB", "btb"), ("DFPB", "mt")):
+        ref, got = both(osb, orc, lambda m: script(m, cls, lsname))
+        assert got[:4] == ref[:4], (cls, lsname, got[:4], ref[:4])
+        assert close(got[4], ref[4]), (cls, lsname)
+    s = osb.BFGS(1e-7, np.zeros(n))
+    run(osb, s, osb.MoreThuente.default(), osb.SeparableQuadratic.generated(n), 3, 30)
+    assert s.path_info()["fused"]
