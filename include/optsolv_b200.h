@@ -228,9 +228,10 @@ int osb_minimize(osb_solver* s, osb_linesearch* ls, osb_objective* obj, int64_t 
  *   "qn_kernel"          kernel variant of the H pass (diagnostics, default 0).  Full storage: 1 = TMA-staged ring.  Packed
  *                        storage: bit 0 = two 256-thread CTAs per SM, bit 1 = ping-pong (out-of-place) storage,
  *                        bit 2 = zero-first column partials (round-1 behaviour)
- *   "fused_iteration"   -1 / 1 = (default) whole outer iterations in ONE cooperative kernel whenever the lazy schedule on
- *                        packed storage runs under device-resident control (line search on every SM, H pass, fold and
- *                        multi-GPU exchange separated by grid barriers only); 0 = one launch per phase
+ *   "fused_iteration"    whole outer iterations in ONE cooperative kernel (lazy schedule on packed storage under
+ *                        device-resident control: line search on every SM, H pass, fold and multi-GPU exchange separated by
+ *                        grid barriers only): -1 = auto (default: on with several GPUs, off with one), 1 = on, 0 = one launch
+ *                        per phase
  *   "profile_kernels"    1 = one launch per phase, the H pass(es) bracketed with CUDA events (osb_solver_kernel_timing)
  *   "profile_iter"       1 = the fused kernel records where its time goes (osb_solver_iter_profile) */
 int osb_solver_set_option(osb_solver* s, const char* name, int64_t value);
@@ -266,8 +267,10 @@ int osb_solver_kernel_timing(const osb_solver* s, double out[3]);
  * out[7] whole iterations ran in the fused cooperative kernel */
 int osb_solver_path_info(const osb_solver* s, int64_t out[8]);
 /* option "profile_iter": mean ms per iteration in out[0] head (epilogue, line search, next iterate), out[1] H pass,
- * out[2] fold + exchange of the fused iteration kernel (globaltimer stamps of CTA 0); out[3] = iterations covered */
-int osb_solver_iter_profile(osb_solver* s, double out[4]);
+ * out[2] fold + exchange of the fused iteration kernel (globaltimer stamps of CTA 0); out[3] = iterations covered;
+ * out[4..14] = sub-phases of the head (ms per iteration): 4 epilogue loads, 5 its grid sum, 6 u + direction, 7 trial steps,
+ * 8 their grid sum, 9 line-search automaton, 10 next iterate, 11 its grid sum */
+int osb_solver_iter_profile(osb_solver* s, double out[16]);
 /* device time (ms, CUDA events on the context stream) and outer iterations of the last minimize */
 int osb_solver_last_timing(const osb_solver* s, double* ms, int64_t* iterations);
 
@@ -291,6 +294,9 @@ int osb_batched_bfgs_rosenbrock_generated(osb_ctx* ctx, int64_t n, int64_t n_pro
  *   which = 0: h = H y (read n^2)   1: fused rank-2 update + u = H' g (read + write n^2)
  *           2: Broyden H^T s        3: plain device copy of H (cudaMemcpyAsync D2D) for calibration */
 int osb_bench_qn_kernel(osb_ctx* ctx, int which, int64_t n, int reps, int variant, double* ms_out);
+/* mean microseconds of one grid barrier of the fused iteration kernel's shape (one 512-thread CTA per SM, cooperative
+ * launch): the fixed cost the kernel pays four times per iteration */
+int osb_bench_grid_sync(osb_ctx* ctx, int reps, double* us_out);
 /* mean ms per launch of the DMMA Hessian assembly X^T D X of a logistic-regression objective (m n^2 MACs on the lower triangle) */
 int osb_bench_syrk(osb_ctx* ctx, osb_objective* logistic, int reps, double* ms_out);
 

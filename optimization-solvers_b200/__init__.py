@@ -103,6 +103,7 @@ def lib():
                                                            i32p, i32p, i32p, _dp]),
             "osb_bench_qn_kernel": (ci, [_vp, ci, i64, ci, ci, _dp]),
             "osb_bench_syrk": (ci, [_vp, _vp, ci, _dp]),
+            "osb_bench_grid_sync": (ci, [_vp, ci, _dp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -885,9 +886,12 @@ class _Solver:
     def iter_profile(self):
         """Option "profile_iter" = 1: mean ms per iteration spent in the head (epilogue, line search, step), the H pass and
         the fold + exchange of the fused iteration kernel (globaltimer stamps of CTA 0), and the iterations covered."""
-        out = (C.c_double * 4)()
+        out = (C.c_double * 16)()
         _check(lib().osb_solver_iter_profile(self.handle, out))
-        return dict(head_ms=out[0], pass_ms=out[1], fold_ms=out[2], iterations=int(out[3]))
+        names = {4: "epilogue_loads", 5: "epilogue_grid_sum", 6: "u_and_direction", 7: "trial_steps", 8: "trials_grid_sum",
+                 9: "automaton", 10: "next_iterate", 11: "step_grid_sum", 12: "barrier_wait_for_last_cta_sum", 13: "barrier_release_after_last_sum"}
+        return dict(head_ms=out[0], pass_ms=out[1], fold_ms=out[2], iterations=int(out[3]),
+                    head_parts_us={v: round(out[k] * 1e3, 3) for k, v in names.items()})
 
     def kernel_timing(self):
         out = (C.c_double * 3)()
@@ -990,6 +994,14 @@ def bench_qn_kernel(which, n, reps=20, variant=0, ctx=None):
     ms = C.c_double()
     _check(lib().osb_bench_qn_kernel(ctx.handle, which, n, reps, variant, C.byref(ms)))
     return ms.value
+
+
+def bench_grid_sync(reps=200, ctx=None):
+    """Mean microseconds of one grid barrier of the fused iteration kernel's shape."""
+    ctx = ctx or default_context()
+    us = C.c_double()
+    _check(lib().osb_bench_grid_sync(ctx.handle, reps, C.byref(us)))
+    return us.value
 
 
 def bench_syrk(logistic, reps=3, ctx=None):

@@ -14,7 +14,7 @@ void ctx_ipc_close(Ctx* ctx);
 }  // namespace osb
 
 using namespace osb;
-namespace osb { double bench_syrk_dmma(Ctx* ctx, Objective* obj, int reps); }
+namespace osb { double bench_syrk_dmma(Ctx* ctx, Objective* obj, int reps); double bench_grid_sync(Ctx* ctx, int reps); }
 
 #define OSB_TRY try {
 #define OSB_CATCH                                  \
@@ -579,19 +579,17 @@ int osb_solver_kernel_timing(const osb_solver* s, double out[3]) {
   out[2] = S(s)->prof_ms[2];
   return OSB_OK;
 }
-int osb_solver_iter_profile(osb_solver* s, double out[4]) {
+int osb_solver_iter_profile(osb_solver* s, double out[16]) {
   OSB_TRY
   Solver* p = S(s);
-  out[0] = out[1] = out[2] = out[3] = 0.0;
+  for (int q = 0; q < 16; ++q) out[q] = 0.0;
   if (!p->d_iter_prof) return OSB_OK;
   p->ctx->use();
   p->ctx->sync();
-  long long v[4];
+  long long v[16];
   OSB_CUDA(cudaMemcpy(v, p->d_iter_prof, sizeof(v), cudaMemcpyDeviceToHost));
   const double its = v[3] > 0 ? (double)v[3] : 1.0;
-  out[0] = (double)v[0] * 1e-6 / its;
-  out[1] = (double)v[1] * 1e-6 / its;
-  out[2] = (double)v[2] * 1e-6 / its;
+  for (int q = 0; q < 16; ++q) out[q] = (double)v[q] * 1e-6 / its;
   out[3] = (double)v[3];
   return OSB_OK;
   OSB_CATCH
@@ -634,6 +632,13 @@ int osb_batched_bfgs_rosenbrock_generated(osb_ctx* ctx, int64_t n, int64_t np, i
   OSB_CATCH
 }
 
+int osb_bench_grid_sync(osb_ctx* ctx, int reps, double* us_out) {
+  OSB_TRY
+  C(ctx)->use();
+  *us_out = bench_grid_sync(C(ctx), reps);
+  return OSB_OK;
+  OSB_CATCH
+}
 int osb_bench_syrk(osb_ctx* ctx, osb_objective* logistic, int reps, double* ms_out) {
   OSB_TRY
   C(ctx)->use();

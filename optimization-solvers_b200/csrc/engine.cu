@@ -155,6 +155,14 @@ __global__ void set_identity_kernel(double* H, int64_t ld, int64_t nrows, int64_
     H[i * ld + row0 + i] = 1.0;
 }
 __global__ void accept_trial_kernel(DevState* st) { st->f = st->ft; }
+__global__ void reset_run_flags_kernel(DevState* st) {  // ls_solver.rs:74: k = 0; a fresh run
+  st->k = 0;
+  st->done = 0;
+  st->status = OSB_MAX_ITER_REACHED;
+  st->reason = OSB_REASON_NONE;
+  st->skip = 0;
+  st->ls_evals = 0;
+}
 
 // ---- Solver -------------------------------------------------------------------------------
 static bool kind_is_qn(int k) { return k >= OSB_BFGS && k <= OSB_SR1B; }
@@ -782,20 +790,16 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
     u_valid = false;
   }
   if (!u_valid) recompute_u();
-  // control block: keep f / norms, reset the run flags
-  fetch_state();
-  h_state->k = 0;
-  h_state->done = 0;
-  h_state->status = OSB_MAX_ITER_REACHED;
-  h_state->reason = OSB_REASON_NONE;
-  h_state->skip = 0;
-  h_state->ls_evals = 0;
-  push_state();
+  // control block: keep f / norms, reset the run flags (on the device: no host round trip before the first launch)
+  reset_run_flags_kernel<<<1, 1, 0, stm>>>(d_state);
+  ctx->counters[0]++;
+  if (cb != nullptr || record_trace) fetch_state();  // (the trace wants f before the first iteration)
   if (!d_ls_buf) d_ls_buf = (LSParams*)pool_get(0, sizeof(LSParams));
   LSParams* d_ls = d_ls_buf;
   OSB_CUDA(cudaMemcpyAsync(d_ls, &ls->p, sizeof(LSParams), cudaMemcpyHostToDevice, stm));
   // polling: a snapshot of the control block every POLL iterations, at most two in flight
   const int POLL = 4;
+  const int64_t ITER_CHUNK = 32;  // fused iteration kernel: outer iterations per cooperative launch
   if (!poll_snap) poll_snap = (DevState*)pool_get(1, 2 * sizeof(DevState));
   DevState* snap = poll_snap;
   std::memset(snap, 0, 2 * sizeof(DevState));
@@ -818,7 +822,11 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
   last_sym_sharded = sym_sharded;
   last_p2p = epi_p2p;
   // whole iterations in one cooperative kernel (qn_iter.cu): packed lazy schedule on one GPU or sharded by tile pairs
-  iter_path = opt_fused != 0 && !profile_kernels && qn_schedule == 1 && qn_storage == 1 && h_symmetric &&
+  // (auto: on several GPUs, where it removes the fold / exchange kernel, the replicated cluster head and two launch
+  //  boundaries per iteration; on one GPU the three-launch path is still ~3 % faster because the stand-alone pass kernel
+  //  compiles to a tighter loop — profiles/r02_fused_iteration.md)
+  const bool fused_wanted = opt_fused > 0 || (opt_fused < 0 && ctx->world > 1);
+  iter_path = fused_wanted && !profile_kernels && qn_schedule == 1 && qn_storage == 1 && h_symmetric &&
               (qn_kind == QN_BFGS || qn_kind == QN_DFP) && (ctx->world == 1 || sym_sharded) && head_variant == 0 &&
               (qn_variant & 7) == 0 && qn_iter_supported(ctx, obj->functor_kind(), n, ctx->world);
   if (iter_path) {
@@ -831,9 +839,9 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
     }
     if (gpart.p == nullptr) gpart.alloc_pooled(qn_iter_gpart_doubles(ctx));
     if (profile_iter && !d_iter_prof) {
-      OSB_CUDA(cudaMalloc(&d_iter_prof, 4 * sizeof(long long)));
+      OSB_CUDA(cudaMalloc(&d_iter_prof, 16 * sizeof(long long)));
     }
-    if (profile_iter) OSB_CUDA(cudaMemsetAsync(d_iter_prof, 0, 4 * sizeof(long long), stm));
+    if (profile_iter) OSB_CUDA(cudaMemsetAsync(d_iter_prof, 0, 16 * sizeof(long long), stm));
     QNIterArgs a{};
     a.n = n;
     a.ld = ld;
@@ -918,7 +926,9 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
   for (int64_t it = 0; it < max_iter && !stop; it += chunk) {
     if (iter_path) {
       // up to POLL iterations per launch; one per launch when a callback / trace wants every iteration's state
-      chunk = (cb != nullptr || record_trace) ? 1 : std::min<int64_t>(POLL, max_iter - it);
+      // (a launch that finds convergence simply ends, and later launches return at once: the chunk only bounds how far
+      //  the host runs ahead of the device)
+      chunk = (cb != nullptr || record_trace) ? 1 : std::min<int64_t>(ITER_CHUNK, max_iter - it);
       QNIterArgs a = iter_args;
       a.iters = (int)chunk;
       qn_launch_iter(ctx, iter_fn_kind, iter_fn_a, iter_fn_b, bounded, iter_ls_kind, a);

@@ -35,84 +35,97 @@ constexpr int IT_NSPEC = 16;   // backtracking trials per grid reduction
 constexpr int IT_GPK = 64;     // doubles per CTA in one grid-reduction buffer
 constexpr int IT_MAXG = 256;   // largest grid
 
+int qn_iter_grid(Ctx* ctx);
+
+// State carried across the iterations of one launch: identical in every thread of every CTA (every thread writes the
+// same values).  It lives in SHARED memory: not in registers, because nothing should be live across the streaming pass
+// (with the scalars in registers the 120-register loop of the pass re-materialised its row addresses every step: 447 us
+// per pass instead of 400), and not in local memory, because every grid barrier invalidates L1 (fence -> CCTL.IVALL)
+// and each first touch of a stack line after a barrier then costs an L2 / DRAM round trip: with the state on the stack
+// the three grid sums of the head took 12 us each instead of 2.
+struct IterCarry {
+  double f0, s_norm, y_norm, ys_prev, yh;
+  double pc0, pc1, pc2, cc0, cc1, cc2;
+  double t_last, gd0_last, ss, yy;
+  long long k;
+  unsigned long long seq;
+  int has_s, has_y, skip_prev, pending, epi_owed, ls_evals, status, reason, done, gbuf;
+  LSParams p;
+};
+
 struct IterSmem {
+  IterCarry c;
   double w[IT_GPK * IT_NW];
   double res[IT_GPK];
   double2 part[2][IT_NT / 2];
   int ext[IT_MAXG];
+  long long prof[16];  // leader only: [0..2] accumulated ns in head / pass / fold, [3] last stamp, [4..15] head sub-phases
 };
 
-// grid-wide sum of K values; result in every thread of every CTA, identical bits everywhere
-template <int K>
-__device__ __forceinline__ void grid_sum(double (&acc)[K], const QNIterArgs& a, int& gbuf, IterSmem& sm, cg::grid_group& grid) {
-  static_assert(K <= IT_GPK, "grid reduction buffer too small");
+// Grid-wide sums, compact on purpose: the head runs once per 400 us pass, i.e. with a cold instruction cache, and a
+// cold straight-line body costs ~8 cycles per instruction (round 1 measured 86 us for an 11k-instruction head; the first
+// version of this kernel, with the 16 trial steps and a 50-value shuffle reduction fully unrolled, spent 38 us per
+// iteration in the head).  Everything here is a rolled loop.
+//   step 1 (caller): every warp leaves its partial of value k in sm.w[k * IT_NW + warp]  (warp_put)
+//   step 2: thread k adds the IT_NW warp partials in warp order -> this CTA's partial, to global memory
+//   step 3: grid barrier; warp w adds the G CTA partials of the values k = w, w + IT_NW, ... in CTA order -> sm.res[k]
+// Result in sm.res[0..K), identical bits in every CTA and on every rank.
+__device__ __forceinline__ long long iter_stamp();
+__device__ __noinline__ void iter_submark(const QNIterArgs& a, IterSmem& sm, int slot) {
+  if (a.prof == nullptr || blockIdx.x != 0 || threadIdx.x != 0) return;
+  long long now;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+  sm.prof[slot] += now - sm.prof[15];
+  sm.prof[15] = now;
+}
+// (`active`: this warp holds data — warps beyond the CTA's chunk contribute an exact zero without the 10 shuffles; with
+//  112 elements per CTA only 2 of the 16 warps are active, and 50 values x 16 warps x 10 SHFL was 4 us of the head)
+__device__ __forceinline__ void warp_put(IterSmem& sm, int k, double v, bool active = true) {
+  if (active) v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sm.w[k * IT_NW + (threadIdx.x >> 5)] = active ? v : 0.0;
+}
+__device__ __forceinline__ void grid_reduce(const QNIterArgs& a, IterSmem& sm, int K, int* gbuf_io, bool is_min) {
+  cg::grid_group grid = cg::this_grid();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (K <= 4) {
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const double v = warp_sum(acc[k]);
-      if (lane == 0) sm.w[k * IT_NW + warp] = v;
-    }
-  } else {
-#pragma unroll
-    for (int k0 = 0; k0 < K; k0 += 16) {
-      double v[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = (k0 + i < K) ? acc[k0 + i] : 0.0;
-      const double r = warp_sum16(v);  // lane l holds the warp sum of value l >> 1
-      if ((lane & 1) == 0 && k0 + (lane >> 1) < K) sm.w[(k0 + (lane >> 1)) * IT_NW + warp] = r;
-    }
-  }
+  const int gbuf = *gbuf_io;
   __syncthreads();
-  if (threadIdx.x < K) {
-    double v = 0.0;
-#pragma unroll
-    for (int wq = 0; wq < IT_NW; ++wq) v = v + sm.w[threadIdx.x * IT_NW + wq];
+  if ((int)threadIdx.x < K) {
+    double v = is_min ? INFINITY : 0.0;
+#pragma unroll 1
+    for (int wq = 0; wq < IT_NW; ++wq) {
+      const double x = sm.w[threadIdx.x * IT_NW + wq];
+      v = is_min ? fmin(v, x) : v + x;
+    }
     a.gpart[((size_t)gbuf * gridDim.x + blockIdx.x) * IT_GPK + threadIdx.x] = v;
   }
   grid.sync();
+  // 8 lanes per value: lane q of the group adds the partials of the CTAs q, q + 8, ... in that order (loads issued in
+  // batches of 8 before the adds), then an 8-lane tree: fixed shape, hence the same bits in every CTA and on every rank
   const double* base = a.gpart + (size_t)gbuf * gridDim.x * IT_GPK;
-  for (int k = warp; k < K; k += IT_NW) {
-    double v = 0.0;
-    for (int c = lane; c < (int)gridDim.x; c += 32) v = v + __ldcg(base + (size_t)c * IT_GPK + k);
-    v = warp_sum(v);
-    if (lane == 0) sm.res[k] = v;
-  }
-  __syncthreads();
+  const int sub = lane & 7;
+#pragma unroll 1
+  for (int k0 = 0; k0 < K; k0 += IT_NT / 8) {
+    const int k = k0 + (int)(threadIdx.x >> 3);
+    double v = is_min ? INFINITY : 0.0;
+    if (k < K) {
+#pragma unroll 1
+      for (int cq = sub; cq < (int)gridDim.x; cq += 64) {
+        double x[8];
 #pragma unroll
-  for (int k = 0; k < K; ++k) acc[k] = sm.res[k];
-  gbuf ^= 1;
-}
-
-__device__ __forceinline__ double grid_min(double v, const QNIterArgs& a, int& gbuf, IterSmem& sm, cg::grid_group& grid) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  v = warp_min(v);
-  if (lane == 0) sm.w[warp] = v;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double m = INFINITY;
-    for (int wq = 0; wq < IT_NW; ++wq) m = fmin(m, sm.w[wq]);
-    a.gpart[((size_t)gbuf * gridDim.x + blockIdx.x) * IT_GPK] = m;
-  }
-  grid.sync();
-  const double* base = a.gpart + (size_t)gbuf * gridDim.x * IT_GPK;
-  if (warp == 0) {
-    double m = INFINITY;
-    for (int c = lane; c < (int)gridDim.x; c += 32) m = fmin(m, __ldcg(base + (size_t)c * IT_GPK));
-    m = warp_min(m);
-    if (lane == 0) sm.res[0] = m;
+        for (int e = 0; e < 8; ++e) x[e] = (cq + 8 * e < (int)gridDim.x) ? __ldcg(base + (size_t)(cq + 8 * e) * IT_GPK + k) : (is_min ? INFINITY : 0.0);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v = is_min ? fmin(v, x[e]) : v + x[e];
+      }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+      v = is_min ? fmin(v, ov) : v + ov;
+    }
+    if (k < K && sub == 0) sm.res[k] = v;
   }
   __syncthreads();
-  const double r = sm.res[0];
-  gbuf ^= 1;
-  return r;
-}
-
-// the streaming pass, out of line: its 120-register loop is compiled once per sharding mode and does not share its
-// register allocation with the head code around it
-template <bool SHARDED>
-__device__ __noinline__ void iter_pass(const QNLazyArgs& la, const QNSymArgs& sa, double c0, double c1, double c2) {
-  sym_pass_body<-1, SHARDED, IT_NT, false, false>(la, sa, c0, c1, c2, 0, (int)gridDim.x, (int)blockIdx.x);
+  *gbuf_io = gbuf ^ 1;
 }
 
 __device__ __forceinline__ unsigned long long* iter_flags(double* region, int world) {
@@ -194,396 +207,525 @@ __device__ __forceinline__ void iter_fold(const QNIterArgs& a, IterSmem& sm, int
   __syncthreads();
 }
 
-template <class Fn, bool BOUNDED, bool BT, bool SHARDED>
-__global__ void __launch_bounds__(IT_NT, 1) qn_iter_kernel(const __grid_constant__ QNIterArgs a, const Fn fn) {
+// everything of one outer iteration that comes before the H pass.  Returns 0: go on with the pass, 1: leave the loop.
+template <class Fn, bool BOUNDED, bool BT, bool SHARDED, int KIND>
+__device__ __noinline__ int iter_head(const QNIterArgs& a, const Fn& fn, IterSmem& sm, const bool epi_only) {
+  IterCarry& c = sm.c;
   constexpr int BS = Fn::BS;
-  cg::grid_group grid = cg::this_grid();
-  __shared__ IterSmem sm;
-  DevState* st = a.st;
-  if (st->done) return;
   const int tid = threadIdx.x, G = (int)gridDim.x, cta = (int)blockIdx.x;
-  const bool leader = cta == 0 && tid == 0;
   const int64_t n = a.n;
   // this CTA's chunk of every O(n) vector: cw elements (even, a multiple of the functor block), one block per thread
   const int64_t nb = (n + BS - 1) / BS;
   int64_t bpc = (nb + G - 1) / G;
   if ((bpc * BS) & 1) bpc += 1;
   const int cw = (int)(bpc * BS);
-  const int64_t j0 = (int64_t)cta * cw;
-  const int64_t i0 = j0 + (int64_t)tid * BS;          // first element of this thread's block
-  const bool own = tid < bpc && i0 + BS <= n;         // (n is a multiple of BS for every functor)
-  // ---- state carried across the iterations of this launch (identical in every thread of every CTA)
-  double f0 = st->f;
-  int has_s = st->has_s, has_y = st->has_y;
-  double s_norm = st->s_norm, y_norm = st->y_norm, ys_prev = st->ys, yh = st->yh;
-  int skip_prev = st->skip, pending = st->pending, epi_owed = st->epi;
-  double pc0 = st->pc0, pc1 = st->pc1, pc2 = st->pc2;
-  double cc0 = st->c0, cc1 = st->c1, cc2 = st->c2;
-  long long k = st->k;
-  int ls_evals = st->ls_evals;
-  double t_last = st->t_last, gd0_last = st->gd0;
-  double ss = st->ss, yy = st->yy;
-  unsigned long long seq = SHARDED ? *a.seq : 0ULL;
-  int status = st->status, reason = st->reason, done = 0;
-  LSParams p = *a.lsp;
-  {
-    const int64_t T = (n + QN_R - 1) / QN_R;
-    for (int c = tid; c < G; c += IT_NT) sm.ext[c] = (int)sym_first_row<SHARDED>(T, a.world, a.rank, G, c);
+  const int64_t i0 = (int64_t)cta * cw + (int64_t)tid * BS;  // first element of this thread's block
+  const bool own = tid < bpc && i0 + BS <= n;                // (n is a multiple of BS for every functor)
+  const bool wact = (int64_t)(tid & ~31) < bpc;              // this warp holds at least one block
+  // BackTracking only reads c1 / beta: straight from shared memory.  The other searches mutate their parameters
+  // (GLL window, MoreThuenteB t_max): they work on a per-thread copy, written back by one thread below.
+  LSParams p_local;
+  if (!BT) p_local = c.p;
+  LSParams& p = BT ? c.p : p_local;
+  // Every thread reads what it needs of the carried state into registers FIRST; the writes below (every thread the same
+  // values) come after a barrier, so no thread can see a field another thread has already advanced.
+  int gbuf = c.gbuf;
+  const double f0 = c.f0, ys_prev = c.ys_prev, s_norm_in = c.s_norm, y_norm_in = c.y_norm;
+  const int has_s_in = c.has_s, has_y_in = c.has_y, epi_in = c.epi_owed, skip_in = c.skip_prev, ls_evals_in = c.ls_evals;
+  const long long k_in = c.k;
+  __syncthreads();
+  iter_submark(a, sm, 14);  // (resets the sub-phase clock)
+  if (!epi_only && is_bad(f0)) {  // ls_solver.rs:37-40
+    c.done = 1;
+    c.status = OSB_OUT_OF_DOMAIN;
+    __syncthreads();
+    return 1;
   }
-  int gbuf = 0;
-  // every CTA has read the entry state before anybody can write it
-  grid.sync();
-  QNLazyArgs la{};
-  la.ps = a.ps;
-  la.ph = a.ph;
-  la.y = a.y;
-  la.g = a.g;
-  la.h = a.h;
-  la.w = a.w;
-  la.st = st;
-  QNSymArgs sa{a.P, a.P, a.colpart, n, a.ld, SHARDED ? a.world : 1, SHARDED ? a.rank : 0, a.peers, a.seq, G, 0};
-  long long t_head = 0, t_pass = 0, t_fold = 0, t_mark = 0;
-  const bool timing = a.prof != nullptr && leader;
-  auto stamp = [&]() -> long long {
-    long long v;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
-    return v;
-  };
-  if (timing) t_mark = stamp();
-  int it = 0;
-  for (;; ++it) {
-    const bool epi_only = a.epi_only != 0;
-    if (!epi_only && it >= a.iters) break;
-    if (!epi_only && is_bad(f0)) {  // ls_solver.rs:37-40
-      done = 1;
-      status = OSB_OUT_OF_DOMAIN;
-      break;
-    }
-    // ---- the epilogue the previous pass left owed: coefficients of the update that becomes pending, u = H+ g
-    double ub_[BS];
-    if (epi_owed) {
-      const int par = epi_owed - 1;  // sharded: parity of the exchange buffers holding h, w
-      double hb[BS], wb[BS], sb[BS];
-      double e3[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-      for (int jq = 0; jq < BS; ++jq) {
-        hb[jq] = wb[jq] = sb[jq] = 0.0;
-        if (own) {
-          const int64_t i = i0 + jq;
-          if (SHARDED) {  // rank-ordered sum of the per-rank slots: the same numbers in the same order on every rank
-            const double* bh = a.peers[a.rank] + XSLOT_OFF + ((int64_t)(par * a.world) * 2 + 0) * XSLOT_LD + i;
-            double vh = __ldcg(bh), vw = __ldcg(bh + XSLOT_LD);
-            for (int r = 1; r < a.world; ++r) {
-              vh = vh + __ldcg(bh + (int64_t)r * 2 * XSLOT_LD);
-              vw = vw + __ldcg(bh + (int64_t)r * 2 * XSLOT_LD + XSLOT_LD);
-            }
-            hb[jq] = vh;
-            wb[jq] = vw;
-          } else {
-            hb[jq] = __ldcg(a.h + i);
-            wb[jq] = __ldcg(a.w + i);
-          }
-          sb[jq] = __ldcg(a.s + i);
-          if (!skip_prev) {
-            const double yi = __ldcg(a.y + i), gi = __ldcg(a.g + i);
-            e3[0] = fma(yi, hb[jq], e3[0]);     // y.h
-            e3[1] = fma(sb[jq], gi, e3[1]);     // s.g
-            e3[2] = fma(hb[jq], gi, e3[2]);     // h.g
-          }
-        }
-      }
-      double ca = 0.0, cb = 0.0;
-      if (!skip_prev) {
-        grid_sum<3>(e3, a, gbuf, sm, grid);
-        yh = e3[0];
-        const double sg = e3[1], hg = e3[2];
-        if (a.kind == QN_BFGS) {  // bfgs.rs:115-124, no curvature safeguard
-          const double rho = 1.0 / ys_prev;
-          cc0 = rho * rho * yh + rho;
-          cc1 = -rho;
-          cc2 = 0.0;
-        } else {  // dfp.rs:115-120
-          cc0 = 1.0 / ys_prev;
-          cc1 = 0.0;
-          cc2 = -1.0 / yh;
-        }
-        ca = cc0 * sg + cc1 * hg;
-        cb = cc1 * sg + cc2 * hg;
-        pc0 = cc0;
-        pc1 = cc1;
-        pc2 = cc2;
-        pending = 1;
-      } else {  // bfgs.rs:106-112: no new update; the stored matrix is exact once the pending one is applied
-        pending = 0;
-        pc0 = pc1 = pc2 = 0.0;
-      }
-#pragma unroll
-      for (int jq = 0; jq < BS; ++jq) {
-        ub_[jq] = 0.0;
-        if (own) {
-          const int64_t i = i0 + jq;
-          if (skip_prev) {
-            ub_[jq] = wb[jq];
-          } else {
-            ub_[jq] = wb[jq] + (sb[jq] * ca + hb[jq] * cb);
-            a.ps[i] = sb[jq];
-            a.ph[i] = hb[jq];
-          }
-          a.u[i] = ub_[jq];
-        }
-      }
-      epi_owed = 0;
-    } else {
-#pragma unroll
-      for (int jq = 0; jq < BS; ++jq) ub_[jq] = own ? __ldcg(a.u + i0 + jq) : 0.0;
-    }
-    if (epi_only) break;
-    // ---- has_converged (bfgs.rs:64-76), first two tests
-    if (has_s && s_norm < a.tol) {
-      done = 1;
-      status = OSB_OK;
-      reason = OSB_REASON_S_NORM;
-      break;
-    }
-    if (has_y && y_norm < a.tol) {
-      done = 1;
-      status = OSB_OK;
-      reason = OSB_REASON_Y_NORM;
-      break;
-    }
-    // ---- compute_direction, ||g||^2, g.d — and, for BackTracking, the first IT_NSPEC trial steps in the same sweep
-    double xb[BS], db[BS], gb0[BS];
-    double gg = 0.0, gd = 0.0, tm = INFINITY;
-    const bool need_tmax = !BT && p.kind == LS_MORETHUENTE_B;
+  // ---- the epilogue the previous pass left owed: coefficients of the update that becomes pending, u = H+ g
+  double ub_[BS];
+  if (epi_in) {
+    const int par = epi_in - 1;  // sharded: parity of the exchange buffers holding h, w
+    const bool skip_prev = skip_in != 0;
+    double hb[BS], wb[BS], sb[BS];
+    double e3[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int jq = 0; jq < BS; ++jq) {
-      xb[jq] = db[jq] = gb0[jq] = 0.0;
+      hb[jq] = wb[jq] = sb[jq] = 0.0;
       if (own) {
         const int64_t i = i0 + jq;
-        const double xi = __ldcg(a.x + i), gi = __ldcg(a.g + i);
-        double di;
-        if (BOUNDED) di = fmin(fmax(xi - ub_[jq], a.lb[i]), a.ub[i]) - xi;  // bfgs_b.rs:72-75
-        else di = -ub_[jq];                                                 // bfgs.rs:47
-        xb[jq] = xi;
-        db[jq] = di;
-        gb0[jq] = gi;
-        gg = gg + gi * gi;
-        gd = gd + gi * di;
-        if (need_tmax) {  // morethuente_b.rs:185-197
-          double cand;
-          if (di > 0.0) cand = (a.ls_ub[i] - xi) / di;
-          else if (di < 0.0) cand = (a.ls_lb[i] - xi) / di;
-          else cand = INFINITY;
-          tm = fmin(cand, tm);
+        if (SHARDED) {  // rank-ordered sum of the per-rank slots: the same numbers in the same order on every rank
+          const double* bh = a.peers[a.rank] + XSLOT_OFF + ((int64_t)(par * a.world) * 2 + 0) * XSLOT_LD + i;
+          double vh = __ldcg(bh), vw = __ldcg(bh + XSLOT_LD);
+          for (int r = 1; r < a.world; ++r) {
+            vh = vh + __ldcg(bh + (int64_t)r * 2 * XSLOT_LD);
+            vw = vw + __ldcg(bh + (int64_t)r * 2 * XSLOT_LD + XSLOT_LD);
+          }
+          hb[jq] = vh;
+          wb[jq] = vw;
+        } else {
+          hb[jq] = __ldcg(a.h + i);
+          wb[jq] = __ldcg(a.w + i);
+        }
+        sb[jq] = __ldcg(a.s + i);
+        if (!skip_prev) {
+          const double yi = __ldcg(a.y + i), gi = __ldcg(a.g + i);
+          e3[0] = fma(yi, hb[jq], e3[0]);     // y.h
+          e3[1] = fma(sb[jq], gi, e3[1]);     // s.g
+          e3[2] = fma(hb[jq], gi, e3[2]);     // h.g
         }
       }
     }
-    LSMachine m;
-    int evals = 0;
-    double gd0;
-    if (BT) {
-      // backtracking visits 1, beta, beta^2, ... whatever the outcome of a trial (backtracking.rs:37-55): the first
-      // IT_NSPEC steps are evaluated before g.d is even known, and fed to the automaton in order afterwards
-      double ts[IT_NSPEC];
-      ts[0] = 1.0;
-#pragma unroll
-      for (int q = 1; q < IT_NSPEC; ++q) ts[q] = ts[q - 1] * p.beta;
-      double aS[2 + 3 * IT_NSPEC];
-      aS[0] = gg;
-      aS[1] = gd;
-#pragma unroll
-      for (int q = 0; q < 3 * IT_NSPEC; ++q) aS[2 + q] = 0.0;
-      bool first_round = true;
-      for (;;) {
-        if (own) {
-#pragma unroll
-          for (int q = 0; q < IT_NSPEC; ++q) {
-            double xt[BS], gt[BS];
-#pragma unroll
-            for (int jq = 0; jq < BS; ++jq) {
-              const double td = ts[q] * db[jq];
-              xt[jq] = xb[jq] + td;
-              const double df = xt[jq] - xb[jq];
-              aS[2 + 3 * q + 2] = aS[2 + 3 * q + 2] + df * df;
-            }
-            const double fb = fn.block(i0, xt, gt);
-#pragma unroll
-            for (int jq = 0; jq < BS; ++jq) aS[2 + 3 * q + 1] = aS[2 + 3 * q + 1] + gt[jq] * db[jq];
-            aS[2 + 3 * q] = aS[2 + 3 * q] + fb;
-          }
-        }
-        grid_sum<2 + 3 * IT_NSPEC>(aS, a, gbuf, sm, grid);
-        if (first_round) {
-          if (sqrt(aS[0]) < a.tol) {  // bfgs.rs:74
-            done = 1;
-            status = OSB_OK;
-            reason = OSB_REASON_GRAD_TOL;
-            break;
-          }
-          gd0 = aS[1];
-          m.template begin<LS_BACKTRACKING>(p, f0, gd0, a.max_ls, INFINITY);
-          first_round = false;
-        }
-#pragma unroll
-        for (int q = 0; q < IT_NSPEC; ++q) {
-          if (!m.done && m.request(p) == ts[q]) {
-            m.template feed<LS_BACKTRACKING>(p, aS[2 + 3 * q], aS[2 + 3 * q + 1], aS[2 + 3 * q + 2]);
-            ++evals;
-          }
-        }
-        if (m.done) break;
-        ts[0] = m.request(p);
-#pragma unroll
-        for (int q = 1; q < IT_NSPEC; ++q) ts[q] = ts[q - 1] * p.beta;
-        aS[0] = aS[1] = 0.0;
-#pragma unroll
-        for (int q = 0; q < 3 * IT_NSPEC; ++q) aS[2 + q] = 0.0;
+    double ca = 0.0, cb = 0.0;
+    if (!skip_prev) {
+      warp_put(sm, 0, e3[0], wact);
+      warp_put(sm, 1, e3[1], wact);
+      warp_put(sm, 2, e3[2], wact);
+      iter_submark(a, sm, 4);
+      grid_reduce(a, sm, 3, &gbuf, false);
+      iter_submark(a, sm, 5);
+      const double yh = sm.res[0], sg = sm.res[1], hg = sm.res[2];
+      double c0, c1, c2;
+      if (KIND == QN_BFGS) {  // bfgs.rs:115-124, no curvature safeguard
+        const double rho = 1.0 / ys_prev;
+        c0 = rho * rho * yh + rho;
+        c1 = -rho;
+        c2 = 0.0;
+      } else {  // dfp.rs:115-120
+        c0 = 1.0 / ys_prev;
+        c1 = 0.0;
+        c2 = -1.0 / yh;
       }
-      if (done) break;
-    } else {
-      double a2[2] = {gg, gd};
-      grid_sum<2>(a2, a, gbuf, sm, grid);
-      if (sqrt(a2[0]) < a.tol) {  // bfgs.rs:74
-        done = 1;
-        status = OSB_OK;
-        reason = OSB_REASON_GRAD_TOL;
-        break;
+      ca = c0 * sg + c1 * hg;
+      cb = c1 * sg + c2 * hg;
+      // (all reads of the carried state happened before the barriers of grid_reduce)
+      c.yh = yh;
+      c.cc0 = c.pc0 = c0;
+      c.cc1 = c.pc1 = c1;
+      c.cc2 = c.pc2 = c2;
+      c.pending = 1;
+    } else {  // bfgs.rs:106-112: no new update; the stored matrix is exact once the pending one is applied
+      c.pending = 0;
+      c.pc0 = c.pc1 = c.pc2 = 0.0;
+    }
+#pragma unroll
+    for (int jq = 0; jq < BS; ++jq) {
+      ub_[jq] = 0.0;
+      if (own) {
+        const int64_t i = i0 + jq;
+        if (skip_prev) {
+          ub_[jq] = wb[jq];
+        } else {
+          ub_[jq] = wb[jq] + (sb[jq] * ca + hb[jq] * cb);
+          a.ps[i] = sb[jq];
+          a.ph[i] = hb[jq];
+        }
+        a.u[i] = ub_[jq];
       }
-      gd0 = a2[1];
-      double tmaxc = INFINITY;
-      if (need_tmax) tmaxc = grid_min(tm, a, gbuf, sm, grid);
-      m.begin(p, f0, gd0, a.max_ls, tmaxc);
-      while (!m.done) {
-        const double t = m.request(p);
-        const bool proj = m.wants_projection(p);
-        double a3[3] = {0.0, 0.0, 0.0};
+    }
+    c.epi_owed = 0;
+  } else {
+#pragma unroll
+    for (int jq = 0; jq < BS; ++jq) ub_[jq] = own ? __ldcg(a.u + i0 + jq) : 0.0;
+  }
+  c.gbuf = gbuf;
+  if (epi_only) return 1;
+  // ---- has_converged (bfgs.rs:64-76), first two tests
+  if (has_s_in && s_norm_in < a.tol) {
+    c.done = 1;
+    c.status = OSB_OK;
+    c.reason = OSB_REASON_S_NORM;
+    __syncthreads();
+    return 1;
+  }
+  if (has_y_in && y_norm_in < a.tol) {
+    c.done = 1;
+    c.status = OSB_OK;
+    c.reason = OSB_REASON_Y_NORM;
+    __syncthreads();
+    return 1;
+  }
+  // ---- compute_direction, ||g||^2, g.d — and, for BackTracking, the first IT_NSPEC trial steps in the same sweep
+  double xb[BS], db[BS], gb0[BS];
+  double gg = 0.0, gd = 0.0, tm = INFINITY;
+  const bool need_tmax = !BT && p.kind == LS_MORETHUENTE_B;
+#pragma unroll
+  for (int jq = 0; jq < BS; ++jq) {
+    xb[jq] = db[jq] = gb0[jq] = 0.0;
+    if (own) {
+      const int64_t i = i0 + jq;
+      const double xi = __ldcg(a.x + i), gi = __ldcg(a.g + i);
+      double di;
+      if (BOUNDED) di = fmin(fmax(xi - ub_[jq], a.lb[i]), a.ub[i]) - xi;  // bfgs_b.rs:72-75
+      else di = -ub_[jq];                                                 // bfgs.rs:47
+      xb[jq] = xi;
+      db[jq] = di;
+      gb0[jq] = gi;
+      gg = gg + gi * gi;
+      gd = gd + gi * di;
+      if (need_tmax) {  // morethuente_b.rs:185-197
+        double cand;
+        if (di > 0.0) cand = (a.ls_ub[i] - xi) / di;
+        else if (di < 0.0) cand = (a.ls_lb[i] - xi) / di;
+        else cand = INFINITY;
+        tm = fmin(cand, tm);
+      }
+    }
+  }
+  iter_submark(a, sm, 6);
+  LSMachine m;
+  int evals = 0;
+  double gd0 = 0.0;
+  if (BT) {
+    // backtracking visits 1, beta, beta^2, ... whatever the outcome of a trial (backtracking.rs:37-55): the first
+    // IT_NSPEC steps are evaluated before g.d is even known, and fed to the automaton in order afterwards
+    double t0 = 1.0;
+    bool first_round = true;
+    for (;;) {
+      warp_put(sm, 0, first_round ? gg : 0.0, wact);
+      warp_put(sm, 1, first_round ? gd : 0.0, wact);
+      double tq = t0;
+#pragma unroll 1
+      for (int q = 0; q < IT_NSPEC; ++q) {
+        double f3[3] = {0.0, 0.0, 0.0};
         if (own) {
           double xt[BS], gt[BS];
 #pragma unroll
           for (int jq = 0; jq < BS; ++jq) {
-            const double td = t * db[jq];
-            double v = xb[jq] + td;
-            if (proj) v = fmin(fmax(v, a.ls_lb[i0 + jq]), a.ls_ub[i0 + jq]);  // backtracking_b.rs:65-67
-            xt[jq] = v;
-            const double df = v - xb[jq];
-            a3[2] = a3[2] + df * df;
+            const double td = tq * db[jq];
+            xt[jq] = xb[jq] + td;
+            const double df = xt[jq] - xb[jq];
+            f3[2] = f3[2] + df * df;
           }
-          const double fb = fn.block(i0, xt, gt);
+          f3[0] = fn.block(i0, xt, gt);
 #pragma unroll
-          for (int jq = 0; jq < BS; ++jq) a3[1] = a3[1] + gt[jq] * db[jq];
-          a3[0] = a3[0] + fb;
+          for (int jq = 0; jq < BS; ++jq) f3[1] = f3[1] + gt[jq] * db[jq];
         }
-        grid_sum<3>(a3, a, gbuf, sm, grid);
-        m.feed(p, a3[0], a3[1], a3[2]);
-        ++evals;
+        warp_put(sm, 2 + 3 * q, f3[0], wact);
+        warp_put(sm, 3 + 3 * q, f3[1], wact);
+        warp_put(sm, 4 + 3 * q, f3[2], wact);
+        tq = tq * p.beta;
       }
+      iter_submark(a, sm, 7);
+      grid_reduce(a, sm, 2 + 3 * IT_NSPEC, &gbuf, false);
+      iter_submark(a, sm, 8);
+      if (first_round) {
+        if (sqrt(sm.res[0]) < a.tol) {  // bfgs.rs:74
+          c.done = 1;
+          c.status = OSB_OK;
+          c.reason = OSB_REASON_GRAD_TOL;
+          c.gbuf = gbuf;
+          __syncthreads();
+          return 1;
+        }
+        gd0 = sm.res[1];
+        m.template begin<LS_BACKTRACKING>(p, f0, gd0, a.max_ls, INFINITY);
+        first_round = false;
+      }
+      tq = t0;
+#pragma unroll 1
+      for (int q = 0; q < IT_NSPEC; ++q) {
+        if (m.done) break;
+        if (m.request(p) == tq) {
+          m.template feed<LS_BACKTRACKING>(p, sm.res[2 + 3 * q], sm.res[3 + 3 * q], sm.res[4 + 3 * q]);
+          ++evals;
+        }
+        tq = tq * p.beta;
+      }
+      if (m.done) break;
+      t0 = m.request(p);
+      __syncthreads();  // sm.res is rewritten by the next round
     }
-    const double t = m.result;
-    // ---- next = x + t d (ls_solver.rs:60); oracle(next) (bfgs.rs:98); s, y, norms, y.s
-    double a4[4] = {0.0, 0.0, 0.0, 0.0};
-    if (own) {
-      double xn[BS], gn[BS];
+  } else {
+    warp_put(sm, 0, gg, wact);
+    warp_put(sm, 1, gd, wact);
+    grid_reduce(a, sm, 2, &gbuf, false);
+    if (sqrt(sm.res[0]) < a.tol) {  // bfgs.rs:74
+      c.done = 1;
+      c.status = OSB_OK;
+      c.reason = OSB_REASON_GRAD_TOL;
+      c.gbuf = gbuf;
+      __syncthreads();
+      return 1;
+    }
+    gd0 = sm.res[1];
+    double tmaxc = INFINITY;
+    if (need_tmax) {
+      __syncthreads();
+      const double wm = warp_min(tm);
+      if ((tid & 31) == 0) sm.w[tid >> 5] = wm;
+      grid_reduce(a, sm, 1, &gbuf, true);
+      tmaxc = sm.res[0];
+    }
+    m.begin(p, f0, gd0, a.max_ls, tmaxc);
+    while (!m.done) {
+      const double t = m.request(p);
+      const bool proj = m.wants_projection(p);
+      double a3[3] = {0.0, 0.0, 0.0};
+      if (own) {
+        double xt[BS], gt[BS];
 #pragma unroll
-      for (int jq = 0; jq < BS; ++jq) {
-        const double td = t * db[jq];
-        xn[jq] = xb[jq] + td;
-      }
-      const double fb = fn.block(i0, xn, gn);
-      a4[3] = fb;
+        for (int jq = 0; jq < BS; ++jq) {
+          const double td = t * db[jq];
+          double v = xb[jq] + td;
+          if (proj) v = fmin(fmax(v, a.ls_lb[i0 + jq]), a.ls_ub[i0 + jq]);  // backtracking_b.rs:65-67
+          xt[jq] = v;
+          const double df = v - xb[jq];
+          a3[2] = a3[2] + df * df;
+        }
+        const double fb = fn.block(i0, xt, gt);
 #pragma unroll
-      for (int jq = 0; jq < BS; ++jq) {
-        const int64_t i = i0 + jq;
-        const double si = xn[jq] - xb[jq];
-        const double yi = gn[jq] - gb0[jq];
-        a.s[i] = si;
-        a.y[i] = yi;
-        a.x[i] = xn[jq];
-        a.g[i] = gn[jq];
-        a4[0] = a4[0] + si * si;
-        a4[1] = a4[1] + yi * yi;
-        a4[2] = a4[2] + yi * si;
+        for (int jq = 0; jq < BS; ++jq) a3[1] = a3[1] + gt[jq] * db[jq];
+        a3[0] = a3[0] + fb;
       }
-    }
-    grid_sum<4>(a4, a, gbuf, sm, grid);  // (its grid barrier also publishes s, y, x, g, ps, ph to the pass below)
-    ss = a4[0];
-    yy = a4[1];
-    ys_prev = a4[2];
-    f0 = a4[3];
-    s_norm = sqrt(ss);
-    y_norm = sqrt(yy);
-    has_s = has_y = 1;
-    skip_prev = (s_norm < a.tol || y_norm < a.tol) ? 1 : 0;  // bfgs.rs:106-112
-    t_last = t;
-    gd0_last = gd0;
-    k += 1;
-    ls_evals += evals + 1;
-    if (timing) {
-      const long long now = stamp();
-      t_head += now - t_mark;
-      t_mark = now;
-    }
-    // ---- the H pass: pending update + h = H y + w = H g over (this rank's share of) the packed triangle
-    iter_pass<SHARDED>(la, sa, pc0, pc1, pc2);
-    grid.sync();
-    if (timing) {
-      const long long now = stamp();
-      t_pass += now - t_mark;
-      t_mark = now;
-    }
-    // ---- fold of the column partials (+ exchange): h, w of this CTA's chunk, complete
-    seq += 1ULL;
-    iter_fold<SHARDED>(a, sm, j0, cw, seq, st);
-    epi_owed = SHARDED ? 1 + (int)(seq & 1ULL) : 1;
-    if (timing) {
-      const long long now = stamp();
-      t_fold += now - t_mark;
-      t_mark = now;
+      __syncthreads();  // sm.res of the previous round has been consumed by every thread
+      warp_put(sm, 0, a3[0], wact);
+      warp_put(sm, 1, a3[1], wact);
+      warp_put(sm, 2, a3[2], wact);
+      grid_reduce(a, sm, 3, &gbuf, false);
+      m.feed(p, sm.res[0], sm.res[1], sm.res[2]);
+      ++evals;
     }
   }
-  // ---- persist the carried state (one thread; every CTA holds the same values)
-  if (leader) {
-    st->f = f0;
-    st->ft = f0;
-    st->gd0 = gd0_last;
-    st->ss = ss;
-    st->yy = yy;
-    st->ys = ys_prev;
-    st->yh = yh;
-    st->s_norm = s_norm;
-    st->y_norm = y_norm;
-    st->has_s = has_s;
-    st->has_y = has_y;
-    st->skip = skip_prev;
-    st->c0 = cc0;
-    st->c1 = cc1;
-    st->c2 = cc2;
-    st->pc0 = pc0;
-    st->pc1 = pc1;
-    st->pc2 = pc2;
-    st->pending = pending;
-    st->epi = epi_owed;
-    st->t_last = t_last;
-    st->k = k;
-    st->ls_evals = ls_evals;
-    if (done) {
-      st->done = 1;
-      st->status = status;
-      st->reason = reason;
+  iter_submark(a, sm, 9);
+  const double t = m.result;
+  // ---- next = x + t d (ls_solver.rs:60); oracle(next) (bfgs.rs:98); s, y, norms, y.s
+  double a4[4] = {0.0, 0.0, 0.0, 0.0};
+  if (own) {
+    double xn[BS], gn[BS];
+#pragma unroll
+    for (int jq = 0; jq < BS; ++jq) {
+      const double td = t * db[jq];
+      xn[jq] = xb[jq] + td;
     }
-    if (SHARDED) *a.seq = seq;
-    if (p.kind == LS_GLL || p.kind == LS_MORETHUENTE_B) *a.lsp = p;  // only f_previous / t_max persist across iterations
-    if (timing) {
-      a.prof[0] += t_head;
-      a.prof[1] += t_pass;
-      a.prof[2] += t_fold;
+    const double fb = fn.block(i0, xn, gn);
+    a4[3] = fb;
+#pragma unroll
+    for (int jq = 0; jq < BS; ++jq) {
+      const int64_t i = i0 + jq;
+      const double si = xn[jq] - xb[jq];
+      const double yi = gn[jq] - gb0[jq];
+      a.s[i] = si;
+      a.y[i] = yi;
+      a.x[i] = xn[jq];
+      a.g[i] = gn[jq];
+      a4[0] = a4[0] + si * si;
+      a4[1] = a4[1] + yi * yi;
+      a4[2] = a4[2] + yi * si;
+    }
+  }
+  iter_submark(a, sm, 10);
+  __syncthreads();  // sm.res of the line search has been consumed by every thread
+  warp_put(sm, 0, a4[0], wact);
+  warp_put(sm, 1, a4[1], wact);
+  warp_put(sm, 2, a4[2], wact);
+  warp_put(sm, 3, a4[3], wact);
+  grid_reduce(a, sm, 4, &gbuf, false);  // (its grid barrier also publishes s, y, x, g, ps, ph to the pass that follows)
+  iter_submark(a, sm, 11);
+  {
+    const double ss = sm.res[0], yy = sm.res[1], ys = sm.res[2], fn_ = sm.res[3];
+    const double sn = sqrt(ss), yn = sqrt(yy);
+    c.ss = ss;
+    c.yy = yy;
+    c.ys_prev = ys;
+    c.f0 = fn_;
+    c.s_norm = sn;
+    c.y_norm = yn;
+    c.has_s = c.has_y = 1;
+    c.skip_prev = (sn < a.tol || yn < a.tol) ? 1 : 0;  // bfgs.rs:106-112
+    c.t_last = t;
+    c.gd0_last = gd0;
+    c.k = k_in + 1;
+    c.ls_evals = ls_evals_in + evals + 1;
+    c.gbuf = gbuf;
+  }
+  if (!BT && (p.kind == LS_GLL || p.kind == LS_MORETHUENTE_B)) {  // only f_previous / t_max persist across iterations
+    __syncthreads();
+    if (tid == 0) c.p = p_local;
+  }
+  __syncthreads();
+  return 0;
+}
+
+// fold of the column partials (+ exchange) for this CTA's chunk, out of line like the head
+template <class Fn, bool SHARDED>
+__device__ __noinline__ void iter_tail(const QNIterArgs& a, IterSmem& sm) {
+  IterCarry& c = sm.c;
+  constexpr int BS = Fn::BS;
+  const int G = (int)gridDim.x;
+  const int64_t nb = (a.n + BS - 1) / BS;
+  int64_t bpc = (nb + G - 1) / G;
+  if ((bpc * BS) & 1) bpc += 1;
+  const int cw = (int)(bpc * BS);
+  const unsigned long long seq = c.seq + 1ULL;
+  iter_fold<SHARDED>(a, sm, (int64_t)blockIdx.x * cw, cw, seq, a.st);
+  __syncthreads();
+  c.seq = seq;
+  c.epi_owed = SHARDED ? 1 + (int)(seq & 1ULL) : 1;
+  __syncthreads();
+}
+
+__device__ __noinline__ void iter_load_state(const QNIterArgs& a, IterCarry& c, bool sharded) {
+  const DevState* st = a.st;
+  c.f0 = st->f;
+  c.has_s = st->has_s;
+  c.has_y = st->has_y;
+  c.s_norm = st->s_norm;
+  c.y_norm = st->y_norm;
+  c.ys_prev = st->ys;
+  c.yh = st->yh;
+  c.skip_prev = st->skip;
+  c.pending = st->pending;
+  c.epi_owed = st->epi;
+  c.pc0 = st->pc0;
+  c.pc1 = st->pc1;
+  c.pc2 = st->pc2;
+  c.cc0 = st->c0;
+  c.cc1 = st->c1;
+  c.cc2 = st->c2;
+  c.k = st->k;
+  c.ls_evals = st->ls_evals;
+  c.t_last = st->t_last;
+  c.gd0_last = st->gd0;
+  c.ss = st->ss;
+  c.yy = st->yy;
+  c.seq = sharded ? *a.seq : 0ULL;
+  c.status = st->status;
+  c.reason = st->reason;
+  c.done = 0;
+  c.gbuf = 0;
+  c.p = *a.lsp;
+}
+
+// persist the carried state (one thread; every CTA holds the same values)
+__device__ __noinline__ void iter_store_state(const QNIterArgs& a, const IterCarry& c, bool sharded) {
+  DevState* st = a.st;
+  st->f = c.f0;
+  st->ft = c.f0;
+  st->gd0 = c.gd0_last;
+  st->ss = c.ss;
+  st->yy = c.yy;
+  st->ys = c.ys_prev;
+  st->yh = c.yh;
+  st->s_norm = c.s_norm;
+  st->y_norm = c.y_norm;
+  st->has_s = c.has_s;
+  st->has_y = c.has_y;
+  st->skip = c.skip_prev;
+  st->c0 = c.cc0;
+  st->c1 = c.cc1;
+  st->c2 = c.cc2;
+  st->pc0 = c.pc0;
+  st->pc1 = c.pc1;
+  st->pc2 = c.pc2;
+  st->pending = c.pending;
+  st->epi = c.epi_owed;
+  st->t_last = c.t_last;
+  st->k = c.k;
+  st->ls_evals = c.ls_evals;
+  if (c.done) {
+    st->done = 1;
+    st->status = c.status;
+    st->reason = c.reason;
+  }
+  if (sharded) *a.seq = c.seq;
+  if (c.p.kind == LS_GLL || c.p.kind == LS_MORETHUENTE_B) *a.lsp = c.p;  // only f_previous / t_max persist across iterations
+}
+
+__device__ __forceinline__ long long iter_stamp() {
+  long long v;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+  return v;
+}
+
+__device__ __noinline__ void iter_mark(const QNIterArgs& a, IterSmem& sm, int slot) {
+  if (a.prof == nullptr || blockIdx.x != 0 || threadIdx.x != 0) return;
+  const long long now = iter_stamp();
+  sm.prof[slot] += now - sm.prof[3];
+  sm.prof[3] = now;
+}
+
+template <class Fn, bool BOUNDED, bool BT, bool SHARDED, int KIND>
+__global__ void __launch_bounds__(IT_NT, 1) qn_iter_kernel(const __grid_constant__ QNIterArgs a, const __grid_constant__ Fn fn) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ IterSmem sm;
+  if (a.st->done) return;
+  const bool leader = blockIdx.x == 0 && threadIdx.x == 0;
+  iter_load_state(a, sm.c, SHARDED);
+  __syncthreads();
+  {
+    const int64_t T = (a.n + QN_R - 1) / QN_R;
+    for (int q = threadIdx.x; q < (int)gridDim.x; q += IT_NT) sm.ext[q] = (int)sym_first_row<SHARDED>(T, a.world, a.rank, (int)gridDim.x, q);
+  }
+  grid.sync();  // every CTA has read the entry state before anybody can write it
+  // (time stamps live in shared memory, not in registers: nothing but &c and the loop counter is live across the pass)
+  if (a.prof != nullptr && leader) {
+    for (int q = 0; q < 16; ++q) sm.prof[q] = 0;
+    sm.prof[3] = iter_stamp();
+    sm.prof[15] = sm.prof[3];
+  }
+  int it = 0;
+  if (a.epi_only) {
+    iter_head<Fn, BOUNDED, BT, SHARDED, KIND>(a, fn, sm, true);
+  } else {
+    for (; it < a.iters; ++it) {
+      if (iter_head<Fn, BOUNDED, BT, SHARDED, KIND>(a, fn, sm, false)) break;
+      iter_mark(a, sm, 0);
+      // ---- the H pass: pending update + h = H y + w = H g over (this rank's share of) the packed triangle.  Inlined,
+      // every pointer straight from the kernel's constant bank; only &c is live across it.
+      {
+        QNLazyArgs la{};
+        la.ps = a.ps;
+        la.ph = a.ph;
+        la.y = a.y;
+        la.g = a.g;
+        la.h = a.h;
+        la.w = a.w;
+        const QNSymArgs sa{a.P, a.P, a.colpart, a.n, a.ld, SHARDED ? a.world : 1, SHARDED ? a.rank : 0, a.peers, a.seq, (int)gridDim.x, 0};
+        sym_pass_body<KIND, SHARDED, IT_NT, false, false>(la, sa, sm.c.pc0, sm.c.pc1, sm.c.pc2, 0, (int)gridDim.x, (int)blockIdx.x);
+      }
+      grid.sync();
+      iter_mark(a, sm, 1);
+      iter_tail<Fn, SHARDED>(a, sm);
+      iter_mark(a, sm, 2);
+    }
+  }
+  if (leader) {
+    iter_store_state(a, sm.c, SHARDED);
+    if (a.prof != nullptr) {
+      a.prof[0] += sm.prof[0];
+      a.prof[1] += sm.prof[1];
+      a.prof[2] += sm.prof[2];
       a.prof[3] += it;
+      for (int q = 4; q < 15; ++q) a.prof[q] += sm.prof[q];
     }
   }
 }
 
+// calibration: the fixed cost of one grid barrier of this kernel's shape (148 CTAs x 512 threads, cooperative launch)
+__global__ void __launch_bounds__(IT_NT, 1) grid_sync_bench_kernel(int reps, long long* out) {
+  cg::grid_group grid = cg::this_grid();
+  grid.sync();
+  const long long t0 = iter_stamp();
+  for (int r = 0; r < reps; ++r) grid.sync();
+  const long long t1 = iter_stamp();
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = t1 - t0;
+}
+double bench_grid_sync(Ctx* ctx, int reps) {
+  long long* d_out = nullptr;
+  OSB_CUDA(cudaMalloc(&d_out, sizeof(long long)));
+  void* params[] = {(void*)&reps, (void*)&d_out};
+  for (int rep = 0; rep < 2; ++rep)
+    OSB_CUDA(cudaLaunchCooperativeKernel((const void*)grid_sync_bench_kernel, dim3(qn_iter_grid(ctx)), dim3(IT_NT), params, 0, ctx->stream));
+  long long ns = 0;
+  OSB_CUDA(cudaMemcpyAsync(&ns, d_out, sizeof(ns), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->sync();
+  cudaFree(d_out);
+  return (double)ns * 1e-3 / reps;  // us per barrier
+}
+
 // ---- host side ------------------------------------------------------------------------------
 int qn_iter_grid(Ctx* ctx) { return ctx->num_sms < IT_MAXG ? ctx->num_sms : IT_MAXG; }
-int64_t qn_iter_gpart_doubles(Ctx* ctx) { return 2 * (int64_t)qn_iter_grid(ctx) * IT_GPK; }
+int64_t qn_iter_gpart_doubles(Ctx* ctx) { return 2 * (int64_t)qn_iter_grid(ctx) * IT_GPK + IT_MAXG; }
 
 bool qn_iter_supported(Ctx* ctx, int functor_kind, int64_t n, int world) {
   if (functor_kind != FN_ROSENBROCK && functor_kind != FN_SEPQUAD) return false;
@@ -604,14 +746,20 @@ bool qn_iter_supported(Ctx* ctx, int functor_kind, int64_t n, int world) {
   return coop != 0;
 }
 
-template <class Fn, bool BOUNDED, bool BT, bool SHARDED>
-static void launch_iter_k(Ctx* ctx, const QNIterArgs& a, const Fn& fn) {
-  auto kern = qn_iter_kernel<Fn, BOUNDED, BT, SHARDED>;
+template <class Fn, bool BOUNDED, bool BT, bool SHARDED, int KIND>
+static void launch_iter_kk(Ctx* ctx, const QNIterArgs& a, const Fn& fn) {
+  auto kern = qn_iter_kernel<Fn, BOUNDED, BT, SHARDED, KIND>;
   QNIterArgs aa = a;
   Fn f = fn;
   void* params[] = {(void*)&aa, (void*)&f};
   OSB_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(qn_iter_grid(ctx)), dim3(IT_NT), params, 0, ctx->stream));
   ctx->counters[0]++;
+}
+
+template <class Fn, bool BOUNDED, bool BT, bool SHARDED>
+static void launch_iter_k(Ctx* ctx, const QNIterArgs& a, const Fn& fn) {
+  if (a.kind == QN_BFGS) launch_iter_kk<Fn, BOUNDED, BT, SHARDED, QN_BFGS>(ctx, a, fn);
+  else launch_iter_kk<Fn, BOUNDED, BT, SHARDED, QN_DFP>(ctx, a, fn);
 }
 
 template <class Fn>
