@@ -407,6 +407,8 @@ def apply_debug_options(solver, args):
         solver.set_option("use_p2p", 0)
     if args.no_fused:
         solver.set_option("fused_iteration", 0)
+    if args.fused:
+        solver.set_option("fused_iteration", 1)
     return solver
 
 
@@ -622,7 +624,7 @@ def run_c3(args, env):
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload, "n": n, "line_search": "BackTracking(1e-4,0.5)", "tol": TOL,
                            "max_iter_line_search": MAX_LS, "options_set": "none (library defaults)" if not any(
-                               v is not None for v in (args.schedule, args.storage, args.qn_kernel, args.head, args.engine)) and not args.no_fused else "debug flags",
+                               v is not None for v in (args.schedule, args.storage, args.qn_kernel, args.head, args.engine)) and not args.no_fused and not args.fused else "debug flags",
                            "kernel": info["kernel"],
                            "engine": info["engine"], "schedule": info["schedule_name"], "storage": info["storage_name"],
                            "l2": "inputs larger than L2 (H = %.2f GiB per GPU, streamed every step)" % (
@@ -795,6 +797,7 @@ def main():
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL all-gathers instead of the fused peer-memory exchange")
     ap.add_argument("--schedule", default=None, choices=["lazy", "eager"])
     ap.add_argument("--no-fused", action="store_true", help="one launch per phase instead of the fused iteration kernel")
+    ap.add_argument("--fused", action="store_true", help="the fused iteration kernel also on one GPU (default: several GPUs only)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -837,7 +837,10 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
       colpart.alloc_pooled((int64_t)g_it * 2 * ld);
       colpart_grid = g_it;
     }
-    if (gpart.p == nullptr) gpart.alloc_pooled(qn_iter_gpart_doubles(ctx));
+    if (gpart.p == nullptr) {  // (zeroed once: sequence numbers of the flagged reductions start at 1 and never repeat)
+      gpart.alloc_pooled(qn_iter_gpart_doubles(ctx));
+      gpart.zero(stm);
+    }
     if (profile_iter && !d_iter_prof) {
       OSB_CUDA(cudaMalloc(&d_iter_prof, 16 * sizeof(long long)));
     }

@@ -39,6 +39,8 @@ struct DevState {
   int pending;  // lazy schedule: stored matrix = H - rank2(ps, ph; pc0..pc2) still to be applied
   int pp;       // ping-pong packed storage (pass variant bit 1): 0 = the current matrix is in Hsym, 1 = in Hsym2; toggled on
                 // the device by the fold kernel, so that predicated (no-op) launches after `done` do not flip it
+  int ll_seq;   // fused iteration kernel: sequence number of its flagged grid reductions (never reused: stale words of an
+                // earlier launch can then not be mistaken for fresh ones)
   int epi;      // lazy schedule: h = H y and w = H g are fresh and their O(n) epilogue is still owed (deferred to the next
                 // cluster head, or to qn_launch_epilogue_cluster when no head follows)
 };

@@ -50,6 +50,7 @@ struct IterCarry {
   long long k;
   unsigned long long seq;
   int has_s, has_y, skip_prev, pending, epi_owed, ls_evals, status, reason, done, gbuf;
+  unsigned int llseq;  // sequence number of the flagged (barrier-free) grid reductions; persists in DevState.ll_seq
   LSParams p;
 };
 
@@ -58,6 +59,7 @@ struct IterSmem {
   double w[IT_GPK * IT_NW];
   double res[IT_GPK];
   double2 part[2][IT_NT / 2];
+  double xs[IT_NT], ds[IT_NT];  // this CTA's chunk of x and d (backtracking: one warp per trial step sweeps it)
   int ext[IT_MAXG];
   long long prof[16];  // leader only: [0..2] accumulated ns in head / pass / fold, [3] last stamp, [4..15] head sub-phases
 };
@@ -84,21 +86,53 @@ __device__ __forceinline__ void warp_put(IterSmem& sm, int k, double v, bool act
   if (active) v = warp_sum(v);
   if ((threadIdx.x & 31) == 0) sm.w[k * IT_NW + (threadIdx.x >> 5)] = active ? v : 0.0;
 }
-__device__ __forceinline__ void grid_reduce(const QNIterArgs& a, IterSmem& sm, int K, int* gbuf_io, bool is_min) {
-  cg::grid_group grid = cg::this_grid();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// FLAGGED = false: the sums travel through plain stores + ONE real grid barrier (which also publishes whatever the CTAs
+//   wrote before it: needed in front of the H pass).
+// FLAGGED = true: a pure reduction needs no barrier at all.  Every value is split in two 32-bit halves, each stored
+//   together with the 32-bit sequence number of this reduction in ONE 64-bit word (single-copy atomic); a reader polls
+//   the word until the sequence number matches (the LL protocol of NCCL, between the CTAs of one GPU through L2).  Cost:
+//   one store-to-load propagation instead of fence + barrier + load (5.6 us -> ~1.5 us per reduction, measured).  Two
+//   buffers alternate: a CTA can be at most one reduction ahead of the slowest one, because finishing reduction r means
+//   having read every CTA's words of r.
+// Ksm: the values [0, Ksm) come from the warp partials in sm.w; the values [Ksm, K) were written by the caller straight
+//   into this CTA's row (grid_row).
+__device__ __forceinline__ double* grid_row(const QNIterArgs& a, int gbuf) {
+  return a.gpart + ((size_t)gbuf * gridDim.x + blockIdx.x) * IT_GPK;
+}
+__device__ __forceinline__ unsigned long long* ll_row(const QNIterArgs& a, int buf, int cta) {
+  return reinterpret_cast<unsigned long long*>(a.gpart + 2 * (size_t)gridDim.x * IT_GPK + IT_MAXG) + ((size_t)buf * gridDim.x + cta) * (2 * IT_GPK);
+}
+__device__ __forceinline__ void ll_put(unsigned long long* row, int k, double v, unsigned int seq) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long w0 = (bits & 0xffffffffULL) | ((unsigned long long)seq << 32);
+  const unsigned long long w1 = (bits >> 32) | ((unsigned long long)seq << 32);
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(row + 2 * k), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ double ll_get(const unsigned long long* row, int k, unsigned int seq) {
+  unsigned long long w0, w1;
+  do {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(row + 2 * k) : "memory");
+  } while ((unsigned int)(w0 >> 32) != seq || (unsigned int)(w1 >> 32) != seq);
+  return __longlong_as_double((long long)((w0 & 0xffffffffULL) | (w1 << 32)));
+}
+
+template <bool FLAGGED>
+__device__ __forceinline__ void grid_reduce(const QNIterArgs& a, IterSmem& sm, int K, int Ksm, int* gbuf_io, unsigned int* llseq_io, bool is_min) {
+  const int lane = threadIdx.x & 31;
   const int gbuf = *gbuf_io;
+  const unsigned int seq = *llseq_io + 1u;
   __syncthreads();
-  if ((int)threadIdx.x < K) {
+  if ((int)threadIdx.x < Ksm) {
     double v = is_min ? INFINITY : 0.0;
 #pragma unroll 1
     for (int wq = 0; wq < IT_NW; ++wq) {
       const double x = sm.w[threadIdx.x * IT_NW + wq];
       v = is_min ? fmin(v, x) : v + x;
     }
-    a.gpart[((size_t)gbuf * gridDim.x + blockIdx.x) * IT_GPK + threadIdx.x] = v;
+    if (FLAGGED) ll_put(ll_row(a, (int)(seq & 1u), (int)blockIdx.x), (int)threadIdx.x, v, seq);
+    else grid_row(a, gbuf)[threadIdx.x] = v;
   }
-  grid.sync();
+  if (!FLAGGED) cg::this_grid().sync();
   // 8 lanes per value: lane q of the group adds the partials of the CTAs q, q + 8, ... in that order (loads issued in
   // batches of 8 before the adds), then an 8-lane tree: fixed shape, hence the same bits in every CTA and on every rank
   const double* base = a.gpart + (size_t)gbuf * gridDim.x * IT_GPK;
@@ -109,12 +143,34 @@ __device__ __forceinline__ void grid_reduce(const QNIterArgs& a, IterSmem& sm, i
     double v = is_min ? INFINITY : 0.0;
     if (k < K) {
 #pragma unroll 1
-      for (int cq = sub; cq < (int)gridDim.x; cq += 64) {
-        double x[8];
+      for (int cq = sub; cq < (int)gridDim.x; cq += 80) {
+        double x[10];
+        if (FLAGGED) {
+          // all ten loads are issued before any flag is looked at; a round is repeated until every word carries this
+          // reduction's sequence number (polling one word after the other serialised ten L2 round trips)
+          unsigned long long w0[10], w1[10];
+          bool ok;
+          do {
+            ok = true;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) x[e] = (cq + 8 * e < (int)gridDim.x) ? __ldcg(base + (size_t)(cq + 8 * e) * IT_GPK + k) : (is_min ? INFINITY : 0.0);
+            for (int e = 0; e < 10; ++e) {
+              w0[e] = w1[e] = (unsigned long long)seq << 32;
+              if (cq + 8 * e < (int)gridDim.x)
+                asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0[e]), "=l"(w1[e]) : "l"(ll_row(a, (int)(seq & 1u), cq + 8 * e) + 2 * k) : "memory");
+            }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v = is_min ? fmin(v, x[e]) : v + x[e];
+            for (int e = 0; e < 10; ++e) ok = ok && (unsigned int)(w0[e] >> 32) == seq && (unsigned int)(w1[e] >> 32) == seq;
+          } while (!ok);
+#pragma unroll
+          for (int e = 0; e < 10; ++e)
+            x[e] = (cq + 8 * e < (int)gridDim.x) ? __longlong_as_double((long long)((w0[e] & 0xffffffffULL) | (w1[e] << 32))) : (is_min ? INFINITY : 0.0);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 10; ++e)
+            x[e] = (cq + 8 * e < (int)gridDim.x) ? __ldcg(base + (size_t)(cq + 8 * e) * IT_GPK + k) : (is_min ? INFINITY : 0.0);
+        }
+#pragma unroll
+        for (int e = 0; e < 10; ++e) v = is_min ? fmin(v, x[e]) : v + x[e];
       }
     }
 #pragma unroll
@@ -125,7 +181,8 @@ __device__ __forceinline__ void grid_reduce(const QNIterArgs& a, IterSmem& sm, i
     if (k < K && sub == 0) sm.res[k] = v;
   }
   __syncthreads();
-  *gbuf_io = gbuf ^ 1;
+  if (FLAGGED) *llseq_io = seq;
+  else *gbuf_io = gbuf ^ 1;
 }
 
 __device__ __forceinline__ unsigned long long* iter_flags(double* region, int world) {
@@ -192,12 +249,13 @@ __device__ __forceinline__ void iter_fold(const QNIterArgs& a, IterSmem& sm, int
     if (SHARDED) {
       const int64_t off = XSLOT_OFF + ((int64_t)(par * a.world + a.rank) * 2 + vec) * XSLOT_LD + j;
       for (int p = 0; p < a.world; ++p) *reinterpret_cast<double2*>(a.peers[p] + off) = make_double2(vx, vy);
-      __threadfence_system();  // this thread's peer stores are performed before the flag below is raised
     } else {
       *reinterpret_cast<double2*>(rowarr + j) = make_double2(vx, vy);
     }
   }
   if (SHARDED) {
+    // the CTA barrier orders every thread's peer stores before the flag threads; their release stores (system scope,
+    // cumulative) then publish the chunk — one fence per flag thread instead of one per storing thread
     __syncthreads();
     if (tid < a.world) {
       st_release_sys(iter_flags(a.peers[tid], a.world) + (int64_t)a.rank * XFLAG2_LD + blockIdx.x, seq);
@@ -230,6 +288,7 @@ __device__ __noinline__ int iter_head(const QNIterArgs& a, const Fn& fn, IterSme
   // Every thread reads what it needs of the carried state into registers FIRST; the writes below (every thread the same
   // values) come after a barrier, so no thread can see a field another thread has already advanced.
   int gbuf = c.gbuf;
+  unsigned int llseq = c.llseq;
   const double f0 = c.f0, ys_prev = c.ys_prev, s_norm_in = c.s_norm, y_norm_in = c.y_norm;
   const int has_s_in = c.has_s, has_y_in = c.has_y, epi_in = c.epi_owed, skip_in = c.skip_prev, ls_evals_in = c.ls_evals;
   const long long k_in = c.k;
@@ -281,7 +340,7 @@ __device__ __noinline__ int iter_head(const QNIterArgs& a, const Fn& fn, IterSme
       warp_put(sm, 1, e3[1], wact);
       warp_put(sm, 2, e3[2], wact);
       iter_submark(a, sm, 4);
-      grid_reduce(a, sm, 3, &gbuf, false);
+      grid_reduce<true>(a, sm, 3, 3, &gbuf, &llseq, false);
       iter_submark(a, sm, 5);
       const double yh = sm.res[0], sg = sm.res[1], hg = sm.res[2];
       double c0, c1, c2;
@@ -328,6 +387,7 @@ __device__ __noinline__ int iter_head(const QNIterArgs& a, const Fn& fn, IterSme
     for (int jq = 0; jq < BS; ++jq) ub_[jq] = own ? __ldcg(a.u + i0 + jq) : 0.0;
   }
   c.gbuf = gbuf;
+    c.llseq = llseq;
   if (epi_only) return 1;
   // ---- has_converged (bfgs.rs:64-76), first two tests
   if (has_s_in && s_norm_in < a.tol) {
@@ -371,6 +431,20 @@ __device__ __noinline__ int iter_head(const QNIterArgs& a, const Fn& fn, IterSme
       }
     }
   }
+  const int64_t j0 = (int64_t)cta * cw;
+  int nblk = 0;
+  if (BT) {
+    const int64_t left = (n - j0) / BS;
+    nblk = (int)(left < 0 ? 0 : (left < bpc ? left : bpc));
+    if (own) {
+#pragma unroll
+      for (int jq = 0; jq < BS; ++jq) {
+        sm.xs[tid * BS + jq] = xb[jq];
+        sm.ds[tid * BS + jq] = db[jq];
+      }
+    }
+    __syncthreads();
+  }
   iter_submark(a, sm, 6);
   LSMachine m;
   int evals = 0;
@@ -383,30 +457,40 @@ __device__ __noinline__ int iter_head(const QNIterArgs& a, const Fn& fn, IterSme
     for (;;) {
       warp_put(sm, 0, first_round ? gg : 0.0, wact);
       warp_put(sm, 1, first_round ? gd : 0.0, wact);
-      double tq = t0;
-#pragma unroll 1
-      for (int q = 0; q < IT_NSPEC; ++q) {
+      // One warp per trial step: warp q evaluates t0 beta^q over the whole chunk (x and d staged in shared memory), its
+      // lanes walking the blocks l, l + 32, ...; one interleaved shuffle tree for the three sums, and lane 0 writes the
+      // CTA's partial directly.  (16 steps x 112 elements on 2 warps, with 48 serial shuffle trees, took 8 us.)
+      {
+        const int q = tid >> 5, lane = tid & 31;
+        double tq = t0;
+        for (int e = 0; e < q; ++e) tq = tq * p.beta;  // the same products, in the same order, as the automaton's t *= beta
         double f3[3] = {0.0, 0.0, 0.0};
-        if (own) {
-          double xt[BS], gt[BS];
+#pragma unroll 1
+        for (int b = lane; b < nblk; b += 32) {
+          double xt[BS], gt[BS], dd[BS];
 #pragma unroll
           for (int jq = 0; jq < BS; ++jq) {
-            const double td = tq * db[jq];
-            xt[jq] = xb[jq] + td;
-            const double df = xt[jq] - xb[jq];
+            const double xq = sm.xs[b * BS + jq];
+            dd[jq] = sm.ds[b * BS + jq];
+            const double td = tq * dd[jq];
+            xt[jq] = xq + td;
+            const double df = xt[jq] - xq;
             f3[2] = f3[2] + df * df;
           }
-          f3[0] = fn.block(i0, xt, gt);
+          f3[0] = f3[0] + fn.block(j0 + (int64_t)b * BS, xt, gt);
 #pragma unroll
-          for (int jq = 0; jq < BS; ++jq) f3[1] = f3[1] + gt[jq] * db[jq];
+          for (int jq = 0; jq < BS; ++jq) f3[1] = f3[1] + gt[jq] * dd[jq];
         }
-        warp_put(sm, 2 + 3 * q, f3[0], wact);
-        warp_put(sm, 3 + 3 * q, f3[1], wact);
-        warp_put(sm, 4 + 3 * q, f3[2], wact);
-        tq = tq * p.beta;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          f3[0] = f3[0] + __shfl_xor_sync(0xffffffffu, f3[0], o);
+          f3[1] = f3[1] + __shfl_xor_sync(0xffffffffu, f3[1], o);
+          f3[2] = f3[2] + __shfl_xor_sync(0xffffffffu, f3[2], o);
+        }
+        if (lane < 3) ll_put(ll_row(a, (int)((llseq + 1u) & 1u), cta), 2 + 3 * q + lane, lane == 0 ? f3[0] : lane == 1 ? f3[1] : f3[2], llseq + 1u);
       }
       iter_submark(a, sm, 7);
-      grid_reduce(a, sm, 2 + 3 * IT_NSPEC, &gbuf, false);
+      grid_reduce<true>(a, sm, 2 + 3 * IT_NSPEC, 2, &gbuf, &llseq, false);
       iter_submark(a, sm, 8);
       if (first_round) {
         if (sqrt(sm.res[0]) < a.tol) {  // bfgs.rs:74
@@ -414,6 +498,7 @@ __device__ __noinline__ int iter_head(const QNIterArgs& a, const Fn& fn, IterSme
           c.status = OSB_OK;
           c.reason = OSB_REASON_GRAD_TOL;
           c.gbuf = gbuf;
+    c.llseq = llseq;
           __syncthreads();
           return 1;
         }
@@ -421,7 +506,7 @@ __device__ __noinline__ int iter_head(const QNIterArgs& a, const Fn& fn, IterSme
         m.template begin<LS_BACKTRACKING>(p, f0, gd0, a.max_ls, INFINITY);
         first_round = false;
       }
-      tq = t0;
+      double tq = t0;
 #pragma unroll 1
       for (int q = 0; q < IT_NSPEC; ++q) {
         if (m.done) break;
@@ -438,12 +523,13 @@ __device__ __noinline__ int iter_head(const QNIterArgs& a, const Fn& fn, IterSme
   } else {
     warp_put(sm, 0, gg, wact);
     warp_put(sm, 1, gd, wact);
-    grid_reduce(a, sm, 2, &gbuf, false);
+    grid_reduce<true>(a, sm, 2, 2, &gbuf, &llseq, false);
     if (sqrt(sm.res[0]) < a.tol) {  // bfgs.rs:74
       c.done = 1;
       c.status = OSB_OK;
       c.reason = OSB_REASON_GRAD_TOL;
       c.gbuf = gbuf;
+    c.llseq = llseq;
       __syncthreads();
       return 1;
     }
@@ -453,7 +539,7 @@ __device__ __noinline__ int iter_head(const QNIterArgs& a, const Fn& fn, IterSme
       __syncthreads();
       const double wm = warp_min(tm);
       if ((tid & 31) == 0) sm.w[tid >> 5] = wm;
-      grid_reduce(a, sm, 1, &gbuf, true);
+      grid_reduce<true>(a, sm, 1, 1, &gbuf, &llseq, true);
       tmaxc = sm.res[0];
     }
     m.begin(p, f0, gd0, a.max_ls, tmaxc);
@@ -481,7 +567,7 @@ __device__ __noinline__ int iter_head(const QNIterArgs& a, const Fn& fn, IterSme
       warp_put(sm, 0, a3[0], wact);
       warp_put(sm, 1, a3[1], wact);
       warp_put(sm, 2, a3[2], wact);
-      grid_reduce(a, sm, 3, &gbuf, false);
+      grid_reduce<true>(a, sm, 3, 3, &gbuf, &llseq, false);
       m.feed(p, sm.res[0], sm.res[1], sm.res[2]);
       ++evals;
     }
@@ -519,7 +605,7 @@ __device__ __noinline__ int iter_head(const QNIterArgs& a, const Fn& fn, IterSme
   warp_put(sm, 1, a4[1], wact);
   warp_put(sm, 2, a4[2], wact);
   warp_put(sm, 3, a4[3], wact);
-  grid_reduce(a, sm, 4, &gbuf, false);  // (its grid barrier also publishes s, y, x, g, ps, ph to the pass that follows)
+  grid_reduce<false>(a, sm, 4, 4, &gbuf, &llseq, false);  // (its grid barrier also publishes s, y, x, g, ps, ph to the pass that follows)
   iter_submark(a, sm, 11);
   {
     const double ss = sm.res[0], yy = sm.res[1], ys = sm.res[2], fn_ = sm.res[3];
@@ -537,6 +623,7 @@ __device__ __noinline__ int iter_head(const QNIterArgs& a, const Fn& fn, IterSme
     c.k = k_in + 1;
     c.ls_evals = ls_evals_in + evals + 1;
     c.gbuf = gbuf;
+    c.llseq = llseq;
   }
   if (!BT && (p.kind == LS_GLL || p.kind == LS_MORETHUENTE_B)) {  // only f_previous / t_max persist across iterations
     __syncthreads();
@@ -593,6 +680,7 @@ __device__ __noinline__ void iter_load_state(const QNIterArgs& a, IterCarry& c, 
   c.reason = st->reason;
   c.done = 0;
   c.gbuf = 0;
+  c.llseq = (unsigned int)st->ll_seq;
   c.p = *a.lsp;
 }
 
@@ -622,6 +710,7 @@ __device__ __noinline__ void iter_store_state(const QNIterArgs& a, const IterCar
   st->t_last = c.t_last;
   st->k = c.k;
   st->ls_evals = c.ls_evals;
+  st->ll_seq = (int)c.llseq;
   if (c.done) {
     st->done = 1;
     st->status = c.status;
@@ -725,7 +814,9 @@ double bench_grid_sync(Ctx* ctx, int reps) {
 
 // ---- host side ------------------------------------------------------------------------------
 int qn_iter_grid(Ctx* ctx) { return ctx->num_sms < IT_MAXG ? ctx->num_sms : IT_MAXG; }
-int64_t qn_iter_gpart_doubles(Ctx* ctx) { return 2 * (int64_t)qn_iter_grid(ctx) * IT_GPK + IT_MAXG; }
+int64_t qn_iter_gpart_doubles(Ctx* ctx) {  // 2 plain buffers | spare | 2 flagged buffers of 2 words per value
+  return 2 * (int64_t)qn_iter_grid(ctx) * IT_GPK + IT_MAXG + 2 * (int64_t)qn_iter_grid(ctx) * 2 * IT_GPK;
+}
 
 bool qn_iter_supported(Ctx* ctx, int functor_kind, int64_t n, int world) {
   if (functor_kind != FN_ROSENBROCK && functor_kind != FN_SEPQUAD) return false;

@@ -42,7 +42,8 @@ def main():
         x0 = rosen_x0(n, 5)
         res = []
         for c in (ctx, solo):
-            s = getattr(osb, kind)(1e-8, x0, ctx=c).set_option("engine", 2).set_option("qn_schedule", sched)
+            # full n x n storage, row-block sharded (the packed triangle, the default storage, is checked below)
+            s = getattr(osb, kind)(1e-8, x0, ctx=c).set_option("engine", 2).set_option("qn_schedule", sched).set_option("qn_storage", 0)
             s.set_option("use_p2p", p2p)
             try:
                 s.minimize(osb.BackTracking(1e-4, 0.5), osb.ExtendedRosenbrock(n, ctx=c), iters, 20)
