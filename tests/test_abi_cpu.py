@@ -207,3 +207,64 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "sample" in line["cpu_baseline"]
     assert line["e2e"] == {"value": line["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["config"]["n"] == 16384 and "workload" in line["config"]
+
+
+def test_rust_ffi_matches_the_header():
+    """rust/src/gpu/ffi.rs (the `extern "C"` block the crate's `gpu` module binds) against include/optsolv_b200.h: the same
+    symbol set, the same argument counts, pointer-ness of every argument, every enum constant with the same value.  No Rust
+    toolchain exists in this image, so this is the check that keeps the two files from drifting apart."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "optsolv_b200.h")).read(), flags=re.S)
+    rs = open(os.path.join(root, "rust", "src", "gpu", "ffi.rs")).read()
+    c_protos = {}
+    for m in re.finditer(r"\n\s*((?:const\s+)?[A-Za-z_][A-Za-z0-9_ ]*?[\s\*]+)(osb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr):
+        if "typedef" in m.group(1):
+            continue
+        args = re.sub(r"\s+", " ", m.group(3)).strip()
+        alist = [] if args == "void" else [a.strip() for a in args.split(",")]
+        c_protos[m.group(2)] = (["*" in a or "[" in a or a.split()[0].endswith("_fn") for a in alist], m.group(1).strip() != "void")
+    r_protos = {}
+    for m in re.finditer(r"pub fn (osb_[a-z0-9_]+)\((.*?)\)( -> [^;]+)?;", rs):
+        args = m.group(2).strip()
+        alist = [] if not args else [a.strip() for a in re.split(r",\s*(?=[a-zA-Z_#][a-zA-Z0-9_#]*\s*:)", args)]
+        r_protos[m.group(1)] = (["*" in a.split(":", 1)[1] or "_fn" in a.split(":", 1)[1] for a in alist], m.group(3) is not None)
+    assert set(c_protos) == set(r_protos), (sorted(set(c_protos) ^ set(r_protos)))
+    assert len(c_protos) >= 70
+    for name, (c_args, c_ret) in c_protos.items():
+        r_args, r_ret = r_protos[name]
+        assert len(c_args) == len(r_args), (name, len(c_args), len(r_args))
+        assert c_args == r_args, (name, c_args, r_args)
+        assert c_ret == r_ret, name
+    c_enums = dict((k, int(v)) for k, v in re.findall(r"\b(OSB_[A-Z0-9_]+)\s*=\s*(\d+)", hdr))
+    r_enums = dict((k, int(v)) for k, v in re.findall(r"pub const (OSB_[A-Z0-9_]+): c_int = (\d+);", rs))
+    assert c_enums == r_enums and len(c_enums) >= 30
+    # and the library exports every one of them
+    import importlib
+    osb = importlib.import_module("optimization-solvers_b200")
+    assert set(osb.exported_symbols()) == set(c_protos)
+
+
+def test_rust_gpu_module_covers_the_solver_and_line_search_matrix():
+    """The `gpu` module mirrors the reference's public surface for the path: 13 solver structs + PnormDescent, each with
+    `impl LineSearchSolver` whose `minimize` is overridden, the 6 line searches described through `LineSearch::gpu_spec`,
+    and every extern symbol it calls is declared in ffi.rs."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    mod = open(os.path.join(root, "rust", "src", "gpu", "mod.rs")).read()
+    ffi = open(os.path.join(root, "rust", "src", "gpu", "ffi.rs")).read()
+    spec = open(os.path.join(root, "rust", "src", "line_search", "gpu_spec.rs")).read()
+    solvers = ["BFGS", "DFP", "Broyden", "BFGSB", "DFPB", "BroydenB", "SR1B", "GradientDescent", "ProjectedGradientDescent",
+               "SpectralProjectedGradient", "Newton", "ProjectedNewton", "SpectralProjectedNewton", "PnormDescent"]
+    for s in solvers:
+        assert re.search(r"(quasi_newton(_bounded)?!\(%s,|pub struct %s \{)" % (s, s), mod), s
+        assert re.search(r"(gpu_solver!\(%s,|quasi_newton(_bounded)?!\(%s,)" % (s, s), mod), s
+    assert "impl LineSearchSolver for $name" in mod and "fn minimize<LS: LineSearch>" in mod and "GpuSolverCore::minimize(self" in mod
+    for ls in ("BackTracking", "BackTrackingB", "MoreThuente", "MoreThuenteB", "GLLQuadratic", "NoSearch"):
+        assert "LineSearchSpec::%s" % ls in mod and "impl %s {" % ls in spec, ls
+    declared = set(re.findall(r"pub fn (osb_[a-z0-9_]+)\(", ffi))
+    used = set(re.findall(r"ffi::(osb_[a-z0-9_]+)\(", mod))
+    assert used <= declared, sorted(used - declared)
+    assert len(used) >= 35
