@@ -232,6 +232,9 @@ int osb_minimize(osb_solver* s, osb_linesearch* ls, osb_objective* obj, int64_t 
  *                        device-resident control: line search on every SM, H pass, fold and multi-GPU exchange separated by
  *                        grid barriers only): -1 = auto (default: on with several GPUs, off with one), 1 = on, 0 = one launch
  *                        per phase
+ *   "fused_stream"       ProjectedGradientDescent / SpectralProjectedGradient on a block-functor objective: -1 / 1 = (default)
+ *                        ONE kernel per line-search trial (direction, projection, objective, all dot products and the
+ *                        projected-gradient norm: 4 vector reads + 2 writes), 0 = one launch per vector expression
  *   "profile_kernels"    1 = one launch per phase, the H pass(es) bracketed with CUDA events (osb_solver_kernel_timing)
  *   "profile_iter"       1 = the fused kernel records where its time goes (osb_solver_iter_profile) */
 int osb_solver_set_option(osb_solver* s, const char* name, int64_t value);
@@ -264,7 +267,7 @@ int osb_solver_kernel_timing(const osb_solver* s, double out[3]);
 /* which path the last minimize() took (the defaults are "auto"): out[0] engine (1 host-driven, 2 device-resident control),
  * out[1] schedule in force (0 eager, 1 lazy), out[2] storage in force (0 full n x n, 1 packed lower triangle), out[3] packed
  * triangle sharded over the ranks, out[4] fused peer-memory exchange used, out[5] ranks, out[6] kernel variant,
- * out[7] whole iterations ran in the fused cooperative kernel */
+ * out[7] bit 0: whole iterations ran in the fused cooperative kernel, bit 1: PGD / SPG ran one fused kernel per trial */
 int osb_solver_path_info(const osb_solver* s, int64_t out[8]);
 /* option "profile_iter": mean ms per iteration in out[0] head (epilogue, line search, next iterate), out[1] H pass,
  * out[2] fold + exchange of the fused iteration kernel (globaltimer stamps of CTA 0); out[3] = iterations covered;

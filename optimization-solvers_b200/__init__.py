@@ -874,9 +874,9 @@ class _Solver:
         return dict(engine={1: "host-driven control", 2: "device-resident control"}.get(eng, "none"), schedule=sched, storage=stor,
                     schedule_name=("lazy: 1 RMW pass of the stored matrix per iteration" if sched == 1 else "eager: gemv + fused update (3 n^2 8 B)"),
                     storage_name=("packed lower triangle, 8-row tiles (n^2 8 B per pass)" if stor == 1 else "full n x n row-major"),
-                    sharded_packed=bool(shard), p2p=bool(p2p), world=world, variant=variant, fused=bool(fused),
+                    sharded_packed=bool(shard), p2p=bool(p2p), world=world, variant=variant, fused=bool(fused & 1), fused_stream=bool(fused & 2),
                     kernel=("qn_iter_kernel: whole iterations (line search, H pass, fold, exchange) in one cooperative launch"
-                            if fused else "one launch per phase (head, pass, fold)"),
+                            if fused & 1 else "one launch per phase (head, pass, fold)"),
                     parallelism=("1 GPU" if world == 1 else
                                  "packed triangle sharded by tile pairs over %d GPUs; per-rank {h, w} contributions stored into every "
                                  "peer's slot (NVLink stores + flags), summed in rank order" % world if shard else

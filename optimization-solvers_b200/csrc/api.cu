@@ -412,6 +412,7 @@ int osb_solver_set_option(osb_solver* s, const char* name, int64_t value) {
   else if (nm == "head_kernel") S(s)->head_variant = (int)value;
   else if (nm == "profile_kernels") S(s)->profile_kernels = (int)value;
   else if (nm == "fused_iteration") S(s)->opt_fused = (int)value;
+  else if (nm == "fused_stream") S(s)->opt_stream = (int)value;
   else if (nm == "profile_iter") S(s)->profile_iter = (int)value;
   else throw Error(OSB_ERROR_INPUT_PARAMS, "unknown option " + nm);
   return OSB_OK;
@@ -603,7 +604,7 @@ int osb_solver_path_info(const osb_solver* s, int64_t out[8]) {
   out[4] = p->last_p2p ? 1 : 0;
   out[5] = p->ctx->world;
   out[6] = p->qn_variant;
-  out[7] = p->last_fused ? 1 : 0;
+  out[7] = (p->last_fused ? 1 : 0) | (p->last_stream ? 2 : 0);
   return OSB_OK;
 }
 int osb_solver_last_timing(const osb_solver* s, double* ms, int64_t* iters) {

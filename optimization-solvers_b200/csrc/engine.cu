@@ -647,7 +647,83 @@ int Solver::minimize(LineSearch* ls, Objective* obj, int64_t max_iter, int64_t m
   return rc;
 }
 
+__global__ void accept_stream_kernel(DevState* st) { st->f = st->fz[0]; }
+
+// ProjectedGradientDescent / SpectralProjectedGradient on a block-functor objective: the whole iteration is ONE fused
+// kernel per line-search trial (Objective::stream_trial): 4 vector reads + 2 writes, against ~14 vector passes with one
+// launch per vector expression.  The first trial step (every supported search starts at t = 1) is issued together with
+// the convergence scalar and g.d of x_k, so one host fetch serves has_converged, the direction scalars and the first
+// Armijo test.  projected_gradient_descent.rs:50-109, spg.rs:76-145, ls_solver.rs:66-111.
+int Solver::minimize_stream(LineSearch* ls, Objective* obj, int64_t max_iter, int64_t max_ls, osb_callback_fn cb, void* user) {
+  k = 0;  // ls_solver.rs:74
+  reason = OSB_REASON_NONE;
+  trace.clear();
+  LSParams& lp = ls->p;
+  const bool scale = kind == OSB_SPG;
+  cudaStream_t stm = ctx->stream;
+  if (!have_eval) {
+    obj->eval(x.p, &d_state->f, g.p, nullptr);
+    have_eval = true;
+  }
+  const double t0 = 1.0;  // BackTracking(B), GLLQuadratic and NoSearch all start from t = 1
+  const bool proj0 = lp.kind == LS_BACKTRACKING_B;
+  double* fz = d_state->fz;
+  while (max_iter > k) {
+    obj->stream_trial(x.p, g.p, lb.p, ub.p, lambda, scale, t0, proj0, ls->lb.p, ls->ub.p, xt.p, gt.p, fz);
+    ctx->counters[2]++;
+    fetch_state();
+    const double f = h_state->f;
+    if (is_bad(f)) return OSB_OUT_OF_DOMAIN;  // ls_solver.rs:37-40
+    if (rmax(0.0, h_state->fz[7]) < tol) {    // projected_gradient_descent.rs:76-83 (number.rs:27-31 folds from 0.0)
+      reason = OSB_REASON_PROJ_GRAD_TOL;
+      return OSB_OK;
+    }
+    LSMachine m;
+    m.begin(lp, f, h_state->fz[4], max_ls, h_state->fz[5]);
+    bool have_first = true;
+    while (!m.done) {
+      const double t = m.request(lp);
+      const bool pj = m.wants_projection(lp);
+      if (!(have_first && t == t0 && pj == proj0)) {
+        obj->stream_trial(x.p, g.p, lb.p, ub.p, lambda, scale, t, pj, ls->lb.p, ls->ub.p, xt.p, gt.p, fz);
+        ctx->counters[2]++;
+        fetch_state();
+      }
+      have_first = false;
+      m.feed(lp, h_state->fz[0], h_state->fz[1], h_state->fz[2]);
+    }
+    const double t = m.result;
+    if (!m.last_eval_is_result) {  // next = x + t d, un-projected (ls_solver.rs:60; projected_gradient_descent.rs:103)
+      obj->stream_trial(x.p, g.p, lb.p, ub.p, lambda, scale, t, false, ls->lb.p, ls->ub.p, xt.p, gt.p, fz);
+      fetch_state();
+    }
+    if (kind == OSB_SPG) {  // spg.rs:134-143: s.y <= 0 -> lambda_max, else clamp(s.s / s.y)
+      const double sy = h_state->fz[3], ss = h_state->fz[2];
+      if (sy <= 0.) lambda = lambda_max;
+      else lambda = rmax(rmin(ss / sy, lambda_max), lambda_min);
+    }
+    std::swap(x.p, xt.p);
+    std::swap(g.p, gt.p);
+    accept_stream_kernel<<<1, 1, 0, stm>>>(d_state);
+    ctx->counters[0]++;
+    have_eval = true;
+    if (record_trace) trace.push_back(TraceRec{f, t, NAN, NAN});
+    k += 1;  // ls_solver.rs:104
+    if (cb) {
+      ctx->sync();
+      cb(user, reinterpret_cast<osb_solver*>(this));
+    }
+  }
+  return OSB_MAX_ITER_REACHED;  // ls_solver.rs:109-110
+}
+
 int Solver::minimize_host(LineSearch* ls, Objective* obj, int64_t max_iter, int64_t max_ls, osb_callback_fn cb, void* user) {
+  last_stream = false;
+  if ((kind == OSB_PGD || kind == OSB_SPG) && opt_stream != 0 && obj->has_stream_trial() &&
+      (ls->p.kind == LS_BACKTRACKING || ls->p.kind == LS_BACKTRACKING_B || ls->p.kind == LS_GLL || ls->p.kind == LS_NOSEARCH)) {
+    last_stream = true;
+    return minimize_stream(ls, obj, max_iter, max_ls, cb, user);
+  }
   if (is_qn && qn_schedule != 1) {  // eager: works on the exact, full matrix (lazy: the stored matrix may lag / be packed)
     flush_pending();
     ensure_full();

@@ -29,6 +29,9 @@ struct DevState {
   double c0, c1, c2;  // rank-2 update coefficients (kind-specific, see qn_kernels.cu)
   double pc0, pc1, pc2;  // lazy schedule: coefficients of the update that is still PENDING on the stored matrix
   double t_last;
+  // fused streaming trial of PGD / SPG (8 contiguous): f_t, g_t.d, ||x_t - x||^2, s.y, g.d, feasible-step candidate,
+  // ||d||_inf, ||projected gradient||_inf
+  double fz[8];
   long long k;
   int has_s, has_y;
   int skip;    // bfgs.rs:106-112: s_norm < tol || y_norm < tol -> H not updated
@@ -161,6 +164,16 @@ struct Objective {
   // one line-search trial: xt = [P](x + t d); (ft, gt) = eval(xt); out3 = {ft, gt.d, ||xt - x||^2}
   virtual void trial(const double* x, const double* d, double t, bool project, const double* lb, const double* ub,
                      double* xt, double* gt, double* d_out3);
+  // Fused trial step of the projected-gradient family (PGD / SPG, block-functor objectives): ONE kernel reads x, g, lb, ub
+  // and writes x_t, g_t; the direction d = P(x - lam g) - x is formed on the fly and never stored.
+  //   x_t = [P_ls](x + t d),  (f_t, g_t) = eval(x_t)
+  //   out8 = {f_t, g_t.d, ||x_t - x||^2, (x_t - x).(g_t - g), g.d, min feasible step, ||d||_inf, ||proj grad(x)||_inf}
+  // Returns false when the objective has no fused form (the caller then takes one launch per vector expression).
+  virtual bool has_stream_trial() const { return false; }
+  virtual bool stream_trial(const double*, const double*, const double*, const double*, double, bool, double, bool, const double*,
+                            const double*, double*, double*, double*) {
+    return false;
+  }
 };
 
 Objective* make_dense_quadratic(Ctx*, int64_t n, const double* A_host, const double* b_host);
@@ -363,6 +376,8 @@ struct Solver {
   bool sym_pingpong_dirty = false;
   // fused iteration kernel (qn_iter.cu): -1 = auto (on whenever it applies), 0 = off (one launch per phase)
   int opt_fused = -1;
+  int opt_stream = -1;           // PGD / SPG: one fused kernel per trial step (-1 / 1 = on whenever it applies, 0 = off)
+  bool last_stream = false;
   bool iter_path = false;        // this minimize() runs whole iterations in one cooperative kernel
   QNIterArgs iter_args{};        // last launch parameters (the epilogue-only launch re-uses them)
   int iter_fn_kind = 0, iter_ls_kind = 0;
@@ -414,6 +429,7 @@ struct Solver {
  private:
   int minimize_host(LineSearch* ls, Objective* obj, int64_t max_iter, int64_t max_ls, osb_callback_fn cb, void* user);
   int minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, int64_t max_ls, osb_callback_fn cb, void* user);
+  int minimize_stream(LineSearch* ls, Objective* obj, int64_t max_iter, int64_t max_ls, osb_callback_fn cb, void* user);
   bool device_engine_supported(const LineSearch* ls, const Objective* obj) const;
   void compute_conv_scalar(Objective* obj);
   int compute_direction(Objective* obj, LineSearch* ls);

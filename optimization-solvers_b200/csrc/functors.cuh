@@ -26,14 +26,28 @@ struct RosenbrockFn {
   }
 };
 
-// Separable quadratic f = sum 0.5 c_i (x_i - a_i)^2  (twin of oracle `SeparableQuadratic`)
+// Separable quadratic f = sum 0.5 c_i (x_i - a_i)^2  (twin of oracle `SeparableQuadratic`).
+// c == nullptr: the GENERATED problem — c_i = 1 + (hash(7, i) & 255) / 16, a_i = int16(hash(8, i)) 2^-14 are recomputed
+// from the integer hash instead of being read (two splitmix64 per coordinate are free next to an HBM-bound stream, and
+// at n = 2^28 the two 2 GiB coefficient vectors were a third of the traffic of a trial step); index0 is the global
+// index of local coordinate 0 (index-range sharding).
 struct SepQuadFn {
   static constexpr int BS = 1;
   const double* c;
   const double* a;
+  int64_t index0;
   HD double block(int64_t i0, const double* xb, double* gb) const {
-    const double dlt = xb[0] - a[i0];
-    const double cd = c[i0] * dlt;
+    double ci, ai;
+    if (c != nullptr) {
+      ci = c[i0];
+      ai = a[i0];
+    } else {
+      const uint64_t gi = (uint64_t)(index0 + i0);
+      ci = 1.0 + (double)(hash3(7, gi, 0) & 0xFF) / 16.0;
+      ai = (double)h16(8, gi, 0) * 6.103515625e-05;  // 2^-14
+    }
+    const double dlt = xb[0] - ai;
+    const double cd = ci * dlt;
     gb[0] = cd;
     return 0.5 * (cd * dlt);
   }

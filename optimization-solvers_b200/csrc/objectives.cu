@@ -74,6 +74,62 @@ struct FunctorObjective : Objective {
     };
     launch_mapreduce<3>(ctx, f, n / Fn::BS, RedOps<3>{{RED_SUM, RED_SUM, RED_SUM}}, d_out3);
   }
+  // spg.rs:81-84 / projected_gradient_descent.rs:56-59 (direction), ls_solver.rs:60 + backtracking_b.rs:65-67 (trial point),
+  // spg.rs:129-141 (s.s, s.y), ls_solver.rs:121-133 + number.rs:27-31 (projected gradient), morethuente_b.rs:185-197
+  // (feasible step): the arithmetic of each coordinate is the one of vec_projected_direction + trial + vec_sy, in the
+  // same order, so the iterates (and the active set, defined by exact ==) do not change — only the number of passes:
+  // 4 reads + 2 writes per trial instead of ~14 vector passes per iteration.
+  bool has_stream_trial() const override { return true; }
+  bool stream_trial(const double* x, const double* g, const double* lb, const double* ub, double lam, bool scale, double t,
+                    bool project, const double* ls_lb, const double* ls_ub, double* xt, double* gt, double* d_out8) override {
+    calls++;
+    ctx->counters[1]++;
+    const Fn f_ = fn;
+    auto f = [=] __device__(int64_t b, double(&acc)[8]) {
+      double xb[Fn::BS], gb[Fn::BS], db[Fn::BS], x0[Fn::BS], g0[Fn::BS];
+      const int64_t i0 = b * Fn::BS;
+#pragma unroll
+      for (int j = 0; j < Fn::BS; ++j) {
+        const int64_t i = i0 + j;
+        const double xi = x[i], gi = g[i], lo = lb[i], hi = ub[i];
+        const double wi = scale ? lam * gi : gi;
+        double v = xi - wi;
+        v = fmin(fmax(v, lo), hi);
+        const double di = v - xi;
+        acc[4] = acc[4] + gi * di;
+        double cand;
+        if (di > 0.0) cand = (hi - xi) / di;
+        else if (di < 0.0) cand = (lo - xi) / di;
+        else cand = INFINITY;
+        acc[5] = fmin(cand, acc[5]);
+        acc[6] = fmax(acc[6], fabs(di));
+        double pg = gi;
+        if ((xi == lo && pg > 0.0) || (xi == hi && pg < 0.0)) pg = 0.0;
+        acc[7] = fmax(acc[7], fabs(pg));
+        const double td = t * di;
+        double xv = xi + td;
+        if (project) xv = fmin(fmax(xv, ls_lb[i]), ls_ub[i]);
+        xt[i] = xv;
+        const double df = xv - xi;
+        acc[2] = acc[2] + df * df;
+        xb[j] = xv;
+        db[j] = di;
+        x0[j] = xi;
+        g0[j] = gi;
+      }
+      const double fb = f_.block(i0, xb, gb);
+#pragma unroll
+      for (int j = 0; j < Fn::BS; ++j) {
+        gt[i0 + j] = gb[j];
+        acc[1] = acc[1] + gb[j] * db[j];
+        const double yi = gb[j] - g0[j], si = xb[j] - x0[j];
+        acc[3] = acc[3] + yi * si;
+      }
+      acc[0] = acc[0] + fb;
+    };
+    launch_mapreduce<8>(ctx, f, n / Fn::BS, RedOps<8>{{RED_SUM, RED_SUM, RED_SUM, RED_SUM, RED_SUM, RED_MIN, RED_MAX, RED_MAX}}, d_out8);
+    return true;
+  }
 };
 
 Objective* make_rosenbrock(Ctx* ctx, int64_t n) {
@@ -81,21 +137,13 @@ Objective* make_rosenbrock(Ctx* ctx, int64_t n) {
   return new FunctorObjective<RosenbrockFn>(ctx, n, FN_ROSENBROCK);
 }
 
-__global__ void gen_sepquad_kernel(int64_t n, double* c, double* a, int64_t index0) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const uint64_t gi = (uint64_t)(index0 + i);  // global coordinate (index-range sharding: this rank holds [index0, index0 + n))
-    c[i] = 1.0 + (double)(hash3(7, gi, 0) & 0xFF) / 16.0;
-    a[i] = (double)h16(8, gi, 0) * 6.103515625e-05;  // 2^-14
-  }
-}
+// the generated separable problem keeps no coefficient vectors: SepQuadFn recomputes c_i, a_i from the integer hash
+// (4 GiB less memory and a third less traffic per trial at n = 2^28); index0 = global index of local coordinate 0
 Objective* make_sepquad_generated(Ctx* ctx, int64_t n, int64_t index0) {
   auto* o = new FunctorObjective<SepQuadFn>(ctx, n, FN_SEPQUAD);
-  o->pa.alloc(qn_ld(n));
-  o->pb.alloc(qn_ld(n));
-  gen_sepquad_kernel<<<ctx->red_grid(n), RED_THREADS, 0, ctx->stream>>>(n, o->pa.p, o->pb.p, index0);
-  ctx->counters[0]++;
-  o->fn.c = o->pa.p;
-  o->fn.a = o->pb.p;
+  o->fn.c = nullptr;
+  o->fn.a = nullptr;
+  o->fn.index0 = index0;
   return o;
 }
 

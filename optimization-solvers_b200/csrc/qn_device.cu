@@ -885,6 +885,7 @@ void qn_device_launch_head(Ctx* ctx, int functor_kind, const double* fn_a, const
     SepQuadFn fn;
     fn.c = fn_a;
     fn.a = fn_b;
+    fn.index0 = 0;
     if ((head_variant == 0 || head_variant == 3) && launch_head_cluster(ctx, fn, bounded, d_ls, ls_kind, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub, head_variant == 0, epi)) return;
     if (head_variant <= 1 && launch_head_fast(ctx, fn, bounded, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub)) return;
     launch_head(ctx, fn, bounded, d_ls, n, tol, max_ls, st, x, g, d, xt, gt, s, y, u, lb, ub, ls_lb, ls_ub);

@@ -875,6 +875,7 @@ void qn_launch_iter(Ctx* ctx, int functor_kind, const double* fn_a, const double
     SepQuadFn fn;
     fn.c = fn_a;
     fn.a = fn_b;
+    fn.index0 = 0;
     launch_iter_fn(ctx, a, fn, bounded, bt, sharded);
   } else {
     throw Error(OSB_ERR_UNSUPPORTED, "objective has no block functor for the device-resident engine");

@@ -726,3 +726,46 @@ def test_fused_iteration_kernel_other_searches_and_bounds(osb, orc):
     s = osb.BFGS(1e-7, np.zeros(n)).set_option("fused_iteration", 1)
     run(osb, s, osb.MoreThuente.default(), osb.SeparableQuadratic.generated(n), 3, 30)
     assert s.path_info()["fused"]
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("solver,lsname", [("SPG", "gll"), ("SPG", "bt"), ("PGD", "bt"), ("PGD", "btb"), ("SPG", "nosearch")])
+def test_fused_stream_trial_is_bit_identical_to_one_launch_per_expression(osb, solver, lsname):
+    """PGD / SPG on a block-functor objective run ONE fused kernel per line-search trial (Objective::stream_trial: direction,
+    projection, objective, every dot product and the projected-gradient norm in 4 vector reads + 2 writes).  Per coordinate
+    the arithmetic is the one of the separate kernels in the same order, and the reductions run over the same index space:
+    same iteration count, reason, iterate, objective and active set, bit for bit."""
+    n = 1 << 15
+    lb, ub = np.full(n, -1.0), np.full(n, 1.0)
+    out = []
+    for fused in (1, 0):
+        obj = osb.SeparableQuadratic.generated(n)
+        if solver == "SPG":
+            s = osb.SpectralProjectedGradient(1e-6, np.zeros(n), obj, lb, ub)
+        else:
+            s = osb.ProjectedGradientDescent(1e-6, np.zeros(n), lb, ub)
+        s.set_option("fused_stream", fused)
+        ls = {"gll": lambda: osb.GLLQuadratic(1e-4, 10), "bt": lambda: osb.BackTracking(1e-4, 0.5),
+              "btb": lambda: osb.BackTrackingB(1e-4, 0.5, lb, ub), "nosearch": lambda: osb.NoSearch()}[lsname]()
+        st = run(osb, s, ls, obj, 60, 50)
+        assert s.path_info()["fused_stream"] == bool(fused)
+        out.append((st, s.k(), s.termination_reason(), s.x(), s.f(), s.active_set(), s.lambda_() if solver == "SPG" else 0.0))
+    a, b = out
+    assert a[:3] == b[:3], (a[:3], b[:3])
+    assert np.array_equal(a[3], b[3]) and a[4] == b[4] and np.array_equal(a[5], b[5]) and a[6] == b[6]
+
+
+def test_fused_stream_trial_rosenbrock_blocks(osb, orc):
+    # block size 2 (Rosenbrock): the fused kernel sums over blocks instead of coordinates — same results to rounding
+    n = 4096
+    lb, ub = np.full(n, -2.0), np.full(n, 0.9)
+
+    def script(m):
+        obj = m.ExtendedRosenbrock(n) if m is osb else m.ExtendedRosenbrock()
+        s = m.ProjectedGradientDescent(1e-6, rosen_x0(n, 71), lb, ub)
+        st = run(m, s, m.BackTracking(1e-4, 0.5), obj, 25, 40)
+        return st, s.k(), s.termination_reason(), s.x(), s.active_set()
+
+    ref, got = both(osb, orc, script)
+    assert got[:3] == ref[:3]
+    assert close(got[3], ref[3]) and np.array_equal(got[4], ref[4])
