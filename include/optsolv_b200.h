@@ -78,6 +78,17 @@ const char* osb_last_error_string(void);
 /* library / build identification, e.g. "optsolv_b200 0.1 sm_100a" */
 const char* osb_version(void);
 
+/* ---- Tracer (src/tracer.rs:5-63): the library emits the reference's own events — same targets, levels and messages —
+ * through ONE callback, on the thread that called osb_minimize; the host side routes them into its tracing subscriber
+ * (Rust: the crate's `Tracer` unchanged; Python mirror: `Tracer.build()`).  Events: "solver" error "Minimization
+ * completed: next iterate is out of domain" (ls_solver.rs:38), "solver" info "Minimization completed: convergence in {k}
+ * iterations" (:82-86), "solver" warn "Minimization completed: max iter reached during minimization" (:109), "bfgs" warn
+ * "Minimization completed: next iterate too close" / "... gradient next iterate too close" (bfgs.rs:68,71 and siblings),
+ * "newton" warn "Hessian is singular. Using gradient descent direction." (newton/mod.rs:44).  level: 1 error, 2 warn,
+ * 3 info, 4 debug, 5 trace.  NULL removes the callback (default: no events). */
+typedef void (*osb_log_fn)(void* user, int level, const char* target, const char* message);
+int osb_set_log_callback(osb_log_fn fn, void* user);
+
 /* ---- context: one per GPU (one process per GPU) -------------------------------------------- */
 int osb_ctx_create(int device, osb_ctx** out);
 /* Row-block sharded multi-GPU context.  `nccl_unique_id` is the 128-byte ncclUniqueId produced

