@@ -940,6 +940,18 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
       gpart.alloc_pooled(qn_iter_gpart_doubles(ctx));
       gpart.zero(stm);
     }
+    if (sym_sharded) {
+      if (iter_wt.p == nullptr) {  // flat partition of this rank's tiles over the CTAs (built once per solver)
+        std::vector<int> tab;
+        qn_iter_build_worktable(ctx, n, tab);
+        iter_wt.alloc_pooled((int64_t)(tab.size() + 1) / 2 + 1);
+        OSB_CUDA(cudaMemcpyAsync(iter_wt.p, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice, stm));
+        ctx->sync();  // (tab is a local)
+        rowpart.alloc_pooled(3 * 2 * ld);
+        rowpart.zero(stm);
+      }
+      colpart.zero(stm);  // the flat pass adds into zeroed column partials (the fold leaves them zeroed again)
+    }
     if (profile_iter && !d_iter_prof) {
       OSB_CUDA(cudaMalloc(&d_iter_prof, 16 * sizeof(long long)));
     }
@@ -974,6 +986,8 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
     a.rank = sym_sharded ? ctx->rank : 0;
     a.peers = sym_sharded ? ctx->d_peers : nullptr;
     a.seq = ctx->d_seq;
+    a.wt = sym_sharded ? reinterpret_cast<const int*>(iter_wt.p) : nullptr;
+    a.rowpart = sym_sharded ? rowpart.p : nullptr;
     a.prof = profile_iter ? d_iter_prof : nullptr;
     iter_args = a;
     iter_fn_kind = obj->functor_kind();

@@ -218,11 +218,16 @@ __device__ __forceinline__ void iter_fold(const QNIterArgs& a, IterSmem& sm, int
         acc.x = acc.x + v[k].x;
         acc.y = acc.y + v[k].y;
       }
+      if (SHARDED) {  // flat partition: the pass adds into zeroed partials; this thread is the only reader of these words
+#pragma unroll
+        for (int k = 0; k < 8; ++k) *reinterpret_cast<double2*>(const_cast<double*>(src) + (int64_t)(c + k) * 2 * a.ld) = make_double2(0.0, 0.0);
+      }
     }
     for (; c < ce; ++c) {
       const double2 v = j < sm.ext[c] ? __ldcg(reinterpret_cast<const double2*>(src + (int64_t)c * 2 * a.ld)) : make_double2(0.0, 0.0);
       acc.x = acc.x + v.x;
       acc.y = acc.y + v.y;
+      if (SHARDED) *reinterpret_cast<double2*>(const_cast<double*>(src) + (int64_t)c * 2 * a.ld) = make_double2(0.0, 0.0);
     }
   }
   __syncthreads();
@@ -236,14 +241,21 @@ __device__ __forceinline__ void iter_fold(const QNIterArgs& a, IterSmem& sm, int
       tot.y = tot.y + sm.part[vec][q * cwpp + pr].y;
     }
     double* rowarr = vec == 0 ? a.h : a.w;
-    bool local = true;
-    if (SHARDED) {  // the row sums of rows j, j + 1 exist on this rank only when it owns their tile
+    double2 rs = make_double2(0.0, 0.0);
+    if (SHARDED) {  // the row sums of rows j, j + 1 exist on this rank only when it owns their tile: its pieces' slots, in order
       const int64_t T = (a.n + QN_R - 1) / QN_R, tile = j / QN_R;
       const int64_t pairi = tile < T / 2 ? tile : T - 1 - tile;
-      local = (pairi % a.world) == a.rank;
+      if ((pairi % a.world) == a.rank) {
+        const int np = a.wt[4 * (int)gridDim.x + (int)symsh_pos_of(T, a.world, a.rank, tile)];
+        for (int sl = 0; sl < np; ++sl) {
+          const double2 v = __ldcg(reinterpret_cast<const double2*>(a.rowpart + ((int64_t)sl * 2 + vec) * a.ld + j));
+          rs.x = rs.x + v.x;
+          rs.y = rs.y + v.y;
+        }
+      }
+    } else {
+      rs = __ldcg(reinterpret_cast<const double2*>(rowarr + j));
     }
-    double2 rs = make_double2(0.0, 0.0);
-    if (local) rs = __ldcg(reinterpret_cast<const double2*>(rowarr + j));
     const double vx = rs.x + tot.x;
     const double vy = (j + 1 < a.n) ? rs.y + tot.y : 0.0;
     if (SHARDED) {
@@ -314,10 +326,29 @@ __device__ __noinline__ int iter_head(const QNIterArgs& a, const Fn& fn, IterSme
         const int64_t i = i0 + jq;
         if (SHARDED) {  // rank-ordered sum of the per-rank slots: the same numbers in the same order on every rank
           const double* bh = a.peers[a.rank] + XSLOT_OFF + ((int64_t)(par * a.world) * 2 + 0) * XSLOT_LD + i;
-          double vh = __ldcg(bh), vw = __ldcg(bh + XSLOT_LD);
-          for (int r = 1; r < a.world; ++r) {
-            vh = vh + __ldcg(bh + (int64_t)r * 2 * XSLOT_LD);
-            vw = vw + __ldcg(bh + (int64_t)r * 2 * XSLOT_LD + XSLOT_LD);
+          double vh = 0.0, vw = 0.0;
+#pragma unroll 1
+          for (int r0 = 0; r0 < a.world; r0 += 8) {  // eight slots' loads in flight, then the adds in rank order
+            double th[8], tw[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              th[e] = tw[e] = 0.0;
+              if (r0 + e < a.world) {
+                th[e] = __ldcg(bh + (int64_t)(r0 + e) * 2 * XSLOT_LD);
+                tw[e] = __ldcg(bh + (int64_t)(r0 + e) * 2 * XSLOT_LD + XSLOT_LD);
+              }
+            }
+            if (r0 == 0) {
+              vh = th[0];
+              vw = tw[0];
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              if ((r0 > 0 || e > 0) && r0 + e < a.world) {
+                vh = vh + th[e];
+                vw = vw + tw[e];
+              }
+            }
           }
           hb[jq] = vh;
           wb[jq] = vw;
@@ -743,7 +774,10 @@ __global__ void __launch_bounds__(IT_NT, 1) qn_iter_kernel(const __grid_constant
   __syncthreads();
   {
     const int64_t T = (a.n + QN_R - 1) / QN_R;
-    for (int q = threadIdx.x; q < (int)gridDim.x; q += IT_NT) sm.ext[q] = (int)sym_first_row<SHARDED>(T, a.world, a.rank, (int)gridDim.x, q);
+    // one GPU: partial vector q is valid on the columns below the first row of CTA q's first tile; sharded (flat
+    // partition): the partials are zeroed by the fold, every column is valid
+    for (int q = threadIdx.x; q < (int)gridDim.x; q += IT_NT)
+      sm.ext[q] = SHARDED ? 0x7fffffff : (int)sym_first_row<false>(T, 1, 0, (int)gridDim.x, q);
   }
   grid.sync();  // every CTA has read the entry state before anybody can write it
   // (time stamps live in shared memory, not in registers: nothing but &c and the loop counter is live across the pass)
@@ -770,7 +804,8 @@ __global__ void __launch_bounds__(IT_NT, 1) qn_iter_kernel(const __grid_constant
         la.h = a.h;
         la.w = a.w;
         const QNSymArgs sa{a.P, a.P, a.colpart, a.n, a.ld, SHARDED ? a.world : 1, SHARDED ? a.rank : 0, a.peers, a.seq, (int)gridDim.x, 0};
-        sym_pass_body<KIND, SHARDED, IT_NT, false, false>(la, sa, sm.c.pc0, sm.c.pc1, sm.c.pc2, 0, (int)gridDim.x, (int)blockIdx.x);
+        if (SHARDED) sym_pass_body<KIND, true, IT_NT, false, false, true>(la, sa, sm.c.pc0, sm.c.pc1, sm.c.pc2, 0, (int)gridDim.x, (int)blockIdx.x, a.wt, a.rowpart);
+        else sym_pass_body<KIND, false, IT_NT, false, false>(la, sa, sm.c.pc0, sm.c.pc1, sm.c.pc2, 0, (int)gridDim.x, (int)blockIdx.x);
       }
       grid.sync();
       iter_mark(a, sm, 1);
@@ -810,6 +845,41 @@ double bench_grid_sync(Ctx* ctx, int reps) {
   ctx->sync();
   cudaFree(d_out);
   return (double)ns * 1e-3 / reps;  // us per barrier
+}
+
+// flat partition of this rank's tiles over the CTAs of the fused kernel (layout: qn_sym.cuh)
+void qn_iter_build_worktable(Ctx* ctx, int64_t n, std::vector<int>& tab) {
+  const int G = qn_iter_grid(ctx);
+  const int64_t T = (n + QN_R - 1) / QN_R;
+  const int64_t ntl = 2 * symsh_local_pairs(T, ctx->world, ctx->rank);
+  std::vector<int> steps((size_t)ntl);
+  int64_t S = 0;
+  for (int64_t q = 0; q < ntl; ++q) {
+    steps[(size_t)q] = sym_tile_steps(symsh_tile_at(T, ctx->world, ctx->rank, q), n, IT_NT);
+    S += steps[(size_t)q];
+  }
+  tab.assign((size_t)(4 * G + ntl), 0);
+  int64_t q = 0;
+  int s = 0;
+  for (int c = 0; c < G; ++c) {
+    int64_t cnt = (int64_t)(c + 1) * S / G - (int64_t)c * S / G;
+    tab[4 * c] = (int)q;
+    tab[4 * c + 1] = s;
+    tab[4 * c + 2] = (int)cnt;
+    tab[4 * c + 3] = q < ntl ? tab[(size_t)(4 * G + q)] : 0;  // pieces of tile q handed out so far = this piece's slot
+    while (cnt > 0 && q < ntl) {
+      const int take = (int)std::min<int64_t>(steps[(size_t)q] - s, cnt);
+      tab[(size_t)(4 * G + q)] += 1;
+      cnt -= take;
+      s += take;
+      if (s == steps[(size_t)q]) {
+        q += 1;
+        s = 0;
+      }
+    }
+  }
+  for (int64_t t = 0; t < ntl; ++t)
+    OSB_REQUIRE(tab[(size_t)(4 * G + t)] >= 1 && tab[(size_t)(4 * G + t)] <= SYM_FLAT_SLOTS, OSB_ERR_UNSUPPORTED, "flat partition: a tile is cut into too many pieces");
 }
 
 // ---- host side ------------------------------------------------------------------------------
