@@ -118,9 +118,11 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def fp64_peak_tflops():
-    """Calibration only: cuBLAS DGEMM 8192^3 through torch (FP64 tensor-core path), best of 5.  MEASURED_PEAKS.json has no
-    FP64 figure; the DMMA Hessian assembly and the batched mode are reported against this number."""
+def fp64_peak_tflops(sustained_s=0.0):
+    """Calibration only: cuBLAS DGEMM 8192^3 through torch (FP64 tensor-core path).  MEASURED_PEAKS.json has no FP64 figure;
+    the DMMA Hessian assembly and the batched mode are reported against these numbers.  Returns the burst figure (best of
+    5, ~30 ms each) or, with sustained_s > 0, (burst, sustained): back-to-back products for sustained_s seconds — the
+    denominator for a kernel that itself runs for seconds (clocks drop under sustained FP64 tensor load)."""
     import torch
     n = 8192
     a = torch.randn(n, n, dtype=torch.float64, device="cuda")
@@ -136,9 +138,20 @@ def fp64_peak_tflops():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         best = ms if best is None else min(best, ms)
+    burst = 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    sustained = None
+    if sustained_s > 0:
+        reps = max(1, int(sustained_s / (best * 1e-3)))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        sustained = 2.0 * n ** 3 * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12
     del a, b
     torch.cuda.empty_cache()
-    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    return burst if sustained_s <= 0 else (burst, sustained)
 
 
 def ncu_traffic():
@@ -715,7 +728,7 @@ def run_other(args, env):
         t0 = time.time()
         obj = osb.LogisticRegression.generated(m, n, 1.0, ctx=ctx)
         gen_s = time.time() - t0
-        fp64 = fp64_peak_tflops()
+        fp64_burst, fp64 = fp64_peak_tflops(sustained_s=4.0)  # the assembly runs for seconds: sustained figure
         syrk_ms = osb.bench_syrk(obj, 2, ctx=ctx)
         sampler = ClockSampler(env.local_rank)
         sampler.start()
@@ -733,7 +746,8 @@ def run_other(args, env):
         value = it / (ms * 1e-3)
         flops = float(ml) * n * n  # SYRK convention (lower triangle), SURVEY 8d
         roofline = {"bound": "tensor", "kernel": "syrk_dmma_kernel (X^T D X on FP64 DMMA)", "achieved": flops / (syrk_ms * 1e-3) / 1e12, "peak": fp64,
-                    "peak_source": "cuBLAS DGEMM 8192^3 measured in this run", "unit": "TFLOP/s", "frac": flops / (syrk_ms * 1e-3) / 1e12 / fp64,
+                    "peak_source": "cuBLAS DGEMM 8192^3 back to back for 4 s in this run (sustained; burst best-of-5: %.1f TFLOP/s)" % fp64_burst,
+                    "peak_burst": fp64_burst, "unit": "TFLOP/s", "frac": flops / (syrk_ms * 1e-3) / 1e12 / fp64,
                     "traffic": None, "ms_per_launch": syrk_ms, "algorithmic_flops_per_launch": flops}
         e2e = {"value": value, "unit": unit, "h2d_bytes_per_step": int(n * 8 / max(it, 1)), "d2h_bytes_per_step": 200,
                "what": "X is generated on the device (65.5 GB does not fit a host buffer): minimize() wall time equals the device time"}

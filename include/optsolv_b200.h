@@ -306,7 +306,8 @@ int osb_batched_bfgs_rosenbrock_generated(osb_ctx* ctx, int64_t n, int64_t n_pro
 /* ---- micro-benchmark hooks for bench.py / ncu (device-resident inputs, no host traffic) ---- */
 /* runs `reps` back-to-back launches of one hot kernel on an n*n H and returns the mean ms/launch:
  *   which = 0: h = H y (read n^2)   1: fused rank-2 update + u = H' g (read + write n^2)
- *           2: Broyden H^T s        3: plain device copy of H (cudaMemcpyAsync D2D) for calibration */
+ *           2: Broyden H^T s        3: plain device copy of H (cudaMemcpyAsync D2D) for calibration
+ *           4: the lazy pass over the packed lower triangle alone (read + write n^2/2), variant = option "qn_kernel" */
 int osb_bench_qn_kernel(osb_ctx* ctx, int which, int64_t n, int reps, int variant, double* ms_out);
 /* mean microseconds of one grid barrier of the fused iteration kernel's shape (one 512-thread CTA per SM, cooperative
  * launch): the fixed cost the kernel pays four times per iteration */

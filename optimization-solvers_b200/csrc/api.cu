@@ -658,7 +658,7 @@ int osb_bench_qn_kernel(osb_ctx* ctxh, int which, int64_t n, int reps, int varia
   Ctx* ctx = C(ctxh);
   ctx->use();
   const int64_t ld = qn_ld(n);
-  DBuf H(qn_rows_padded(n) * ld), H2, a(ld), b(ld), c(ld), out(ld), scratch;
+  DBuf H(which == 4 ? ld : qn_rows_padded(n) * ld), H2, a(ld), b(ld), c(ld), out(ld), scratch;
   DevState* st = nullptr;
   OSB_CUDA(cudaMalloc(&st, sizeof(DevState)));
   DevState hs;
@@ -678,6 +678,45 @@ int osb_bench_qn_kernel(osb_ctx* ctxh, int which, int64_t n, int reps, int varia
     for (int64_t i = 0; i < n; ++i) v[i] = (double)h16(23, (uint64_t)i, 0) / 32768.0;
     c.upload(v.data(), ld, ctx->stream);
     ctx->sync();
+  }
+  if (which == 4) {  // the packed-triangle pass alone (variant = option "qn_kernel"), on a synthetic matrix
+    OSB_REQUIRE(ctx->world == 1, OSB_ERR_UNSUPPORTED, "kernel micro-benchmarks run on a single-GPU context");
+    DBuf P(qn_sym_doubles(n)), P2, colpart((int64_t)2 * ctx->num_sms * 2 * ld);
+    if (variant & 2) P2.alloc(qn_sym_doubles(n));
+    hs.pc0 = 1e-9;
+    hs.pc1 = -1e-9;
+    hs.pc2 = 1e-9;
+    OSB_CUDA(cudaMemcpyAsync(st, &hs, sizeof(hs), cudaMemcpyHostToDevice, ctx->stream));
+    qn_sym_set_identity(ctx, n, P.p);
+    colpart.zero(ctx->stream);
+    QNLazyArgs la{};
+    la.ld = ld;
+    la.n = n;
+    la.nrows = n;
+    la.st = st;
+    la.ps = a.p;
+    la.ph = b.p;
+    la.y = c.p;
+    la.g = a.p;
+    la.s = b.p;
+    la.h = out.p;
+    la.w = H.p;  // (any n-vector scratch)
+    la.kind = QN_BFGS;
+    cudaEvent_t f0, f1;
+    OSB_CUDA(cudaEventCreate(&f0));
+    OSB_CUDA(cudaEventCreate(&f1));
+    for (int i = 0; i < 3; ++i) qn_launch_lazy_sym(ctx, la, P.p, (variant & 2) ? P2.p : P.p, colpart.p, n, ld, 0, variant);
+    OSB_CUDA(cudaEventRecord(f0, ctx->stream));
+    for (int i = 0; i < reps; ++i) qn_launch_lazy_sym(ctx, la, P.p, (variant & 2) ? P2.p : P.p, colpart.p, n, ld, 0, variant);
+    OSB_CUDA(cudaEventRecord(f1, ctx->stream));
+    OSB_CUDA(cudaEventSynchronize(f1));
+    float fms = 0.f;
+    OSB_CUDA(cudaEventElapsedTime(&fms, f0, f1));
+    *ms_out = (double)fms / reps;
+    cudaEventDestroy(f0);
+    cudaEventDestroy(f1);
+    cudaFree(st);
+    return OSB_OK;
   }
   if (which == 2) scratch.alloc(((n + 63) / 64) * ld);
   if (which == 3) H2.alloc(qn_rows_padded(n) * ld);

@@ -95,119 +95,182 @@ __global__ void __launch_bounds__(LG_T) logit_grad_stage2(int64_t n, int64_t nsp
 }
 
 // ---- Hessian: C = X^T diag(d) X (+ lambda I) on DMMA ------------------------------------------
-constexpr int SY_TILE = 128;  // output tile edge
-constexpr int SY_KC = 16;     // samples per shared-memory panel
+// mma.sync m8n8k4 f64 is the hardware shape (SASS DMMA.8x8x4; the larger PTX shapes m16n8k{4,8,16} assemble to
+// sequences of the same instruction on sm_100a — checked with cuobjdump — and tcgen05 has no FP64 kind).
+// Persistent CTAs walk a list of (K split, output tile) units, split-major, so that at any moment the whole GPU streams
+// the same rows of X (they are then L2 hits for all but the first reader) and the last wave is 1/56 of a CTA's work
+// instead of 1/15 (2080 lower-triangular 128 x 128 tiles do not divide by 148 SMs).  Each unit accumulates its K range
+// for one tile and stores a partial tile; a second kernel adds the SY_SPLIT partials of every element in split order
+// (deterministic), adds lambda on the diagonal and mirrors into the upper triangle.
+// Operands move global -> shared with 16-byte cp.async in a 4-stage ring (no register staging); the Hessian weights d_k
+// multiply the A fragments as they are read from shared memory, so both panels are raw rows of X and a diagonal tile
+// loads only one.
+constexpr int SY_TILE = 128;   // output tile edge
+constexpr int SY_KC = 16;      // samples per pipeline stage
+constexpr int SY_STAGES = 4;
 constexpr int SY_LD = SY_TILE + 4;  // padded row stride (conflict-free fragment reads)
-constexpr int SY_T = 256;     // 8 warps: 4 (rows) x 2 (cols), 32 x 64 outputs per warp
+constexpr int SY_T = 256;      // 8 warps: 4 (rows) x 2 (cols), 32 x 64 outputs per warp
+constexpr int SY_SPLIT = 4;    // K splits per tile
 
 __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 16 : 0;  // src-size 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+struct SyrkSmem {
+  double A[SY_STAGES][SY_KC][SY_LD];
+  double B[SY_STAGES][SY_KC][SY_LD];
+  double dk[SY_STAGES][SY_KC];
+};
 
 __global__ void __launch_bounds__(SY_T, 1)
-syrk_dmma_kernel(int64_t m, int64_t n, const double* __restrict__ X, const double* __restrict__ dcoef, double lambda, double* __restrict__ C,
-                 int64_t ldc, int accumulate_lambda) {
-  // lower-triangular tile index -> (ti, tj), tj <= ti
-  const int nt = (int)((n + SY_TILE - 1) / SY_TILE);
+syrk_dmma_kernel(int64_t m, int64_t n, const double* __restrict__ X, const double* __restrict__ dcoef, double* __restrict__ Cpart, int ntiles) {
+  extern __shared__ __align__(16) unsigned char sy_raw[];
+  SyrkSmem& sm = *reinterpret_cast<SyrkSmem*>(sy_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wr = warp >> 1, wc = warp & 1;  // warp tile origin: rows wr*32, cols wc*64
+  const int64_t kper = ((m + SY_SPLIT - 1) / SY_SPLIT + SY_KC - 1) / SY_KC * SY_KC;  // samples per split (whole stages)
+  const int nunits = ntiles * SY_SPLIT;
+  for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+    const int split = u / ntiles;
+    int t = u % ntiles, ti = 0;
+    while (t > ti) {  // lower-triangular tile index -> (ti, tj), tj <= ti
+      t -= ti + 1;
+      ++ti;
+    }
+    const int tj = t;
+    const bool diag = ti == tj;
+    const int64_t i0 = (int64_t)ti * SY_TILE, j0 = (int64_t)tj * SY_TILE;
+    const int64_t kbeg = (int64_t)split * kper, kend = kbeg + kper < m ? kbeg + kper : m;
+    const int npanels = kend > kbeg ? (int)((kend - kbeg + SY_KC - 1) / SY_KC) : 0;
+    double acc[4][8][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    // one stage = SY_KC rows x 128 doubles per operand = 1024 16-byte chunks per operand, 4 (+4) per thread
+    auto issue = [&](int p) {
+      if (p < npanels) {
+        const int st = p % SY_STAGES;
+        const int64_t k0 = kbeg + (int64_t)p * SY_KC;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int chunk = tid + c * SY_T;  // 0..1023
+          const int kk = chunk >> 6;         // 64 chunks per row
+          const int cc = (chunk & 63) * 2;
+          const int64_t k = k0 + kk;
+          const bool kok = k < kend;
+          const int64_t krow = kok ? k : kbeg;  // (a valid address even when the copy is zero-filled)
+          cp_async16(&sm.A[st][kk][cc], X + krow * n + i0 + cc, kok && i0 + cc < n);
+          if (!diag) cp_async16(&sm.B[st][kk][cc], X + krow * n + j0 + cc, kok && j0 + cc < n);
+        }
+        if (tid < SY_KC) sm.dk[st][tid] = (k0 + tid < kend) ? dcoef[k0 + tid] : 0.0;
+      }
+      cp_async_commit();  // (an empty group keeps the group count in step with the panel count)
+    };
+    __syncthreads();  // the previous unit's readers are done with the ring
+#pragma unroll
+    for (int p = 0; p < SY_STAGES - 1; ++p) issue(p);
+    for (int p = 0; p < npanels; ++p) {
+      cp_async_wait<SY_STAGES - 2>();  // panel p has landed (this thread's copies) ...
+      __syncthreads();                 // ... and everybody's; stage (p - 1) % STAGES is free again
+      issue(p + SY_STAGES - 1);
+      const int st = p % SY_STAGES;
+      const double (*As)[SY_LD] = sm.A[st];
+      const double (*Bs)[SY_LD] = diag ? sm.A[st] : sm.B[st];
+#pragma unroll
+      for (int k4 = 0; k4 < SY_KC / 4; ++k4) {
+        double af[4], bf[8];
+        const int kr = k4 * 4 + (lane & 3);
+        const double dkv = sm.dk[st][kr];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) af[a] = As[kr][wr * 32 + a * 8 + (lane >> 2)] * dkv;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) bf[b] = Bs[kr][wc * 64 + b * 8 + (lane >> 2)];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 8; ++b) dmma_884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+      }
+    }
+    // this unit's partial tile (row-major 128 x 128)
+    double* out = Cpart + ((int64_t)split * ntiles + (u % ntiles)) * (SY_TILE * SY_TILE);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const int r = wr * 32 + a * 8 + (lane >> 2);
+        const int c = wc * 64 + b * 8 + (lane & 3) * 2;
+        *reinterpret_cast<double2*>(out + r * SY_TILE + c) = make_double2(acc[a][b][0], acc[a][b][1]);
+      }
+  }
+}
+
+// C = sum over the splits (in split order) of the partial tiles, + lambda on the diagonal, mirrored
+__global__ void __launch_bounds__(256) syrk_reduce_kernel(int64_t n, const double* __restrict__ Cpart, int ntiles, double lambda, int add_lambda,
+                                                          double* __restrict__ C, int64_t ldc) {
   int t = blockIdx.x, ti = 0;
   while (t > ti) {
     t -= ti + 1;
     ++ti;
   }
   const int tj = t;
-  (void)nt;
   const int64_t i0 = (int64_t)ti * SY_TILE, j0 = (int64_t)tj * SY_TILE;
-  extern __shared__ double sy_smem[];  // 2 x (A panel, B panel), each SY_KC x SY_LD doubles
-  double (*As)[SY_KC][SY_LD] = reinterpret_cast<double (*)[SY_KC][SY_LD]>(sy_smem);
-  double (*Bs)[SY_KC][SY_LD] = reinterpret_cast<double (*)[SY_KC][SY_LD]>(sy_smem + 2 * SY_KC * SY_LD);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wr = warp >> 1, wc = warp & 1;  // warp tile origin: rows wr*32, cols wc*64
-  double acc[4][8][2];
+  const double* base = Cpart + (int64_t)blockIdx.x * (SY_TILE * SY_TILE);
+  for (int e = threadIdx.x; e < SY_TILE * SY_TILE / 2; e += 256) {
+    const int r = e / (SY_TILE / 2), c = (e % (SY_TILE / 2)) * 2;
+    double2 v = *reinterpret_cast<const double2*>(base + r * SY_TILE + c);
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+    for (int sp = 1; sp < SY_SPLIT; ++sp) {
+      const double2 w = *reinterpret_cast<const double2*>(base + (int64_t)sp * ntiles * (SY_TILE * SY_TILE) + r * SY_TILE + c);
+      v.x = v.x + w.x;
+      v.y = v.y + w.y;
+    }
+    const int64_t i = i0 + r;
 #pragma unroll
-    for (int b = 0; b < 8; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-  // global -> register staging: each panel is SY_KC rows x 128 doubles = 1024 16-byte chunks per operand
-  double2 ra[4], rb[4];
-  auto load_panel = [&](int64_t k0) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int chunk = tid + c * SY_T;      // 0..1023
-      const int kk = chunk >> 6;             // 64 chunks per row
-      const int cc = (chunk & 63) * 2;
-      const int64_t k = k0 + kk;
-      double2 va = make_double2(0.0, 0.0), vb = make_double2(0.0, 0.0);
-      if (k < m) {
-        const double dk = dcoef[k];
-        if (i0 + cc < n) {  // n is even (pairs), so a chunk is either wholly inside or outside
-          va = ld_stream_nc(X + k * n + i0 + cc);
-          va.x *= dk;
-          va.y *= dk;
-        }
-        if (j0 + cc < n) vb = ld_stream_nc(X + k * n + j0 + cc);
+    for (int q = 0; q < 2; ++q) {
+      const int64_t jx = j0 + c + q;
+      double val = q == 0 ? v.x : v.y;
+      if (i < n && jx < n && jx <= i) {
+        if (add_lambda && i == jx) val += lambda;
+        C[i * ldc + jx] = val;
+        C[jx * ldc + i] = val;
       }
-      ra[c] = va;
-      rb[c] = vb;
     }
-  };
-  auto store_panel = [&](int buf) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int chunk = tid + c * SY_T;
-      const int kk = chunk >> 6;
-      const int cc = (chunk & 63) * 2;
-      *reinterpret_cast<double2*>(&As[buf][kk][cc]) = ra[c];
-      *reinterpret_cast<double2*>(&Bs[buf][kk][cc]) = rb[c];
-    }
-  };
-  const int64_t npanels = (m + SY_KC - 1) / SY_KC;
-  load_panel(0);
-  store_panel(0);
-  __syncthreads();
-  for (int64_t p = 0; p < npanels; ++p) {
-    const int buf = (int)(p & 1);
-    if (p + 1 < npanels) load_panel((p + 1) * SY_KC);
-#pragma unroll
-    for (int k4 = 0; k4 < SY_KC / 4; ++k4) {
-      double af[4], bf[8];
-      const int kr = k4 * 4 + (lane & 3);
-#pragma unroll
-      for (int a = 0; a < 4; ++a) af[a] = As[buf][kr][wr * 32 + a * 8 + (lane >> 2)];
-#pragma unroll
-      for (int b = 0; b < 8; ++b) bf[b] = Bs[buf][kr][wc * 64 + b * 8 + (lane >> 2)];
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 8; ++b) dmma_884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
-    }
-    if (p + 1 < npanels) store_panel(buf ^ 1);
-    __syncthreads();
   }
-  // epilogue: C[i][j] for the lower triangle, mirrored into the upper one
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 8; ++b)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int64_t i = i0 + wr * 32 + a * 8 + (lane >> 2);
-        const int64_t j = j0 + wc * 64 + b * 8 + (lane & 3) * 2 + e;
-        if (i < n && j < n && j <= i) {
-          double v = acc[a][b][e];
-          if (accumulate_lambda && i == j) v += lambda;
-          C[i * ldc + j] = v;
-          C[j * ldc + i] = v;
-        }
-      }
 }
 
-constexpr size_t SY_SMEM = sizeof(double) * 4 * SY_KC * SY_LD;
+constexpr size_t SY_SMEM = sizeof(SyrkSmem);
 static void syrk_set_smem() {
   static bool done = false;
   if (!done) {
     OSB_CUDA(cudaFuncSetAttribute(syrk_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM));
     done = true;
   }
+}
+static int syrk_ntiles(int64_t n) {
+  const int nt = (int)((n + SY_TILE - 1) / SY_TILE);
+  return nt * (nt + 1) / 2;
+}
+static int64_t syrk_part_doubles(int64_t n) { return (int64_t)SY_SPLIT * syrk_ntiles(n) * SY_TILE * SY_TILE; }
+// H = X^T D X (+ lambda I when add_lambda) into hess (row-major, ldc), both triangles
+static void syrk_launch(Ctx* ctx, int64_t m, int64_t n, const double* X, const double* dc, double lambda, int add_lambda, double* part,
+                        double* hess, int64_t ldc) {
+  syrk_set_smem();
+  const int ntiles = syrk_ntiles(n);
+  const int grid = std::min(ctx->num_sms, ntiles * SY_SPLIT);
+  syrk_dmma_kernel<<<grid, SY_T, SY_SMEM, ctx->stream>>>(m, n, X, dc, part, ntiles);
+  syrk_reduce_kernel<<<ntiles, 256, 0, ctx->stream>>>(n, part, ntiles, lambda, add_lambda, hess, ldc);
+  ctx->counters[0] += 2;
 }
 
 __global__ void logit_finish_f_kernel(const double* __restrict__ tmp2, double lambda, double* __restrict__ d_f) {
@@ -218,7 +281,7 @@ struct LogisticObjective : Objective {
   int64_t m;        // local sample count (sample-sharded across ranks)
   int64_t m_total;
   double lambda;
-  DBuf X, ysign, loss, gc, dc, partial, tmp;
+  DBuf X, ysign, loss, gc, dc, partial, tmp, hpart;  // hpart: SY_SPLIT partial tiles per output tile of the Hessian
   int64_t rows_per_split, nsplit;
   LogisticObjective(Ctx* c, int64_t m_, int64_t n_, double lam) : Objective(c, n_), m_total(m_), lambda(lam) {
     OSB_REQUIRE(n_ % 2 == 0, OSB_ERROR_INPUT_PARAMS, "logistic regression needs an even feature count");
@@ -266,12 +329,9 @@ struct LogisticObjective : Objective {
     logit_finish_f_kernel<<<1, 1, 0, st>>>(tmp.p, lambda, d_f);
     ctx->counters[0]++;
     if (hess) {
-      const int nt = (int)((n + SY_TILE - 1) / SY_TILE);
-      const int ntiles = nt * (nt + 1) / 2;
       const int64_t ldc = qn_ld(n);
-      syrk_set_smem();
-      syrk_dmma_kernel<<<ntiles, SY_T, SY_SMEM, st>>>(m, n, X.p, dc.p, lambda, hess, ldc, ctx->world > 1 ? 0 : 1);
-      ctx->counters[0]++;
+      if (hpart.p == nullptr) hpart.alloc(syrk_part_doubles(n));
+      syrk_launch(ctx, m, n, X.p, dc.p, lambda, ctx->world > 1 ? 0 : 1, hpart.p, hess, ldc);
       if (ctx->world > 1) {
         ctx_all_reduce_sum(ctx, hess, n * ldc);
         const double lam = lambda;
@@ -293,22 +353,20 @@ double bench_syrk_dmma(Ctx* ctx, Objective* obj, int reps) {
   DBuf hess(qn_rows_padded(n) * ldc), w(ldc);
   w.zero(ctx->stream);
   logit_margin_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(o->m, n, o->X.p, o->ysign.p, w.p, o->loss.p, o->gc.p, o->dc.p);
-  const int nt = (int)((n + SY_TILE - 1) / SY_TILE);
-  const int ntiles = nt * (nt + 1) / 2;
+  if (o->hpart.p == nullptr) o->hpart.alloc(syrk_part_doubles(n));
   cudaEvent_t e0, e1;
   OSB_CUDA(cudaEventCreate(&e0));
   OSB_CUDA(cudaEventCreate(&e1));
-  syrk_set_smem();
-  syrk_dmma_kernel<<<ntiles, SY_T, SY_SMEM, ctx->stream>>>(o->m, n, o->X.p, o->dc.p, o->lambda, hess.p, ldc, 1);
+  syrk_launch(ctx, o->m, n, o->X.p, o->dc.p, o->lambda, 1, o->hpart.p, hess.p, ldc);
   OSB_CUDA(cudaEventRecord(e0, ctx->stream));
-  for (int r = 0; r < reps; ++r) syrk_dmma_kernel<<<ntiles, SY_T, SY_SMEM, ctx->stream>>>(o->m, n, o->X.p, o->dc.p, o->lambda, hess.p, ldc, 1);
+  for (int r = 0; r < reps; ++r) syrk_launch(ctx, o->m, n, o->X.p, o->dc.p, o->lambda, 1, o->hpart.p, hess.p, ldc);
   OSB_CUDA(cudaEventRecord(e1, ctx->stream));
   OSB_CUDA(cudaEventSynchronize(e1));
   float ms = 0.f;
   OSB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  ctx->counters[0] += reps + 2;
+  ctx->counters[0] += 1;
   return (double)ms / reps;
 }
 

@@ -62,6 +62,7 @@ struct IterSmem {
   double xs[IT_NT], ds[IT_NT];  // this CTA's chunk of x and d (backtracking: one warp per trial step sweeps it)
   int ext[IT_MAXG];
   long long prof[16];  // leader only: [0..2] accumulated ns in head / pass / fold, [3] last stamp, [4..15] head sub-phases
+  int prof_skip;       // iterations left out of the profile (the first one of a launch: it absorbs the ranks' launch skew)
 };
 
 // Grid-wide sums, compact on purpose: the head runs once per 400 us pass, i.e. with a cold instruction cache, and a
@@ -783,6 +784,7 @@ __global__ void __launch_bounds__(IT_NT, 1) qn_iter_kernel(const __grid_constant
   // (time stamps live in shared memory, not in registers: nothing but &c and the loop counter is live across the pass)
   if (a.prof != nullptr && leader) {
     for (int q = 0; q < 16; ++q) sm.prof[q] = 0;
+    sm.prof_skip = 0;
     sm.prof[3] = iter_stamp();
     sm.prof[15] = sm.prof[3];
   }
@@ -811,6 +813,12 @@ __global__ void __launch_bounds__(IT_NT, 1) qn_iter_kernel(const __grid_constant
       iter_mark(a, sm, 1);
       iter_tail<Fn, SHARDED>(a, sm);
       iter_mark(a, sm, 2);
+      if (a.prof != nullptr && leader && it == 0 && a.iters > 1) {
+        // the first iteration of a launch waits for the slowest rank's kernel to START: not part of the steady state
+        for (int q = 0; q < 15; ++q)
+          if (q != 3) sm.prof[q] = 0;
+        sm.prof_skip = 1;
+      }
     }
   }
   if (leader) {
@@ -819,7 +827,7 @@ __global__ void __launch_bounds__(IT_NT, 1) qn_iter_kernel(const __grid_constant
       a.prof[0] += sm.prof[0];
       a.prof[1] += sm.prof[1];
       a.prof[2] += sm.prof[2];
-      a.prof[3] += it;
+      a.prof[3] += it - sm.prof_skip;
       for (int q = 4; q < 15; ++q) a.prof[q] += sm.prof[q];
     }
   }

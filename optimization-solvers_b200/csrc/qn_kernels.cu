@@ -791,6 +791,241 @@ __global__ void __launch_bounds__(NT, 512 / NT) qn_lazy_sym_kernel(QNLazyArgs a,
   sym_pass_body<KIND, SHARDED, NT, OOP, ZERO>(a, sa, st->pc0, st->pc1, st->pc2, pp, (int)gridDim.x, (int)blockIdx.x);
 }
 
+// ---- the packed pass with a shared-memory ring (qn_kernel bit 3) ----------------------------------------------------
+// Same tiles, same thread -> column mapping and the same order of every sum as sym_pass_body (hence the same bits); what
+// changes is who waits for HBM.  In the register-staged pass a warp issues the 8 row loads of a column step, waits for
+// them, computes, stores and only then issues the next step's loads: with 16 warps per SM and nothing in flight across a
+// step border the SM idles for one memory latency per step (~0.8 us against ~2.9 us of transfer).  Here thread 0
+// streams the CTA's (tile, column step) sequence into a ring of 3 stages of 8 rows x 1024 columns (64 KiB each) with bulk
+// asynchronous copies (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP), two steps ahead of the arithmetic and
+// straight across tile borders; the 16 warps read a stage with conflict-free 128-bit LDS, apply the pending update,
+// accumulate row and column sums and store the new elements to global memory from registers.
+constexpr int SR_T = 512;                // one column pair of the stage per thread; thread 0 doubles as the producer
+                                         // (a 17th warp would cap the kernel at 96 registers)
+constexpr int SR_CW = 2 * SR_T;          // columns per stage
+constexpr int SR_STAGES = 3;
+constexpr size_t SR_STAGE_DOUBLES = (size_t)QN_R * SR_CW;
+constexpr size_t SR_SMEM = SR_STAGES * SR_STAGE_DOUBLES * sizeof(double) + 128;
+
+__device__ __forceinline__ void bulk_load_hint(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, unsigned long long pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+               : "memory");
+}
+
+// EXP (timing experiments only, results are wrong): bit 0 = no column-partial RMW, bit 1 = no stores of the new
+// elements, bit 2 = no arithmetic (the loaded element is stored back) and no tile-end reduction
+template <int KIND, bool SHARDED, int EXP = 0>
+__global__ void __launch_bounds__(SR_T, 1) qn_sym_ring_kernel(QNLazyArgs a, QNSymArgs sa) {
+  DevState* st = a.st;
+  if (st->done) return;
+  extern __shared__ __align__(128) unsigned char sr_smem[];
+  double* stage = reinterpret_cast<double*>(sr_smem);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sr_smem + SR_STAGES * SR_STAGE_DOUBLES * sizeof(double));
+  uint64_t* empty = full + SR_STAGES;
+  __shared__ double red2[2][SR_T / 32][16];
+  __shared__ double4 rowv2[2][QN_R];
+  const double c0 = st->pc0, c1 = st->pc1, c2 = st->pc2;
+  const unsigned long long pol = l2_evict_first_policy();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int grid = (int)gridDim.x, cta = (int)blockIdx.x;
+  const int64_t n = sa.n, ld = sa.ld;
+  const int64_t ntiles = (n + QN_R - 1) / QN_R;
+  if (tid == 0) {
+    for (int s_ = 0; s_ < SR_STAGES; ++s_) {
+      mbar_init(&full[s_], 1);
+      mbar_init(&empty[s_], SR_T / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // ===== producer state (thread 0): walks the same (tile, column step) sequence, SR_STAGES - 1 steps ahead =====
+  int p_step = -1, p_cb = 0, p_lpad = 0, p_rows = 0, p_it = 0;
+  const double* p_base = nullptr;
+  bool p_done = false;
+  auto produce = [&]() {
+    if (p_done) return;
+    if (p_cb >= p_lpad) {  // next tile
+      for (;;) {
+        ++p_step;
+        const int64_t tile = sym_cta_tile<SHARDED>(ntiles, sa.world, sa.rank, grid, cta, p_step);
+        if (tile < 0) {
+          if (SHARDED || (p_step & 1) == 0) {
+            p_done = true;
+            return;
+          }
+          continue;
+        }
+        const int64_t r0 = tile * QN_R;
+        p_rows = (int)((n - r0) < QN_R ? (n - r0) : QN_R);
+        p_lpad = (int)sym_lpad(tile);
+        p_base = sa.P + (SHARDED ? symsh_tile_offset(tile, ntiles, sa.world) : sym_tile_offset(tile));
+        p_cb = 0;
+        break;
+      }
+    }
+    const int s_ = p_it % SR_STAGES;
+    mbar_wait(&empty[s_], (uint32_t)(((p_it / SR_STAGES) & 1) ^ 1));  // (fresh barrier: parity 1 passes at once)
+    const int cw = p_lpad - p_cb < SR_CW ? p_lpad - p_cb : SR_CW;
+    const uint32_t bytes_row = (uint32_t)(cw * sizeof(double));
+    mbar_expect_tx(&full[s_], bytes_row * (uint32_t)p_rows);
+    double* dst = stage + (size_t)s_ * SR_STAGE_DOUBLES;
+    for (int r = 0; r < p_rows; ++r) bulk_load_hint(dst + (size_t)r * SR_CW, p_base + (int64_t)r * p_lpad + p_cb, bytes_row, &full[s_], pol);
+    p_cb += SR_CW;
+    ++p_it;
+  };
+  if (tid == 0) {
+#pragma unroll 1
+    for (int k = 0; k < SR_STAGES - 1; ++k) produce();
+  }
+  // ===== the arithmetic =====
+  const double* __restrict__ p = a.ps;
+  const double* __restrict__ q = a.ph;
+  const double* __restrict__ yv = a.y;
+  const double* __restrict__ gv = a.g;
+  double* __restrict__ cph = sa.colpart + (int64_t)cta * 2 * ld;
+  double* __restrict__ cpw = cph + ld;
+  int tpar = 0, it = 0;
+  bool first = true;
+  for (int64_t step = 0;; ++step) {
+    const int64_t tile = sym_cta_tile<SHARDED>(ntiles, sa.world, sa.rank, grid, cta, step);
+    if (tile < 0) {
+      if (SHARDED || (step & 1) == 0) break;
+      continue;
+    }
+    const int64_t r0 = tile * QN_R;
+    const int rows_here = (int)((n - r0) < QN_R ? (n - r0) : QN_R);
+    const int lpad = (int)sym_lpad(tile);
+    const int ncols = (int)(r0 + QN_R < n ? r0 + QN_R : n);
+    double ah[QN_R], aw[QN_R];
+#pragma unroll
+    for (int r = 0; r < QN_R; ++r) ah[r] = aw[r] = 0.0;
+    tpar ^= 1;
+    double4* rowv = rowv2[tpar];
+    double (*red)[16] = red2[tpar];
+    if (tid < QN_R) {
+      const bool ok = tid < rows_here;
+      const int64_t i = r0 + tid;
+      rowv[tid] = ok ? make_double4(p[i], q[i], yv[i], gv[i]) : make_double4(0.0, 0.0, 0.0, 0.0);
+    }
+    __syncthreads();  // (A)
+    double* __restrict__ obase = sa.P + (SHARDED ? symsh_tile_offset(tile, ntiles, sa.world) : sym_tile_offset(tile));
+    // the O(n) vectors of a step come from L2: loaded one step ahead, behind the previous step's arithmetic
+    double2 gn = make_double2(0.0, 0.0), yn = gn, pn = gn, qn = gn;
+    if (2 * tid < ncols) {
+      gn = ld_vec2(gv + 2 * tid);
+      yn = ld_vec2(yv + 2 * tid);
+      pn = ld_vec2(p + 2 * tid);
+      qn = ld_vec2(q + 2 * tid);
+    }
+    for (int cb = 0; cb < lpad; cb += SR_CW, ++it) {
+      const int s_ = it % SR_STAGES;
+      const int col = cb + 2 * tid;
+      const bool v0 = col < ncols, v1 = col + 1 < ncols;
+      const bool cok = v0 && col < (int)r0 && !(EXP & 1);
+      const double2 gj = gn, yj = yn, pj = pn, qj = qn;
+      double2 oh = make_double2(0.0, 0.0), ow = make_double2(0.0, 0.0);
+      if (cok && !first) {
+        oh = *reinterpret_cast<double2*>(cph + col);
+        ow = *reinterpret_cast<double2*>(cpw + col);
+      }
+      if (col + SR_CW < ncols) {
+        gn = ld_vec2(gv + col + SR_CW);
+        yn = ld_vec2(yv + col + SR_CW);
+        pn = ld_vec2(p + col + SR_CW);
+        qn = ld_vec2(q + col + SR_CW);
+      }
+      if (tid == 0) produce();  // the stage the CTA finished one step ago is refilled with the step after next
+      __syncwarp();
+      mbar_wait(&full[s_], (uint32_t)((it / SR_STAGES) & 1));
+      if (v0) {
+        const double* src = stage + (size_t)s_ * SR_STAGE_DOUBLES + 2 * tid;
+        double ch0 = 0.0, ch1 = 0.0, cw0 = 0.0, cw1 = 0.0;
+#pragma unroll
+        for (int r = 0; r < QN_R; ++r) {
+          if (r < rows_here) {
+            const double2 hv = *reinterpret_cast<const double2*>(src + (size_t)r * SR_CW);
+            const double4 rv = rowv[r];
+            const double pi = rv.x, qi = rv.y;
+            double2 hn;
+            if (EXP & 4) {
+              hn = hv;
+              ah[r] += hv.x + pi;
+            } else {
+            if (KIND == QN_BFGS) {
+              const double cx = pi * qj.x + qi * pj.x, cy = pi * qj.y + qi * pj.y;
+              hn.x = fma(c0, pi * pj.x, fma(c1, cx, hv.x));
+              hn.y = fma(c0, pi * pj.y, fma(c1, cy, hv.y));
+            } else {
+              hn.x = fma(c2, qi * qj.x, fma(c0, pi * pj.x, hv.x));
+              hn.y = fma(c2, qi * qj.y, fma(c0, pi * pj.y, hv.y));
+            }
+            if (!v1) hn.y = 0.0;
+            ah[r] = fma(hn.x, yj.x, ah[r]);
+            ah[r] = fma(hn.y, yj.y, ah[r]);
+            aw[r] = fma(hn.x, gj.x, aw[r]);
+            aw[r] = fma(hn.y, gj.y, aw[r]);
+            ch0 = fma(hn.x, rv.z, ch0);
+            ch1 = fma(hn.y, rv.z, ch1);
+            cw0 = fma(hn.x, rv.w, cw0);
+            cw1 = fma(hn.y, rv.w, cw1);
+            }
+            if (!(EXP & 2)) st_stream_ef(obase + (int64_t)r * lpad + col, hn, pol);
+          }
+        }
+        if (cok) {
+          oh.x += ch0;
+          ow.x += cw0;
+          oh.y += ch1;
+          ow.y += cw1;
+          *reinterpret_cast<double2*>(cph + col) = oh;
+          *reinterpret_cast<double2*>(cpw + col) = ow;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s_]);  // this warp's reads of the stage are done
+    }
+    first = false;
+    if (EXP & 4) {
+      if (ah[0] + ah[1] + ah[2] + ah[3] + ah[4] + ah[5] + ah[6] + ah[7] == 1.2345e-300) a.h[r0] = 1.0;  // (keeps the loads alive)
+      continue;
+    }
+    {
+      double v16[16];
+#pragma unroll
+      for (int r = 0; r < QN_R; ++r) {
+        v16[r] = ah[r];
+        v16[QN_R + r] = aw[r];
+      }
+      const double ws = warp_sum16(v16);
+      if ((lane & 1) == 0) red[warp][lane >> 1] = ws;
+    }
+    __syncthreads();  // (B)
+    if (tid < 2 * QN_R) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < SR_T / 32; ++w) v = v + red[w][tid];
+      const int r = tid % QN_R;
+      if (r < rows_here) {
+        if (tid < QN_R) a.h[r0 + r] = v;
+        else a.w[r0 + r] = v;
+      }
+    }
+  }
+}
+
+// the same pass with the column partials of the first `sc` columns in (dynamic) shared memory
+constexpr int SMCP_MAX_COLS = 13824;  // 2 x 13824 x 8 B = 216 KiB next to 4.6 KiB of static shared memory
+template <int KIND, bool SHARDED>
+__global__ void __launch_bounds__(512, 1) qn_lazy_sym_smcp_kernel(QNLazyArgs a, QNSymArgs sa, int sc) {
+  DevState* st = a.st;
+  if (st->done) return;
+  extern __shared__ __align__(16) unsigned char smcp_raw[];
+  sym_pass_body<KIND, SHARDED, 512, false, false, false, true>(a, sa, st->pc0, st->pc1, st->pc2, 0, (int)gridDim.x, (int)blockIdx.x, nullptr, nullptr,
+                                                                reinterpret_cast<double*>(smcp_raw), sc);
+}
+
 // h_j += sum over CTAs of the column partials; then, depending on the mode, the O(n) epilogue by the last CTA (host
 // engine), nothing (the next cluster head runs it), or — sharded — the push of this rank's contribution to every peer.
 // Fixed summation shape: FOLD_G groups of consecutive CTAs summed in order, then the groups in order.
@@ -1015,6 +1250,43 @@ int qn_sym_grid(Ctx* ctx, int64_t n, int variant) {
 
 template <int KIND, bool SHARDED>
 static void launch_sym_pass(int grid, cudaStream_t stream, const QNLazyArgs& a, const QNSymArgs& sa, int variant) {
+  if (variant & 128) {  // column partials in shared memory
+    static bool attr3 = false;
+    if (!attr3) {
+      OSB_CUDA(cudaFuncSetAttribute(qn_lazy_sym_smcp_kernel<KIND, SHARDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SMCP_MAX_COLS * 8));
+      attr3 = true;
+    }
+    const int sc = (int)std::min<int64_t>(sa.ld, SMCP_MAX_COLS);
+    qn_lazy_sym_smcp_kernel<KIND, SHARDED><<<grid, 512, (size_t)2 * sc * 8, stream>>>(a, sa, sc);
+    return;
+  }
+  if (variant & 8) {  // shared-memory ring fed by bulk asynchronous copies
+    static bool attr = false;
+    if (!attr) {
+      OSB_CUDA(cudaFuncSetAttribute(qn_sym_ring_kernel<KIND, SHARDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_SMEM));
+      attr = true;
+    }
+    const int e = (variant >> 4) & 7;
+    if (e != 0 && KIND == QN_BFGS && !SHARDED) {  // timing experiments (wrong results)
+      static bool attr2 = false;
+      if (!attr2) {
+        OSB_CUDA(cudaFuncSetAttribute(qn_sym_ring_kernel<QN_BFGS, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_SMEM));
+        OSB_CUDA(cudaFuncSetAttribute(qn_sym_ring_kernel<QN_BFGS, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_SMEM));
+        OSB_CUDA(cudaFuncSetAttribute(qn_sym_ring_kernel<QN_BFGS, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_SMEM));
+        OSB_CUDA(cudaFuncSetAttribute(qn_sym_ring_kernel<QN_BFGS, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_SMEM));
+        OSB_CUDA(cudaFuncSetAttribute(qn_sym_ring_kernel<QN_BFGS, false, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_SMEM));
+        attr2 = true;
+      }
+      if (e == 1) qn_sym_ring_kernel<QN_BFGS, false, 1><<<grid, SR_T, SR_SMEM, stream>>>(a, sa);
+      else if (e == 2) qn_sym_ring_kernel<QN_BFGS, false, 2><<<grid, SR_T, SR_SMEM, stream>>>(a, sa);
+      else if (e == 4) qn_sym_ring_kernel<QN_BFGS, false, 4><<<grid, SR_T, SR_SMEM, stream>>>(a, sa);
+      else if (e == 5) qn_sym_ring_kernel<QN_BFGS, false, 5><<<grid, SR_T, SR_SMEM, stream>>>(a, sa);
+      else qn_sym_ring_kernel<QN_BFGS, false, 7><<<grid, SR_T, SR_SMEM, stream>>>(a, sa);
+      return;
+    }
+    qn_sym_ring_kernel<KIND, SHARDED><<<grid, SR_T, SR_SMEM, stream>>>(a, sa);
+    return;
+  }
   switch (variant & 7) {
     case 0: qn_lazy_sym_kernel<KIND, SHARDED, 512, false, false><<<grid, 512, 0, stream>>>(a, sa); break;
     case 1: qn_lazy_sym_kernel<KIND, SHARDED, 256, false, false><<<grid, 256, 0, stream>>>(a, sa); break;

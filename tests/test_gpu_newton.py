@@ -21,9 +21,9 @@ def run(m, solver, ls, oracle, mi, ml):
         return type(e).__name__
 
 
-@pytest.mark.parametrize("m,n", [(512, 64), (300, 200), (1000, 130)])
+@pytest.mark.parametrize("m,n", [(512, 64), (300, 200), (1000, 130), (37, 258), (5000, 384)])
 def test_logistic_objective_matches_oracle(osb, orc, m, n):
-    # f, g (two passes over X) and the DMMA Hessian X^T D X + lambda I, tiles with ragged edges included
+    # f, g (two passes over X) and the DMMA Hessian X^T D X + lambda I: ragged tiles, K splits that are empty or partial
     rng = np.random.default_rng(m + n)
     w = rng.standard_normal(n) * 0.3
     a = osb.LogisticRegression.generated(m, n, 1.0)(w)
