@@ -800,6 +800,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) qn_lazy_sym_kernel(QNLazyArgs a,
 // asynchronous copies (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP), two steps ahead of the arithmetic and
 // straight across tile borders; the 16 warps read a stage with conflict-free 128-bit LDS, apply the pending update,
 // accumulate row and column sums and store the new elements to global memory from registers.
+// MEASURED (profiles/r02_packed_pass_experiments.md): 0.416 ms against 0.397 ms for the register-staged pass at n = 16384 —
+// bytes in flight are not what limits the pass; the variant stays selectable (bit-identical, tested) as the evidence.
 constexpr int SR_T = 512;                // one column pair of the stage per thread; thread 0 doubles as the producer
                                          // (a 17th warp would cap the kernel at 96 registers)
 constexpr int SR_CW = 2 * SR_T;          // columns per stage
@@ -814,9 +816,7 @@ __device__ __forceinline__ void bulk_load_hint(void* smem_dst, const void* gsrc,
                : "memory");
 }
 
-// EXP (timing experiments only, results are wrong): bit 0 = no column-partial RMW, bit 1 = no stores of the new
-// elements, bit 2 = no arithmetic (the loaded element is stored back) and no tile-end reduction
-template <int KIND, bool SHARDED, int EXP = 0>
+template <int KIND, bool SHARDED>
 __global__ void __launch_bounds__(SR_T, 1) qn_sym_ring_kernel(QNLazyArgs a, QNSymArgs sa) {
   DevState* st = a.st;
   if (st->done) return;
@@ -923,7 +923,7 @@ __global__ void __launch_bounds__(SR_T, 1) qn_sym_ring_kernel(QNLazyArgs a, QNSy
       const int s_ = it % SR_STAGES;
       const int col = cb + 2 * tid;
       const bool v0 = col < ncols, v1 = col + 1 < ncols;
-      const bool cok = v0 && col < (int)r0 && !(EXP & 1);
+      const bool cok = v0 && col < (int)r0;
       const double2 gj = gn, yj = yn, pj = pn, qj = qn;
       double2 oh = make_double2(0.0, 0.0), ow = make_double2(0.0, 0.0);
       if (cok && !first) {
@@ -949,10 +949,6 @@ __global__ void __launch_bounds__(SR_T, 1) qn_sym_ring_kernel(QNLazyArgs a, QNSy
             const double4 rv = rowv[r];
             const double pi = rv.x, qi = rv.y;
             double2 hn;
-            if (EXP & 4) {
-              hn = hv;
-              ah[r] += hv.x + pi;
-            } else {
             if (KIND == QN_BFGS) {
               const double cx = pi * qj.x + qi * pj.x, cy = pi * qj.y + qi * pj.y;
               hn.x = fma(c0, pi * pj.x, fma(c1, cx, hv.x));
@@ -970,8 +966,7 @@ __global__ void __launch_bounds__(SR_T, 1) qn_sym_ring_kernel(QNLazyArgs a, QNSy
             ch1 = fma(hn.y, rv.z, ch1);
             cw0 = fma(hn.x, rv.w, cw0);
             cw1 = fma(hn.y, rv.w, cw1);
-            }
-            if (!(EXP & 2)) st_stream_ef(obase + (int64_t)r * lpad + col, hn, pol);
+            st_stream_ef(obase + (int64_t)r * lpad + col, hn, pol);
           }
         }
         if (cok) {
@@ -987,10 +982,6 @@ __global__ void __launch_bounds__(SR_T, 1) qn_sym_ring_kernel(QNLazyArgs a, QNSy
       if (lane == 0) mbar_arrive(&empty[s_]);  // this warp's reads of the stage are done
     }
     first = false;
-    if (EXP & 4) {
-      if (ah[0] + ah[1] + ah[2] + ah[3] + ah[4] + ah[5] + ah[6] + ah[7] == 1.2345e-300) a.h[r0] = 1.0;  // (keeps the loads alive)
-      continue;
-    }
     {
       double v16[16];
 #pragma unroll
@@ -1013,17 +1004,6 @@ __global__ void __launch_bounds__(SR_T, 1) qn_sym_ring_kernel(QNLazyArgs a, QNSy
       }
     }
   }
-}
-
-// the same pass with the column partials of the first `sc` columns in (dynamic) shared memory
-constexpr int SMCP_MAX_COLS = 13824;  // 2 x 13824 x 8 B = 216 KiB next to 4.6 KiB of static shared memory
-template <int KIND, bool SHARDED>
-__global__ void __launch_bounds__(512, 1) qn_lazy_sym_smcp_kernel(QNLazyArgs a, QNSymArgs sa, int sc) {
-  DevState* st = a.st;
-  if (st->done) return;
-  extern __shared__ __align__(16) unsigned char smcp_raw[];
-  sym_pass_body<KIND, SHARDED, 512, false, false, false, true>(a, sa, st->pc0, st->pc1, st->pc2, 0, (int)gridDim.x, (int)blockIdx.x, nullptr, nullptr,
-                                                                reinterpret_cast<double*>(smcp_raw), sc);
 }
 
 // h_j += sum over CTAs of the column partials; then, depending on the mode, the O(n) epilogue by the last CTA (host
@@ -1250,39 +1230,11 @@ int qn_sym_grid(Ctx* ctx, int64_t n, int variant) {
 
 template <int KIND, bool SHARDED>
 static void launch_sym_pass(int grid, cudaStream_t stream, const QNLazyArgs& a, const QNSymArgs& sa, int variant) {
-  if (variant & 128) {  // column partials in shared memory
-    static bool attr3 = false;
-    if (!attr3) {
-      OSB_CUDA(cudaFuncSetAttribute(qn_lazy_sym_smcp_kernel<KIND, SHARDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SMCP_MAX_COLS * 8));
-      attr3 = true;
-    }
-    const int sc = (int)std::min<int64_t>(sa.ld, SMCP_MAX_COLS);
-    qn_lazy_sym_smcp_kernel<KIND, SHARDED><<<grid, 512, (size_t)2 * sc * 8, stream>>>(a, sa, sc);
-    return;
-  }
   if (variant & 8) {  // shared-memory ring fed by bulk asynchronous copies
     static bool attr = false;
     if (!attr) {
       OSB_CUDA(cudaFuncSetAttribute(qn_sym_ring_kernel<KIND, SHARDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_SMEM));
       attr = true;
-    }
-    const int e = (variant >> 4) & 7;
-    if (e != 0 && KIND == QN_BFGS && !SHARDED) {  // timing experiments (wrong results)
-      static bool attr2 = false;
-      if (!attr2) {
-        OSB_CUDA(cudaFuncSetAttribute(qn_sym_ring_kernel<QN_BFGS, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_SMEM));
-        OSB_CUDA(cudaFuncSetAttribute(qn_sym_ring_kernel<QN_BFGS, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_SMEM));
-        OSB_CUDA(cudaFuncSetAttribute(qn_sym_ring_kernel<QN_BFGS, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_SMEM));
-        OSB_CUDA(cudaFuncSetAttribute(qn_sym_ring_kernel<QN_BFGS, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_SMEM));
-        OSB_CUDA(cudaFuncSetAttribute(qn_sym_ring_kernel<QN_BFGS, false, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_SMEM));
-        attr2 = true;
-      }
-      if (e == 1) qn_sym_ring_kernel<QN_BFGS, false, 1><<<grid, SR_T, SR_SMEM, stream>>>(a, sa);
-      else if (e == 2) qn_sym_ring_kernel<QN_BFGS, false, 2><<<grid, SR_T, SR_SMEM, stream>>>(a, sa);
-      else if (e == 4) qn_sym_ring_kernel<QN_BFGS, false, 4><<<grid, SR_T, SR_SMEM, stream>>>(a, sa);
-      else if (e == 5) qn_sym_ring_kernel<QN_BFGS, false, 5><<<grid, SR_T, SR_SMEM, stream>>>(a, sa);
-      else qn_sym_ring_kernel<QN_BFGS, false, 7><<<grid, SR_T, SR_SMEM, stream>>>(a, sa);
-      return;
     }
     qn_sym_ring_kernel<KIND, SHARDED><<<grid, SR_T, SR_SMEM, stream>>>(a, sa);
     return;

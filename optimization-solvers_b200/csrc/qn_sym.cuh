@@ -156,14 +156,10 @@ constexpr int SYM_FLAT_SLOTS = 3;
 // 128-register streaming loop is sensitive to anything that stays live across it).  NT = threads per CTA: 512 (one
 // CTA per SM) or 256 (two independent CTAs per SM: one streams while the other drains into its tile-end reduction).
 // OOP: ping-pong storage, the pass reads sa.P and writes sa.Pout.  ZERO: legacy zero-first partials.
-// SMCP: the CTA's column partials of the first `sc` columns live in shared memory (smcp[0..sc) for h, smcp[sc..2 sc) for w)
-// for the whole pass and are written to the global partial vector once at the end: the per-step read-modify-write of the
-// partials (2 x 16 B loads + 2 x 16 B stores per thread against 8 + 8 of H) then never leaves the SM.  Column j receives
-// contributions from the tiles below it, so the first 84 % of the columns carry 97.6 % of that traffic at n = 16384.
-template <int KIND, bool SHARDED, int NT, bool OOP, bool ZERO, bool FLAT = false, bool SMCP = false>
+template <int KIND, bool SHARDED, int NT, bool OOP, bool ZERO, bool FLAT = false>
 __device__ __forceinline__ void sym_pass_body(const QNLazyArgs& a, const QNSymArgs& sa, const double c0, const double c1, const double c2,
                                               const int pp, const int grid, const int cta, const int* __restrict__ wt = nullptr,
-                                              double* __restrict__ rowpart = nullptr, double* __restrict__ smcp = nullptr, const int sc = 0) {
+                                              double* __restrict__ rowpart = nullptr) {
   const unsigned long long pol = l2_evict_first_policy();
   __shared__ double red2[2][NT / 32][16];  // double-buffered by tile parity: two barriers per tile instead of four
   __shared__ double4 rowv2[2][QN_R];       // p_i, q_i, y_i, g_i of the tile's rows
@@ -182,9 +178,6 @@ __device__ __forceinline__ void sym_pass_body(const QNLazyArgs& a, const QNSymAr
       *reinterpret_cast<double2*>(cpw + j) = make_double2(0.0, 0.0);
     }
     __syncthreads();
-  }
-  if (SMCP) {  // (visible to everybody after barrier (A) of the first tile)
-    for (int j = 2 * threadIdx.x; j < 2 * sc; j += 2 * NT) *reinterpret_cast<double2*>(smcp + j) = make_double2(0.0, 0.0);
   }
   const int64_t ntiles = (n + QN_R - 1) / QN_R;
   bool first = !ZERO && !FLAT;  // (flat partition: the column partials are zero when the pass starts, see the fold)
@@ -278,15 +271,7 @@ __device__ __forceinline__ void sym_pass_body(const QNLazyArgs& a, const QNSymAr
           st_stream_ef(obase + r * lpad + col, hn, pol);
         }
       }
-      if (SMCP && cok && col < sc) {
-        double2 oh = *reinterpret_cast<double2*>(smcp + col), ow = *reinterpret_cast<double2*>(smcp + sc + col);
-        oh.x += ch0;
-        ow.x += cw0;
-        oh.y += ch1;
-        ow.y += cw1;
-        *reinterpret_cast<double2*>(smcp + col) = oh;
-        *reinterpret_cast<double2*>(smcp + sc + col) = ow;
-      } else if (cok) {
+      if (cok) {
         double2 oh = make_double2(0.0, 0.0), ow = make_double2(0.0, 0.0);
         if (!first) {
           oh = *reinterpret_cast<double2*>(cph + col);
@@ -330,15 +315,6 @@ __device__ __forceinline__ void sym_pass_body(const QNLazyArgs& a, const QNSymAr
       fq += 1;
       fs = 0;
       fslot = 0;
-    }
-  }
-  if (SMCP) {  // the shared-memory partials become the head of the CTA's global partial vector (what the fold reads)
-    __syncthreads();
-    const int64_t valid = sym_first_row<SHARDED>(ntiles, sa.world, sa.rank, grid, cta);
-    const int lim = valid < sc ? (int)valid : sc;
-    for (int j = 2 * threadIdx.x; j < lim; j += 2 * NT) {
-      *reinterpret_cast<double2*>(cph + j) = *reinterpret_cast<const double2*>(smcp + j);
-      *reinterpret_cast<double2*>(cpw + j) = *reinterpret_cast<const double2*>(smcp + sc + j);
     }
   }
 }
