@@ -47,8 +47,9 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed")
     if procs or not os.path.exists(OUT):
-        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-ldl", "-ccbin", "/usr/bin/g++"]
+        cmd = [NVCC, "-shared", "-o", OUT + ".tmp"] + objs + ["-ldl", "-ccbin", "/usr/bin/g++"]
         subprocess.check_call(cmd)
+        os.replace(OUT + ".tmp", OUT)  # (a snapshot of the tree never sees a half-written library)
     return OUT
 
 

@@ -10,6 +10,7 @@
 //                     `done` flag a few iterations behind (no host round trip on the critical path).
 #include "engine.cuh"
 
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -85,6 +86,10 @@ std::vector<PoolEntry> g_pool;
 constexpr size_t POOL_MAX_ENTRIES = 256;
 constexpr size_t POOL_MAX_BYTES = (size_t)8 << 30;
 }  // namespace
+
+// flag values of the in-kernel callback snapshots: unique over the process, so a recycled pinned ring never holds a
+// value a later launch waits for
+static std::atomic<unsigned long long> g_snap_seq{1ULL << 20};
 
 void* pool_get(int kind, size_t bytes) {
   int dev = 0;
@@ -223,7 +228,6 @@ Solver::Solver(Ctx* c, int kind_, int64_t n_, double tol_, const double* x0, con
                                                       : QN_BROYDEN;
     if (ctx->world > 1) {
       OSB_REQUIRE(n % (ctx->world * 8) == 0, OSB_ERROR_INPUT_PARAMS, "row-sharded H needs n divisible by 8 * world");
-      OSB_REQUIRE(qn_kind != QN_BROYDEN, OSB_ERR_UNSUPPORTED, "Broyden (non-symmetric H) is single-GPU only");
       nrows = n / ctx->world;
       row0 = nrows * ctx->rank;
     } else {
@@ -283,6 +287,9 @@ Solver::~Solver() {
   pool_put(1, 2 * sizeof(DevState), cb_snap);
   pool_put(1, 2 * sizeof(double) * (size_t)ld, cb_xsnap);
   pool_put(1, 2 * sizeof(double) * (size_t)ld, cb_gsnap);
+  pool_put(1, 2 * 16 * 2 * sizeof(double) * (size_t)ld, snap_x);
+  pool_put(1, 2 * 16 * sizeof(DevState), snap_st);
+  pool_put(1, 2 * 16 * sizeof(unsigned long long), snap_flag);
   pool_put(0, sizeof(LSParams), d_ls_buf);
   pool_put(1, 2 * sizeof(DevState), poll_snap);
   if (d_iter_prof) cudaFree(d_iter_prof);
@@ -505,8 +512,19 @@ void Solver::ensure_packed() {
     if (sym_sharded) qn_sym_set_identity_sharded(ctx, n, Hsym.p);
     else qn_sym_set_identity(ctx, n, Hsym.p);
     H_virtual_identity = false;
+  } else if (sym_sharded) {
+    // The matrix exists as row blocks (set_inv_hessian, or an earlier run on the row-block layout); a rank's tile pairs
+    // are spread over every row block, so row blocks -> tile pairs is an all-to-all.  It happens once per solve, not per
+    // iteration: gather the blocks into an n x n scratch on every rank (NCCL all-gather, 2 GiB at n = 16384), pack the
+    // local pairs out of it, drop the scratch and the row block.
+    OSB_REQUIRE(n % ctx->world == 0, OSB_ERR_UNSUPPORTED, "row blocks of unequal height");  // (guarded by the caller)
+    DBuf full;
+    full.alloc(qn_rows_padded(n) * ld);
+    OSB_CUDA(cudaMemcpyAsync(full.p + row0 * ld, H.p, sizeof(double) * (size_t)(nrows * ld), cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->all_gather_inplace(full.p, nrows * ld);
+    qn_sym_pack_sharded(ctx, full.p, ld, n, Hsym.p);
+    ctx->sync();
   } else {
-    OSB_REQUIRE(!sym_sharded, OSB_ERR_UNSUPPORTED, "sharded packed storage starts from H = I");  // (guarded by the caller)
     qn_sym_pack(ctx, H.p, ld, n, Hsym.p);
   }
   sym_current = true;
@@ -586,7 +604,10 @@ void Solver::qn_after_step() {
     ctx->all_gather_inplace(h.p, nrows);
     ctx->all_gather_inplace(u.p, nrows);
   }
-  if (qn_kind == QN_BROYDEN) qn_launch_gemvT(ctx, H.p, ld, nrows, row0, st, s.p, vvec.p, scratch.p);
+  if (qn_kind == QN_BROYDEN) {  // v = H^T s (broyden.rs:115-117): column sums over the local rows, summed over the row blocks
+    qn_launch_gemvT(ctx, H.p, ld, nrows, row0, st, s.p, vvec.p, scratch.p);
+    if (ctx->world > 1) ctx_all_reduce_sum(ctx, vvec.p, n);
+  }
   if (!fuse_coef) qn_launch_coef(ctx, qn_kind, n, d_state, s.p, y.p, h.p, pvec.p);
   const double* p = (qn_kind == QN_BFGS || qn_kind == QN_DFP) ? s.p : pvec.p;
   // pass 2: fused rank-2 read-modify-write + u = H' g_new
@@ -912,10 +933,9 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
   // lazy schedule + cluster head: the O(n) epilogue of the pass runs at the top of the next head (8 SMs instead of 1)
   epi_p2p = ctx->world > 1 && ctx->p2p_ready && ld <= XCHG_LD && use_p2p;
   // packed symmetric storage sharded by tile pairs: needs the fused peer-memory exchange, the cluster head (it sums the
-  // per-rank slots), an even tile count, and a matrix that never existed as row blocks on this rank (H = I so far, or
-  // already packed): row blocks -> tile pairs would be an all-to-all
+  // per-rank slots) and an even tile count; a matrix that exists as row blocks is redistributed once (ensure_packed)
   sym_sharded = ctx->world > 1 && qn_storage == 1 && qn_schedule == 1 && epi_p2p && h_symmetric && (qn_kind == QN_BFGS || qn_kind == QN_DFP) &&
-                n % 16 == 0 && n <= XSLOT_LD && (n / 16) >= ctx->world && (H_virtual_identity || sym_current) &&
+                n % 16 == 0 && n <= XSLOT_LD && (n / 16) >= ctx->world && (H_virtual_identity || sym_current || n % ctx->world == 0) &&
                 qn_device_head_is_cluster(obj->functor_kind(), n, head_variant);
   if (!sym_sharded && sym_current && ctx->world > 1) sym_to_full();
   last_sym_sharded = sym_sharded;
@@ -940,14 +960,18 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
       gpart.alloc_pooled(qn_iter_gpart_doubles(ctx));
       gpart.zero(stm);
     }
-    if (sym_sharded) {
+    // how a rank's tiles are spread over the CTAs: whole tiles in snake order (auto), or the flat partition (equal column
+    // steps per CTA, tiles cut into pieces; option flat_partition = 1).  Measured (profiles/r02_scaling.md): the flat
+    // partition balances the pass but its fold reads and re-zeroes every CTA's whole partial vector and sums piece slots.
+    iter_flat = sym_sharded && opt_flat > 0;
+    if (iter_flat) {
       if (iter_wt.p == nullptr) {  // flat partition of this rank's tiles over the CTAs (built once per solver)
         std::vector<int> tab;
-        qn_iter_build_worktable(ctx, n, tab);
+        const int slots = qn_iter_build_worktable(ctx, n, tab);
         iter_wt.alloc_pooled((int64_t)(tab.size() + 1) / 2 + 1);
         OSB_CUDA(cudaMemcpyAsync(iter_wt.p, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice, stm));
         ctx->sync();  // (tab is a local)
-        rowpart.alloc_pooled(3 * 2 * ld);
+        rowpart.alloc_pooled((int64_t)slots * 2 * ld);
         rowpart.zero(stm);
       }
       colpart.zero(stm);  // the flat pass adds into zeroed column partials (the fold leaves them zeroed again)
@@ -986,8 +1010,8 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
     a.rank = sym_sharded ? ctx->rank : 0;
     a.peers = sym_sharded ? ctx->d_peers : nullptr;
     a.seq = ctx->d_seq;
-    a.wt = sym_sharded ? reinterpret_cast<const int*>(iter_wt.p) : nullptr;
-    a.rowpart = sym_sharded ? rowpart.p : nullptr;
+    a.wt = iter_flat ? reinterpret_cast<const int*>(iter_wt.p) : nullptr;
+    a.rowpart = iter_flat ? rowpart.p : nullptr;
     a.prof = profile_iter ? d_iter_prof : nullptr;
     iter_args = a;
     iter_fn_kind = obj->functor_kind();
@@ -1015,6 +1039,56 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
     OSB_CUDA(cudaEventCreateWithFlags(&cbev[1], cudaEventDisableTiming));
     cb_f_before = h_state->f;
   }
+  // Fused iteration kernel + run-ahead: the kernel itself writes every iteration's snapshot into pinned host memory
+  // (QNIterArgs.snap_*), so a launch still runs SNAP_CHUNK iterations while the host delivers the callbacks behind it.
+  constexpr int64_t SNAP_CHUNK = 16;
+  struct SnapLaunch {
+    int half, count;
+    unsigned long long seq0;
+  };
+  const bool snap_mode = run_ahead && iter_path;
+  SnapLaunch snap_prev{0, 0, 0ULL};
+  int snap_half = 0;
+  if (snap_mode && !snap_x) {
+    snap_x = (double*)pool_get(1, 2 * SNAP_CHUNK * 2 * sizeof(double) * (size_t)ld);
+    snap_st = (DevState*)pool_get(1, 2 * SNAP_CHUNK * sizeof(DevState));
+    snap_flag = (unsigned long long*)pool_get(1, 2 * SNAP_CHUNK * sizeof(unsigned long long));
+  }
+  // delivers the iterations of one launch in order; false = the solve ended inside it (or before it)
+  auto deliver_launch = [&](const SnapLaunch& L) -> bool {
+    for (int j = 0; j < L.count; ++j) {
+      volatile unsigned long long* fl = snap_flag + (size_t)L.half * SNAP_CHUNK + j;
+      const unsigned long long want = L.seq0 + (unsigned long long)j + 1ULL;
+      bool launch_over = false;
+      for (unsigned spins = 0; *fl != want; ++spins) {
+        if ((spins & 255u) != 255u) continue;
+        if (launch_over) return false;  // the kernel has ended and never published slot j: it found `done` earlier
+        const cudaError_t q = cudaEventQuery(cbev[L.half]);
+        if (q == cudaSuccess) launch_over = true;  // (one more look at the flag before giving up)
+        else if (q != cudaErrorNotReady) OSB_CUDA(q);
+      }
+      std::atomic_thread_fence(std::memory_order_acquire);
+      ctx->counters[3]++;
+      const DevState& sn = snap_st[(size_t)L.half * SNAP_CHUNK + j];
+      if (sn.done) return false;
+      k = sn.k;
+      has_s = has_y = true;
+      s_norm = sn.s_norm;
+      y_norm = sn.y_norm;
+      if (record_trace) trace.push_back(TraceRec{cb_f_before, sn.t_last, s_norm, y_norm});
+      cb_f_before = sn.f;
+      if (cb) {
+        cb_x_mirror = snap_x + ((size_t)L.half * SNAP_CHUNK + j) * 2 * ld;
+        cb_g_mirror = cb_x_mirror + ld;
+        cb_state_mirror = &snap_st[(size_t)L.half * SNAP_CHUNK + j];
+        cb(user, reinterpret_cast<osb_solver*>(this));
+        cb_x_mirror = nullptr;
+        cb_g_mirror = nullptr;
+        cb_state_mirror = nullptr;
+      }
+    }
+    return true;
+  };
   // returns false when the snapshot says the head found convergence at the START of that iteration (no k += 1, no callback)
   auto deliver = [&](int sl) -> bool {
     OSB_CUDA(cudaEventSynchronize(cbev[sl]));
@@ -1044,10 +1118,35 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
       // up to POLL iterations per launch; one per launch when a callback / trace wants every iteration's state
       // (a launch that finds convergence simply ends, and later launches return at once: the chunk only bounds how far
       //  the host runs ahead of the device)
-      chunk = (cb != nullptr || record_trace) ? 1 : std::min<int64_t>(ITER_CHUNK, max_iter - it);
+      chunk = snap_mode ? std::min<int64_t>(SNAP_CHUNK, max_iter - it)
+                        : (cb != nullptr || record_trace) ? 1 : std::min<int64_t>(ITER_CHUNK, max_iter - it);
       QNIterArgs a = iter_args;
       a.iters = (int)chunk;
+      if (snap_mode) {  // this launch publishes its iterations into one half of the pinned ring
+        a.snap_x = snap_x + (size_t)snap_half * SNAP_CHUNK * 2 * ld;
+        a.snap_st = snap_st + (size_t)snap_half * SNAP_CHUNK;
+        a.snap_flag = snap_flag + (size_t)snap_half * SNAP_CHUNK;
+        a.snap_seq0 = g_snap_seq.fetch_add((unsigned long long)chunk);
+      }
       qn_launch_iter(ctx, iter_fn_kind, iter_fn_a, iter_fn_b, bounded, iter_ls_kind, a);
+      if (snap_mode) {
+        OSB_CUDA(cudaEventRecord(cbev[snap_half], stm));
+        SnapLaunch cur{snap_half, (int)chunk, a.snap_seq0};
+        lazy_used = true;
+        u_valid = true;
+        if (sym_sharded) {
+          ctx->counters[4] += chunk;
+          ctx->counters[5] += chunk;
+        }
+        // deliver the PREVIOUS launch's iterations while this one runs (its ring half is the other one)
+        if (snap_prev.count > 0 && !deliver_launch(snap_prev)) {
+          snap_prev.count = 0;
+          break;
+        }
+        snap_prev = cur;
+        snap_half ^= 1;
+        continue;
+      }
       if (sym_sharded) {
         ctx->counters[4] += chunk;  // fused exchanges
         ctx->counters[5] += chunk;  // passes over the sharded packed triangle
@@ -1110,6 +1209,7 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
     }
   }
   if (run_ahead) {
+    if (snap_prev.count > 0) deliver_launch(snap_prev);
     if (cb_prev >= 0) deliver(cb_prev);
     cudaEventDestroy(cbev[0]);
     cudaEventDestroy(cbev[1]);

@@ -270,6 +270,7 @@ void qn_sym_set_identity(Ctx* ctx, int64_t n, double* P);
 int64_t qn_sym_doubles_sharded(int64_t n, int world, int rank);
 void qn_sym_layout(int64_t n, int world, int64_t tile, int* owner, int64_t* offset, int64_t* lpad);
 void qn_sym_set_identity_sharded(Ctx* ctx, int64_t n, double* P);
+void qn_sym_pack_sharded(Ctx* ctx, const double* Hfull, int64_t ld, int64_t n, double* P);  // every rank holds the full matrix
 void qn_sym_unpack_sharded(Ctx* ctx, const double* P, int64_t ld, int64_t n, double* Hfull_zeroed);
 void qn_sym_unpack(Ctx* ctx, const double* P, int64_t ld, int64_t n, double* H);
 void qn_launch_lazy_sym(Ctx* ctx, const QNLazyArgs& a, double* P, double* Pout, double* colpart, int64_t n, int64_t ld, int phase, int variant);
@@ -297,12 +298,20 @@ struct QNIterArgs {
   const int* wt;    // sharded: flat-partition work table (qn_sym.cuh), 4 ints per CTA then the piece count of every local tile
   double* rowpart;  // sharded: row sums of the tile pieces, [slot][h | w][ld]
   long long* prof;  // optional [16]: ns in head / pass / fold+exchange (CTA 0), iterations, head sub-phases
+  // Run-ahead snapshots for host callbacks / traces (null: none): PINNED HOST memory written from inside the kernel, so a
+  // launch keeps running many iterations while the host delivers ls_solver.rs:104-107's callback from the snapshots.
+  // Iteration j of this launch: x then g at snap_x + j * 2 * ld, the scalars a callback may read at snap_st + j, and
+  // finally (st.release.sys) the flag snap_flag[j] = snap_seq0 + j + 1.
+  double* snap_x;
+  DevState* snap_st;
+  unsigned long long* snap_flag;
+  unsigned long long snap_seq0;
 };
 
 bool qn_iter_supported(Ctx* ctx, int functor_kind, int64_t n, int world);
 int qn_iter_grid(Ctx* ctx);
 int64_t qn_iter_gpart_doubles(Ctx* ctx);
-void qn_iter_build_worktable(Ctx* ctx, int64_t n, std::vector<int>& table);  // flat partition of this rank's tiles
+int qn_iter_build_worktable(Ctx* ctx, int64_t n, std::vector<int>& table);  // flat partition of this rank's tiles; returns the piece slots needed
 void qn_launch_iter(Ctx* ctx, int functor_kind, const double* fn_a, const double* fn_b, bool bounded, int ls_kind, const QNIterArgs& a);
 // apply a pending update to the stored matrix (getters, engine switches)
 void qn_launch_flush(Ctx* ctx, int kind, double* M, int64_t ld, int64_t nrows, int64_t row0, DevState* st, const double* ps,
@@ -379,6 +388,11 @@ struct Solver {
   bool sym_pingpong_dirty = false;
   // fused iteration kernel (qn_iter.cu): -1 = auto (on whenever it applies), 0 = off (one launch per phase)
   int opt_fused = -1;
+  int opt_flat = -1;             // fused sharded kernel: 1 = flat partition of the rank's tiles (qn_sym.cuh); -1 / 0 = whole tiles per CTA
+  bool iter_flat = false;
+  double* snap_x = nullptr;      // pinned ring of in-kernel callback snapshots (2 halves x 16 iterations x {x, g})
+  DevState* snap_st = nullptr;
+  unsigned long long* snap_flag = nullptr;
   int opt_stream = -1;           // PGD / SPG: one fused kernel per trial step (-1 / 1 = on whenever it applies, 0 = off)
   bool last_stream = false;
   bool iter_path = false;        // this minimize() runs whole iterations in one cooperative kernel

@@ -51,6 +51,7 @@ struct IterCarry {
   unsigned long long seq;
   int has_s, has_y, skip_prev, pending, epi_owed, ls_evals, status, reason, done, gbuf;
   unsigned int llseq;  // sequence number of the flagged (barrier-free) grid reductions; persists in DevState.ll_seq
+  int snap_it;         // host-callback snapshots published so far in this launch (QNIterArgs.snap_*)
   LSParams p;
 };
 
@@ -192,8 +193,9 @@ __device__ __forceinline__ unsigned long long* iter_flags(double* region, int wo
 
 // h, w of the fold: columns [j0, j0 + cw) of this CTA.  One GPU: written in place over the row sums.  Sharded: this
 // rank's contribution goes into slot `rank` of every rank's exchange region, then the chunk flags.
-template <bool SHARDED>
+template <int SH>  // 0: one GPU, 1: sharded by tile pairs, whole tiles dealt to the CTAs, 2: sharded, flat partition (qn_sym.cuh)
 __device__ __forceinline__ void iter_fold(const QNIterArgs& a, IterSmem& sm, int64_t j0, int cw, unsigned long long seq, DevState* st) {
+  constexpr bool SHARDED = SH != 0, FLAT = SH == 2;
   const int G = (int)gridDim.x;
   const int cwp = cw / 2;
   int cwpp = 1;
@@ -219,7 +221,7 @@ __device__ __forceinline__ void iter_fold(const QNIterArgs& a, IterSmem& sm, int
         acc.x = acc.x + v[k].x;
         acc.y = acc.y + v[k].y;
       }
-      if (SHARDED) {  // flat partition: the pass adds into zeroed partials; this thread is the only reader of these words
+      if (FLAT) {  // flat partition: the pass adds into zeroed partials; this thread is the only reader of these words
 #pragma unroll
         for (int k = 0; k < 8; ++k) *reinterpret_cast<double2*>(const_cast<double*>(src) + (int64_t)(c + k) * 2 * a.ld) = make_double2(0.0, 0.0);
       }
@@ -228,7 +230,7 @@ __device__ __forceinline__ void iter_fold(const QNIterArgs& a, IterSmem& sm, int
       const double2 v = j < sm.ext[c] ? __ldcg(reinterpret_cast<const double2*>(src + (int64_t)c * 2 * a.ld)) : make_double2(0.0, 0.0);
       acc.x = acc.x + v.x;
       acc.y = acc.y + v.y;
-      if (SHARDED) *reinterpret_cast<double2*>(const_cast<double*>(src) + (int64_t)c * 2 * a.ld) = make_double2(0.0, 0.0);
+      if (FLAT) *reinterpret_cast<double2*>(const_cast<double*>(src) + (int64_t)c * 2 * a.ld) = make_double2(0.0, 0.0);
     }
   }
   __syncthreads();
@@ -247,11 +249,15 @@ __device__ __forceinline__ void iter_fold(const QNIterArgs& a, IterSmem& sm, int
       const int64_t T = (a.n + QN_R - 1) / QN_R, tile = j / QN_R;
       const int64_t pairi = tile < T / 2 ? tile : T - 1 - tile;
       if ((pairi % a.world) == a.rank) {
-        const int np = a.wt[4 * (int)gridDim.x + (int)symsh_pos_of(T, a.world, a.rank, tile)];
-        for (int sl = 0; sl < np; ++sl) {
-          const double2 v = __ldcg(reinterpret_cast<const double2*>(a.rowpart + ((int64_t)sl * 2 + vec) * a.ld + j));
-          rs.x = rs.x + v.x;
-          rs.y = rs.y + v.y;
+        if (FLAT) {
+          const int np = a.wt[4 * (int)gridDim.x + (int)symsh_pos_of(T, a.world, a.rank, tile)];
+          for (int sl = 0; sl < np; ++sl) {
+            const double2 v = __ldcg(reinterpret_cast<const double2*>(a.rowpart + ((int64_t)sl * 2 + vec) * a.ld + j));
+            rs.x = rs.x + v.x;
+            rs.y = rs.y + v.y;
+          }
+        } else {
+          rs = __ldcg(reinterpret_cast<const double2*>(rowarr + j));
         }
       }
     } else {
@@ -278,9 +284,27 @@ __device__ __forceinline__ void iter_fold(const QNIterArgs& a, IterSmem& sm, int
   __syncthreads();
 }
 
+// scalars of the snapshot + its flag (one thread of the leader CTA; x and g were stored by their owners before the grid sum)
+__device__ __noinline__ void iter_publish(const QNIterArgs& a, const IterCarry& c, int slot) {
+  DevState* h = a.snap_st + slot;
+  h->f = c.f0;
+  h->k = c.k;
+  h->s_norm = c.s_norm;
+  h->y_norm = c.y_norm;
+  h->has_s = c.has_s;
+  h->has_y = c.has_y;
+  h->t_last = c.t_last;
+  h->ls_evals = c.ls_evals;
+  h->done = c.done;
+  h->status = c.status;
+  h->reason = c.reason;
+  st_release_sys(a.snap_flag + slot, a.snap_seq0 + (unsigned long long)slot + 1ULL);
+}
+
 // everything of one outer iteration that comes before the H pass.  Returns 0: go on with the pass, 1: leave the loop.
-template <class Fn, bool BOUNDED, bool BT, bool SHARDED, int KIND>
+template <class Fn, bool BOUNDED, bool BT, int SH, int KIND>
 __device__ __noinline__ int iter_head(const QNIterArgs& a, const Fn& fn, IterSmem& sm, const bool epi_only) {
+  constexpr bool SHARDED = SH != 0;
   IterCarry& c = sm.c;
   constexpr int BS = Fn::BS;
   const int tid = threadIdx.x, G = (int)gridDim.x, cta = (int)blockIdx.x;
@@ -305,6 +329,7 @@ __device__ __noinline__ int iter_head(const QNIterArgs& a, const Fn& fn, IterSme
   const double f0 = c.f0, ys_prev = c.ys_prev, s_norm_in = c.s_norm, y_norm_in = c.y_norm;
   const int has_s_in = c.has_s, has_y_in = c.has_y, epi_in = c.epi_owed, skip_in = c.skip_prev, ls_evals_in = c.ls_evals;
   const long long k_in = c.k;
+  const int snap_in = c.snap_it;
   __syncthreads();
   iter_submark(a, sm, 14);  // (resets the sub-phase clock)
   if (!epi_only && is_bad(f0)) {  // ls_solver.rs:37-40
@@ -626,12 +651,21 @@ __device__ __noinline__ int iter_head(const QNIterArgs& a, const Fn& fn, IterSme
       a.y[i] = yi;
       a.x[i] = xn[jq];
       a.g[i] = gn[jq];
+      if (a.snap_x != nullptr) {  // this iteration's snapshot for the host callback (pinned host memory)
+        double* sx = a.snap_x + (int64_t)snap_in * 2 * a.ld;
+        sx[i] = xn[jq];
+        sx[a.ld + i] = gn[jq];
+      }
       a4[0] = a4[0] + si * si;
       a4[1] = a4[1] + yi * yi;
       a4[2] = a4[2] + yi * si;
     }
   }
   iter_submark(a, sm, 10);
+  if (a.snap_x != nullptr) {  // one system fence per CTA, ordered after every thread's snapshot stores by the barrier and
+    __syncthreads();          // before this CTA's contribution to the grid sum below by the next one
+    if (tid == 0) __threadfence_system();
+  }
   __syncthreads();  // sm.res of the line search has been consumed by every thread
   warp_put(sm, 0, a4[0], wact);
   warp_put(sm, 1, a4[1], wact);
@@ -653,6 +687,7 @@ __device__ __noinline__ int iter_head(const QNIterArgs& a, const Fn& fn, IterSme
     c.t_last = t;
     c.gd0_last = gd0;
     c.k = k_in + 1;
+    c.snap_it = snap_in + 1;
     c.ls_evals = ls_evals_in + evals + 1;
     c.gbuf = gbuf;
     c.llseq = llseq;
@@ -662,12 +697,15 @@ __device__ __noinline__ int iter_head(const QNIterArgs& a, const Fn& fn, IterSme
     if (tid == 0) c.p = p_local;
   }
   __syncthreads();
+  // the grid sum above completed => every CTA's snapshot stores are fenced: the leader publishes the iteration
+  if (a.snap_st != nullptr && cta == 0 && tid == 0) iter_publish(a, c, snap_in);
   return 0;
 }
 
 // fold of the column partials (+ exchange) for this CTA's chunk, out of line like the head
-template <class Fn, bool SHARDED>
+template <class Fn, int SH>
 __device__ __noinline__ void iter_tail(const QNIterArgs& a, IterSmem& sm) {
+  constexpr bool SHARDED = SH != 0;
   IterCarry& c = sm.c;
   constexpr int BS = Fn::BS;
   const int G = (int)gridDim.x;
@@ -676,7 +714,7 @@ __device__ __noinline__ void iter_tail(const QNIterArgs& a, IterSmem& sm) {
   if ((bpc * BS) & 1) bpc += 1;
   const int cw = (int)(bpc * BS);
   const unsigned long long seq = c.seq + 1ULL;
-  iter_fold<SHARDED>(a, sm, (int64_t)blockIdx.x * cw, cw, seq, a.st);
+  iter_fold<SH>(a, sm, (int64_t)blockIdx.x * cw, cw, seq, a.st);
   __syncthreads();
   c.seq = seq;
   c.epi_owed = SHARDED ? 1 + (int)(seq & 1ULL) : 1;
@@ -713,6 +751,7 @@ __device__ __noinline__ void iter_load_state(const QNIterArgs& a, IterCarry& c, 
   c.done = 0;
   c.gbuf = 0;
   c.llseq = (unsigned int)st->ll_seq;
+  c.snap_it = 0;
   c.p = *a.lsp;
 }
 
@@ -765,8 +804,9 @@ __device__ __noinline__ void iter_mark(const QNIterArgs& a, IterSmem& sm, int sl
   sm.prof[3] = now;
 }
 
-template <class Fn, bool BOUNDED, bool BT, bool SHARDED, int KIND>
+template <class Fn, bool BOUNDED, bool BT, int SH, int KIND>
 __global__ void __launch_bounds__(IT_NT, 1) qn_iter_kernel(const __grid_constant__ QNIterArgs a, const __grid_constant__ Fn fn) {
+  constexpr bool SHARDED = SH != 0, FLAT = SH == 2;
   cg::grid_group grid = cg::this_grid();
   __shared__ IterSmem sm;
   if (a.st->done) return;
@@ -775,10 +815,10 @@ __global__ void __launch_bounds__(IT_NT, 1) qn_iter_kernel(const __grid_constant
   __syncthreads();
   {
     const int64_t T = (a.n + QN_R - 1) / QN_R;
-    // one GPU: partial vector q is valid on the columns below the first row of CTA q's first tile; sharded (flat
-    // partition): the partials are zeroed by the fold, every column is valid
+    // whole tiles per CTA: partial vector q is valid on the columns below the first row of CTA q's first tile; flat
+    // partition: the partials are zeroed by the fold, every column is valid
     for (int q = threadIdx.x; q < (int)gridDim.x; q += IT_NT)
-      sm.ext[q] = SHARDED ? 0x7fffffff : (int)sym_first_row<false>(T, 1, 0, (int)gridDim.x, q);
+      sm.ext[q] = FLAT ? 0x7fffffff : (int)sym_first_row<SHARDED>(T, a.world, a.rank, (int)gridDim.x, q);
   }
   grid.sync();  // every CTA has read the entry state before anybody can write it
   // (time stamps live in shared memory, not in registers: nothing but &c and the loop counter is live across the pass)
@@ -790,10 +830,13 @@ __global__ void __launch_bounds__(IT_NT, 1) qn_iter_kernel(const __grid_constant
   }
   int it = 0;
   if (a.epi_only) {
-    iter_head<Fn, BOUNDED, BT, SHARDED, KIND>(a, fn, sm, true);
+    iter_head<Fn, BOUNDED, BT, SH, KIND>(a, fn, sm, true);
   } else {
     for (; it < a.iters; ++it) {
-      if (iter_head<Fn, BOUNDED, BT, SHARDED, KIND>(a, fn, sm, false)) break;
+      if (iter_head<Fn, BOUNDED, BT, SH, KIND>(a, fn, sm, false)) {
+        if (a.snap_st != nullptr && leader) iter_publish(a, sm.c, sm.c.snap_it);  // done: tells the host to stop waiting
+        break;
+      }
       iter_mark(a, sm, 0);
       // ---- the H pass: pending update + h = H y + w = H g over (this rank's share of) the packed triangle.  Inlined,
       // every pointer straight from the kernel's constant bank; only &c is live across it.
@@ -806,12 +849,12 @@ __global__ void __launch_bounds__(IT_NT, 1) qn_iter_kernel(const __grid_constant
         la.h = a.h;
         la.w = a.w;
         const QNSymArgs sa{a.P, a.P, a.colpart, a.n, a.ld, SHARDED ? a.world : 1, SHARDED ? a.rank : 0, a.peers, a.seq, (int)gridDim.x, 0};
-        if (SHARDED) sym_pass_body<KIND, true, IT_NT, false, false, true>(la, sa, sm.c.pc0, sm.c.pc1, sm.c.pc2, 0, (int)gridDim.x, (int)blockIdx.x, a.wt, a.rowpart);
-        else sym_pass_body<KIND, false, IT_NT, false, false>(la, sa, sm.c.pc0, sm.c.pc1, sm.c.pc2, 0, (int)gridDim.x, (int)blockIdx.x);
+        if (FLAT) sym_pass_body<KIND, true, IT_NT, false, false, true>(la, sa, sm.c.pc0, sm.c.pc1, sm.c.pc2, 0, (int)gridDim.x, (int)blockIdx.x, a.wt, a.rowpart);
+        else sym_pass_body<KIND, SHARDED, IT_NT, false, false>(la, sa, sm.c.pc0, sm.c.pc1, sm.c.pc2, 0, (int)gridDim.x, (int)blockIdx.x);
       }
       grid.sync();
       iter_mark(a, sm, 1);
-      iter_tail<Fn, SHARDED>(a, sm);
+      iter_tail<Fn, SH>(a, sm);
       iter_mark(a, sm, 2);
       if (a.prof != nullptr && leader && it == 0 && a.iters > 1) {
         // the first iteration of a launch waits for the slowest rank's kernel to START: not part of the steady state
@@ -856,7 +899,7 @@ double bench_grid_sync(Ctx* ctx, int reps) {
 }
 
 // flat partition of this rank's tiles over the CTAs of the fused kernel (layout: qn_sym.cuh)
-void qn_iter_build_worktable(Ctx* ctx, int64_t n, std::vector<int>& tab) {
+int qn_iter_build_worktable(Ctx* ctx, int64_t n, std::vector<int>& tab) {
   const int G = qn_iter_grid(ctx);
   const int64_t T = (n + QN_R - 1) / QN_R;
   const int64_t ntl = 2 * symsh_local_pairs(T, ctx->world, ctx->rank);
@@ -886,8 +929,12 @@ void qn_iter_build_worktable(Ctx* ctx, int64_t n, std::vector<int>& tab) {
       }
     }
   }
-  for (int64_t t = 0; t < ntl; ++t)
-    OSB_REQUIRE(tab[(size_t)(4 * G + t)] >= 1 && tab[(size_t)(4 * G + t)] <= SYM_FLAT_SLOTS, OSB_ERR_UNSUPPORTED, "flat partition: a tile is cut into too many pieces");
+  int maxpieces = 1;  // = piece slots the row-sum buffer needs (a tile has at most n / 1024 + 1 steps, hence pieces)
+  for (int64_t t = 0; t < ntl; ++t) {
+    OSB_REQUIRE(tab[(size_t)(4 * G + t)] >= 1, OSB_ERR_UNSUPPORTED, "flat partition: a tile was left out");
+    maxpieces = std::max(maxpieces, tab[(size_t)(4 * G + t)]);
+  }
+  return maxpieces;
 }
 
 // ---- host side ------------------------------------------------------------------------------
@@ -915,9 +962,9 @@ bool qn_iter_supported(Ctx* ctx, int functor_kind, int64_t n, int world) {
   return coop != 0;
 }
 
-template <class Fn, bool BOUNDED, bool BT, bool SHARDED, int KIND>
+template <class Fn, bool BOUNDED, bool BT, int SH, int KIND>
 static void launch_iter_kk(Ctx* ctx, const QNIterArgs& a, const Fn& fn) {
-  auto kern = qn_iter_kernel<Fn, BOUNDED, BT, SHARDED, KIND>;
+  auto kern = qn_iter_kernel<Fn, BOUNDED, BT, SH, KIND>;
   QNIterArgs aa = a;
   Fn f = fn;
   void* params[] = {(void*)&aa, (void*)&f};
@@ -925,36 +972,41 @@ static void launch_iter_kk(Ctx* ctx, const QNIterArgs& a, const Fn& fn) {
   ctx->counters[0]++;
 }
 
-template <class Fn, bool BOUNDED, bool BT, bool SHARDED>
+template <class Fn, bool BOUNDED, bool BT, int SH>
 static void launch_iter_k(Ctx* ctx, const QNIterArgs& a, const Fn& fn) {
-  if (a.kind == QN_BFGS) launch_iter_kk<Fn, BOUNDED, BT, SHARDED, QN_BFGS>(ctx, a, fn);
-  else launch_iter_kk<Fn, BOUNDED, BT, SHARDED, QN_DFP>(ctx, a, fn);
+  if (a.kind == QN_BFGS) launch_iter_kk<Fn, BOUNDED, BT, SH, QN_BFGS>(ctx, a, fn);
+  else launch_iter_kk<Fn, BOUNDED, BT, SH, QN_DFP>(ctx, a, fn);
 }
 
 template <class Fn>
-static void launch_iter_fn(Ctx* ctx, const QNIterArgs& a, const Fn& fn, bool bounded, bool bt, bool sharded) {
-#define OSB_IT(B, T, S) launch_iter_k<Fn, B, T, S>(ctx, a, fn)
+static void launch_iter_fn(Ctx* ctx, const QNIterArgs& a, const Fn& fn, bool bounded, bool bt, int sh) {
+#define OSB_IT(B, T)                                   \
+  do {                                                 \
+    if (sh == 0) launch_iter_k<Fn, B, T, 0>(ctx, a, fn);      \
+    else if (sh == 1) launch_iter_k<Fn, B, T, 1>(ctx, a, fn); \
+    else launch_iter_k<Fn, B, T, 2>(ctx, a, fn);              \
+  } while (0)
   if (bounded) {
-    if (bt) { if (sharded) OSB_IT(true, true, true); else OSB_IT(true, true, false); }
-    else { if (sharded) OSB_IT(true, false, true); else OSB_IT(true, false, false); }
+    if (bt) OSB_IT(true, true);
+    else OSB_IT(true, false);
   } else {
-    if (bt) { if (sharded) OSB_IT(false, true, true); else OSB_IT(false, true, false); }
-    else { if (sharded) OSB_IT(false, false, true); else OSB_IT(false, false, false); }
+    if (bt) OSB_IT(false, true);
+    else OSB_IT(false, false);
   }
 #undef OSB_IT
 }
 
 void qn_launch_iter(Ctx* ctx, int functor_kind, const double* fn_a, const double* fn_b, bool bounded, int ls_kind, const QNIterArgs& a) {
   const bool bt = ls_kind == LS_BACKTRACKING;
-  const bool sharded = a.world > 1;
+  const int sh = a.world > 1 ? (a.wt != nullptr ? 2 : 1) : 0;  // a work table selects the flat partition
   if (functor_kind == FN_ROSENBROCK) {
-    launch_iter_fn(ctx, a, RosenbrockFn{}, bounded, bt, sharded);
+    launch_iter_fn(ctx, a, RosenbrockFn{}, bounded, bt, sh);
   } else if (functor_kind == FN_SEPQUAD) {
     SepQuadFn fn;
     fn.c = fn_a;
     fn.a = fn_b;
     fn.index0 = 0;
-    launch_iter_fn(ctx, a, fn, bounded, bt, sharded);
+    launch_iter_fn(ctx, a, fn, bounded, bt, sh);
   } else {
     throw Error(OSB_ERR_UNSUPPORTED, "objective has no block functor for the device-resident engine");
   }

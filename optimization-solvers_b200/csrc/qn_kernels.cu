@@ -1180,6 +1180,27 @@ void qn_sym_set_identity_sharded(Ctx* ctx, int64_t n, double* P) {
   qn_symsh_identity_kernel<<<ctx->red_grid(n), RED_THREADS, 0, ctx->stream>>>(n, P, ctx->world, ctx->rank);
   ctx->counters[0]++;
 }
+// a FULL n x n matrix (every rank holds all of it) -> this rank's tile pairs
+__global__ void __launch_bounds__(256) qn_symsh_pack_kernel(const double* __restrict__ H, int64_t ld, int64_t n, double* __restrict__ P, int world,
+                                                           int rank) {
+  const int64_t T = (n + QN_R - 1) / QN_R;
+  const int64_t nlp = symsh_local_pairs(T, world, rank);
+  for (int64_t q = blockIdx.x; q < 2 * nlp; q += gridDim.x) {
+    const int64_t pairi = (q >> 1) * world + rank;
+    const int64_t tile = (q & 1) == 0 ? pairi : T - 1 - pairi;
+    const int64_t r0 = tile * QN_R, lpad = sym_lpad(tile);
+    const int64_t ncols = r0 + QN_R < n ? r0 + QN_R : n;
+    double* base = P + symsh_tile_offset(tile, T, world);
+    for (int64_t e = threadIdx.x; e < QN_R * lpad; e += blockDim.x) {
+      const int64_t r = e / lpad, c = e % lpad;
+      base[e] = (r0 + r < n && c < ncols) ? H[(r0 + r) * ld + c] : 0.0;
+    }
+  }
+}
+void qn_sym_pack_sharded(Ctx* ctx, const double* Hfull, int64_t ld, int64_t n, double* P) {
+  qn_symsh_pack_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(Hfull, ld, n, P, ctx->world, ctx->rank);
+  ctx->counters[0]++;
+}
 // this rank's tiles -> a FULL n x n matrix (both triangles of every owned element; everything else untouched, i.e.
 // zero in a zeroed buffer): the sum over ranks of these matrices is H
 __global__ void __launch_bounds__(256) qn_symsh_unpack_kernel(const double* __restrict__ P, int64_t ld, int64_t n, double* __restrict__ H,

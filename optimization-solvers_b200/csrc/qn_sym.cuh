@@ -132,25 +132,25 @@ __host__ __device__ inline int64_t sym_first_row(int64_t ntiles, int world, int 
 // ---- flat partition of a rank's tiles (fused iteration kernel, several GPUs) ------------------------------------------
 // With few tiles per CTA the static dealing above quantises badly: at 8 GPUs a rank has 256 tiles for 148 CTAs, the CTAs
 // holding one of the 40 longest tiles carry 1.0 n columns against a mean of 0.865 n (15.6 % over).  The flat partition
-// lines the rank's tiles up in decreasing length, counts their column steps (8 rows x 2 NT columns each) and gives every
-// CTA an equal, contiguous range of steps: a tile may be cut at a step border into up to three pieces, which are
-// processed by neighbouring CTAs and leave their row sums in piece slots (the fold adds the slots in order; the column
-// partials are per CTA as before).  The table is built on the host (sym_flat_build) and lives in global memory:
-// 4 ints per CTA {first tile position, first step inside it, steps to do, piece slot of that first tile}, then one int
-// per local tile position = its number of pieces.
-__host__ __device__ inline int64_t symsh_tile_at(int64_t T, int world, int rank, int64_t q) {  // position q (decreasing length) -> tile
-  const int64_t nlp = symsh_local_pairs(T, world, rank);
-  return q < nlp ? T - 1 - (rank + q * world) : rank + (2 * nlp - 1 - q) * world;
+// lines the rank's tiles up in STORAGE order — pair by pair, the long tile of a pair then the short one, so that every
+// stretch of the line holds the same mix of long and short tiles (a line in decreasing length left the last CTAs with
+// ~60 one-step tiles each, whose per-tile fixed costs made them the stragglers: 0.234 ms against 0.210 at 2 GPUs) —
+// counts their column steps (8 rows x 2 NT columns each) and gives every CTA an equal, contiguous range of steps: a
+// tile may be cut at a step border into pieces, which are processed by neighbouring CTAs and leave their row
+// sums in piece slots (the fold adds the slots in order; the column partials are per CTA as before).  The table is built
+// on the host (qn_iter_build_worktable) and lives in global memory: 4 ints per CTA {first tile position, first step
+// inside it, steps to do, piece slot of that first tile}, then one int per local tile position = its number of pieces.
+__host__ __device__ inline int64_t symsh_tile_at(int64_t T, int world, int rank, int64_t q) {  // line position q -> tile
+  const int64_t pairi = rank + (q >> 1) * world;
+  return (q & 1) == 0 ? T - 1 - pairi : pairi;
 }
 __host__ __device__ inline int64_t symsh_pos_of(int64_t T, int world, int rank, int64_t tile) {   // inverse, for a tile of this rank
-  const int64_t nlp = symsh_local_pairs(T, world, rank);
-  return tile >= T / 2 ? (T - 1 - tile - rank) / world : 2 * nlp - 1 - (tile - rank) / world;
+  return tile >= T / 2 ? 2 * ((T - 1 - tile - rank) / world) : 2 * ((tile - rank) / world) + 1;
 }
 __host__ __device__ inline int sym_tile_steps(int64_t tile, int64_t n, int nt) {
   const int64_t ncols = (tile + 1) * QN_R < n ? (tile + 1) * QN_R : n;
   return (int)((ncols + 2 * nt - 1) / (2 * nt));
 }
-constexpr int SYM_FLAT_SLOTS = 3;
 
 // SHARDED is a template parameter so that the single-GPU instantiation keeps exactly its own loop structure (the
 // 128-register streaming loop is sensitive to anything that stays live across it).  NT = threads per CTA: 512 (one

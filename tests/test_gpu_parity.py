@@ -639,6 +639,40 @@ def test_run_ahead_callbacks_deliver_the_same_sequence(osb):
             assert np.array_equal(a[6][key], b[6][key])
 
 
+def test_fused_kernel_publishes_callback_snapshots_from_inside_the_launch(osb):
+    """fused_iteration = 1 with run-ahead callbacks: the kernel writes every iteration's x, g, f, k, norms into a pinned
+    host ring and keeps running (16 iterations per launch) while the host delivers the callbacks behind it.  The sequence
+    the callback sees, the trace and the final state equal the stalling delivery (one iteration per launch) bit for bit:
+    a run that hits max_iter across several launches, one that converges inside a launch, and a bounded solver."""
+    def go(run_ahead, mk_solver, obj_fn, max_iter):
+        seen = []
+        s = mk_solver().set_option("fused_iteration", 1).set_option("callback_run_ahead", run_ahead).record_trace(True)
+        st = "Ok"
+        try:
+            s.minimize(osb.BackTracking(1e-4, 0.5), obj_fn(), max_iter, 30,
+                       callback=lambda sv: seen.append((sv.k(), sv.x().copy(), sv.f(), sv.s_norm(), sv.y_norm(), sv.grad().copy())))
+        except osb.MaxIterReached:
+            st = "MaxIterReached"
+        assert s.path_info()["fused"]
+        return st, s.k(), s.termination_reason(), s.x(), s.f(), seen, s.trace()
+
+    n = 2048
+    lb, ub = np.full(n, -0.9), np.full(n, 1.1)
+    cases = ((lambda: osb.BFGS(1e-8, rosen_x0(n, 47)), lambda: osb.ExtendedRosenbrock(n), 41),
+             (lambda: osb.BFGS(1e-7, np.zeros(512)), lambda: osb.SeparableQuadratic.generated(512), 300),
+             (lambda: osb.DFP(1e-8, rosen_x0(n, 48)), lambda: osb.ExtendedRosenbrock(n), 20),
+             (lambda: osb.BFGSB(1e-8, np.clip(rosen_x0(n, 49), lb, ub), lb, ub), lambda: osb.ExtendedRosenbrock(n), 19))
+    for mk, obj_fn, mi in cases:
+        a = go(0, mk, obj_fn, mi)
+        b = go(1, mk, obj_fn, mi)
+        assert a[:3] == b[:3] and np.array_equal(a[3], b[3]) and a[4] == b[4]
+        assert len(a[5]) == len(b[5]) == a[1]
+        for (ka, xa, fa, sa, ya, ga), (kb, xb, fb, sb, yb, gb) in zip(a[5], b[5]):
+            assert ka == kb and np.array_equal(xa, xb) and fa == fb and sa == sb and ya == yb and np.array_equal(ga, gb)
+        for key in ("f", "t"):
+            assert np.array_equal(a[6][key], b[6][key])
+
+
 @pytest.mark.parametrize("kind", ["BFGS", "DFP"])
 def test_packed_symmetric_storage_matches_full_storage(osb, orc, kind):
     """qn_storage = 1: only the lower triangle of H lives in HBM (n^2 * 8 B per iteration); transposed
