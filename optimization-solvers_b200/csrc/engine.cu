@@ -287,9 +287,10 @@ Solver::~Solver() {
   pool_put(1, 2 * sizeof(DevState), cb_snap);
   pool_put(1, 2 * sizeof(double) * (size_t)ld, cb_xsnap);
   pool_put(1, 2 * sizeof(double) * (size_t)ld, cb_gsnap);
-  pool_put(1, 2 * 16 * 2 * sizeof(double) * (size_t)ld, snap_x);
-  pool_put(1, 2 * 16 * sizeof(DevState), snap_st);
+  pool_put(0, 2 * 16 * 2 * sizeof(double) * (size_t)ld, snap_x);
+  pool_put(0, 2 * 16 * sizeof(DevState), snap_st);
   pool_put(1, 2 * 16 * sizeof(unsigned long long), snap_flag);
+  if (snap_stream) cudaStreamDestroy(snap_stream);
   pool_put(0, sizeof(LSParams), d_ls_buf);
   pool_put(1, 2 * sizeof(DevState), poll_snap);
   if (d_iter_prof) cudaFree(d_iter_prof);
@@ -942,8 +943,10 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
   last_p2p = epi_p2p;
   // whole iterations in one cooperative kernel (qn_iter.cu): packed lazy schedule on one GPU or sharded by tile pairs
   // (auto: on several GPUs, where it removes the fold / exchange kernel, the replicated cluster head and two launch
-  //  boundaries per iteration; on one GPU the three-launch path is still ~3 % faster because the stand-alone pass kernel
-  //  compiles to a tighter loop — profiles/r02_fused_iteration.md)
+  //  boundaries per iteration.  On one GPU the three-launch path is 1-3 % faster without callbacks — the stand-alone pass
+  //  kernel compiles to a tighter loop — and 4 % slower with a per-iteration callback (0.462 against 0.445 ms, the fused
+  //  kernel publishes its snapshots from inside the launch for free, profiles/r02_callbacks.md); auto does NOT switch on
+  //  the presence of a callback, because the two paths sum in different orders and a callback must not change the bits)
   const bool fused_wanted = opt_fused > 0 || (opt_fused < 0 && ctx->world > 1);
   iter_path = fused_wanted && !profile_kernels && qn_schedule == 1 && qn_storage == 1 && h_symmetric &&
               (qn_kind == QN_BFGS || qn_kind == QN_DFP) && (ctx->world == 1 || sym_sharded) && head_variant == 0 &&
@@ -1039,8 +1042,9 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
     OSB_CUDA(cudaEventCreateWithFlags(&cbev[1], cudaEventDisableTiming));
     cb_f_before = h_state->f;
   }
-  // Fused iteration kernel + run-ahead: the kernel itself writes every iteration's snapshot into pinned host memory
-  // (QNIterArgs.snap_*), so a launch still runs SNAP_CHUNK iterations while the host delivers the callbacks behind it.
+  // Fused iteration kernel + run-ahead: the kernel itself writes every iteration's snapshot into a device ring and raises
+  // a flag in pinned host memory (QNIterArgs.snap_*); the host copies the slot out on a side stream.  A launch therefore
+  // still runs SNAP_CHUNK iterations while the host delivers the callbacks behind it.
   constexpr int64_t SNAP_CHUNK = 16;
   struct SnapLaunch {
     int half, count;
@@ -1050,9 +1054,10 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
   SnapLaunch snap_prev{0, 0, 0ULL};
   int snap_half = 0;
   if (snap_mode && !snap_x) {
-    snap_x = (double*)pool_get(1, 2 * SNAP_CHUNK * 2 * sizeof(double) * (size_t)ld);
-    snap_st = (DevState*)pool_get(1, 2 * SNAP_CHUNK * sizeof(DevState));
+    snap_x = (double*)pool_get(0, 2 * SNAP_CHUNK * 2 * sizeof(double) * (size_t)ld);
+    snap_st = (DevState*)pool_get(0, 2 * SNAP_CHUNK * sizeof(DevState));
     snap_flag = (unsigned long long*)pool_get(1, 2 * SNAP_CHUNK * sizeof(unsigned long long));
+    OSB_CUDA(cudaStreamCreateWithFlags(&snap_stream, cudaStreamNonBlocking));
   }
   // delivers the iterations of one launch in order; false = the solve ended inside it (or before it)
   auto deliver_launch = [&](const SnapLaunch& L) -> bool {
@@ -1069,7 +1074,13 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
       }
       std::atomic_thread_fence(std::memory_order_acquire);
       ctx->counters[3]++;
-      const DevState& sn = snap_st[(size_t)L.half * SNAP_CHUNK + j];
+      // the slot is complete in device memory: copy it out beside the running kernel (copy engine, side stream)
+      const size_t slot = (size_t)L.half * SNAP_CHUNK + j;
+      OSB_CUDA(cudaMemcpyAsync(&cb_snap[0], snap_st + slot, sizeof(DevState), cudaMemcpyDeviceToHost, snap_stream));
+      OSB_CUDA(cudaMemcpyAsync(cb_xsnap, snap_x + slot * 2 * ld, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, snap_stream));
+      if (cb) OSB_CUDA(cudaMemcpyAsync(cb_gsnap, snap_x + slot * 2 * ld + ld, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, snap_stream));
+      OSB_CUDA(cudaStreamSynchronize(snap_stream));
+      const DevState& sn = cb_snap[0];
       if (sn.done) return false;
       k = sn.k;
       has_s = has_y = true;
@@ -1078,9 +1089,9 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
       if (record_trace) trace.push_back(TraceRec{cb_f_before, sn.t_last, s_norm, y_norm});
       cb_f_before = sn.f;
       if (cb) {
-        cb_x_mirror = snap_x + ((size_t)L.half * SNAP_CHUNK + j) * 2 * ld;
-        cb_g_mirror = cb_x_mirror + ld;
-        cb_state_mirror = &snap_st[(size_t)L.half * SNAP_CHUNK + j];
+        cb_x_mirror = cb_xsnap;
+        cb_g_mirror = cb_gsnap;
+        cb_state_mirror = &cb_snap[0];
         cb(user, reinterpret_cast<osb_solver*>(this));
         cb_x_mirror = nullptr;
         cb_g_mirror = nullptr;

@@ -298,10 +298,10 @@ struct QNIterArgs {
   const int* wt;    // sharded: flat-partition work table (qn_sym.cuh), 4 ints per CTA then the piece count of every local tile
   double* rowpart;  // sharded: row sums of the tile pieces, [slot][h | w][ld]
   long long* prof;  // optional [16]: ns in head / pass / fold+exchange (CTA 0), iterations, head sub-phases
-  // Run-ahead snapshots for host callbacks / traces (null: none): PINNED HOST memory written from inside the kernel, so a
-  // launch keeps running many iterations while the host delivers ls_solver.rs:104-107's callback from the snapshots.
-  // Iteration j of this launch: x then g at snap_x + j * 2 * ld, the scalars a callback may read at snap_st + j, and
-  // finally (st.release.sys) the flag snap_flag[j] = snap_seq0 + j + 1.
+  // Run-ahead snapshots for host callbacks / traces (null: none), written from inside the kernel so that a launch keeps
+  // running many iterations while the host delivers ls_solver.rs:104-107's callback behind it.  Iteration j of this
+  // launch: x then g at snap_x + j * 2 * ld and the scalars a callback may read at snap_st + j (DEVICE ring), then
+  // (st.release.sys) the flag snap_flag[j] = snap_seq0 + j + 1 in PINNED HOST memory; the host copies the slot out.
   double* snap_x;
   DevState* snap_st;
   unsigned long long* snap_flag;
@@ -390,9 +390,10 @@ struct Solver {
   int opt_fused = -1;
   int opt_flat = -1;             // fused sharded kernel: 1 = flat partition of the rank's tiles (qn_sym.cuh); -1 / 0 = whole tiles per CTA
   bool iter_flat = false;
-  double* snap_x = nullptr;      // pinned ring of in-kernel callback snapshots (2 halves x 16 iterations x {x, g})
-  DevState* snap_st = nullptr;
-  unsigned long long* snap_flag = nullptr;
+  double* snap_x = nullptr;      // device ring of in-kernel callback snapshots (2 halves x 16 iterations x {x, g})
+  DevState* snap_st = nullptr;   // device ring of their scalars
+  unsigned long long* snap_flag = nullptr;  // pinned host flags
+  cudaStream_t snap_stream = nullptr;       // side stream of the copies out of the ring (runs beside the kernel)
   int opt_stream = -1;           // PGD / SPG: one fused kernel per trial step (-1 / 1 = on whenever it applies, 0 = off)
   bool last_stream = false;
   bool iter_path = false;        // this minimize() runs whole iterations in one cooperative kernel

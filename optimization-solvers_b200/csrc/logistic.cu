@@ -109,7 +109,6 @@ constexpr int SY_TILE = 128;   // output tile edge
 constexpr int SY_KC = 16;      // samples per pipeline stage
 constexpr int SY_STAGES = 4;
 constexpr int SY_LD = SY_TILE + 4;  // padded row stride (conflict-free fragment reads)
-constexpr int SY_T = 256;      // 8 warps: 4 (rows) x 2 (cols), 32 x 64 outputs per warp
 constexpr int SY_SPLIT = 4;    // K splits per tile
 
 __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b) {
@@ -132,12 +131,14 @@ struct SyrkSmem {
   double dk[SY_STAGES][SY_KC];
 };
 
-__global__ void __launch_bounds__(SY_T, 1)
+template <int NWC>  // warps along the columns of the tile: 2 (8 warps, 32 x 64 per warp) or 4 (16 warps, 32 x 32 per warp)
+__global__ void __launch_bounds__(128 * NWC, 1)
 syrk_dmma_kernel(int64_t m, int64_t n, const double* __restrict__ X, const double* __restrict__ dcoef, double* __restrict__ Cpart, int ntiles) {
   extern __shared__ __align__(16) unsigned char sy_raw[];
   SyrkSmem& sm = *reinterpret_cast<SyrkSmem*>(sy_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wr = warp >> 1, wc = warp & 1;  // warp tile origin: rows wr*32, cols wc*64
+  constexpr int NT = 128 * NWC, WCOLS = SY_TILE / NWC, NB = WCOLS / 8;
+  const int wr = warp / NWC, wc = warp % NWC;  // warp tile origin: rows wr * 32, cols wc * WCOLS
   const int64_t kper = ((m + SY_SPLIT - 1) / SY_SPLIT + SY_KC - 1) / SY_KC * SY_KC;  // samples per split (whole stages)
   const int nunits = ntiles * SY_SPLIT;
   for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
@@ -152,19 +153,19 @@ syrk_dmma_kernel(int64_t m, int64_t n, const double* __restrict__ X, const doubl
     const int64_t i0 = (int64_t)ti * SY_TILE, j0 = (int64_t)tj * SY_TILE;
     const int64_t kbeg = (int64_t)split * kper, kend = kbeg + kper < m ? kbeg + kper : m;
     const int npanels = kend > kbeg ? (int)((kend - kbeg + SY_KC - 1) / SY_KC) : 0;
-    double acc[4][8][2];
+    double acc[4][NB][2];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int b = 0; b < 8; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+      for (int b = 0; b < NB; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
     // one stage = SY_KC rows x 128 doubles per operand = 1024 16-byte chunks per operand, 4 (+4) per thread
     auto issue = [&](int p) {
       if (p < npanels) {
         const int st = p % SY_STAGES;
         const int64_t k0 = kbeg + (int64_t)p * SY_KC;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int chunk = tid + c * SY_T;  // 0..1023
+        for (int c = 0; c < 1024 / NT; ++c) {
+          const int chunk = tid + c * NT;  // 0..1023
           const int kk = chunk >> 6;         // 64 chunks per row
           const int cc = (chunk & 63) * 2;
           const int64_t k = k0 + kk;
@@ -189,17 +190,17 @@ syrk_dmma_kernel(int64_t m, int64_t n, const double* __restrict__ X, const doubl
       const double (*Bs)[SY_LD] = diag ? sm.A[st] : sm.B[st];
 #pragma unroll
       for (int k4 = 0; k4 < SY_KC / 4; ++k4) {
-        double af[4], bf[8];
+        double af[4], bf[NB];
         const int kr = k4 * 4 + (lane & 3);
         const double dkv = sm.dk[st][kr];
 #pragma unroll
         for (int a = 0; a < 4; ++a) af[a] = As[kr][wr * 32 + a * 8 + (lane >> 2)] * dkv;
 #pragma unroll
-        for (int b = 0; b < 8; ++b) bf[b] = Bs[kr][wc * 64 + b * 8 + (lane >> 2)];
+        for (int b = 0; b < NB; ++b) bf[b] = Bs[kr][wc * WCOLS + b * 8 + (lane >> 2)];
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
-          for (int b = 0; b < 8; ++b) dmma_884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+          for (int b = 0; b < NB; ++b) dmma_884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
       }
     }
     // this unit's partial tile (row-major 128 x 128)
@@ -207,9 +208,9 @@ syrk_dmma_kernel(int64_t m, int64_t n, const double* __restrict__ X, const doubl
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int b = 0; b < 8; ++b) {
+      for (int b = 0; b < NB; ++b) {
         const int r = wr * 32 + a * 8 + (lane >> 2);
-        const int c = wc * 64 + b * 8 + (lane & 3) * 2;
+        const int c = wc * WCOLS + b * 8 + (lane & 3) * 2;
         *reinterpret_cast<double2*>(out + r * SY_TILE + c) = make_double2(acc[a][b][0], acc[a][b][1]);
       }
   }
@@ -250,10 +251,12 @@ __global__ void __launch_bounds__(256) syrk_reduce_kernel(int64_t n, const doubl
 }
 
 constexpr size_t SY_SMEM = sizeof(SyrkSmem);
+static int g_syrk_warps = 8;  // warps per CTA (bench hook: a negative `reps` of osb_bench_syrk selects 16)
 static void syrk_set_smem() {
   static bool done = false;
   if (!done) {
-    OSB_CUDA(cudaFuncSetAttribute(syrk_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM));
+    OSB_CUDA(cudaFuncSetAttribute(syrk_dmma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM));
+    OSB_CUDA(cudaFuncSetAttribute(syrk_dmma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM));
     done = true;
   }
 }
@@ -268,7 +271,8 @@ static void syrk_launch(Ctx* ctx, int64_t m, int64_t n, const double* X, const d
   syrk_set_smem();
   const int ntiles = syrk_ntiles(n);
   const int grid = std::min(ctx->num_sms, ntiles * SY_SPLIT);
-  syrk_dmma_kernel<<<grid, SY_T, SY_SMEM, ctx->stream>>>(m, n, X, dc, part, ntiles);
+  if (g_syrk_warps == 16) syrk_dmma_kernel<4><<<grid, 512, SY_SMEM, ctx->stream>>>(m, n, X, dc, part, ntiles);
+  else syrk_dmma_kernel<2><<<grid, 256, SY_SMEM, ctx->stream>>>(m, n, X, dc, part, ntiles);
   syrk_reduce_kernel<<<ntiles, 256, 0, ctx->stream>>>(n, part, ntiles, lambda, add_lambda, hess, ldc);
   ctx->counters[0] += 2;
 }
@@ -350,6 +354,8 @@ double bench_syrk_dmma(Ctx* ctx, Objective* obj, int reps) {
   auto* o = dynamic_cast<LogisticObjective*>(obj);
   OSB_REQUIRE(o != nullptr, OSB_ERROR_INPUT_PARAMS, "not a logistic objective");
   const int64_t n = o->n, ldc = qn_ld(n);
+  g_syrk_warps = reps < 0 ? 16 : 8;
+  if (reps < 0) reps = -reps;
   DBuf hess(qn_rows_padded(n) * ldc), w(ldc);
   w.zero(ctx->stream);
   logit_margin_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(o->m, n, o->X.p, o->ysign.p, w.p, o->loss.p, o->gc.p, o->dc.p);

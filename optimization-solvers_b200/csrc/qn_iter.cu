@@ -284,7 +284,10 @@ __device__ __forceinline__ void iter_fold(const QNIterArgs& a, IterSmem& sm, int
   __syncthreads();
 }
 
-// scalars of the snapshot + its flag (one thread of the leader CTA; x and g were stored by their owners before the grid sum)
+// scalars of the snapshot (device ring) + its flag (the ONLY store to host memory: SM stores of the 256 KB of x and g to
+// pinned memory plus a system fence per CTA cost 45 us per iteration, profiles/r02_callbacks.md; the host copies the
+// slot out with a DMA on a side stream once it sees the flag).  One thread of the leader CTA; x and g were stored by
+// their owners before the grid barrier.
 __device__ __noinline__ void iter_publish(const QNIterArgs& a, const IterCarry& c, int slot) {
   DevState* h = a.snap_st + slot;
   h->f = c.f0;
@@ -651,7 +654,7 @@ __device__ __noinline__ int iter_head(const QNIterArgs& a, const Fn& fn, IterSme
       a.y[i] = yi;
       a.x[i] = xn[jq];
       a.g[i] = gn[jq];
-      if (a.snap_x != nullptr) {  // this iteration's snapshot for the host callback (pinned host memory)
+      if (a.snap_x != nullptr) {  // this iteration's snapshot for the host callback (device ring, copied out by a DMA)
         double* sx = a.snap_x + (int64_t)snap_in * 2 * a.ld;
         sx[i] = xn[jq];
         sx[a.ld + i] = gn[jq];
@@ -662,10 +665,6 @@ __device__ __noinline__ int iter_head(const QNIterArgs& a, const Fn& fn, IterSme
     }
   }
   iter_submark(a, sm, 10);
-  if (a.snap_x != nullptr) {  // one system fence per CTA, ordered after every thread's snapshot stores by the barrier and
-    __syncthreads();          // before this CTA's contribution to the grid sum below by the next one
-    if (tid == 0) __threadfence_system();
-  }
   __syncthreads();  // sm.res of the line search has been consumed by every thread
   warp_put(sm, 0, a4[0], wact);
   warp_put(sm, 1, a4[1], wact);
@@ -697,7 +696,7 @@ __device__ __noinline__ int iter_head(const QNIterArgs& a, const Fn& fn, IterSme
     if (tid == 0) c.p = p_local;
   }
   __syncthreads();
-  // the grid sum above completed => every CTA's snapshot stores are fenced: the leader publishes the iteration
+  // the grid barrier of the sum above ordered every CTA's snapshot stores before this point: the leader publishes
   if (a.snap_st != nullptr && cta == 0 && tid == 0) iter_publish(a, c, snap_in);
   return 0;
 }

@@ -640,8 +640,9 @@ def test_run_ahead_callbacks_deliver_the_same_sequence(osb):
 
 
 def test_fused_kernel_publishes_callback_snapshots_from_inside_the_launch(osb):
-    """fused_iteration = 1 with run-ahead callbacks: the kernel writes every iteration's x, g, f, k, norms into a pinned
-    host ring and keeps running (16 iterations per launch) while the host delivers the callbacks behind it.  The sequence
+    """fused_iteration = 1 with run-ahead callbacks: the kernel writes every iteration's x, g, f, k, norms into a device
+    ring, raises a flag in pinned host memory and keeps running (16 iterations per launch) while the host copies the slot
+    out on a side stream and delivers the callbacks behind it.  The sequence
     the callback sees, the trace and the final state equal the stalling delivery (one iteration per launch) bit for bit:
     a run that hits max_iter across several launches, one that converges inside a launch, and a bounded solver."""
     def go(run_ahead, mk_solver, obj_fn, max_iter):
