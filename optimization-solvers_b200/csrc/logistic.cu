@@ -102,12 +102,10 @@ __global__ void __launch_bounds__(LG_T) logit_grad_stage2(int64_t n, int64_t nsp
 // instead of 1/15 (2080 lower-triangular 128 x 128 tiles do not divide by 148 SMs).  Each unit accumulates its K range
 // for one tile and stores a partial tile; a second kernel adds the SY_SPLIT partials of every element in split order
 // (deterministic), adds lambda on the diagonal and mirrors into the upper triangle.
-// Operands move global -> shared with 16-byte cp.async in a 4-stage ring (no register staging); the Hessian weights d_k
+// Operands move global -> shared with 16-byte cp.async in a ring of SY_STAGES stages of SY_KC samples (no register staging); the Hessian weights d_k
 // multiply the A fragments as they are read from shared memory, so both panels are raw rows of X and a diagonal tile
 // loads only one.
 constexpr int SY_TILE = 128;   // output tile edge
-constexpr int SY_KC = 16;      // samples per pipeline stage
-constexpr int SY_STAGES = 4;
 constexpr int SY_LD = SY_TILE + 4;  // padded row stride (conflict-free fragment reads)
 constexpr int SY_SPLIT = 4;    // K splits per tile
 
@@ -125,21 +123,25 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+template <int KC, int STAGES>
 struct SyrkSmem {
-  double A[SY_STAGES][SY_KC][SY_LD];
-  double B[SY_STAGES][SY_KC][SY_LD];
-  double dk[SY_STAGES][SY_KC];
+  double A[STAGES][KC][SY_LD];
+  double B[STAGES][KC][SY_LD];
+  double dk[STAGES][KC];
 };
 
-template <int NWC>  // warps along the columns of the tile: 2 (8 warps, 32 x 64 per warp) or 4 (16 warps, 32 x 32 per warp)
+// NWC: warps along the columns of the tile: 2 (8 warps, 32 x 64 per warp) or 4 (16 warps, 32 x 32 per warp);
+// KC samples per pipeline stage, STAGES stages
+template <int NWC, int KC, int STAGES>
 __global__ void __launch_bounds__(128 * NWC, 1)
 syrk_dmma_kernel(int64_t m, int64_t n, const double* __restrict__ X, const double* __restrict__ dcoef, double* __restrict__ Cpart, int ntiles) {
   extern __shared__ __align__(16) unsigned char sy_raw[];
-  SyrkSmem& sm = *reinterpret_cast<SyrkSmem*>(sy_raw);
+  using Smem = SyrkSmem<KC, STAGES>;
+  Smem& sm = *reinterpret_cast<Smem*>(sy_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NT = 128 * NWC, WCOLS = SY_TILE / NWC, NB = WCOLS / 8;
   const int wr = warp / NWC, wc = warp % NWC;  // warp tile origin: rows wr * 32, cols wc * WCOLS
-  const int64_t kper = ((m + SY_SPLIT - 1) / SY_SPLIT + SY_KC - 1) / SY_KC * SY_KC;  // samples per split (whole stages)
+  const int64_t kper = ((m + SY_SPLIT - 1) / SY_SPLIT + KC - 1) / KC * KC;  // samples per split (whole stages)
   const int nunits = ntiles * SY_SPLIT;
   for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
     const int split = u / ntiles;
@@ -152,20 +154,20 @@ syrk_dmma_kernel(int64_t m, int64_t n, const double* __restrict__ X, const doubl
     const bool diag = ti == tj;
     const int64_t i0 = (int64_t)ti * SY_TILE, j0 = (int64_t)tj * SY_TILE;
     const int64_t kbeg = (int64_t)split * kper, kend = kbeg + kper < m ? kbeg + kper : m;
-    const int npanels = kend > kbeg ? (int)((kend - kbeg + SY_KC - 1) / SY_KC) : 0;
+    const int npanels = kend > kbeg ? (int)((kend - kbeg + KC - 1) / KC) : 0;
     double acc[4][NB][2];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int b = 0; b < NB; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-    // one stage = SY_KC rows x 128 doubles per operand = 1024 16-byte chunks per operand, 4 (+4) per thread
+    // one stage = KC rows x 128 doubles per operand = 64 KC 16-byte chunks per operand
     auto issue = [&](int p) {
       if (p < npanels) {
-        const int st = p % SY_STAGES;
-        const int64_t k0 = kbeg + (int64_t)p * SY_KC;
+        const int st = p % STAGES;
+        const int64_t k0 = kbeg + (int64_t)p * KC;
 #pragma unroll
-        for (int c = 0; c < 1024 / NT; ++c) {
-          const int chunk = tid + c * NT;  // 0..1023
+        for (int c = 0; c < KC * 64 / NT; ++c) {
+          const int chunk = tid + c * NT;  // 0 .. 64 KC - 1
           const int kk = chunk >> 6;         // 64 chunks per row
           const int cc = (chunk & 63) * 2;
           const int64_t k = k0 + kk;
@@ -174,22 +176,22 @@ syrk_dmma_kernel(int64_t m, int64_t n, const double* __restrict__ X, const doubl
           cp_async16(&sm.A[st][kk][cc], X + krow * n + i0 + cc, kok && i0 + cc < n);
           if (!diag) cp_async16(&sm.B[st][kk][cc], X + krow * n + j0 + cc, kok && j0 + cc < n);
         }
-        if (tid < SY_KC) sm.dk[st][tid] = (k0 + tid < kend) ? dcoef[k0 + tid] : 0.0;
+        if (tid < KC) sm.dk[st][tid] = (k0 + tid < kend) ? dcoef[k0 + tid] : 0.0;
       }
       cp_async_commit();  // (an empty group keeps the group count in step with the panel count)
     };
     __syncthreads();  // the previous unit's readers are done with the ring
 #pragma unroll
-    for (int p = 0; p < SY_STAGES - 1; ++p) issue(p);
+    for (int p = 0; p < STAGES - 1; ++p) issue(p);
     for (int p = 0; p < npanels; ++p) {
-      cp_async_wait<SY_STAGES - 2>();  // panel p has landed (this thread's copies) ...
+      cp_async_wait<STAGES - 2>();  // panel p has landed (this thread's copies) ...
       __syncthreads();                 // ... and everybody's; stage (p - 1) % STAGES is free again
-      issue(p + SY_STAGES - 1);
-      const int st = p % SY_STAGES;
+      issue(p + STAGES - 1);
+      const int st = p % STAGES;
       const double (*As)[SY_LD] = sm.A[st];
       const double (*Bs)[SY_LD] = diag ? sm.A[st] : sm.B[st];
 #pragma unroll
-      for (int k4 = 0; k4 < SY_KC / 4; ++k4) {
+      for (int k4 = 0; k4 < KC / 4; ++k4) {
         double af[4], bf[NB];
         const int kr = k4 * 4 + (lane & 3);
         const double dkv = sm.dk[st][kr];
@@ -250,13 +252,12 @@ __global__ void __launch_bounds__(256) syrk_reduce_kernel(int64_t n, const doubl
   }
 }
 
-constexpr size_t SY_SMEM = sizeof(SyrkSmem);
-static int g_syrk_warps = 8;  // warps per CTA (bench hook: a negative `reps` of osb_bench_syrk selects 16)
+constexpr int SY_KC = 48, SY_STAGES = 2;  // measured at m = 262144: 16 x 4 stages 28.5, 32 x 3 29.8, 48 x 2 30.6 TFLOP/s (one CTA barrier per stage)
+constexpr size_t SY_SMEM = sizeof(SyrkSmem<SY_KC, SY_STAGES>);
 static void syrk_set_smem() {
   static bool done = false;
   if (!done) {
-    OSB_CUDA(cudaFuncSetAttribute(syrk_dmma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM));
-    OSB_CUDA(cudaFuncSetAttribute(syrk_dmma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM));
+    OSB_CUDA(cudaFuncSetAttribute(syrk_dmma_kernel<2, SY_KC, SY_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM));
     done = true;
   }
 }
@@ -271,8 +272,7 @@ static void syrk_launch(Ctx* ctx, int64_t m, int64_t n, const double* X, const d
   syrk_set_smem();
   const int ntiles = syrk_ntiles(n);
   const int grid = std::min(ctx->num_sms, ntiles * SY_SPLIT);
-  if (g_syrk_warps == 16) syrk_dmma_kernel<4><<<grid, 512, SY_SMEM, ctx->stream>>>(m, n, X, dc, part, ntiles);
-  else syrk_dmma_kernel<2><<<grid, 256, SY_SMEM, ctx->stream>>>(m, n, X, dc, part, ntiles);
+  syrk_dmma_kernel<2, SY_KC, SY_STAGES><<<grid, 256, SY_SMEM, ctx->stream>>>(m, n, X, dc, part, ntiles);
   syrk_reduce_kernel<<<ntiles, 256, 0, ctx->stream>>>(n, part, ntiles, lambda, add_lambda, hess, ldc);
   ctx->counters[0] += 2;
 }
@@ -354,8 +354,6 @@ double bench_syrk_dmma(Ctx* ctx, Objective* obj, int reps) {
   auto* o = dynamic_cast<LogisticObjective*>(obj);
   OSB_REQUIRE(o != nullptr, OSB_ERROR_INPUT_PARAMS, "not a logistic objective");
   const int64_t n = o->n, ldc = qn_ld(n);
-  g_syrk_warps = reps < 0 ? 16 : 8;
-  if (reps < 0) reps = -reps;
   DBuf hess(qn_rows_padded(n) * ldc), w(ldc);
   w.zero(ctx->stream);
   logit_margin_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(o->m, n, o->X.p, o->ysign.p, w.p, o->loss.p, o->gc.p, o->dc.p);
