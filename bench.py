@@ -412,8 +412,6 @@ def apply_debug_options(solver, args):
         solver.set_option("qn_storage", 1 if args.storage == "sym" else 0)
     if args.qn_kernel is not None:
         solver.set_option("qn_kernel", args.qn_kernel)
-    if args.flat:
-        solver.set_option("flat_partition", 1)
     if args.head is not None:
         solver.set_option("head_kernel", args.head)
     if args.engine is not None:
@@ -639,7 +637,7 @@ def run_c3(args, env):
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload, "n": n, "line_search": "BackTracking(1e-4,0.5)", "tol": TOL,
                            "max_iter_line_search": MAX_LS, "options_set": "none (library defaults)" if not any(
-                               v is not None for v in (args.schedule, args.storage, args.qn_kernel, args.head, args.engine)) and not args.no_fused and not args.fused and not args.flat else "debug flags",
+                               v is not None for v in (args.schedule, args.storage, args.qn_kernel, args.head, args.engine)) and not args.no_fused and not args.fused else "debug flags",
                            "kernel": info["kernel"],
                            "engine": info["engine"], "schedule": info["schedule_name"], "storage": info["storage_name"],
                            "l2": "inputs larger than L2 (H = %.2f GiB per GPU, streamed every step)" % (
@@ -802,7 +800,6 @@ def main():
     ap.add_argument("--config", default="C3", choices=sorted(METRICS))
     ap.add_argument("--n", type=int, default=N_DIM, help="C3 problem dimension (the benchmark line is only valid at 16384)")
     ap.add_argument("--m", type=int, default=1 << 20, help="C5a sample count")
-    ap.add_argument("--flat", action="store_true", help="debug: flat partition of a rank's tiles in the fused multi-GPU kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batched", action="store_true")
     ap.add_argument("--cpu-threads", type=int, default=0, help="cpu_baseline leg: 1 = the reference's own threading, 0 = all host cores")

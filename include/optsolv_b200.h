@@ -240,8 +240,6 @@ int osb_minimize(osb_solver* s, osb_linesearch* ls, osb_objective* obj, int64_t 
  *                        storage: bit 0 = two 256-thread CTAs per SM, bit 1 = ping-pong (out-of-place) storage,
  *                        bit 2 = zero-first column partials (round-1 behaviour), bit 3 = shared-memory ring fed by
  *                        cp.async.bulk (bit-identical to 0; measured 5 % slower, profiles/r02_packed_pass_experiments.md)
- *   "flat_partition"     fused iteration kernel on several GPUs: 1 = every CTA gets an equal range of 1024-column steps of
- *                        the rank's tiles (tiles cut into pieces), -1 / 0 = (default) whole tiles dealt in snake order
  *   "fused_iteration"    whole outer iterations in ONE cooperative kernel (lazy schedule on packed storage under
  *                        device-resident control: line search on every SM, H pass, fold and multi-GPU exchange separated by
  *                        grid barriers only): -1 = auto (default: on with several GPUs, off with one), 1 = on, 0 = one launch

@@ -410,7 +410,6 @@ int osb_solver_set_option(osb_solver* s, const char* name, int64_t value) {
   else if (nm == "record_trace") S(s)->record_trace = (int)value;
   else if (nm == "callback_run_ahead") S(s)->callback_run_ahead = (int)value;
   else if (nm == "qn_kernel") S(s)->qn_variant = (int)value;
-  else if (nm == "flat_partition") S(s)->opt_flat = (int)value;
   else if (nm == "qn_schedule") S(s)->opt_schedule = (int)value;
   else if (nm == "qn_storage") S(s)->opt_storage = (int)value;
   else if (nm == "use_p2p") S(s)->use_p2p = (int)value;

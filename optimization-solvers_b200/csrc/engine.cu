@@ -963,22 +963,6 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
       gpart.alloc_pooled(qn_iter_gpart_doubles(ctx));
       gpart.zero(stm);
     }
-    // how a rank's tiles are spread over the CTAs: whole tiles in snake order (auto), or the flat partition (equal column
-    // steps per CTA, tiles cut into pieces; option flat_partition = 1).  Measured (profiles/r02_scaling.md): the flat
-    // partition balances the pass but its fold reads and re-zeroes every CTA's whole partial vector and sums piece slots.
-    iter_flat = sym_sharded && opt_flat > 0;
-    if (iter_flat) {
-      if (iter_wt.p == nullptr) {  // flat partition of this rank's tiles over the CTAs (built once per solver)
-        std::vector<int> tab;
-        const int slots = qn_iter_build_worktable(ctx, n, tab);
-        iter_wt.alloc_pooled((int64_t)(tab.size() + 1) / 2 + 1);
-        OSB_CUDA(cudaMemcpyAsync(iter_wt.p, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice, stm));
-        ctx->sync();  // (tab is a local)
-        rowpart.alloc_pooled((int64_t)slots * 2 * ld);
-        rowpart.zero(stm);
-      }
-      colpart.zero(stm);  // the flat pass adds into zeroed column partials (the fold leaves them zeroed again)
-    }
     if (profile_iter && !d_iter_prof) {
       OSB_CUDA(cudaMalloc(&d_iter_prof, 16 * sizeof(long long)));
     }
@@ -1013,8 +997,6 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
     a.rank = sym_sharded ? ctx->rank : 0;
     a.peers = sym_sharded ? ctx->d_peers : nullptr;
     a.seq = ctx->d_seq;
-    a.wt = iter_flat ? reinterpret_cast<const int*>(iter_wt.p) : nullptr;
-    a.rowpart = iter_flat ? rowpart.p : nullptr;
     a.prof = profile_iter ? d_iter_prof : nullptr;
     iter_args = a;
     iter_fn_kind = obj->functor_kind();

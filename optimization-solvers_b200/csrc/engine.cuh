@@ -295,8 +295,6 @@ struct QNIterArgs {
   int world, rank;
   double* const* peers;
   unsigned long long* seq;
-  const int* wt;    // sharded: flat-partition work table (qn_sym.cuh), 4 ints per CTA then the piece count of every local tile
-  double* rowpart;  // sharded: row sums of the tile pieces, [slot][h | w][ld]
   long long* prof;  // optional [16]: ns in head / pass / fold+exchange (CTA 0), iterations, head sub-phases
   // Run-ahead snapshots for host callbacks / traces (null: none), written from inside the kernel so that a launch keeps
   // running many iterations while the host delivers ls_solver.rs:104-107's callback behind it.  Iteration j of this
@@ -311,7 +309,6 @@ struct QNIterArgs {
 bool qn_iter_supported(Ctx* ctx, int functor_kind, int64_t n, int world);
 int qn_iter_grid(Ctx* ctx);
 int64_t qn_iter_gpart_doubles(Ctx* ctx);
-int qn_iter_build_worktable(Ctx* ctx, int64_t n, std::vector<int>& table);  // flat partition of this rank's tiles; returns the piece slots needed
 void qn_launch_iter(Ctx* ctx, int functor_kind, const double* fn_a, const double* fn_b, bool bounded, int ls_kind, const QNIterArgs& a);
 // apply a pending update to the stored matrix (getters, engine switches)
 void qn_launch_flush(Ctx* ctx, int kind, double* M, int64_t ld, int64_t nrows, int64_t row0, DevState* st, const double* ps,
@@ -388,8 +385,6 @@ struct Solver {
   bool sym_pingpong_dirty = false;
   // fused iteration kernel (qn_iter.cu): -1 = auto (on whenever it applies), 0 = off (one launch per phase)
   int opt_fused = -1;
-  int opt_flat = -1;             // fused sharded kernel: 1 = flat partition of the rank's tiles (qn_sym.cuh); -1 / 0 = whole tiles per CTA
-  bool iter_flat = false;
   double* snap_x = nullptr;      // device ring of in-kernel callback snapshots (2 halves x 16 iterations x {x, g})
   DevState* snap_st = nullptr;   // device ring of their scalars
   unsigned long long* snap_flag = nullptr;  // pinned host flags
@@ -402,7 +397,6 @@ struct Solver {
   const double* iter_fn_a = nullptr;
   const double* iter_fn_b = nullptr;
   DBuf gpart;                    // grid-reduction partials
-  DBuf iter_wt, rowpart;         // sharded: work table of the flat partition, row sums of the tile pieces
   long long* d_iter_prof = nullptr;  // option "profile_iter": ns in head / pass / fold (CTA 0) and iterations
   int profile_iter = 0;
   void ensure_packed();          // the packed copy holds the current matrix (identity / pack on first use)

@@ -193,9 +193,9 @@ __device__ __forceinline__ unsigned long long* iter_flags(double* region, int wo
 
 // h, w of the fold: columns [j0, j0 + cw) of this CTA.  One GPU: written in place over the row sums.  Sharded: this
 // rank's contribution goes into slot `rank` of every rank's exchange region, then the chunk flags.
-template <int SH>  // 0: one GPU, 1: sharded by tile pairs, whole tiles dealt to the CTAs, 2: sharded, flat partition (qn_sym.cuh)
+template <int SH>  // 0: one GPU, 1: packed triangle sharded by tile pairs over the ranks
 __device__ __forceinline__ void iter_fold(const QNIterArgs& a, IterSmem& sm, int64_t j0, int cw, unsigned long long seq, DevState* st) {
-  constexpr bool SHARDED = SH != 0, FLAT = SH == 2;
+  constexpr bool SHARDED = SH != 0;
   const int G = (int)gridDim.x;
   const int cwp = cw / 2;
   int cwpp = 1;
@@ -221,16 +221,11 @@ __device__ __forceinline__ void iter_fold(const QNIterArgs& a, IterSmem& sm, int
         acc.x = acc.x + v[k].x;
         acc.y = acc.y + v[k].y;
       }
-      if (FLAT) {  // flat partition: the pass adds into zeroed partials; this thread is the only reader of these words
-#pragma unroll
-        for (int k = 0; k < 8; ++k) *reinterpret_cast<double2*>(const_cast<double*>(src) + (int64_t)(c + k) * 2 * a.ld) = make_double2(0.0, 0.0);
-      }
     }
     for (; c < ce; ++c) {
       const double2 v = j < sm.ext[c] ? __ldcg(reinterpret_cast<const double2*>(src + (int64_t)c * 2 * a.ld)) : make_double2(0.0, 0.0);
       acc.x = acc.x + v.x;
       acc.y = acc.y + v.y;
-      if (FLAT) *reinterpret_cast<double2*>(const_cast<double*>(src) + (int64_t)c * 2 * a.ld) = make_double2(0.0, 0.0);
     }
   }
   __syncthreads();
@@ -245,21 +240,10 @@ __device__ __forceinline__ void iter_fold(const QNIterArgs& a, IterSmem& sm, int
     }
     double* rowarr = vec == 0 ? a.h : a.w;
     double2 rs = make_double2(0.0, 0.0);
-    if (SHARDED) {  // the row sums of rows j, j + 1 exist on this rank only when it owns their tile: its pieces' slots, in order
+    if (SHARDED) {  // the row sums of rows j, j + 1 exist on this rank only when it owns their tile: 
       const int64_t T = (a.n + QN_R - 1) / QN_R, tile = j / QN_R;
       const int64_t pairi = tile < T / 2 ? tile : T - 1 - tile;
-      if ((pairi % a.world) == a.rank) {
-        if (FLAT) {
-          const int np = a.wt[4 * (int)gridDim.x + (int)symsh_pos_of(T, a.world, a.rank, tile)];
-          for (int sl = 0; sl < np; ++sl) {
-            const double2 v = __ldcg(reinterpret_cast<const double2*>(a.rowpart + ((int64_t)sl * 2 + vec) * a.ld + j));
-            rs.x = rs.x + v.x;
-            rs.y = rs.y + v.y;
-          }
-        } else {
-          rs = __ldcg(reinterpret_cast<const double2*>(rowarr + j));
-        }
-      }
+      if ((pairi % a.world) == a.rank) rs = __ldcg(reinterpret_cast<const double2*>(rowarr + j));
     } else {
       rs = __ldcg(reinterpret_cast<const double2*>(rowarr + j));
     }
@@ -805,7 +789,7 @@ __device__ __noinline__ void iter_mark(const QNIterArgs& a, IterSmem& sm, int sl
 
 template <class Fn, bool BOUNDED, bool BT, int SH, int KIND>
 __global__ void __launch_bounds__(IT_NT, 1) qn_iter_kernel(const __grid_constant__ QNIterArgs a, const __grid_constant__ Fn fn) {
-  constexpr bool SHARDED = SH != 0, FLAT = SH == 2;
+  constexpr bool SHARDED = SH != 0;
   cg::grid_group grid = cg::this_grid();
   __shared__ IterSmem sm;
   if (a.st->done) return;
@@ -814,10 +798,9 @@ __global__ void __launch_bounds__(IT_NT, 1) qn_iter_kernel(const __grid_constant
   __syncthreads();
   {
     const int64_t T = (a.n + QN_R - 1) / QN_R;
-    // whole tiles per CTA: partial vector q is valid on the columns below the first row of CTA q's first tile; flat
-    // partition: the partials are zeroed by the fold, every column is valid
+    // partial vector q is valid on the columns below the first row of CTA q's first tile
     for (int q = threadIdx.x; q < (int)gridDim.x; q += IT_NT)
-      sm.ext[q] = FLAT ? 0x7fffffff : (int)sym_first_row<SHARDED>(T, a.world, a.rank, (int)gridDim.x, q);
+      sm.ext[q] = (int)sym_first_row<SHARDED>(T, a.world, a.rank, (int)gridDim.x, q);
   }
   grid.sync();  // every CTA has read the entry state before anybody can write it
   // (time stamps live in shared memory, not in registers: nothing but &c and the loop counter is live across the pass)
@@ -848,8 +831,7 @@ __global__ void __launch_bounds__(IT_NT, 1) qn_iter_kernel(const __grid_constant
         la.h = a.h;
         la.w = a.w;
         const QNSymArgs sa{a.P, a.P, a.colpart, a.n, a.ld, SHARDED ? a.world : 1, SHARDED ? a.rank : 0, a.peers, a.seq, (int)gridDim.x, 0};
-        if (FLAT) sym_pass_body<KIND, true, IT_NT, false, false, true>(la, sa, sm.c.pc0, sm.c.pc1, sm.c.pc2, 0, (int)gridDim.x, (int)blockIdx.x, a.wt, a.rowpart);
-        else sym_pass_body<KIND, SHARDED, IT_NT, false, false>(la, sa, sm.c.pc0, sm.c.pc1, sm.c.pc2, 0, (int)gridDim.x, (int)blockIdx.x);
+        sym_pass_body<KIND, SHARDED, IT_NT, false, false>(la, sa, sm.c.pc0, sm.c.pc1, sm.c.pc2, 0, (int)gridDim.x, (int)blockIdx.x);
       }
       grid.sync();
       iter_mark(a, sm, 1);
@@ -895,45 +877,6 @@ double bench_grid_sync(Ctx* ctx, int reps) {
   ctx->sync();
   cudaFree(d_out);
   return (double)ns * 1e-3 / reps;  // us per barrier
-}
-
-// flat partition of this rank's tiles over the CTAs of the fused kernel (layout: qn_sym.cuh)
-int qn_iter_build_worktable(Ctx* ctx, int64_t n, std::vector<int>& tab) {
-  const int G = qn_iter_grid(ctx);
-  const int64_t T = (n + QN_R - 1) / QN_R;
-  const int64_t ntl = 2 * symsh_local_pairs(T, ctx->world, ctx->rank);
-  std::vector<int> steps((size_t)ntl);
-  int64_t S = 0;
-  for (int64_t q = 0; q < ntl; ++q) {
-    steps[(size_t)q] = sym_tile_steps(symsh_tile_at(T, ctx->world, ctx->rank, q), n, IT_NT);
-    S += steps[(size_t)q];
-  }
-  tab.assign((size_t)(4 * G + ntl), 0);
-  int64_t q = 0;
-  int s = 0;
-  for (int c = 0; c < G; ++c) {
-    int64_t cnt = (int64_t)(c + 1) * S / G - (int64_t)c * S / G;
-    tab[4 * c] = (int)q;
-    tab[4 * c + 1] = s;
-    tab[4 * c + 2] = (int)cnt;
-    tab[4 * c + 3] = q < ntl ? tab[(size_t)(4 * G + q)] : 0;  // pieces of tile q handed out so far = this piece's slot
-    while (cnt > 0 && q < ntl) {
-      const int take = (int)std::min<int64_t>(steps[(size_t)q] - s, cnt);
-      tab[(size_t)(4 * G + q)] += 1;
-      cnt -= take;
-      s += take;
-      if (s == steps[(size_t)q]) {
-        q += 1;
-        s = 0;
-      }
-    }
-  }
-  int maxpieces = 1;  // = piece slots the row-sum buffer needs (a tile has at most n / 1024 + 1 steps, hence pieces)
-  for (int64_t t = 0; t < ntl; ++t) {
-    OSB_REQUIRE(tab[(size_t)(4 * G + t)] >= 1, OSB_ERR_UNSUPPORTED, "flat partition: a tile was left out");
-    maxpieces = std::max(maxpieces, tab[(size_t)(4 * G + t)]);
-  }
-  return maxpieces;
 }
 
 // ---- host side ------------------------------------------------------------------------------
@@ -982,8 +925,7 @@ static void launch_iter_fn(Ctx* ctx, const QNIterArgs& a, const Fn& fn, bool bou
 #define OSB_IT(B, T)                                   \
   do {                                                 \
     if (sh == 0) launch_iter_k<Fn, B, T, 0>(ctx, a, fn);      \
-    else if (sh == 1) launch_iter_k<Fn, B, T, 1>(ctx, a, fn); \
-    else launch_iter_k<Fn, B, T, 2>(ctx, a, fn);              \
+    else launch_iter_k<Fn, B, T, 1>(ctx, a, fn);              \
   } while (0)
   if (bounded) {
     if (bt) OSB_IT(true, true);
@@ -997,7 +939,7 @@ static void launch_iter_fn(Ctx* ctx, const QNIterArgs& a, const Fn& fn, bool bou
 
 void qn_launch_iter(Ctx* ctx, int functor_kind, const double* fn_a, const double* fn_b, bool bounded, int ls_kind, const QNIterArgs& a) {
   const bool bt = ls_kind == LS_BACKTRACKING;
-  const int sh = a.world > 1 ? (a.wt != nullptr ? 2 : 1) : 0;  // a work table selects the flat partition
+  const int sh = a.world > 1 ? 1 : 0;
   if (functor_kind == FN_ROSENBROCK) {
     launch_iter_fn(ctx, a, RosenbrockFn{}, bounded, bt, sh);
   } else if (functor_kind == FN_SEPQUAD) {

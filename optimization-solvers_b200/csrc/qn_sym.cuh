@@ -129,37 +129,13 @@ __host__ __device__ inline int64_t sym_first_row(int64_t ntiles, int world, int 
   return t < 0 ? 0 : t * QN_R;
 }
 
-// ---- flat partition of a rank's tiles (fused iteration kernel, several GPUs) ------------------------------------------
-// With few tiles per CTA the static dealing above quantises badly: at 8 GPUs a rank has 256 tiles for 148 CTAs, the CTAs
-// holding one of the 40 longest tiles carry 1.0 n columns against a mean of 0.865 n (15.6 % over).  The flat partition
-// lines the rank's tiles up in STORAGE order — pair by pair, the long tile of a pair then the short one, so that every
-// stretch of the line holds the same mix of long and short tiles (a line in decreasing length left the last CTAs with
-// ~60 one-step tiles each, whose per-tile fixed costs made them the stragglers: 0.234 ms against 0.210 at 2 GPUs) —
-// counts their column steps (8 rows x 2 NT columns each) and gives every CTA an equal, contiguous range of steps: a
-// tile may be cut at a step border into pieces, which are processed by neighbouring CTAs and leave their row
-// sums in piece slots (the fold adds the slots in order; the column partials are per CTA as before).  The table is built
-// on the host (qn_iter_build_worktable) and lives in global memory: 4 ints per CTA {first tile position, first step
-// inside it, steps to do, piece slot of that first tile}, then one int per local tile position = its number of pieces.
-__host__ __device__ inline int64_t symsh_tile_at(int64_t T, int world, int rank, int64_t q) {  // line position q -> tile
-  const int64_t pairi = rank + (q >> 1) * world;
-  return (q & 1) == 0 ? T - 1 - pairi : pairi;
-}
-__host__ __device__ inline int64_t symsh_pos_of(int64_t T, int world, int rank, int64_t tile) {   // inverse, for a tile of this rank
-  return tile >= T / 2 ? 2 * ((T - 1 - tile - rank) / world) : 2 * ((tile - rank) / world) + 1;
-}
-__host__ __device__ inline int sym_tile_steps(int64_t tile, int64_t n, int nt) {
-  const int64_t ncols = (tile + 1) * QN_R < n ? (tile + 1) * QN_R : n;
-  return (int)((ncols + 2 * nt - 1) / (2 * nt));
-}
-
 // SHARDED is a template parameter so that the single-GPU instantiation keeps exactly its own loop structure (the
 // 128-register streaming loop is sensitive to anything that stays live across it).  NT = threads per CTA: 512 (one
 // CTA per SM) or 256 (two independent CTAs per SM: one streams while the other drains into its tile-end reduction).
 // OOP: ping-pong storage, the pass reads sa.P and writes sa.Pout.  ZERO: legacy zero-first partials.
-template <int KIND, bool SHARDED, int NT, bool OOP, bool ZERO, bool FLAT = false>
+template <int KIND, bool SHARDED, int NT, bool OOP, bool ZERO>
 __device__ __forceinline__ void sym_pass_body(const QNLazyArgs& a, const QNSymArgs& sa, const double c0, const double c1, const double c2,
-                                              const int pp, const int grid, const int cta, const int* __restrict__ wt = nullptr,
-                                              double* __restrict__ rowpart = nullptr) {
+                                              const int pp, const int grid, const int cta) {
   const unsigned long long pol = l2_evict_first_policy();
   __shared__ double red2[2][NT / 32][16];  // double-buffered by tile parity: two barriers per tile instead of four
   __shared__ double4 rowv2[2][QN_R];       // p_i, q_i, y_i, g_i of the tile's rows
@@ -180,31 +156,12 @@ __device__ __forceinline__ void sym_pass_body(const QNLazyArgs& a, const QNSymAr
     __syncthreads();
   }
   const int64_t ntiles = (n + QN_R - 1) / QN_R;
-  bool first = !ZERO && !FLAT;  // (flat partition: the column partials are zero when the pass starts, see the fold)
-  int fq = 0, fs = 0, fleft = 0, fslot = 0;  // flat partition: tile position, first step, steps left, piece slot
-  if (FLAT) {
-    fq = wt[4 * cta];
-    fs = wt[4 * cta + 1];
-    fleft = wt[4 * cta + 2];
-    fslot = wt[4 * cta + 3];
-  }
+  bool first = !ZERO;
   for (int64_t step = 0;; ++step) {
-    int64_t tile;
-    int cbeg = 0, cend = 0x7fffffff;
-    if (FLAT) {
-      if (fleft <= 0) break;
-      tile = symsh_tile_at(ntiles, sa.world, sa.rank, fq);
-      const int st_ = sym_tile_steps(tile, n, NT);
-      const int take = st_ - fs < fleft ? st_ - fs : fleft;
-      cbeg = fs * 2 * NT;
-      cend = (fs + take) * 2 * NT;
-      fleft -= take;
-    } else {
-      tile = sym_cta_tile<SHARDED>(ntiles, sa.world, sa.rank, grid, cta, step);
-      if (tile < 0) {
-        if (SHARDED || (step & 1) == 0) break;  // (one GPU, odd step: only the middle tile of an odd count is skipped)
-        continue;
-      }
+    const int64_t tile = sym_cta_tile<SHARDED>(ntiles, sa.world, sa.rank, grid, cta, step);
+    if (tile < 0) {
+      if (SHARDED || (step & 1) == 0) break;  // (one GPU, odd step: only the middle tile of an odd count is skipped)
+      continue;
     }
     const int64_t r0 = tile * QN_R;
     const int rows_here = (int)((n - r0) < QN_R ? (n - r0) : QN_R);
@@ -225,7 +182,7 @@ __device__ __forceinline__ void sym_pass_body(const QNLazyArgs& a, const QNSymAr
     const int64_t toff = SHARDED ? symsh_tile_offset(tile, ntiles, sa.world) : sym_tile_offset(tile);
     const double* __restrict__ base = (OOP && pp ? sa.Pout : sa.P) + toff;
     double* __restrict__ obase = (OOP && !pp ? sa.Pout : sa.P) + toff;
-    for (int col = cbeg + 2 * threadIdx.x; col < (FLAT && cend < (int)lpad ? cend : (int)lpad); col += 2 * NT) {
+    for (int col = 2 * threadIdx.x; col < (int)lpad; col += 2 * NT) {
       // element validity: columns >= ncols are padding (never stored, never updated)
       const bool v0 = col < ncols, v1 = col + 1 < ncols;
       if (!v0) continue;
@@ -303,18 +260,9 @@ __device__ __forceinline__ void sym_pass_body(const QNLazyArgs& a, const QNSymAr
       for (int w = 0; w < NT / 32; ++w) v = v + red[w][threadIdx.x];
       const int r = threadIdx.x % QN_R;
       if (r < rows_here) {
-        if (FLAT) {  // this piece's share of the row sums, in its slot
-          rowpart[((int64_t)fslot * 2 + (threadIdx.x < QN_R ? 0 : 1)) * ld + r0 + r] = v;
-        } else {
-          if (threadIdx.x < QN_R) a.h[r0 + r] = v;
-          else a.w[r0 + r] = v;
-        }
+        if (threadIdx.x < QN_R) a.h[r0 + r] = v;
+        else a.w[r0 + r] = v;
       }
-    }
-    if (FLAT) {
-      fq += 1;
-      fs = 0;
-      fslot = 0;
     }
   }
 }

@@ -60,13 +60,11 @@ def main():
         ok &= bool(same)
     # ---- packed symmetric storage sharded by tile pairs (fused peer-memory exchange of per-rank slots, summed in rank
     # order by the head): same trajectory as one GPU to rounding of the summation order, identical on all ranks
-    for kind, n, iters, flat in (("BFGS", 2048, 40, 0), ("DFP", 1024, 25, 0), ("BFGS", 16384, 12, 0),
-                                 ("BFGS", 2048, 40, 1), ("DFP", 1024, 25, 1), ("BFGS", 16384, 12, 1)):
+    for kind, n, iters in (("BFGS", 2048, 40), ("DFP", 1024, 25), ("BFGS", 16384, 12)):
         x0 = rosen_x0(n, 5)
         res = []
         for c in (ctx, solo):
             s = getattr(osb, kind)(1e-8, x0, ctx=c).set_option("engine", 2).set_option("qn_schedule", 1).set_option("qn_storage", 1)
-            s.set_option("flat_partition", flat)  # whole tiles per CTA (default) / equal column steps per CTA
             try:
                 s.minimize(osb.BackTracking(1e-4, 0.5), osb.ExtendedRosenbrock(n, ctx=c), iters, 20)
             except osb.MaxIterReached:
@@ -82,12 +80,12 @@ def main():
         dx = float(np.max(np.abs(res[0][1] - res[1][1])))
         dH = float(np.max(np.abs(res[0][3][rows] - res[1][3][rows])))
         good = res[0][0] == res[1][0] and res[0][4] > 0 and res[1][4] == 0 and same_on_ranks and dx <= 1e-9 and dH <= 1e-8 * max(1.0, float(np.max(np.abs(res[1][3][rows]))))
-        print("rank %d %s n=%d k=%d/%d packed storage sharded by tile pairs (flat partition %d): ranks identical %s, max|dx| vs one GPU %.2e, max|dH| %.2e -> %s"
-              % (rank, kind, n, res[0][0], res[1][0], flat, same_on_ranks, dx, dH, good), flush=True)
+        print("rank %d %s n=%d k=%d/%d packed storage sharded by tile pairs: ranks identical %s, max|dx| vs one GPU %.2e, max|dH| %.2e -> %s"
+              % (rank, kind, n, res[0][0], res[1][0], same_on_ranks, dx, dH, good), flush=True)
         ok &= bool(good)
 
     # ---- packed sharded storage starting from a user matrix (set_approx_inv_hessian: the matrix arrives as row blocks and is
-    # redistributed into tile pairs once), n chosen so that a tile of the flat partition is cut into more than 3 pieces
+    # redistributed into tile pairs once)
     for kind, n, iters in (("BFGS", 2048, 15), ("BFGS", 8192, 8)):
         rng = np.random.default_rng(17)
         x0 = rosen_x0(n, 7)
@@ -97,9 +95,7 @@ def main():
         H0 = 0.5 * (H0 + H0.T)
         res = []
         for c in (ctx, solo):
-            s = getattr(osb, kind)(1e-8, x0, ctx=c)  # library defaults ...
-            if n == 8192:
-                s.set_option("flat_partition", 1)  # ... except here: pieces of a tile in more than 3 slots
+            s = getattr(osb, kind)(1e-8, x0, ctx=c)  # library defaults
             s.set_approx_inv_hessian(H0)
             try:
                 s.minimize(osb.BackTracking(1e-4, 0.5), osb.ExtendedRosenbrock(n, ctx=c), iters, 20)
