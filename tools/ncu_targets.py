@@ -2,7 +2,8 @@
   sym    - default BFGS path, n = 16384, 12 iterations  (qn_lazy_sym_kernel, qn_sym_fold_kernel, cluster head)
   fused  - the same through the fused iteration kernel, 3 launches of 4 iterations (qn_iter_kernel)
   stream - SPG on the generated separable quadratic, n = 2^26, 6 iterations (stream_trial kernel)
-  syrk   - logistic Hessian, m = 32768, n = 8192 (syrk_dmma_kernel, syrk_reduce_kernel)"""
+  syrk   - logistic Hessian, m = 32768, n = 8192 (syrk_dmma_kernel, syrk_reduce_kernel)
+  batched - 32768 BFGS solves of extended Rosenbrock, n = 32 (batched_bfgs_kernel)"""
 import importlib, sys
 import numpy as np
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
@@ -29,6 +30,9 @@ elif what == "stream":
     except osb.MaxIterReached:
         pass
     print(s.path_info()["fused_stream"], s.k())
+elif what == "batched":
+    r = osb.batched_bfgs_rosenbrock(32, 32768)
+    print(r["ms"] if isinstance(r, dict) else r)
 else:
     obj = osb.LogisticRegression.generated(32768, 8192, 1.0)
     print(osb.bench_syrk(obj, 1))
