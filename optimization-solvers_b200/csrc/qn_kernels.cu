@@ -791,15 +791,6 @@ __global__ void __launch_bounds__(NT, 512 / NT) qn_lazy_sym_kernel(QNLazyArgs a,
   sym_pass_body<KIND, SHARDED, NT, OOP, ZERO>(a, sa, st->pc0, st->pc1, st->pc2, pp, (int)gridDim.x, (int)blockIdx.x);
 }
 
-// the packed pass in column-walk order (qn_kernel bit 4; qn_sym.cuh)
-template <int KIND, bool SHARDED>
-__global__ void __launch_bounds__(512, 1) qn_lazy_sym_cw_kernel(QNLazyArgs a, QNSymArgs sa) {
-  DevState* st = a.st;
-  if (st->done) return;
-  __shared__ CwSmem<512> sm;
-  sym_pass_body_cw<KIND, SHARDED, 512>(a, sa, st->pc0, st->pc1, st->pc2, (int)gridDim.x, (int)blockIdx.x, sm);
-}
-
 // ---- the packed pass with a shared-memory ring (qn_kernel bit 3) ----------------------------------------------------
 // Same tiles, same thread -> column mapping and the same order of every sum as sym_pass_body (hence the same bits); what
 // changes is who waits for HBM.  In the register-staged pass a warp issues the 8 row loads of a column step, waits for
@@ -1260,10 +1251,6 @@ int qn_sym_grid(Ctx* ctx, int64_t n, int variant) {
 
 template <int KIND, bool SHARDED>
 static void launch_sym_pass(int grid, cudaStream_t stream, const QNLazyArgs& a, const QNSymArgs& sa, int variant) {
-  if (variant & 16) {  // column-walk order
-    qn_lazy_sym_cw_kernel<KIND, SHARDED><<<grid, 512, 0, stream>>>(a, sa);
-    return;
-  }
   if (variant & 8) {  // shared-memory ring fed by bulk asynchronous copies
     static bool attr = false;
     if (!attr) {

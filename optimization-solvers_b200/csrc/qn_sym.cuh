@@ -268,162 +268,4 @@ __device__ __forceinline__ void sym_pass_body(const QNLazyArgs& a, const QNSymAr
 }
 
 
-// ---- the pass in column-walk order ----------------------------------------------------------------------------------
-// Same tiles per CTA, same element arithmetic, different ORDER of a CTA's (tile, column step) units: column step by
-// column step over (a chunk of up to CW_MAXT of) the CTA's tiles instead of tile by tile.  What that buys:
-//   * the four O(n) column vectors of a step are loaded once per chunk and stay in registers while the CTA visits its
-//     tiles (tile by tile they are re-read for every tile: 0.6 GB of L2 -> SM traffic per pass at n = 16384, ncu);
-//   * the column sums of a step accumulate in four registers across the tiles and are stored once (tile by tile every
-//     unit read-modify-writes the CTA's partial vector: +25 % L2 transactions);
-//   * no CTA barrier per tile: a unit's 16 row sums are reduced inside each warp (warp_sum16) and added into that warp's
-//     own shared-memory slot of the tile; one barrier and one cross-warp sum per chunk finish the rows.
-// A row's result depends only on its tile (steps in order inside each warp slot, warps in order), not on the grid or the
-// number of GPUs, like before; it is NOT bit-identical to the tile-by-tile order (different association).
-constexpr int CW_MAXT = 16;
-template <int NT>
-struct CwSmem {
-  double acc[CW_MAXT][NT / 32][16];  // [tile of the chunk][warp][8 row sums of h, 8 of w]
-  double4 rowv[CW_MAXT][QN_R];       // p_i, q_i, y_i, g_i of the tile's rows
-  long long toff[CW_MAXT];
-  int r0[CW_MAXT], lpad[CW_MAXT], rows[CW_MAXT], ncols[CW_MAXT];
-  int ntl, next_step, done;
-};
-
-template <int KIND, bool SHARDED, int NT>
-__device__ __forceinline__ void sym_pass_body_cw(const QNLazyArgs& a, const QNSymArgs& sa, const double c0, const double c1, const double c2,
-                                                 const int grid, const int cta, CwSmem<NT>& sm) {
-  const unsigned long long pol = l2_evict_first_policy();
-  const int64_t n = sa.n, ld = sa.ld;
-  const double* __restrict__ p = a.ps;
-  const double* __restrict__ q = a.ph;
-  const double* __restrict__ yv = a.y;
-  const double* __restrict__ gv = a.g;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double* __restrict__ cph = sa.colpart + (int64_t)cta * 2 * ld;
-  double* __restrict__ cpw = cph + ld;
-  const int64_t ntiles = (n + QN_R - 1) / QN_R;
-  if (tid == 0) {
-    sm.next_step = 0;
-    sm.done = 0;
-  }
-  bool first = true;
-  for (;;) {
-    __syncthreads();  // the previous chunk's slots and tile table are no longer read
-    if (tid == 0) {   // the next (up to) CW_MAXT tiles of this CTA, in its dealing order (the first one is the longest)
-      int cnt = 0, step = sm.next_step;
-      while (cnt < CW_MAXT && !sm.done) {
-        const int64_t tile = sym_cta_tile<SHARDED>(ntiles, sa.world, sa.rank, grid, cta, step);
-        if (tile < 0) {
-          if (SHARDED || (step & 1) == 0) sm.done = 1;
-          else ++step;
-          continue;
-        }
-        const int64_t r0 = tile * QN_R;
-        sm.r0[cnt] = (int)r0;
-        sm.rows[cnt] = (int)((n - r0) < QN_R ? (n - r0) : QN_R);
-        sm.lpad[cnt] = (int)sym_lpad(tile);
-        sm.ncols[cnt] = (int)(r0 + QN_R < n ? r0 + QN_R : n);
-        sm.toff[cnt] = SHARDED ? symsh_tile_offset(tile, ntiles, sa.world) : sym_tile_offset(tile);
-        ++cnt;
-        ++step;
-      }
-      sm.ntl = cnt;
-      sm.next_step = step;
-    }
-    __syncthreads();
-    const int ntl = sm.ntl;
-    if (ntl == 0) break;
-    if (tid < ntl * QN_R) {
-      const int tl = tid / QN_R, r = tid % QN_R;
-      const bool ok = r < sm.rows[tl];
-      const int64_t i = sm.r0[tl] + r;
-      sm.rowv[tl][r] = ok ? make_double4(p[i], q[i], yv[i], gv[i]) : make_double4(0.0, 0.0, 0.0, 0.0);
-    }
-    for (int e = tid; e < ntl * (NT / 32) * 16; e += NT) (&sm.acc[0][0][0])[e] = 0.0;
-    __syncthreads();
-    const int maxlpad = sm.lpad[0], maxcols = sm.ncols[0], colvalid = sm.r0[0];  // (columns >= r0 of the longest tile get no column sums)
-    for (int cb = 0; cb < maxlpad; cb += 2 * NT) {
-      const int col = cb + 2 * tid;
-      double2 gj = make_double2(0.0, 0.0), yj = gj, pj = gj, qj = gj;
-      if (col < maxcols) {
-        gj = ld_vec2(gv + col);
-        yj = ld_vec2(yv + col);
-        pj = ld_vec2(p + col);
-        qj = ld_vec2(q + col);
-      }
-      double ch0 = 0.0, ch1 = 0.0, cw0 = 0.0, cw1 = 0.0;
-#pragma unroll 1
-      for (int tl = 0; tl < ntl; ++tl) {
-        const int lpad = sm.lpad[tl];
-        if (cb >= lpad) continue;  // (uniform over the CTA)
-        const int ncols = sm.ncols[tl], rows_here = sm.rows[tl];
-        const bool v0 = col < ncols, v1 = col + 1 < ncols;
-        const bool cok = col < sm.r0[tl];
-        double* __restrict__ base = sa.P + sm.toff[tl];
-        double2 hv[QN_R];
-#pragma unroll
-        for (int r = 0; r < QN_R; ++r) hv[r] = (v0 && r < rows_here) ? ld_stream_ef(base + (int64_t)r * lpad + col, pol) : make_double2(0.0, 0.0);
-        double v16[16];
-#pragma unroll
-        for (int r = 0; r < QN_R; ++r) {
-          double ahr = 0.0, awr = 0.0;
-          if (v0 && r < rows_here) {
-            const double4 rv = sm.rowv[tl][r];
-            const double pi = rv.x, qi = rv.y;
-            double2 hn;
-            if (KIND == QN_BFGS) {
-              const double cx = pi * qj.x + qi * pj.x, cy = pi * qj.y + qi * pj.y;
-              hn.x = fma(c0, pi * pj.x, fma(c1, cx, hv[r].x));
-              hn.y = fma(c0, pi * pj.y, fma(c1, cy, hv[r].y));
-            } else {
-              hn.x = fma(c2, qi * qj.x, fma(c0, pi * pj.x, hv[r].x));
-              hn.y = fma(c2, qi * qj.y, fma(c0, pi * pj.y, hv[r].y));
-            }
-            if (!v1) hn.y = 0.0;
-            ahr = fma(hn.y, yj.y, hn.x * yj.x);
-            awr = fma(hn.y, gj.y, hn.x * gj.x);
-            if (cok) {
-              ch0 = fma(hn.x, rv.z, ch0);
-              ch1 = fma(hn.y, rv.z, ch1);
-              cw0 = fma(hn.x, rv.w, cw0);
-              cw1 = fma(hn.y, rv.w, cw1);
-            }
-            st_stream_ef(base + (int64_t)r * lpad + col, hn, pol);
-          }
-          v16[r] = ahr;
-          v16[QN_R + r] = awr;
-        }
-        const double ws = warp_sum16(v16);
-        if ((lane & 1) == 0) sm.acc[tl][warp][lane >> 1] += ws;  // (always the same lane: no synchronisation needed)
-      }
-      if (col < colvalid) {
-        if (first) {
-          *reinterpret_cast<double2*>(cph + col) = make_double2(ch0, ch1);
-          *reinterpret_cast<double2*>(cpw + col) = make_double2(cw0, cw1);
-        } else {
-          double2 oh = *reinterpret_cast<double2*>(cph + col), ow = *reinterpret_cast<double2*>(cpw + col);
-          oh.x += ch0;
-          oh.y += ch1;
-          ow.x += cw0;
-          ow.y += cw1;
-          *reinterpret_cast<double2*>(cph + col) = oh;
-          *reinterpret_cast<double2*>(cpw + col) = ow;
-        }
-      }
-    }
-    first = false;
-    __syncthreads();
-    if (tid < ntl * 16) {
-      const int tl = tid >> 4, vq = tid & 15, r = vq % QN_R;
-      double v = 0.0;
-#pragma unroll
-      for (int w = 0; w < NT / 32; ++w) v = v + sm.acc[tl][w][vq];
-      if (r < sm.rows[tl]) {
-        if (vq < QN_R) a.h[sm.r0[tl] + r] = v;
-        else a.w[sm.r0[tl] + r] = v;
-      }
-    }
-  }
-}
-
 }  // namespace osb

@@ -639,28 +639,6 @@ def test_run_ahead_callbacks_deliver_the_same_sequence(osb):
             assert np.array_equal(a[6][key], b[6][key])
 
 
-@pytest.mark.parametrize("cls", ["BFGS", "DFP"])
-def test_column_walk_pass_matches_the_tile_by_tile_pass(osb, cls):
-    """qn_kernel bit 4: the CTA visits its (tile, column step) units column step by column step (column vectors and
-    column sums stay in registers, row sums in per-warp shared-memory slots).  Same element arithmetic, different
-    association of the row and column sums: x and H agree to rounding, k and the line-search counts are equal; sizes
-    cover one tile, ragged tiles, more than CW_MAXT = 16 tiles per CTA (n = 20000: two chunks)."""
-    for n in (6, 250, 1030, 2056, 4099, 16384, 20000):
-        x0 = rosen_x0(n, 33) if n % 2 == 0 else np.linspace(-1.0, 1.0, n)
-        out = []
-        for variant in (0, 16):
-            obj = osb.ExtendedRosenbrock(n) if n % 2 == 0 else osb.SeparableQuadratic.generated(n)
-            s = getattr(osb, cls)(1e-9, x0).set_option("qn_schedule", 1).set_option("qn_storage", 1).set_option("qn_kernel", variant)
-            st = run(osb, s, osb.BackTracking(1e-4, 0.5), obj, 9, 20)
-            assert s.path_info()["storage"] == 1 and s.path_info()["variant"] == variant
-            out.append((st, s.k(), s.x(), s.approx_inv_hessian() if n <= 4099 else None, s.f()))
-        assert out[0][:2] == out[1][:2]
-        assert close(out[0][2], out[1][2], rtol=1e-10), n
-        assert abs(out[0][4] - out[1][4]) <= 1e-10 * abs(out[0][4]) + 1e-300
-        if n <= 4099:
-            assert close(out[0][3], out[1][3], rtol=1e-9), n
-
-
 def test_fused_kernel_publishes_callback_snapshots_from_inside_the_launch(osb):
     """fused_iteration = 1 with run-ahead callbacks: the kernel writes every iteration's x, g, f, k, norms into a device
     ring, raises a flag in pinned host memory and keeps running (16 iterations per launch) while the host copies the slot

@@ -6,7 +6,7 @@ import importlib
 osb = importlib.import_module("optimization-solvers_b200")
 n = 16384
 for name, v in (("register-staged (default)", 0), ("2 x 256 threads", 1), ("ping-pong storage", 2), ("zero-first column partials", 4),
-                ("shared-memory ring (cp.async.bulk)", 8), ("column-walk order", 16), ("register-staged (default)", 0), ("column-walk order", 16), ("register-staged again", 0), ("d2d copy of 2 GiB (x0.5)", -1)):
+                ("shared-memory ring (cp.async.bulk)", 8), ("register-staged again", 0), ("d2d copy of 2 GiB (x0.5)", -1)):
     if v < 0:
         ms = osb.bench_qn_kernel(3, n, 20, 0) * 0.5
     else:
