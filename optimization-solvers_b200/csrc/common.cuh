@@ -75,6 +75,26 @@ __device__ __forceinline__ double2 ld_vec2(const double* p) {
 __device__ __forceinline__ void st_stream(double* p, double2 v) {
   asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
+// Programmatic dependent launch: a kernel launched with launch_pdl may be scheduled while the previous kernel of the
+// stream is still draining; its first statement is pdl_wait(), which returns once that kernel has completed and its
+// writes are visible.  What overlaps is the launch latency and the ramp of the CTAs (2-3 us per boundary), three
+// boundaries per iteration on the one-launch-per-phase path.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <class... KArgs, class... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  OSB_CUDA(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...));
+}
+
 // L2 evict-first policy for the H stream: 4 GB pass through L2 every iteration and would otherwise evict
 // what is re-used across launches (the O(n) vectors and, notably, the instruction lines of the small
 // head kernel, whose cold start is bound by instruction fetch).

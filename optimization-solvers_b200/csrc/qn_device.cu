@@ -596,6 +596,7 @@ qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol,
                        double* __restrict__ x, double* __restrict__ g, double* __restrict__ s, double* __restrict__ y,
                        const double* __restrict__ u, const double* __restrict__ lb, const double* __restrict__ ub,
                        const double* __restrict__ ls_lb, const double* __restrict__ ls_ub, int spec_on, HeadEpi epi) {
+  pdl_wait();  // (launched with programmatic stream serialization: the previous kernel's results are complete from here on)
   constexpr int BS = Fn::BS;
   constexpr int KPT = EPT / BS;
   constexpr int NT = HC_CTAS * HC_T;
@@ -827,9 +828,11 @@ static void launch_head_cluster_k(Ctx* ctx, Fn fn, bool bounded, LSParams* d_ls,
                                   double* x, double* g, double* s, double* y, const double* u, const double* lb, const double* ub,
                                   const double* ls_lb, const double* ls_ub, int spec_on, const HeadEpi& epi) {
   if (bounded)
-    qn_head_cluster_kernel<Fn, true, 4, LSK><<<HC_CTAS, HC_T, 0, ctx->stream>>>(fn, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub, spec_on, epi);
+    launch_pdl(qn_head_cluster_kernel<Fn, true, 4, LSK>, dim3(HC_CTAS), dim3(HC_T), 0, ctx->stream, fn, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub,
+               ls_lb, ls_ub, spec_on, epi);
   else
-    qn_head_cluster_kernel<Fn, false, 4, LSK><<<HC_CTAS, HC_T, 0, ctx->stream>>>(fn, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub, ls_lb, ls_ub, spec_on, epi);
+    launch_pdl(qn_head_cluster_kernel<Fn, false, 4, LSK>, dim3(HC_CTAS), dim3(HC_T), 0, ctx->stream, fn, d_ls, n, tol, max_ls, st, x, g, s, y, u, lb, ub,
+               ls_lb, ls_ub, spec_on, epi);
 }
 
 template <class Fn>

@@ -785,6 +785,7 @@ void qn_sym_layout(int64_t n, int world, int64_t tile, int* owner, int64_t* offs
 // the streaming pass as its own launch (host-driven engine, profiling, pass variants)
 template <int KIND, bool SHARDED, int NT, bool OOP, bool ZERO>
 __global__ void __launch_bounds__(NT, 512 / NT) qn_lazy_sym_kernel(QNLazyArgs a, QNSymArgs sa) {
+  pdl_wait();
   DevState* st = a.st;
   if (st->done) return;
   const int pp = OOP ? st->pp : 0;  // which buffer holds the current matrix (toggled by the fold kernel)
@@ -1016,6 +1017,7 @@ constexpr int FOLD_G = FOLD_T / 64;  // groups of partial rows per vector
 constexpr int FOLD_MAXPARTS = 1024;  // >= the largest pass grid (2 CTAs per SM)
 template <int KIND>
 __global__ void __launch_bounds__(FOLD_T) qn_sym_fold_kernel(const __grid_constant__ QNLazyArgs a, QNSymArgs sa, int nparts, unsigned int* ticket) {
+  pdl_wait();
   DevState* st = a.st;
   if (st->done) return;
   if (sa.Pout != sa.P && blockIdx.x == 0 && threadIdx.x == 0) st->pp ^= 1;  // ping-pong: the pass wrote the other buffer
@@ -1261,7 +1263,7 @@ static void launch_sym_pass(int grid, cudaStream_t stream, const QNLazyArgs& a, 
     return;
   }
   switch (variant & 7) {
-    case 0: qn_lazy_sym_kernel<KIND, SHARDED, 512, false, false><<<grid, 512, 0, stream>>>(a, sa); break;
+    case 0: launch_pdl(qn_lazy_sym_kernel<KIND, SHARDED, 512, false, false>, dim3(grid), dim3(512), 0, stream, a, sa); break;
     case 1: qn_lazy_sym_kernel<KIND, SHARDED, 256, false, false><<<grid, 256, 0, stream>>>(a, sa); break;
     case 2: qn_lazy_sym_kernel<KIND, SHARDED, 512, true, false><<<grid, 512, 0, stream>>>(a, sa); break;
     case 3: qn_lazy_sym_kernel<KIND, SHARDED, 256, true, false><<<grid, 256, 0, stream>>>(a, sa); break;
@@ -1285,8 +1287,8 @@ void qn_launch_lazy_sym(Ctx* ctx, const QNLazyArgs& a, double* P, double* Pout, 
       else launch_sym_pass<QN_DFP, false>(grid, ctx->stream, a, sa, variant);
     }
   } else {  // fold of the per-CTA column partials + coefficient epilogue
-    if (a.kind == QN_BFGS) qn_sym_fold_kernel<QN_BFGS><<<fgrid, FOLD_T, 0, ctx->stream>>>(a, sa, grid, a.ticket);
-    else qn_sym_fold_kernel<QN_DFP><<<fgrid, FOLD_T, 0, ctx->stream>>>(a, sa, grid, a.ticket);
+    if (a.kind == QN_BFGS) launch_pdl(qn_sym_fold_kernel<QN_BFGS>, dim3(fgrid), dim3(FOLD_T), 0, ctx->stream, a, sa, grid, a.ticket);
+    else launch_pdl(qn_sym_fold_kernel<QN_DFP>, dim3(fgrid), dim3(FOLD_T), 0, ctx->stream, a, sa, grid, a.ticket);
   }
   ctx->counters[0] += 1;
 }
