@@ -80,6 +80,10 @@ __device__ __forceinline__ void st_stream(double* p, double2 v) {
 // writes are visible.  What overlaps is the launch latency and the ramp of the CTAs (2-3 us per boundary), three
 // boundaries per iteration on the one-launch-per-phase path.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Lets the NEXT kernel of the stream be scheduled as soon as SM resources free up (it still blocks in its pdl_wait until
+// this grid has completed).  Only for kernels whose whole grid is resident at once: a waiting dependent must never hold
+// the slot an unscheduled CTA of this grid needs.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 template <class... KArgs, class... Args>
 inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg{};

@@ -597,6 +597,7 @@ qn_head_cluster_kernel(Fn fn, LSParams* __restrict__ lsp, int64_t n, double tol,
                        const double* __restrict__ u, const double* __restrict__ lb, const double* __restrict__ ub,
                        const double* __restrict__ ls_lb, const double* __restrict__ ls_ub, int spec_on, HeadEpi epi) {
   pdl_wait();  // (launched with programmatic stream serialization: the previous kernel's results are complete from here on)
+  pdl_launch_dependents();  // (8 CTAs)
   constexpr int BS = Fn::BS;
   constexpr int KPT = EPT / BS;
   constexpr int NT = HC_CTAS * HC_T;

@@ -786,6 +786,7 @@ void qn_sym_layout(int64_t n, int world, int64_t tile, int* owner, int64_t* offs
 template <int KIND, bool SHARDED, int NT, bool OOP, bool ZERO>
 __global__ void __launch_bounds__(NT, 512 / NT) qn_lazy_sym_kernel(QNLazyArgs a, QNSymArgs sa) {
   pdl_wait();
+  pdl_launch_dependents();  // (one CTA per SM, one wave)
   DevState* st = a.st;
   if (st->done) return;
   const int pp = OOP ? st->pp : 0;  // which buffer holds the current matrix (toggled by the fold kernel)
@@ -1017,7 +1018,7 @@ constexpr int FOLD_G = FOLD_T / 64;  // groups of partial rows per vector
 constexpr int FOLD_MAXPARTS = 1024;  // >= the largest pass grid (2 CTAs per SM)
 template <int KIND>
 __global__ void __launch_bounds__(FOLD_T) qn_sym_fold_kernel(const __grid_constant__ QNLazyArgs a, QNSymArgs sa, int nparts, unsigned int* ticket) {
-  pdl_wait();
+  pdl_wait();  // (no early trigger here: this grid runs in two waves)
   DevState* st = a.st;
   if (st->done) return;
   if (sa.Pout != sa.P && blockIdx.x == 0 && threadIdx.x == 0) st->pp ^= 1;  // ping-pong: the pass wrote the other buffer
