@@ -52,6 +52,7 @@ struct IterCarry {
   int has_s, has_y, skip_prev, pending, epi_owed, ls_evals, status, reason, done, gbuf;
   unsigned int llseq;  // sequence number of the flagged (barrier-free) grid reductions; persists in DevState.ll_seq
   int snap_it;         // host-callback snapshots published so far in this launch (QNIterArgs.snap_*)
+  int ds_owed;         // the step sums (s.s, y.y, y.s, f+) of the last iteration are still per-CTA partials (IterSmem.ds_part)
   LSParams p;
 };
 
@@ -62,6 +63,7 @@ struct IterSmem {
   double2 part[2][IT_NT / 2];
   double xs[IT_NT], ds[IT_NT];  // this CTA's chunk of x and d (backtracking: one warp per trial step sweeps it)
   int ext[IT_MAXG];
+  double ds_part[4];   // this CTA's partials of the deferred step sums (IterCarry.ds_owed)
   long long prof[16];  // leader only: [0..2] accumulated ns in head / pass / fold, [3] last stamp, [4..15] head sub-phases
   int prof_skip;       // iterations left out of the profile (the first one of a launch: it absorbs the ranks' launch skew)
 };
@@ -313,13 +315,18 @@ __device__ __noinline__ int iter_head(const QNIterArgs& a, const Fn& fn, IterSme
   // values) come after a barrier, so no thread can see a field another thread has already advanced.
   int gbuf = c.gbuf;
   unsigned int llseq = c.llseq;
-  const double f0 = c.f0, ys_prev = c.ys_prev, s_norm_in = c.s_norm, y_norm_in = c.y_norm;
-  const int has_s_in = c.has_s, has_y_in = c.has_y, epi_in = c.epi_owed, skip_in = c.skip_prev, ls_evals_in = c.ls_evals;
+  double f0 = c.f0, ys_prev = c.ys_prev, s_norm_in = c.s_norm, y_norm_in = c.y_norm;
+  int has_s_in = c.has_s, has_y_in = c.has_y, skip_in = c.skip_prev;
+  const int epi_in = c.epi_owed, ls_evals_in = c.ls_evals;
   const long long k_in = c.k;
   const int snap_in = c.snap_it;
+  // The step sums of the previous iteration (s.s, y.y, y.s, f+) may still be per-CTA partials: nothing between the end
+  // of that head and this point needs them, so they ride along with the epilogue's sums in ONE grid reduction instead
+  // of costing one of their own (a pass always leaves an epilogue owed, so ds_in implies epi_in).
+  const bool ds_in = c.ds_owed != 0;
   __syncthreads();
   iter_submark(a, sm, 14);  // (resets the sub-phase clock)
-  if (!epi_only && is_bad(f0)) {  // ls_solver.rs:37-40
+  if (!ds_in && !epi_only && is_bad(f0)) {  // ls_solver.rs:37-40
     c.done = 1;
     c.status = OSB_OUT_OF_DOMAIN;
     __syncthreads();
@@ -329,7 +336,7 @@ __device__ __noinline__ int iter_head(const QNIterArgs& a, const Fn& fn, IterSme
   double ub_[BS];
   if (epi_in) {
     const int par = epi_in - 1;  // sharded: parity of the exchange buffers holding h, w
-    const bool skip_prev = skip_in != 0;
+    bool skip_prev = skip_in != 0;  // (not known yet while ds_in: it follows from the deferred sums below)
     double hb[BS], wb[BS], sb[BS];
     double e3[3] = {0.0, 0.0, 0.0};
 #pragma unroll
@@ -370,7 +377,7 @@ __device__ __noinline__ int iter_head(const QNIterArgs& a, const Fn& fn, IterSme
           wb[jq] = __ldcg(a.w + i);
         }
         sb[jq] = __ldcg(a.s + i);
-        if (!skip_prev) {
+        if (ds_in || !skip_prev) {
           const double yi = __ldcg(a.y + i), gi = __ldcg(a.g + i);
           e3[0] = fma(yi, hb[jq], e3[0]);     // y.h
           e3[1] = fma(sb[jq], gi, e3[1]);     // s.g
@@ -379,14 +386,54 @@ __device__ __noinline__ int iter_head(const QNIterArgs& a, const Fn& fn, IterSme
       }
     }
     double ca = 0.0, cb = 0.0;
-    if (!skip_prev) {
+    double yh = 0.0, sg = 0.0, hg = 0.0;
+    if (ds_in || !skip_prev) {
       warp_put(sm, 0, e3[0], wact);
       warp_put(sm, 1, e3[1], wact);
       warp_put(sm, 2, e3[2], wact);
+      if (ds_in && tid < 4) ll_put(ll_row(a, (int)((llseq + 1u) & 1u), cta), 3 + tid, sm.ds_part[tid], llseq + 1u);
       iter_submark(a, sm, 4);
-      grid_reduce<true>(a, sm, 3, 3, &gbuf, &llseq, false);
+      grid_reduce<true>(a, sm, ds_in ? 7 : 3, 3, &gbuf, &llseq, false);
       iter_submark(a, sm, 5);
-      const double yh = sm.res[0], sg = sm.res[1], hg = sm.res[2];
+      yh = sm.res[0];
+      sg = sm.res[1];
+      hg = sm.res[2];
+      if (ds_in) {  // the deferred step sums: what the end of the previous head would have set
+        const double ss = sm.res[3], yy = sm.res[4], ys = sm.res[5], fn_ = sm.res[6];
+        const double sn = sqrt(ss), yn = sqrt(yy);
+        skip_prev = sn < a.tol || yn < a.tol;  // bfgs.rs:106-112
+        f0 = fn_;
+        ys_prev = ys;
+        s_norm_in = sn;
+        y_norm_in = yn;
+        has_s_in = has_y_in = 1;
+        skip_in = skip_prev ? 1 : 0;
+        __syncthreads();  // every thread has read sm.res
+        c.ss = ss;
+        c.yy = yy;
+        c.ys_prev = ys;
+        c.f0 = fn_;
+        c.s_norm = sn;
+        c.y_norm = yn;
+        c.has_s = c.has_y = 1;
+        c.skip_prev = skip_in;
+        c.ds_owed = 0;
+        c.llseq = llseq;
+        c.gbuf = gbuf;
+        __syncthreads();
+        if (a.snap_st != nullptr) {  // the previous iteration's snapshot (the barrier keeps the other threads' later
+          if (cta == 0 && tid == 0) iter_publish(a, c, snap_in - 1);  // writes of c.done away from the publisher's reads)
+          __syncthreads();
+        }
+        if (!epi_only && is_bad(f0)) {  // ls_solver.rs:37-40 (the epilogue stays owed, as on the undeferred path)
+          c.done = 1;
+          c.status = OSB_OUT_OF_DOMAIN;
+          __syncthreads();
+          return 1;
+        }
+      }
+    }
+    if (!skip_prev) {
       double c0, c1, c2;
       if (KIND == QN_BFGS) {  // bfgs.rs:115-124, no curvature safeguard
         const double rho = 1.0 / ys_prev;
@@ -654,19 +701,19 @@ __device__ __noinline__ int iter_head(const QNIterArgs& a, const Fn& fn, IterSme
   warp_put(sm, 1, a4[1], wact);
   warp_put(sm, 2, a4[2], wact);
   warp_put(sm, 3, a4[3], wact);
-  grid_reduce<false>(a, sm, 4, 4, &gbuf, &llseq, false);  // (its grid barrier also publishes s, y, x, g, ps, ph to the pass that follows)
+  // The four sums stay per-CTA partials (the next head, or the end of the launch, reduces them over the grid); what the
+  // pass needs now is only a grid barrier, which publishes s, y, x, g, ps, ph and the snapshot slot.
+  __syncthreads();
+  if (tid < 4) {
+    double v = 0.0;
+#pragma unroll 1
+    for (int wq = 0; wq < IT_NW; ++wq) v = v + sm.w[tid * IT_NW + wq];
+    sm.ds_part[tid] = v;
+  }
+  cg::this_grid().sync();
   iter_submark(a, sm, 11);
   {
-    const double ss = sm.res[0], yy = sm.res[1], ys = sm.res[2], fn_ = sm.res[3];
-    const double sn = sqrt(ss), yn = sqrt(yy);
-    c.ss = ss;
-    c.yy = yy;
-    c.ys_prev = ys;
-    c.f0 = fn_;
-    c.s_norm = sn;
-    c.y_norm = yn;
-    c.has_s = c.has_y = 1;
-    c.skip_prev = (sn < a.tol || yn < a.tol) ? 1 : 0;  // bfgs.rs:106-112
+    c.ds_owed = 1;
     c.t_last = t;
     c.gd0_last = gd0;
     c.k = k_in + 1;
@@ -680,9 +727,34 @@ __device__ __noinline__ int iter_head(const QNIterArgs& a, const Fn& fn, IterSme
     if (tid == 0) c.p = p_local;
   }
   __syncthreads();
-  // the grid barrier of the sum above ordered every CTA's snapshot stores before this point: the leader publishes
-  if (a.snap_st != nullptr && cta == 0 && tid == 0) iter_publish(a, c, snap_in);
   return 0;
+}
+
+// the deferred step sums at the end of a launch (no next head to carry them): one grid reduction of their own
+__device__ __noinline__ void iter_finalize_ds(const QNIterArgs& a, IterSmem& sm) {
+  IterCarry& c = sm.c;
+  const int tid = threadIdx.x, cta = (int)blockIdx.x;
+  int gbuf = c.gbuf;
+  unsigned int llseq = c.llseq;
+  __syncthreads();
+  if (tid < 4) ll_put(ll_row(a, (int)((llseq + 1u) & 1u), cta), tid, sm.ds_part[tid], llseq + 1u);
+  grid_reduce<true>(a, sm, 4, 0, &gbuf, &llseq, false);
+  const double ss = sm.res[0], yy = sm.res[1], ys = sm.res[2], fn_ = sm.res[3];
+  const double sn = sqrt(ss), yn = sqrt(yy);
+  __syncthreads();
+  c.ss = ss;
+  c.yy = yy;
+  c.ys_prev = ys;
+  c.f0 = fn_;
+  c.s_norm = sn;
+  c.y_norm = yn;
+  c.has_s = c.has_y = 1;
+  c.skip_prev = (sn < a.tol || yn < a.tol) ? 1 : 0;  // bfgs.rs:106-112
+  c.ds_owed = 0;
+  c.llseq = llseq;
+  c.gbuf = gbuf;
+  __syncthreads();
+  if (a.snap_st != nullptr && cta == 0 && tid == 0) iter_publish(a, c, c.snap_it - 1);
 }
 
 // fold of the column partials (+ exchange) for this CTA's chunk, out of line like the head
@@ -735,6 +807,7 @@ __device__ __noinline__ void iter_load_state(const QNIterArgs& a, IterCarry& c, 
   c.gbuf = 0;
   c.llseq = (unsigned int)st->ll_seq;
   c.snap_it = 0;
+  c.ds_owed = 0;
   c.p = *a.lsp;
 }
 
@@ -845,6 +918,7 @@ __global__ void __launch_bounds__(IT_NT, 1) qn_iter_kernel(const __grid_constant
       }
     }
   }
+  if (sm.c.ds_owed) iter_finalize_ds(a, sm);  // (the same value in every thread of every CTA)
   if (leader) {
     iter_store_state(a, sm.c, SHARDED);
     if (a.prof != nullptr) {
