@@ -268,3 +268,18 @@ def test_rust_gpu_module_covers_the_solver_and_line_search_matrix():
     used = set(re.findall(r"ffi::(osb_[a-z0-9_]+)\(", mod))
     assert used <= declared, sorted(used - declared)
     assert len(used) >= 35
+
+
+def test_every_solver_option_is_documented_in_the_header():
+    """osb_solver_set_option: every name the library accepts (csrc/api.cu) is described next to the declaration in
+    include/optsolv_b200.h, and the header describes no option the library would reject."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    api = open(os.path.join(root, "optimization-solvers_b200", "csrc", "api.cu")).read()
+    hdr = open(os.path.join(root, "include", "optsolv_b200.h")).read()
+    accepted = set(re.findall(r'nm == "([a-z0-9_]+)"', api))
+    assert len(accepted) >= 10
+    i = hdr.index("int osb_solver_set_option(")
+    doc = hdr[hdr.rindex("/*", 0, i):i]
+    documented = set(re.findall(r'^ \*   "([a-z0-9_]+)"', doc, flags=re.M))
+    assert accepted == documented, (sorted(accepted - documented), sorted(documented - accepted))
