@@ -493,6 +493,41 @@ def test_benchmark_path_n16384_vs_oracle_rank2(osb, orc):
     assert err <= 1e-8 * scale, (err, scale)
 
 
+@pytest.mark.parametrize("cls,fused", [("DFP", 0), ("BFGSB", 0), ("BFGS", 1)])
+def test_full_size_defaults_of_the_sibling_solvers_vs_oracle_rank2(osb, orc, cls, fused):
+    """n = 16384 with the library's defaults for the sibling paths of the benchmark: DFP (dfp.rs:78-123), bounded BFGS with
+    the projected direction (bfgs_b.rs:67-76, 106-154) and BFGS through the fused iteration kernel (what several GPUs
+    run), each against the oracle's rank-2 form, free running for 5 iterations: same k, x and f within 1e-9 relative, the
+    active set of the bounded solver bit-exact."""
+    n, K = 16384, 5
+    x0 = rosen_x0(n, 1)
+    lb, ub = np.full(n, -1.25), np.full(n, 1.05)
+    out = {}
+    for name, m in (("gpu", osb), ("oracle", orc)):
+        s = m.BFGSB(1e-8, np.clip(x0, lb, ub), lb, ub) if cls == "BFGSB" else getattr(m, cls)(1e-8, x0)
+        if m is orc:
+            s.set_update_form("rank2")
+            obj = m.ExtendedRosenbrock()
+        else:
+            obj = m.ExtendedRosenbrock(n)
+            if fused:
+                s.set_option("fused_iteration", 1)
+        st = run(m, s, m.BackTracking(1e-4, 0.5), obj, K, 20)
+        xk = s.x()
+        out[name] = (st, s.k(), xk, obj(xk).f(), s.s_norm(), s.y_norm(), s.active_set() if cls == "BFGSB" else None)
+        if m is osb:
+            info = s.path_info()
+            assert info["schedule"] == 1 and info["storage"] == 1 and info["fused"] == bool(fused), info
+        del s
+    g, o = out["gpu"], out["oracle"]
+    assert g[0] == o[0] and g[1] == o[1] == K
+    assert close(g[2], o[2], rtol=1e-9)
+    assert abs(g[3] - o[3]) <= 1e-9 * abs(o[3])
+    assert abs(g[4] - o[4]) <= 1e-9 * o[4] and abs(g[5] - o[5]) <= 1e-9 * o[5]
+    if cls == "BFGSB":
+        assert np.array_equal(g[6], o[6])
+
+
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("kind", ["BFGS", "DFP"])
 def test_lazy_schedule_vs_faithful_oracle_and_eager(osb, orc, kind):
