@@ -337,6 +337,39 @@ def test_spg_box_active_set_bit_exact(osb, orc):
         assert 0.3 < np.mean(got[4] != 0) < 0.7
 
 
+def test_full_size_c2_and_large_c5b_vs_oracle(osb, orc):
+    """C2 at its full size (GradientDescent + BackTracking on the generated dense SPD quadratic, n = 16384: 2 GiB of A on
+    both sides, 6 iterations) and C5b at n = 2^22 (SPG + GLL on the generated separable box quadratic, through the fused
+    one-kernel-per-trial path) against the oracle: same k and termination, x (and for C2 f) within 1e-9 relative, the
+    active set bit for bit."""
+    def c2(m):
+        obj = m.DenseQuadratic.generated(16384, True)
+        s = m.GradientDescent(1e-6, obj.x0)
+        st = run(m, s, m.BackTracking(1e-4, 0.5), obj, 6, 100)
+        xk = s.x()
+        return st, s.k(), s.termination_reason(), xk, obj(xk).f()
+
+    ref, got = both(osb, orc, c2)
+    assert got[:3] == ref[:3] and got[1] == 6
+    assert close(got[3], ref[3], rtol=1e-9) and abs(got[4] - ref[4]) <= 1e-9 * abs(ref[4])
+
+    n = 1 << 22
+    lb, ub = np.full(n, -1.0), np.full(n, 1.0)
+
+    def c5b(m):
+        obj = m.SeparableQuadratic.generated(n)
+        s = m.SpectralProjectedGradient(1e-6, np.zeros(n), obj, lb, ub)
+        st = run(m, s, m.GLLQuadratic(1e-4, 10), obj, 40, 50)
+        if m is osb:
+            assert s.path_info()["fused_stream"]
+        return st, s.k(), s.termination_reason(), s.x(), s.active_set()
+
+    ref, got = both(osb, orc, c5b)
+    assert got[:3] == ref[:3], (got[:3], ref[:3])
+    assert np.array_equal(got[4], ref[4])
+    assert close(got[3], ref[3], rtol=1e-9)
+
+
 def test_rosenbrock_lockstep_and_short_horizon(osb, orc):
     """Rosenbrock n = 64 from a perturbed start.  (a) free-running for 12 iterations against the
     oracle's rank-2 form; (b) lock-step: re-synchronise the oracle to the device state before every
