@@ -51,6 +51,23 @@ def test_newton_logistic_vs_oracle(osb, orc, ls):
     assert close(got[3], ref[3]) and close(got[4], ref[4], atol=1e-18)
 
 
+def test_newton_logistic_many_tiles_and_splits_vs_oracle(osb, orc):
+    """C5a at a size where the Hessian assembly runs many 128 x 128 tiles and full K splits (m = 8192, n = 1024: 36 lower
+    tiles x 4 splits of 43 stages) and the blocked Cholesky takes several panels: 3 Newton iterations against the oracle,
+    x and the decrement within 1e-9 relative."""
+    m_, n = 8192, 1024
+
+    def script(m):
+        obj = m.LogisticRegression.generated(m_, n, 1.0)
+        s = m.Newton(1e-12, np.zeros(n))
+        st = run(m, s, m.BackTracking(1e-4, 0.5), obj, 3, 20)
+        return st, s.k(), s.x(), s.decrement_squared()
+
+    ref, got = script(orc), script(osb)
+    assert got[:2] == ref[:2]
+    assert close(got[2], ref[2], rtol=1e-9) and abs(got[3] - ref[3]) <= 1e-9 * abs(ref[3])
+
+
 def test_projected_and_spectral_newton_logistic_vs_oracle(osb, orc):
     m_, n = 1024, 48
     lb, ub = np.full(n, -0.05), np.full(n, 0.05)
