@@ -458,6 +458,7 @@ void Solver::sym_settle_pingpong() {
 }
 void Solver::sym_to_full() {
   if (!sym_current) return;
+  ensure_packed();  // (materialises a still unwritten identity)
   sym_settle_pingpong();
   ensure_full();
   if (ctx->world > 1) {
@@ -519,11 +520,18 @@ void Solver::flush_pending() {
 }
 
 // A pending update means "the stored matrix lags by one rank-2 term": packing the lagging matrix keeps that meaning.
-void Solver::ensure_packed() {
-  if (sym_current) return;
+void Solver::ensure_packed(bool allow_unwritten_identity) {
+  if (sym_current) {
+    if (sym_ident_unwritten && !allow_unwritten_identity) {  // somebody is about to READ the packed memory
+      qn_sym_set_identity(ctx, n, Hsym.p);
+      sym_ident_unwritten = false;
+    }
+    return;
+  }
   if (Hsym.p == nullptr) Hsym.alloc_pooled(sym_sharded ? qn_sym_doubles_sharded(n, ctx->world, ctx->rank) : qn_sym_doubles(n));
   if (H_virtual_identity) {
     if (sym_sharded) qn_sym_set_identity_sharded(ctx, n, Hsym.p);
+    else if (allow_unwritten_identity) sym_ident_unwritten = true;  // (no 1 GiB memset: the first pass writes the triangle)
     else qn_sym_set_identity(ctx, n, Hsym.p);
     H_virtual_identity = false;
   } else if (sym_sharded) {
@@ -538,8 +546,10 @@ void Solver::ensure_packed() {
     ctx->all_gather_inplace(full.p, nrows * ld);
     qn_sym_pack_sharded(ctx, full.p, ld, n, Hsym.p);
     ctx->sync();
+    sym_ident_unwritten = false;
   } else {
     qn_sym_pack(ctx, H.p, ld, n, Hsym.p);
+    sym_ident_unwritten = false;
   }
   sym_current = true;
 }
@@ -554,7 +564,7 @@ void Solver::qn_after_step() {
   if (qn_schedule == 1 && qn_storage == 1 && h_symmetric && (ctx->world == 1 || sym_sharded) && (qn_kind == QN_BFGS || qn_kind == QN_DFP)) {
     // packed symmetric storage: the pass moves n^2 * 8 B (read + write of the lower triangle).  A pending
     // update means "the stored matrix lags by one rank-2 term": packing the lagging matrix keeps that meaning.
-    ensure_packed();
+    ensure_packed(/*allow_unwritten_identity=*/ctx->world == 1 && (qn_variant & 15) == 0);
     QNLazyArgs a{nullptr, ld, nrows, row0, n, d_state, ps.p, ph.p, y.p, g.p, s.p, h.p, wv.p, u.p, ps.p, ph.p,
                  ctx->gemv_ticket, qn_kind, nullptr, ctx->d_seq, 1, 0};
     a.defer_epi = defer_epi ? 1 : 0;
@@ -572,7 +582,8 @@ void Solver::qn_after_step() {
     const bool pingpong = (qn_variant & 2) != 0;
     if (pingpong && Hsym2.n != Hsym.n) Hsym2.alloc_pooled(Hsym.n);
     prof_mark();  // slot 0: the streaming pass, slot 1: the column fold + epilogue
-    qn_launch_lazy_sym(ctx, a, Hsym.p, pingpong ? Hsym2.p : Hsym.p, colpart.p, n, ld, 0, qn_variant);
+    qn_launch_lazy_sym(ctx, a, Hsym.p, pingpong ? Hsym2.p : Hsym.p, colpart.p, n, ld, 0, qn_variant, sym_ident_unwritten);
+    sym_ident_unwritten = false;  // (the pass has written every stored element)
     prof_mark();
     prof_mark();
     qn_launch_lazy_sym(ctx, a, Hsym.p, pingpong ? Hsym2.p : Hsym.p, colpart.p, n, ld, 1, qn_variant);

@@ -273,7 +273,8 @@ void qn_sym_set_identity_sharded(Ctx* ctx, int64_t n, double* P);
 void qn_sym_pack_sharded(Ctx* ctx, const double* Hfull, int64_t ld, int64_t n, double* P);  // every rank holds the full matrix
 void qn_sym_unpack_sharded(Ctx* ctx, const double* P, int64_t ld, int64_t n, double* Hfull_zeroed);
 void qn_sym_unpack(Ctx* ctx, const double* P, int64_t ld, int64_t n, double* H);
-void qn_launch_lazy_sym(Ctx* ctx, const QNLazyArgs& a, double* P, double* Pout, double* colpart, int64_t n, int64_t ld, int phase, int variant);
+void qn_launch_lazy_sym(Ctx* ctx, const QNLazyArgs& a, double* P, double* Pout, double* colpart, int64_t n, int64_t ld, int phase, int variant,
+                        bool identity_unwritten = false);  // identity_unwritten: P is H_0 = I and has not been written yet
 // whole outer iterations in one cooperative kernel (qn_iter.cu): head + line search + H pass + fold + exchange
 constexpr int64_t XFLAG2_LD = 256;  // per-source-rank chunk flags of the fused iteration kernel (one per CTA)
 HD int64_t xflag2_off(int world) { return XSLOT_OFF + 4 * (int64_t)world * XSLOT_LD; }  // doubles; after the {h, w} slots
@@ -399,7 +400,9 @@ struct Solver {
   DBuf gpart;                    // grid-reduction partials
   long long* d_iter_prof = nullptr;  // option "profile_iter": ns in head / pass / fold (CTA 0) and iterations
   int profile_iter = 0;
-  void ensure_packed();          // the packed copy holds the current matrix (identity / pack on first use)
+  void ensure_packed(bool allow_unwritten_identity = false);  // the packed copy holds the current matrix (identity / pack on first use)
+  bool sym_ident_unwritten = false;  // the packed copy IS the current matrix, H_0 = I, but its memory has not been written:
+                                     // the first pass generates the elements (one GPU, default pass variant)
   bool sym_current = false;  // the packed copy (not H) holds the current matrix
   bool h_symmetric = true;   // false after set_inv_hessian with a non-symmetric matrix (then full storage is used)
   void sym_to_full();

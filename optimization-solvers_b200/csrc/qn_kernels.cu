@@ -783,14 +783,14 @@ void qn_sym_layout(int64_t n, int world, int64_t tile, int* owner, int64_t* offs
 }
 
 // the streaming pass as its own launch (host-driven engine, profiling, pass variants)
-template <int KIND, bool SHARDED, int NT, bool OOP, bool ZERO>
+template <int KIND, bool SHARDED, int NT, bool OOP, bool ZERO, bool IDENT = false>
 __global__ void __launch_bounds__(NT, 512 / NT) qn_lazy_sym_kernel(QNLazyArgs a, QNSymArgs sa) {
   pdl_wait();
   pdl_launch_dependents();  // (one CTA per SM, one wave)
   DevState* st = a.st;
   if (st->done) return;
   const int pp = OOP ? st->pp : 0;  // which buffer holds the current matrix (toggled by the fold kernel)
-  sym_pass_body<KIND, SHARDED, NT, OOP, ZERO>(a, sa, st->pc0, st->pc1, st->pc2, pp, (int)gridDim.x, (int)blockIdx.x);
+  sym_pass_body<KIND, SHARDED, NT, OOP, ZERO, IDENT>(a, sa, st->pc0, st->pc1, st->pc2, pp, (int)gridDim.x, (int)blockIdx.x);
 }
 
 // ---- the packed pass with a shared-memory ring (qn_kernel bit 3) ----------------------------------------------------
@@ -1264,7 +1264,15 @@ static void launch_sym_pass(int grid, cudaStream_t stream, const QNLazyArgs& a, 
     return;
   }
   switch (variant & 7) {
-    case 0: launch_pdl(qn_lazy_sym_kernel<KIND, SHARDED, 512, false, false>, dim3(grid), dim3(512), 0, stream, a, sa); break;
+    case 0:
+      if (sa.zeroed == 2) {  // the stored matrix is a still unwritten identity: generate instead of load (one GPU only)
+        QNSymArgs sb = sa;
+        sb.zeroed = 0;
+        launch_pdl(qn_lazy_sym_kernel<KIND, false, 512, false, false, true>, dim3(grid), dim3(512), 0, stream, a, sb);
+      } else {
+        launch_pdl(qn_lazy_sym_kernel<KIND, SHARDED, 512, false, false>, dim3(grid), dim3(512), 0, stream, a, sa);
+      }
+      break;
     case 1: qn_lazy_sym_kernel<KIND, SHARDED, 256, false, false><<<grid, 256, 0, stream>>>(a, sa); break;
     case 2: qn_lazy_sym_kernel<KIND, SHARDED, 512, true, false><<<grid, 512, 0, stream>>>(a, sa); break;
     case 3: qn_lazy_sym_kernel<KIND, SHARDED, 256, true, false><<<grid, 256, 0, stream>>>(a, sa); break;
@@ -1272,12 +1280,13 @@ static void launch_sym_pass(int grid, cudaStream_t stream, const QNLazyArgs& a, 
   }
 }
 
-void qn_launch_lazy_sym(Ctx* ctx, const QNLazyArgs& a, double* P, double* Pout, double* colpart, int64_t n, int64_t ld, int phase, int variant) {
+void qn_launch_lazy_sym(Ctx* ctx, const QNLazyArgs& a, double* P, double* Pout, double* colpart, int64_t n, int64_t ld, int phase, int variant,
+                        bool identity_unwritten) {
   const bool sharded = ctx->world > 1;
   const int grid = qn_sym_grid(ctx, n, variant);
   OSB_REQUIRE(grid <= FOLD_MAXPARTS, OSB_ERR_UNSUPPORTED, "pass grid exceeds the fold's partial table");
   QNSymArgs sa{P, Pout, colpart, n, ld, sharded ? ctx->world : 1, sharded ? ctx->rank : 0, sharded ? ctx->d_peers : nullptr, ctx->d_seq,
-               grid, (variant & 4) ? 1 : 0};
+               grid, (variant & 4) ? 1 : (identity_unwritten ? 2 : 0)};
   const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 63) / 64, (int64_t)ctx->num_sms * 2));
   if (phase == 0) {  // the streaming pass over the packed triangle
     if (sharded) {

@@ -133,7 +133,9 @@ __host__ __device__ inline int64_t sym_first_row(int64_t ntiles, int world, int 
 // 128-register streaming loop is sensitive to anything that stays live across it).  NT = threads per CTA: 512 (one
 // CTA per SM) or 256 (two independent CTAs per SM: one streams while the other drains into its tile-end reduction).
 // OOP: ping-pong storage, the pass reads sa.P and writes sa.Pout.  ZERO: legacy zero-first partials.
-template <int KIND, bool SHARDED, int NT, bool OOP, bool ZERO>
+// IDENT: the stored matrix is the identity and has NOT been written yet (H_0 = I, bfgs.rs:30-33): the elements are
+// generated instead of loaded, so the first pass of a solve writes the triangle once instead of memset + read + write.
+template <int KIND, bool SHARDED, int NT, bool OOP, bool ZERO, bool IDENT = false>
 __device__ __forceinline__ void sym_pass_body(const QNLazyArgs& a, const QNSymArgs& sa, const double c0, const double c1, const double c2,
                                               const int pp, const int grid, const int cta) {
   const unsigned long long pol = l2_evict_first_policy();
@@ -192,7 +194,10 @@ __device__ __forceinline__ void sym_pass_body(const QNLazyArgs& a, const QNSymAr
       const double2 qj = ld_vec2(q + col);
       double2 hv[QN_R];
 #pragma unroll
-      for (int r = 0; r < QN_R; ++r) hv[r] = r < rows_here ? ld_stream_ef(base + r * lpad + col, pol) : make_double2(0.0, 0.0);
+      for (int r = 0; r < QN_R; ++r) {
+        if (IDENT) hv[r] = make_double2(col == (int)r0 + r ? 1.0 : 0.0, col + 1 == (int)r0 + r ? 1.0 : 0.0);
+        else hv[r] = r < rows_here ? ld_stream_ef(base + r * lpad + col, pol) : make_double2(0.0, 0.0);
+      }
       // column contributions only strictly left of the diagonal block (r0 is a multiple of 8 and col is even: the pair
       // (col, col + 1) is on the same side)
       const bool cok = col < (int)r0;
