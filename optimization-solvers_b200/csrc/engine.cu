@@ -87,6 +87,8 @@ constexpr size_t POOL_MAX_ENTRIES = 256;
 constexpr size_t POOL_MAX_BYTES = (size_t)8 << 30;
 }  // namespace
 
+constexpr int64_t SNAP_CHUNK = 32;  // iterations per launch of the fused kernel when it publishes callback snapshots (ring: 2 halves)
+
 // flag values of the in-kernel callback snapshots: unique over the process, so a recycled pinned ring never holds a
 // value a later launch waits for
 static std::atomic<unsigned long long> g_snap_seq{1ULL << 20};
@@ -300,9 +302,9 @@ Solver::~Solver() {
   pool_put(1, 2 * sizeof(DevState), cb_snap);
   pool_put(1, 2 * sizeof(double) * (size_t)ld, cb_xsnap);
   pool_put(1, 2 * sizeof(double) * (size_t)ld, cb_gsnap);
-  pool_put(0, 2 * 16 * 2 * sizeof(double) * (size_t)ld, snap_x);
-  pool_put(0, 2 * 16 * sizeof(DevState), snap_st);
-  pool_put(1, 2 * 16 * sizeof(unsigned long long), snap_flag);
+  pool_put(0, 2 * SNAP_CHUNK * 2 * sizeof(double) * (size_t)ld, snap_x);
+  pool_put(0, 2 * SNAP_CHUNK * sizeof(DevState), snap_st);
+  pool_put(1, 2 * SNAP_CHUNK * sizeof(unsigned long long), snap_flag);
   if (snap_stream) cudaStreamDestroy(snap_stream);
   pool_put(0, sizeof(LSParams), d_ls_buf);
   pool_put(1, 2 * sizeof(DevState), poll_snap);
@@ -1051,7 +1053,6 @@ int Solver::minimize_device(LineSearch* ls, Objective* obj, int64_t max_iter, in
   // Fused iteration kernel + run-ahead: the kernel itself writes every iteration's snapshot into a device ring and raises
   // a flag in pinned host memory (QNIterArgs.snap_*); the host copies the slot out on a side stream.  A launch therefore
   // still runs SNAP_CHUNK iterations while the host delivers the callbacks behind it.
-  constexpr int64_t SNAP_CHUNK = 16;
   struct SnapLaunch {
     int half, count;
     unsigned long long seq0;

@@ -386,7 +386,7 @@ struct Solver {
   bool sym_pingpong_dirty = false;
   // fused iteration kernel (qn_iter.cu): -1 = auto (on whenever it applies), 0 = off (one launch per phase)
   int opt_fused = -1;
-  double* snap_x = nullptr;      // device ring of in-kernel callback snapshots (2 halves x 16 iterations x {x, g})
+  double* snap_x = nullptr;      // device ring of in-kernel callback snapshots (2 halves x 32 iterations x {x, g})
   DevState* snap_st = nullptr;   // device ring of their scalars
   unsigned long long* snap_flag = nullptr;  // pinned host flags
   cudaStream_t snap_stream = nullptr;       // side stream of the copies out of the ring (runs beside the kernel)

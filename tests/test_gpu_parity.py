@@ -709,7 +709,7 @@ def test_run_ahead_callbacks_deliver_the_same_sequence(osb):
 
 def test_fused_kernel_publishes_callback_snapshots_from_inside_the_launch(osb):
     """fused_iteration = 1 with run-ahead callbacks: the kernel writes every iteration's x, g, f, k, norms into a device
-    ring, raises a flag in pinned host memory and keeps running (16 iterations per launch) while the host copies the slot
+    ring, raises a flag in pinned host memory and keeps running (32 iterations per launch) while the host copies the slot
     out on a side stream and delivers the callbacks behind it.  The sequence
     the callback sees, the trace and the final state equal the stalling delivery (one iteration per launch) bit for bit:
     a run that hits max_iter across several launches, one that converges inside a launch, and a bounded solver."""
@@ -727,7 +727,7 @@ def test_fused_kernel_publishes_callback_snapshots_from_inside_the_launch(osb):
 
     n = 2048
     lb, ub = np.full(n, -0.9), np.full(n, 1.1)
-    cases = ((lambda: osb.BFGS(1e-8, rosen_x0(n, 47)), lambda: osb.ExtendedRosenbrock(n), 41),
+    cases = ((lambda: osb.BFGS(1e-8, rosen_x0(n, 47)), lambda: osb.ExtendedRosenbrock(n), 70),
              (lambda: osb.BFGS(1e-7, np.zeros(512)), lambda: osb.SeparableQuadratic.generated(512), 300),
              (lambda: osb.DFP(1e-8, rosen_x0(n, 48)), lambda: osb.ExtendedRosenbrock(n), 20),
              (lambda: osb.BFGSB(1e-8, np.clip(rosen_x0(n, 49), lb, ub), lb, ub), lambda: osb.ExtendedRosenbrock(n), 19))
